@@ -1,0 +1,272 @@
+// b200sfm.cu -- C ABI (include/b200sfm.h) over the device solvers.
+#include "../../include/b200sfm.h"
+
+#include <new>
+
+#include "ba_solver.cuh"
+#include "context.cuh"
+
+namespace {
+
+template <class F>
+int guarded(b200sfm_ctx* ctx, F&& f) {
+  try {
+    return f();
+  } catch (const b200::CudaError& e) {
+    if (ctx) ctx->err = "CUDA error: " + e.msg + " (line " + std::to_string(e.line) + ")";
+    return B200SFM_ERR_CUDA;
+  } catch (const NcclError& e) {
+    if (ctx) ctx->err = "NCCL error: " + e.msg;
+    return B200SFM_ERR_NCCL;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->err = "host allocation failed";
+    return B200SFM_ERR_CUDA;
+  }
+}
+
+int create_common(int device, b200sfm_ctx** out) {
+  if (!out) return B200SFM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return B200SFM_ERR_CUDA;   // no CPU fallback
+  if (device < 0) device = 0;
+  if (device >= ndev) return B200SFM_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return B200SFM_ERR_CUDA;
+  b200sfm_ctx* c = new b200sfm_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&c->h_scal, b200sfm_ctx::kHScal * sizeof(double)) != cudaSuccess) {
+    delete c;
+    return B200SFM_ERR_CUDA;
+  }
+  *out = c;
+  return B200SFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200sfm_version(void) { return B200SFM_VERSION; }
+
+int b200sfm_create(int device, b200sfm_ctx** out) { return create_common(device, out); }
+
+int b200sfm_nccl_unique_id(void* out_id) {
+  if (!out_id) return B200SFM_ERR_INVALID_ARG;
+  std::string err;
+  if (!nccl_api().load(err)) return B200SFM_ERR_NCCL;
+  ncclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) return B200SFM_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == B200SFM_NCCL_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(out_id, &id, sizeof(id));
+  return B200SFM_OK;
+}
+
+int b200sfm_create_dist(int device, int rank, int world_size, const void* nccl_id, b200sfm_ctx** out) {
+  if (world_size < 1 || rank < 0 || rank >= world_size || (world_size > 1 && !nccl_id)) return B200SFM_ERR_INVALID_ARG;
+  int rc = create_common(device, out);
+  if (rc != B200SFM_OK) return rc;
+  b200sfm_ctx* c = *out;
+  c->rank = rank;
+  c->world = world_size;
+  if (world_size > 1) {
+    if (!nccl_api().load(c->err)) { b200sfm_destroy(c); *out = nullptr; return B200SFM_ERR_NCCL; }
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_id, sizeof(id));
+    if (nccl_api().CommInitRank(&c->comm, world_size, id, rank) != ncclSuccess) {
+      b200sfm_destroy(c);
+      *out = nullptr;
+      return B200SFM_ERR_NCCL;
+    }
+  }
+  return B200SFM_OK;
+}
+
+void b200sfm_destroy(b200sfm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  delete ctx;
+}
+
+const char* b200sfm_last_error(const b200sfm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int b200sfm_rank(const b200sfm_ctx* ctx) { return ctx ? ctx->rank : -1; }
+int b200sfm_world_size(const b200sfm_ctx* ctx) { return ctx ? ctx->world : -1; }
+
+// ---- BA ----------------------------------------------------------------------
+void b200sfm_ba_default_opts(b200sfm_ba_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // bundle_adjustment.h:14-32
+  o->optimize_rig_poses = 0;
+  o->optimize_rotations = 1;
+  o->optimize_translation = 1;
+  o->optimize_intrinsics = 1;
+  o->optimize_principal_point = 0;
+  o->optimize_points = 1;
+  o->min_num_view_per_track = 3;
+  o->max_num_iterations = 200;
+  o->thres_loss_function = 1.0;
+  o->function_tolerance = 1e-5;   // optimization_base.h:22
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->pcg_max_iterations = 500;
+  o->pcg_min_iterations = 0;
+  o->pcg_rel_tolerance = 1e-2;
+  o->preconditioner = 1;
+  o->profile_kernels = 0;
+  o->fixed_num_iterations = 0;
+}
+
+int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, int32_t K, const int64_t* pt_obs_begin,
+                              const int32_t* obs_cam, const double* obs_xy, const int32_t* cam_intr,
+                              const int32_t* intr_model, const uint8_t* cam_const_mask, int32_t min_num_view_per_track,
+                              b200sfm_ba_problem** out) {
+  if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (C <= 0 || P <= 0 || N <= 0 || K <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
+  if (!pt_obs_begin || !obs_cam || !obs_xy || !cam_intr || !intr_model) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
+  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+  for (int k = 0; k < K; ++k)
+    if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
+  return guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    auto* p = new b200sfm_ba_problem();
+    try {
+      p->create(ctx, C, P, N, K, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, cam_const_mask,
+                min_num_view_per_track, nullptr);
+    } catch (...) {
+      delete p;
+      throw;
+    }
+    *out = p;
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
+                                 const double* trans, const double* points) {
+  if (!p || !intr_params || !quat_xyzw || !trans || !points) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->set_state(intr_params, quat_xyzw, trans, points, nullptr);
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr_params, double* quat_xyzw, double* trans,
+                                 double* points) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->get_state(intr_params, quat_xyzw, trans, points, nullptr);
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_save_state(b200sfm_ba_problem* p) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->save_state();
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_restore_state(b200sfm_ba_problem* p) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    if (!p->restore_state()) { p->ctx->err = "no saved state"; return (int)B200SFM_ERR_INVALID_ARG; }
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, b200sfm_lm_stats* stats) {
+  if (!p || !opts) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    if (opts->min_num_view_per_track != p->min_views) {
+      p->ctx->err = "min_num_view_per_track differs from the value the problem was created with";
+      return (int)B200SFM_ERR_INVALID_ARG;
+    }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    return p->solve(*opts, stats);
+  });
+}
+
+int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, double* cost) {
+  if (!p || !opts || !cost) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    B200_LAUNCH(p->ctx, b200::k_eff_mask, b200::cdiv(p->C, 256), 256, 0, p->C, p->cam_mask_base.p, 0, 0, p->cam_mask.p);
+    *cost = p->eval_cost(p->cur, opts->thres_loss_function);
+    return (int)B200SFM_OK;
+  });
+}
+
+void b200sfm_ba_problem_free(b200sfm_ba_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  delete p;
+}
+
+int b200sfm_ba_solve(b200sfm_ctx* ctx, const b200sfm_ba_opts* opts, int32_t C, int32_t P, int64_t N, int32_t K,
+                     const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_xy, const int32_t* cam_intr,
+                     const int32_t* intr_model, double* intr_params, double* quat_xyzw, double* trans,
+                     const uint8_t* cam_const_mask, double* points, b200sfm_lm_stats* stats) {
+  if (!ctx || !opts || !intr_params || !quat_xyzw || !trans || !points) return B200SFM_ERR_INVALID_ARG;
+  b200sfm_lm_stats st{};
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+  b200sfm_ba_problem* p = nullptr;
+  const long long launches0 = ctx->launches;
+  int rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    B200_CUDA_OK(cudaEventCreate(&e0)); B200_CUDA_OK(cudaEventCreate(&e1));
+    B200_CUDA_OK(cudaEventCreate(&e2)); B200_CUDA_OK(cudaEventCreate(&e3));
+    B200_CUDA_OK(cudaEventRecord(e0, ctx->stream));
+    return (int)B200SFM_OK;
+  });
+  if (rc != B200SFM_OK) return rc;
+  rc = b200sfm_ba_problem_create(ctx, C, P, N, K, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, cam_const_mask,
+                                 opts->min_num_view_per_track, &p);
+  if (rc == B200SFM_OK) {
+    rc = guarded(ctx, [&]() {
+      st.h2d_bytes = N * 20 + ((long long)P + 1) * 4 + (long long)C * 5 + K * 4;
+      p->set_state(intr_params, quat_xyzw, trans, points, &st);
+      B200_CUDA_OK(cudaEventRecord(e1, ctx->stream));
+      const long long upload_launches = ctx->launches - launches0;
+      b200sfm_lm_stats solve_st = st;
+      solve_st.kernel_launches = upload_launches;
+      int r = p->solve(*opts, &solve_st);
+      if (r != B200SFM_OK) return r;
+      B200_CUDA_OK(cudaEventRecord(e2, ctx->stream));
+      p->get_state(intr_params, quat_xyzw, trans, points, &solve_st);
+      B200_CUDA_OK(cudaEventRecord(e3, ctx->stream));
+      B200_CUDA_OK(cudaEventSynchronize(e3));
+      float a, b, c;
+      B200_CUDA_OK(cudaEventElapsedTime(&a, e0, e1));
+      B200_CUDA_OK(cudaEventElapsedTime(&b, e2, e3));
+      B200_CUDA_OK(cudaEventElapsedTime(&c, e0, e3));
+      solve_st.ms_h2d = a;
+      solve_st.ms_d2h = b;
+      solve_st.ms_total = c;
+      st = solve_st;
+      return (int)B200SFM_OK;
+    });
+  }
+  if (p) b200sfm_ba_problem_free(p);
+  for (cudaEvent_t e : {e0, e1, e2, e3})
+    if (e) cudaEventDestroy(e);
+  if (stats) *stats = st;
+  return rc;
+}
+
+}  // extern "C"

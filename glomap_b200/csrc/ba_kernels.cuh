@@ -1,0 +1,818 @@
+// ba_kernels.cuh -- bundle-adjustment kernels (sm_100a).
+//
+// Replaces the arithmetic Ceres performs for glomap::BundleAdjuster
+// (reference: glomap/estimators/bundle_adjustment.cc:99,115-190,244-317):
+// per-observation reprojection residual + analytic 2x(6+3) Jacobian, Huber
+// corrector, per-point 3x3 Schur marginalisation, implicit-Schur mat-vec.
+//
+// Data layout in HBM (FP64, DESIGN.md "BA layout"):
+//   observations in POINT order (CSR by point): obs_cam[N], obs_pt[N], obs_xy[N]
+//   W[N][18]   6x3 block J_cam^T J_pt of every observation, AoS (144-B rows) so
+//              that a tile of 256 consecutive observations is one contiguous
+//              36,864-B chunk moved by a single TMA bulk copy
+//   V[P][6], Vinv[P][6], gp[P][3]         per point (packed symmetric)
+//   U[C][21], gc[C][6], Sd[C][21], Minv[C][21]   per camera (packed symmetric)
+//   camera-order copies pt_c[Nv], xy_c[Nv], camord_obs[Nv] + segments
+// Point-order kernels run one CTA (256 threads) per tile of whole points with
+// <= 256 observations; one thread per observation, per-point reductions
+// through shared memory.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kCamRec = 8;    // q(4) t(3) packed{mask, intr idx}
+constexpr int kIntrRec = 8;   // fx fy cx cy k1 k2 model pad
+constexpr double kZEps = 1e-12;
+constexpr int kSeg = 256;     // observations per camera-order segment (one warp)
+
+struct BAView {
+  int C, P, K;
+  long long N;
+  int n_tiles;
+  int n_segs;
+  int min_views;
+  // structure
+  const int* obs_cam;
+  const int* obs_pt;
+  const double2* obs_xy;
+  const unsigned* pt_begin;     // [P+1]
+  const int* tile_pt_begin;     // [n_tiles+1]
+  const int* camord_obs;        // [Nv] observation ids sorted by camera
+  const int* pt_c;              // [Nv]
+  const double2* xy_c;          // [Nv]
+  const int* seg_cam;           // [n_segs]
+  const int* seg_begin;         // [n_segs+1] (only within one camera: seg_end = seg_begin2[s])
+  const int* seg_end;
+  // linear system
+  double* W;
+  double* V;
+  double* Vinv;
+  double* gp;
+  double* U;
+  double* gc;
+  double* Sd;
+  double* Minv;
+  double* jscale_c;
+  double* jscale_p;
+  double* Dc;
+};
+
+// Huber (Ceres HuberLoss): returns rho'(s) and rho(s)
+__device__ __forceinline__ void huber(double s, double a, double& rho0, double& rho1) {
+  const double b = a * a;
+  if (s > b) {
+    const double r = sqrt(s);
+    rho0 = 2.0 * a * r - b;
+    rho1 = fmax(2.2250738585072014e-308, a / r);
+  } else {
+    rho0 = s;
+    rho1 = 1.0;
+  }
+}
+
+// Pixel projection with the generic radial form (pinhole models have k = 0,
+// simple models fx = fy).  J = d(px,py)/d(Xc) row-major 2x3.
+__device__ __forceinline__ void project_jac(const double* __restrict__ ir, double x, double y, double z, double& px,
+                                            double& py, double J[6]) {
+  const double iz = 1.0 / z;
+  const double u = x * iz, v = y * iz;
+  const double fx = ir[0], fy = ir[1], cx = ir[2], cy = ir[3], k1 = ir[4], k2 = ir[5];
+  const double r2 = u * u + v * v;
+  const double d = 1.0 + r2 * (k1 + k2 * r2);
+  const double dd = k1 + 2.0 * k2 * r2;
+  px = fx * u * d + cx;
+  py = fy * v * d + cy;
+  const double a00 = d + 2.0 * u * u * dd, a01 = 2.0 * u * v * dd, a11 = d + 2.0 * v * v * dd;
+  J[0] = fx * a00 * iz;
+  J[1] = fx * a01 * iz;
+  J[2] = -fx * iz * (a00 * u + a01 * v);
+  J[3] = fy * a01 * iz;
+  J[4] = fy * a11 * iz;
+  J[5] = -fy * iz * (a01 * u + a11 * v);
+}
+__device__ __forceinline__ void project_only(const double* __restrict__ ir, double x, double y, double z, double& px,
+                                             double& py) {
+  const double iz = 1.0 / z;
+  const double u = x * iz, v = y * iz;
+  const double r2 = u * u + v * v;
+  const double d = 1.0 + r2 * (ir[4] + ir[5] * r2);
+  px = ir[0] * u * d + ir[2];
+  py = ir[1] * v * d + ir[3];
+}
+
+// Everything one observation contributes.  Jc = [Jrot(2x3) | Jtrn(2x3)] and
+// Jp (2x3), already scaled by sqrt(rho') and masked; r scaled by sqrt(rho').
+struct ObsLin {
+  double Jr[6], Jt[6], Jp[6], r[2], rho0;
+  bool valid;
+};
+
+__device__ __forceinline__ void linearize_obs(const double* __restrict__ cam_rec, const double* __restrict__ intr_rec,
+                                              int cam, double X0, double X1, double X2, double2 xy, double huber_a,
+                                              ObsLin& o) {
+  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const long long packed = __double_as_longlong(t4.w);
+  const int mask = (int)(packed & 0xff);
+  const int intr = (int)(packed >> 8);
+  const double q[4] = {q4.x, q4.y, q4.z, q4.w};
+  double R[9];
+  quat_to_R(q, R);
+  const double rx = R[0] * X0 + R[1] * X1 + R[2] * X2;
+  const double ry = R[3] * X0 + R[4] * X1 + R[5] * X2;
+  const double rz = R[6] * X0 + R[7] * X1 + R[8] * X2;
+  const double xc = rx + t4.x, yc = ry + t4.y, zc = rz + t4.z;
+  o.valid = zc > kZEps;
+  if (!o.valid) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.Jr[k] = o.Jt[k] = o.Jp[k] = 0.0;
+    o.r[0] = o.r[1] = 0.0;
+    o.rho0 = 0.0;
+    return;
+  }
+  double px, py, J[6];
+  project_jac(intr_rec + (size_t)intr * kIntrRec, xc, yc, zc, px, py, J);
+  const double r0 = px - xy.x, r1 = py - xy.y;
+  double rho1;
+  huber(r0 * r0 + r1 * r1, huber_a, o.rho0, rho1);
+  const double w = sqrt(rho1);
+  o.r[0] = w * r0;
+  o.r[1] = w * r1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) J[k] *= w;
+  // translation block
+  const bool tvar = !(mask & 2), rvar = !(mask & 1);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o.Jt[k] = tvar ? J[k] : 0.0;
+  // rotation block: J * (-2 [RX]x)   (EigenQuaternionManifold: left perturbation of angle 2|d|)
+  // [v]x = [0 -vz vy; vz 0 -vx; -vy vx 0];  J*(-2[v]x) columns:
+  //   col0 = -2*( J1*vz - J2*vy ), col1 = -2*( -J0*vz + J2*vx ), col2 = -2*( J0*vy - J1*vx )
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const double j0 = J[3 * a], j1 = J[3 * a + 1], j2 = J[3 * a + 2];
+    o.Jr[3 * a + 0] = rvar ? -2.0 * (j1 * rz - j2 * ry) : 0.0;
+    o.Jr[3 * a + 1] = rvar ? -2.0 * (j2 * rx - j0 * rz) : 0.0;
+    o.Jr[3 * a + 2] = rvar ? -2.0 * (j0 * ry - j1 * rx) : 0.0;
+  }
+  // point block: J * R
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) o.Jp[3 * a + b] = J[3 * a] * R[b] + J[3 * a + 1] * R[3 + b] + J[3 * a + 2] * R[6 + b];
+}
+
+// ---------------------------------------------------------------------------
+// camera / intrinsics records
+// ---------------------------------------------------------------------------
+__global__ void ba_build_records(int C, int K, const double* __restrict__ quat, const double* __restrict__ trans,
+                                 const int* __restrict__ cam_intr, const unsigned char* __restrict__ cam_mask,
+                                 const double* __restrict__ intr, const int* __restrict__ intr_model,
+                                 double* __restrict__ cam_rec, double* __restrict__ intr_rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    double* r = cam_rec + (size_t)i * kCamRec;
+    r[0] = quat[4 * i];
+    r[1] = quat[4 * i + 1];
+    r[2] = quat[4 * i + 2];
+    r[3] = quat[4 * i + 3];
+    r[4] = trans[3 * i];
+    r[5] = trans[3 * i + 1];
+    r[6] = trans[3 * i + 2];
+    const long long packed = ((long long)cam_intr[i] << 8) | (long long)cam_mask[i];
+    r[7] = __longlong_as_double(packed);
+  }
+  if (i < K) {
+    const double* p = intr + (size_t)i * 12;
+    double* r = intr_rec + (size_t)i * kIntrRec;
+    const int m = intr_model[i];
+    double fx, fy, cx, cy, k1 = 0, k2 = 0;
+    if (m == 0) { fx = fy = p[0]; cx = p[1]; cy = p[2]; }
+    else if (m == 1) { fx = p[0]; fy = p[1]; cx = p[2]; cy = p[3]; }
+    else if (m == 2) { fx = fy = p[0]; cx = p[1]; cy = p[2]; k1 = p[3]; }
+    else { fx = fy = p[0]; cx = p[1]; cy = p[2]; k1 = p[3]; k2 = p[4]; }
+    r[0] = fx; r[1] = fy; r[2] = cx; r[3] = cy; r[4] = k1; r[5] = k2; r[6] = (double)m; r[7] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: Jacobian + point Schur blocks, point order.  scal[0] += cost,
+// scal[1] = max |g_p|
+// ---------------------------------------------------------------------------
+struct K1Smem {
+  alignas(128) double Wt[kTile * kWDoubles];
+  double red[9][kTile];
+  double scratch[32];
+};
+
+__global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const double* __restrict__ cam_rec,
+                                                             const double* __restrict__ intr_rec,
+                                                             const double* __restrict__ points, double huber_a,
+                                                             int points_var, double* __restrict__ scal) {
+  extern __shared__ unsigned char smem_raw[];
+  K1Smem& sm = *reinterpret_cast<K1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int tile = blockIdx.x;
+  const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
+  const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
+  const int n = (int)(o1 - o0);
+  const int tid = threadIdx.x;
+  const int npts = p1 - p0;
+  // per-point accumulators (thread j <-> point p0 + j)
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  unsigned pb = 0, pe = 0;
+  bool pvalid = false;
+  if (tid < npts) {
+    pb = v.pt_begin[p0 + tid];
+    pe = v.pt_begin[p0 + tid + 1];
+    pvalid = (int)(pe - pb) >= v.min_views;
+  }
+  double cost = 0.0;
+  for (int c0 = 0; c0 < n; c0 += kTile) {
+    const int nc = min(kTile, n - c0);
+    const bool active = tid < nc;
+    ObsLin o;
+    bool use = false;
+    if (active) {
+      const unsigned oi = o0 + c0 + tid;
+      const int pt = v.obs_pt[oi];
+      use = (int)(v.pt_begin[pt + 1] - v.pt_begin[pt]) >= v.min_views;
+      if (use) {
+        const int cam = v.obs_cam[oi];
+        const double2 xy = v.obs_xy[oi];
+        const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+        linearize_obs(cam_rec, intr_rec, cam, X0, X1, X2, xy, huber_a, o);
+        cost += 0.5 * o.rho0;
+      }
+    }
+    if (!use) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) o.Jr[k] = o.Jt[k] = o.Jp[k] = 0.0;
+      o.r[0] = o.r[1] = 0.0;
+    }
+    if (points_var) {
+      // W = [Jr^T; Jt^T] Jp  (6x3), rows of 3 -> smem tile (stride 144 B: conflict-free STS.128)
+      double* wrow = sm.Wt + tid * kWDoubles;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          wrow[3 * a + b] = o.Jr[a] * o.Jp[b] + o.Jr[3 + a] * o.Jp[3 + b];
+          wrow[9 + 3 * a + b] = o.Jt[a] * o.Jp[b] + o.Jt[3 + a] * o.Jp[3 + b];
+        }
+      // V_o (packed sym) and g_o
+      sm.red[0][tid] = o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3];
+      sm.red[1][tid] = o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4];
+      sm.red[2][tid] = o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5];
+      sm.red[3][tid] = o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4];
+      sm.red[4][tid] = o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5];
+      sm.red[5][tid] = o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5];
+      sm.red[6][tid] = o.Jp[0] * o.r[0] + o.Jp[3] * o.r[1];
+      sm.red[7][tid] = o.Jp[1] * o.r[0] + o.Jp[4] * o.r[1];
+      sm.red[8][tid] = o.Jp[2] * o.r[0] + o.Jp[5] * o.r[1];
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tma_store_1d(v.W + (size_t)(o0 + c0) * kWDoubles, sm.Wt, (uint32_t)nc * kWBytes);
+        tma_store_commit();
+      }
+      if (tid < npts && pvalid) {
+        const int lo = max((int)pb - (int)(o0 + c0), 0), hi = min((int)pe - (int)(o0 + c0), nc);
+        for (int i = lo; i < hi; ++i) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc[k] += sm.red[k][i];
+        }
+      }
+      if (tid == 0) tma_store_wait_read();
+      __syncthreads();
+    }
+  }
+  double gmax = 0.0;
+  if (points_var && tid < npts) {
+    const size_t p = (size_t)(p0 + tid);
+    if (pvalid) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v.V[6 * p + k] = acc[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v.gp[3 * p + k] = acc[6 + k];
+        gmax = fmax(gmax, fabs(acc[6 + k]));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v.V[6 * p + k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v.gp[3 * p + k] = 0.0;
+    }
+  }
+  cost = block_sum(cost, sm.scratch);
+  if (tid == 0 && cost != 0.0) atomicAdd(&scal[0], cost);
+  gmax = block_max(gmax, sm.scratch);
+  if (tid == 0 && gmax > 0.0) atomic_max_nonneg(&scal[1], gmax);
+}
+
+// ---------------------------------------------------------------------------
+// K2a: camera blocks U = sum Jc^T Jc (packed 21), gc = sum Jc^T r, camera order.
+// One warp per segment (<= kSeg observations of ONE camera).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double* __restrict__ cam_rec,
+                                                        const double* __restrict__ intr_rec,
+                                                        const double* __restrict__ points, double huber_a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= v.n_segs) return;
+  const int cam = v.seg_cam[warp];
+  const int b = v.seg_begin[warp], e = v.seg_end[warp];
+  double U[21], g[6];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) U[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) g[k] = 0.0;
+  for (int i = b + lane; i < e; i += 32) {
+    const int pt = v.pt_c[i];
+    const double2 xy = v.xy_c[i];
+    const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+    ObsLin o;
+    linearize_obs(cam_rec, intr_rec, cam, X0, X1, X2, xy, huber_a, o);
+    double Jc[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Jc[a][k] = o.Jr[3 * a + k];
+        Jc[a][3 + k] = o.Jt[3 * a + k];
+      }
+    int idx = 0;
+#pragma unroll
+    for (int i2 = 0; i2 < 6; ++i2) {
+#pragma unroll
+      for (int j = i2; j < 6; ++j) U[idx++] += Jc[0][i2] * Jc[0][j] + Jc[1][i2] * Jc[1][j];
+      g[i2] += Jc[0][i2] * o.r[0] + Jc[1][i2] * o.r[1];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    const double s = warp_sum(U[k]);
+    if (lane == k && s != 0.0) atomicAdd(&v.U[(size_t)cam * 21 + k], s);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double s = warp_sum(g[k]);
+    if (lane == 21 + k && s != 0.0) atomicAdd(&v.gc[(size_t)cam * 6 + k], s);
+  }
+}
+
+// After the (all-)reduction of U/gc: masked or unobserved dofs become identity
+// rows, Jacobi scaling is fixed at the first linearisation, max|gc| -> scal[1].
+__global__ void ba_finalize_cams(int C, double* __restrict__ U, double* __restrict__ gc,
+                                 const unsigned char* __restrict__ cam_mask, double* __restrict__ jscale_c,
+                                 int set_jscale, double* __restrict__ scal) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double gmax = 0.0;
+  if (c < C) {
+    const int mask = cam_mask[c];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int di = sym_idx(6, i, i);
+      const bool fixed = (i < 3) ? (mask & 1) : (mask & 2);
+      double d = U[(size_t)c * 21 + di];
+      if (fixed || !(d > 0.0)) {
+        // decouple this dof completely
+        for (int j = 0; j < 6; ++j) U[(size_t)c * 21 + (i <= j ? sym_idx(6, i, j) : sym_idx(6, j, i))] = 0.0;
+        U[(size_t)c * 21 + di] = 1.0;
+        gc[(size_t)c * 6 + i] = 0.0;
+        if (set_jscale) jscale_c[(size_t)c * 6 + i] = -1.0;   // marks "not a variable"
+      } else {
+        if (set_jscale) jscale_c[(size_t)c * 6 + i] = 1.0 / (1.0 + sqrt(d));
+        gmax = fmax(gmax, fabs(gc[(size_t)c * 6 + i]));
+      }
+    }
+  }
+  gmax = warp_max(gmax);
+  if ((threadIdx.x & 31) == 0 && gmax > 0.0) atomic_max_nonneg(&scal[1], gmax);
+}
+
+// LM damping of the camera blocks: Dc = clamp(U_ii js^2, 1e-6, 1e32) / (radius js^2)
+// (levenberg_marquardt_strategy.cc, in the Jacobi-scaled space)
+__global__ void ba_damp_cams(int C, const double* __restrict__ U, const double* __restrict__ jscale_c, double radius,
+                             double* __restrict__ Dc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 6) return;
+  const int c = i / 6, k = i % 6;
+  const double js = jscale_c[i];
+  if (js < 0.0) {
+    Dc[i] = 0.0;
+    return;
+  }
+  const double d = U[(size_t)c * 21 + sym_idx(6, k, k)];
+  const double js2 = js * js;
+  Dc[i] = fmin(fmax(d * js2, 1e-6), 1e32) / (radius * js2);
+}
+
+// Point blocks: Jacobi scale (first linearisation) and Vinv = (V + Dp)^-1
+__device__ __forceinline__ void point_damping(const double* V6, const double* js, double radius, double Dp[3]) {
+  const double d[3] = {V6[0], V6[3], V6[5]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double js2 = js[k] * js[k];
+    Dp[k] = fmin(fmax(d[k] * js2, 1e-6), 1e32) / (radius * js2);
+  }
+}
+__global__ void ba_damp_points(int P, const double* __restrict__ V, double* __restrict__ jscale_p, int set_jscale,
+                               double radius, double* __restrict__ Vinv) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double v6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v6[k] = V[6 * (size_t)p + k];
+  double js[3];
+  if (set_jscale) {
+    js[0] = 1.0 / (1.0 + sqrt(v6[0]));
+    js[1] = 1.0 / (1.0 + sqrt(v6[3]));
+    js[2] = 1.0 / (1.0 + sqrt(v6[5]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) jscale_p[3 * (size_t)p + k] = js[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) js[k] = jscale_p[3 * (size_t)p + k];
+  }
+  double Dp[3];
+  point_damping(v6, js, radius, Dp);
+  v6[0] += Dp[0];
+  v6[3] += Dp[1];
+  v6[5] += Dp[2];
+  double inv[6];
+  sym3_inverse(v6, inv);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Vinv[6 * (size_t)p + k] = inv[k];
+}
+
+// ---------------------------------------------------------------------------
+// K2b: Schur-Jacobi diagonal  Sd_c = sum_{o in c} W_o Vinv_p W_o^T, camera order
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ba_schur_diag(BAView v) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= v.n_segs) return;
+  const int cam = v.seg_cam[warp];
+  const int b = v.seg_begin[warp], e = v.seg_end[warp];
+  double S[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) S[k] = 0.0;
+  for (int i = b + lane; i < e; i += 32) {
+    const int o = v.camord_obs[i];
+    const int pt = v.pt_c[i];
+    double w[18], vi[6];
+    const double2* wp = reinterpret_cast<const double2*>(v.W + (size_t)o * kWDoubles);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double2 t = wp[k];
+      w[2 * k] = t.x;
+      w[2 * k + 1] = t.y;
+    }
+    const double2* vp = reinterpret_cast<const double2*>(v.Vinv + (size_t)pt * 6);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double2 t = vp[k];
+      vi[2 * k] = t.x;
+      vi[2 * k + 1] = t.y;
+    }
+    double T[6][3];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) sym3_mul(vi, &w[3 * r], T[r]);
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c)
+        S[idx++] += T[r][0] * w[3 * c] + T[r][1] * w[3 * c + 1] + T[r][2] * w[3 * c + 2];
+  }
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    const double s = warp_sum(S[k]);
+    if (lane == k && s != 0.0) atomicAdd(&v.Sd[(size_t)cam * 21 + k], s);
+  }
+}
+
+// Preconditioner blocks Minv = (U + Dc - Sd)^-1 (Sd == nullptr: block-Jacobi on U + Dc)
+__global__ void ba_build_precond(int C, const double* __restrict__ U, const double* __restrict__ Dc,
+                                 const double* __restrict__ Sd, double* __restrict__ Minv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) m[k] = U[(size_t)c * 21 + k] - (Sd ? Sd[(size_t)c * 21 + k] : 0.0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) m[sym_idx(6, i, i)] += Dc[(size_t)c * 6 + i];
+  double inv[21];
+  spd_inverse_packed<6>(m, inv);
+#pragma unroll
+  for (int k = 0; k < 21; ++k) Minv[(size_t)c * 21 + k] = inv[k];
+}
+
+// ---------------------------------------------------------------------------
+// K3: implicit Schur pass over one tile of points.
+//   s_p = [g_p] + sum_o W_o^T x_cam(o);  z_p = Vinv_p s_p
+//   MODE 0 (mat-vec):  y_cam -= W_o z_p
+//   MODE 1 (rhs):      s_p = g_p only (no x); y_cam -= W_o z_p
+//   MODE 2 (back-substitution): s_p = g_p + W^T dc; dp = -z_p; points_new = points + dp;
+//          bscal[0] += g_p.dp, bscal[1] += sum Dp dp^2, bscal[2] += |dp|^2, bscal[3] += |points|^2
+// ---------------------------------------------------------------------------
+struct K3Smem {
+  alignas(128) double Wt[kTile * kWDoubles];
+  double t[3][kTile];
+  double z[3][kTile];
+  double scratch[32];
+  alignas(8) uint64_t mbar;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* __restrict__ x, double* __restrict__ y,
+                                                       const double* __restrict__ points,
+                                                       double* __restrict__ points_new, double radius,
+                                                       double* __restrict__ bscal) {
+  extern __shared__ unsigned char smem_raw[];
+  K3Smem& sm = *reinterpret_cast<K3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int tile = blockIdx.x;
+  const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
+  const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
+  const int n = (int)(o1 - o0);
+  const int tid = threadIdx.x;
+  const int npts = p1 - p0;
+  const int nchunks = (n + kTile - 1) / kTile;
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  unsigned pb = 0, pe = 0;
+  bool pvalid = false;
+  if (tid < npts) {
+    pb = v.pt_begin[p0 + tid];
+    pe = v.pt_begin[p0 + tid + 1];
+    pvalid = (int)(pe - pb) >= v.min_views;
+  }
+  double s[3] = {0.0, 0.0, 0.0};
+  double w[18];
+  int cam = 0;
+  // ---- phase A: s_p ----------------------------------------------------------
+  if (MODE != 1) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int c0 = ch * kTile;
+      const int nc = min(kTile, n - c0);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kWBytes);
+        tma_load_1d(sm.Wt, v.W + (size_t)(o0 + c0) * kWDoubles, (uint32_t)nc * kWBytes, &sm.mbar);
+      }
+      double xc[6] = {0, 0, 0, 0, 0, 0};
+      const bool active = tid < nc;
+      if (active) {
+        cam = v.obs_cam[o0 + c0 + tid];
+        const double2* xp = reinterpret_cast<const double2*>(x + (size_t)cam * 6);
+        const double2 a = xp[0], b = xp[1], c = xp[2];
+        xc[0] = a.x; xc[1] = a.y; xc[2] = b.x; xc[3] = b.y; xc[4] = c.x; xc[5] = c.y;
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      double t0 = 0, t1 = 0, t2 = 0;
+      if (active) {
+        const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double2 q = wr[k];
+          w[2 * k] = q.x;
+          w[2 * k + 1] = q.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          t0 += w[3 * r] * xc[r];
+          t1 += w[3 * r + 1] * xc[r];
+          t2 += w[3 * r + 2] * xc[r];
+        }
+      }
+      sm.t[0][tid] = t0;
+      sm.t[1][tid] = t1;
+      sm.t[2][tid] = t2;
+      __syncthreads();
+      if (tid < npts && pvalid) {
+        const int lo = max((int)pb - (int)(o0 + c0), 0), hi = min((int)pe - (int)(o0 + c0), nc);
+        for (int i = lo; i < hi; ++i) {
+          s[0] += sm.t[0][i];
+          s[1] += sm.t[1][i];
+          s[2] += sm.t[2][i];
+        }
+      }
+      if (nchunks > 1) __syncthreads();
+    }
+  }
+  // ---- z_p -------------------------------------------------------------------
+  double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  if (tid < npts) {
+    double z[3] = {0.0, 0.0, 0.0};
+    if (pvalid) {
+      const size_t p = (size_t)(p0 + tid);
+      double g[3] = {0, 0, 0};
+      if (MODE != 0) {
+        g[0] = v.gp[3 * p];
+        g[1] = v.gp[3 * p + 1];
+        g[2] = v.gp[3 * p + 2];
+        s[0] += g[0];
+        s[1] += g[1];
+        s[2] += g[2];
+      }
+      double vi[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vi[k] = v.Vinv[6 * p + k];
+      sym3_mul(vi, s, z);
+      if (MODE == 2) {
+        double v6[6], js[3], Dp[3];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v6[k] = v.V[6 * p + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) js[k] = v.jscale_p[3 * p + k];
+        point_damping(v6, js, radius, Dp);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double dp = -z[k];
+          const double xo = points[3 * p + k];
+          points_new[3 * p + k] = xo + dp;
+          b0 += g[k] * dp;
+          b1 += Dp[k] * dp * dp;
+          b2 += dp * dp;
+          b3 += xo * xo;
+        }
+      }
+    } else if (MODE == 2) {
+      const size_t p = (size_t)(p0 + tid);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) points_new[3 * p + k] = points[3 * p + k];
+    }
+    sm.z[0][tid] = z[0];
+    sm.z[1][tid] = z[1];
+    sm.z[2][tid] = z[2];
+  }
+  if (MODE == 2) {
+    b0 = block_sum(b0, sm.scratch);
+    b1 = block_sum(b1, sm.scratch);
+    b2 = block_sum(b2, sm.scratch);
+    b3 = block_sum(b3, sm.scratch);
+    if (tid == 0) {
+      atomicAdd(&bscal[0], b0);
+      atomicAdd(&bscal[1], b1);
+      atomicAdd(&bscal[2], b2);
+      atomicAdd(&bscal[3], b3);
+    }
+    return;
+  }
+  __syncthreads();
+  // ---- phase B: y_cam -= W_o z_p ---------------------------------------------
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int c0 = ch * kTile;
+    const int nc = min(kTile, n - c0);
+    const bool reload = (MODE == 1) || (nchunks > 1);
+    if (reload) {
+      __syncthreads();
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kWBytes);
+        tma_load_1d(sm.Wt, v.W + (size_t)(o0 + c0) * kWDoubles, (uint32_t)nc * kWBytes, &sm.mbar);
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+    }
+    if (tid < nc) {
+      const unsigned oi = o0 + c0 + tid;
+      if (reload) {
+        cam = v.obs_cam[oi];
+        const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double2 q = wr[k];
+          w[2 * k] = q.x;
+          w[2 * k + 1] = q.y;
+        }
+      }
+      const int pl = v.obs_pt[oi] - p0;
+      const double z0 = sm.z[0][pl], z1 = sm.z[1][pl], z2 = sm.z[2][pl];
+      if (z0 != 0.0 || z1 != 0.0 || z2 != 0.0) {
+        double* yc = y + (size_t)cam * 6;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double val = w[3 * r] * z0 + w[3 * r + 1] * z1 + w[3 * r + 2] * z2;
+          atomicAdd(&yc[r], -val);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// cost-only evaluation (trial step): scal[0] += 1/2 sum rho
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_cost(BAView v, const double* __restrict__ cam_rec,
+                                               const double* __restrict__ intr_rec, const double* __restrict__ points,
+                                               double huber_a, double* __restrict__ scal) {
+  __shared__ double scratch[32];
+  double cost = 0.0;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < v.N; o += (long long)gridDim.x * blockDim.x) {
+    const int pt = v.obs_pt[o];
+    if ((int)(v.pt_begin[pt + 1] - v.pt_begin[pt]) < v.min_views) continue;
+    const int cam = v.obs_cam[o];
+    const double2 xy = v.obs_xy[o];
+    const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+    const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+    const int intr = (int)(__double_as_longlong(t4.w) >> 8);
+    const double q[4] = {q4.x, q4.y, q4.z, q4.w};
+    double R[9];
+    quat_to_R(q, R);
+    const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+    const double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
+    const double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
+    const double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+    if (zc > kZEps) {
+      double px, py;
+      project_only(intr_rec + (size_t)intr * kIntrRec, xc, yc, zc, px, py);
+      const double r0 = px - xy.x, r1 = py - xy.y;
+      double rho0, rho1;
+      huber(r0 * r0 + r1 * r1, huber_a, rho0, rho1);
+      cost += 0.5 * rho0;
+    }
+  }
+  cost = block_sum(cost, scratch);
+  if (threadIdx.x == 0 && cost != 0.0) atomicAdd(&scal[0], cost);
+}
+
+// ---------------------------------------------------------------------------
+// camera update: q_new = exp(d_rot) (x) q (EigenQuaternionManifold), t_new = t + d_t
+//   cscal[0] += gc.dc, cscal[1] += dc.rho (PCG residual), cscal[2] += sum Dc dc^2,
+//   cscal[3] += |x_new - x|^2 (ambient), cscal[4] += |x|^2 (ambient, variable blocks)
+// ---------------------------------------------------------------------------
+__global__ void ba_update_cams(int C, const double* __restrict__ quat, const double* __restrict__ trans,
+                               const double* __restrict__ dc, const double* __restrict__ gc,
+                               const double* __restrict__ resid, const double* __restrict__ Dc,
+                               const double* __restrict__ jscale_c, double* __restrict__ quat_new,
+                               double* __restrict__ trans_new, double* __restrict__ cscal) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  if (c < C) {
+    double d[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const size_t i = (size_t)c * 6 + k;
+      const bool var = jscale_c[i] >= 0.0;
+      d[k] = var ? dc[i] : 0.0;
+      a0 += gc[i] * d[k];
+      a1 += resid[i] * d[k];
+      a2 += Dc[i] * d[k] * d[k];
+    }
+    const double q[4] = {quat[4 * c], quat[4 * c + 1], quat[4 * c + 2], quat[4 * c + 3]};
+    const bool rvar = jscale_c[(size_t)c * 6] >= 0.0 || jscale_c[(size_t)c * 6 + 1] >= 0.0 || jscale_c[(size_t)c * 6 + 2] >= 0.0;
+    const bool tvar = jscale_c[(size_t)c * 6 + 3] >= 0.0 || jscale_c[(size_t)c * 6 + 4] >= 0.0 || jscale_c[(size_t)c * 6 + 5] >= 0.0;
+    const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    double qn[4] = {q[0], q[1], q[2], q[3]};
+    if (nrm > 0.0) {
+      const double sn = sin(nrm) / nrm, cs = cos(nrm);
+      const double ax = sn * d[0], ay = sn * d[1], az = sn * d[2], aw = cs;
+      // Hamilton product (a (x) q), xyzw
+      qn[0] = aw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+      qn[1] = aw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
+      qn[2] = aw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
+      qn[3] = aw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+      const double inv = 1.0 / sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) qn[k] *= inv;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      quat_new[4 * c + k] = qn[k];
+      if (rvar) {
+        a3 += (qn[k] - q[k]) * (qn[k] - q[k]);
+        a4 += q[k] * q[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double t = trans[3 * c + k];
+      trans_new[3 * c + k] = t + d[3 + k];
+      if (tvar) {
+        a3 += d[3 + k] * d[3 + k];
+        a4 += t * t;
+      }
+    }
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  a3 = warp_sum(a3);
+  a4 = warp_sum(a4);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&cscal[0], a0);
+    atomicAdd(&cscal[1], a1);
+    atomicAdd(&cscal[2], a2);
+    atomicAdd(&cscal[3], a3);
+    atomicAdd(&cscal[4], a4);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,507 @@
+// ba_solver.cuh -- host-side driver of the device BA: problem residency,
+// Ceres-semantics Levenberg-Marquardt loop (trust_region_minimizer.cc /
+// levenberg_marquardt_strategy.cc, restated in oracle/ceres_lm.py) with the
+// reduced camera system solved by implicit-Schur PCG on the device.
+// Reference path replaced: glomap/estimators/bundle_adjustment.cc:11-106.
+#pragma once
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ba_kernels.cuh"
+#include "context.cuh"
+#include "pcg.cuh"
+
+namespace b200 {
+
+// ---- structure-building kernels ----------------------------------------------
+__global__ void k_expand_obs_pt(int P, const unsigned* __restrict__ pt_begin, int* __restrict__ obs_pt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  for (unsigned o = pt_begin[p]; o < pt_begin[p + 1]; ++o) obs_pt[o] = p;
+}
+__global__ void k_cam_keys(long long N, int C, int min_views, const int* __restrict__ obs_cam,
+                           const int* __restrict__ obs_pt, const unsigned* __restrict__ pt_begin,
+                           int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ cam_count) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= N) return;
+  const int pt = obs_pt[o];
+  const bool valid = (int)(pt_begin[pt + 1] - pt_begin[pt]) >= min_views;
+  const int cam = obs_cam[o];
+  keys[o] = valid ? cam : C;
+  vals[o] = (int)o;
+  if (valid) atomicAdd(&cam_count[cam], 1);
+}
+__global__ void k_seg_counts(int C, const int* __restrict__ cam_count, int* __restrict__ seg_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) seg_count[c] = (cam_count[c] + kSeg - 1) / kSeg;
+}
+__global__ void k_fill_segs(int C, const int* __restrict__ cam_begin, const int* __restrict__ seg_off,
+                            int* __restrict__ seg_cam, int* __restrict__ seg_begin, int* __restrict__ seg_end) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int b = cam_begin[c], e = cam_begin[c + 1];
+  int s = seg_off[c];
+  for (int i = b; i < e; i += kSeg, ++s) {
+    seg_cam[s] = c;
+    seg_begin[s] = i;
+    seg_end[s] = min(i + kSeg, e);
+  }
+}
+__global__ void k_gather_camorder(int Nv, const int* __restrict__ camord_obs, const int* __restrict__ obs_pt,
+                                  const double2* __restrict__ obs_xy, int* __restrict__ pt_c,
+                                  double2* __restrict__ xy_c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nv) return;
+  const int o = camord_obs[i];
+  pt_c[i] = obs_pt[o];
+  xy_c[i] = obs_xy[o];
+}
+__global__ void k_eff_mask(int C, const unsigned char* __restrict__ base, int fix_rot, int fix_trn,
+                           unsigned char* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (unsigned char)((base ? base[c] : 0) | (fix_rot ? 1 : 0) | (fix_trn ? 2 : 0));
+}
+__global__ void k_normalize_quat(int C, double* __restrict__ q) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = sqrt(q[4 * c] * q[4 * c] + q[4 * c + 1] * q[4 * c + 1] + q[4 * c + 2] * q[4 * c + 2] +
+                        q[4 * c + 3] * q[4 * c + 3]);
+  if (n > 0) {
+    const double inv = 1.0 / n;
+    for (int k = 0; k < 4; ++k) q[4 * c + k] *= inv;
+  }
+}
+// b = -(gc + y)
+__global__ void k_rhs(int n, const double* __restrict__ gc, const double* __restrict__ y, double* __restrict__ b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = -(gc[i] + (y ? y[i] : 0.0));
+}
+
+}  // namespace b200
+
+struct b200sfm_ba_problem {
+  using BAView = b200::BAView;
+  template <class T>
+  using DevBuf = b200::DevBuf<T>;
+
+  b200sfm_ctx* ctx = nullptr;
+  int C = 0, P = 0, K = 0;
+  long long N = 0;
+  int Nv = 0, n_tiles = 0, n_segs = 0, min_views = 3;
+  long long n_obs_used = 0;
+
+  // structure
+  DevBuf<int> obs_cam, obs_pt, tile_pt_begin, camord_obs, pt_c, seg_cam, seg_begin, seg_end, cam_intr, intr_model;
+  DevBuf<double2> obs_xy, xy_c;
+  DevBuf<unsigned> pt_begin;
+  DevBuf<unsigned char> cam_mask_base, cam_mask;
+  // state + candidate + snapshot
+  DevBuf<double> quat[2], trans[2], points[2], intr, quat_saved, trans_saved, points_saved, intr_saved;
+  int cur = 0;
+  DevBuf<double> cam_rec, intr_rec;
+  // linear system
+  DevBuf<double> W, V, Vinv, gp, lin /* U | gc | cost */, Sd, Minv, jscale_c, jscale_p, Dc;
+  // pcg
+  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dots;
+  DevBuf<double> scal;   // [0] cost [1] gmax | [2..5] bscal | [6] cand cost | [8..12] cscal
+  b200::EventTimer timer_lin, timer_mv;
+  size_t smem_k1 = 0, smem_k3 = 0;
+
+  double* U() { return lin.p; }
+  double* gc() { return lin.p + (size_t)C * 21; }
+  double* cost_ptr() { return lin.p + (size_t)C * 27; }
+
+  BAView view() {
+    BAView v;
+    v.C = C; v.P = P; v.K = K; v.N = N; v.n_tiles = n_tiles; v.n_segs = n_segs; v.min_views = min_views;
+    v.obs_cam = obs_cam.p; v.obs_pt = obs_pt.p; v.obs_xy = obs_xy.p; v.pt_begin = pt_begin.p;
+    v.tile_pt_begin = tile_pt_begin.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p; v.xy_c = xy_c.p;
+    v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p;
+    v.W = W.p; v.V = V.p; v.Vinv = Vinv.p; v.gp = gp.p; v.U = U(); v.gc = gc(); v.Sd = Sd.p; v.Minv = Minv.p;
+    v.jscale_c = jscale_c.p; v.jscale_p = jscale_p.p; v.Dc = Dc.p;
+    return v;
+  }
+
+  // -------------------------------------------------------------------------
+  void create(b200sfm_ctx* c, int C_, int P_, long long N_, int K_, const int64_t* h_pt_begin, const int32_t* h_obs_cam,
+              const double* h_obs_xy, const int32_t* h_cam_intr, const int32_t* h_intr_model,
+              const uint8_t* h_cam_mask, int min_views_, b200sfm_lm_stats* st) {
+    using namespace b200;
+    ctx = c; C = C_; P = P_; N = N_; K = K_; min_views = min_views_;
+    cudaStream_t s = ctx->stream;
+    // host: CSR offsets -> uint32, greedy tiling of whole points into <= kTile observations
+    std::vector<unsigned> ptb((size_t)P + 1);
+    std::vector<int> tiles;
+    tiles.reserve((size_t)(N / 200) + 16);
+    tiles.push_back(0);
+    long long tile_obs = 0;
+    int tile_pts = 0;
+    n_obs_used = 0;
+    for (int p = 0; p < P; ++p) {
+      ptb[p] = (unsigned)h_pt_begin[p];
+      const long long len = h_pt_begin[p + 1] - h_pt_begin[p];
+      if (len >= min_views) n_obs_used += len;
+      if (tile_pts > 0 && (tile_obs + len > kTile || tile_pts >= kTile)) {
+        tiles.push_back(p);
+        tile_obs = 0;
+        tile_pts = 0;
+      }
+      tile_obs += len;
+      ++tile_pts;
+    }
+    ptb[P] = (unsigned)h_pt_begin[P];
+    tiles.push_back(P);
+    n_tiles = (int)tiles.size() - 1;
+
+    obs_cam.alloc(N); obs_pt.alloc(N); obs_xy.alloc(N); pt_begin.alloc((size_t)P + 1);
+    tile_pt_begin.alloc(tiles.size()); cam_intr.alloc(C); intr_model.alloc(K);
+    cam_mask_base.alloc(C); cam_mask.alloc(C);
+    obs_cam.upload(h_obs_cam, N, s);
+    obs_xy.upload(reinterpret_cast<const double2*>(h_obs_xy), N, s);
+    pt_begin.upload(ptb.data(), (size_t)P + 1, s);
+    tile_pt_begin.upload(tiles.data(), tiles.size(), s);
+    cam_intr.upload(h_cam_intr, C, s);
+    intr_model.upload(h_intr_model, K, s);
+    if (h_cam_mask) cam_mask_base.upload(h_cam_mask, C, s);
+    else cam_mask_base.zero(s);
+    if (st) st->h2d_bytes += N * 20 + ((long long)P + 1) * 4 + (long long)tiles.size() * 4 + (long long)C * 5 + K * 4;
+
+    B200_LAUNCH(ctx, k_expand_obs_pt, cdiv(P, 256), 256, 0, P, pt_begin.p, obs_pt.p);
+    // camera order
+    DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off;
+    keys.alloc(N); vals.alloc(N); keys_out.alloc(N); camord_obs.alloc(N);
+    cam_count.alloc((size_t)C + 1); seg_count.alloc((size_t)C + 1); cam_begin.alloc((size_t)C + 1); seg_off.alloc((size_t)C + 1);
+    cam_count.zero(s); seg_count.zero(s);
+    B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, C, min_views, obs_cam.p, obs_pt.p, pt_begin.p, keys.p, vals.p,
+                cam_count.p);
+    int end_bit = 1;
+    while ((1ll << end_bit) <= C) ++end_bit;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, vals.p, camord_obs.p, (int)N, 0, end_bit, s);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cam_count.p, cam_begin.p, C + 1, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(std::max(tmp_bytes, scan_bytes) + 16);
+    size_t tb = tmp.bytes();
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_out.p, vals.p, camord_obs.p, (int)N, 0, end_bit, s);
+    ctx->launches += 8;
+    tb = tmp.bytes();
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, cam_count.p, cam_begin.p, C + 1, s);
+    B200_LAUNCH(ctx, k_seg_counts, cdiv(C, 256), 256, 0, C, cam_count.p, seg_count.p);
+    tb = tmp.bytes();
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, seg_count.p, seg_off.p, C + 1, s);
+    ctx->launches += 4;
+    int h_tot[2];
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[0], cam_begin.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[1], seg_off.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    Nv = h_tot[0];
+    n_segs = h_tot[1];
+    seg_cam.alloc(std::max(n_segs, 1)); seg_begin.alloc(std::max(n_segs, 1)); seg_end.alloc(std::max(n_segs, 1));
+    pt_c.alloc(std::max(Nv, 1)); xy_c.alloc(std::max(Nv, 1));
+    B200_LAUNCH(ctx, k_fill_segs, cdiv(C, 256), 256, 0, C, cam_begin.p, seg_off.p, seg_cam.p, seg_begin.p, seg_end.p);
+    if (Nv > 0)
+      B200_LAUNCH(ctx, k_gather_camorder, cdiv(Nv, 256), 256, 0, Nv, camord_obs.p, obs_pt.p, obs_xy.p, pt_c.p, xy_c.p);
+
+    for (int i = 0; i < 2; ++i) {
+      quat[i].alloc((size_t)C * 4); trans[i].alloc((size_t)C * 3); points[i].alloc((size_t)P * 3);
+    }
+    intr.alloc((size_t)K * B200SFM_INTR_STRIDE);
+    cam_rec.alloc((size_t)C * kCamRec); intr_rec.alloc((size_t)K * kIntrRec);
+    W.alloc((size_t)N * kWDoubles); V.alloc((size_t)P * 6); Vinv.alloc((size_t)P * 6); gp.alloc((size_t)P * 3);
+    lin.alloc((size_t)C * 27 + 2); Sd.alloc((size_t)C * 21); Minv.alloc((size_t)C * 21);
+    jscale_c.alloc((size_t)C * 6); jscale_p.alloc((size_t)P * 3); Dc.alloc((size_t)C * 6);
+    px.alloc((size_t)C * 6); pr.alloc((size_t)C * 6); pz.alloc((size_t)C * 6); pp.alloc((size_t)C * 6);
+    pq.alloc((size_t)C * 6); yw.alloc((size_t)C * 6); bvec.alloc((size_t)C * 6);
+    scal.alloc(16);
+    smem_k1 = sizeof(K1Smem) + 128;
+    smem_k3 = sizeof(K3Smem) + 128;
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
+    B200_CUDA_OK(cudaStreamSynchronize(s));   // temporaries go out of scope
+  }
+
+  void set_state(const double* h_intr, const double* h_quat, const double* h_trans, const double* h_points,
+                 b200sfm_lm_stats* st) {
+    cudaStream_t s = ctx->stream;
+    intr.upload(h_intr, (size_t)K * B200SFM_INTR_STRIDE, s);
+    quat[cur].upload(h_quat, (size_t)C * 4, s);
+    trans[cur].upload(h_trans, (size_t)C * 3, s);
+    points[cur].upload(h_points, (size_t)P * 3, s);
+    B200_LAUNCH(ctx, b200::k_normalize_quat, b200::cdiv(C, 256), 256, 0, C, quat[cur].p);
+    if (st) st->h2d_bytes += ((long long)K * B200SFM_INTR_STRIDE + (long long)C * 7 + (long long)P * 3) * 8;
+  }
+  void get_state(double* h_intr, double* h_quat, double* h_trans, double* h_points, b200sfm_lm_stats* st) {
+    cudaStream_t s = ctx->stream;
+    if (h_intr) intr.download(h_intr, (size_t)K * B200SFM_INTR_STRIDE, s);
+    if (h_quat) quat[cur].download(h_quat, (size_t)C * 4, s);
+    if (h_trans) trans[cur].download(h_trans, (size_t)C * 3, s);
+    if (h_points) points[cur].download(h_points, (size_t)P * 3, s);
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    if (st) st->d2h_bytes += ((long long)K * B200SFM_INTR_STRIDE + (long long)C * 7 + (long long)P * 3) * 8;
+  }
+  void save_state() {
+    cudaStream_t s = ctx->stream;
+    if (!quat_saved.p) {
+      quat_saved.alloc((size_t)C * 4); trans_saved.alloc((size_t)C * 3); points_saved.alloc((size_t)P * 3);
+      intr_saved.alloc((size_t)K * B200SFM_INTR_STRIDE);
+    }
+    B200_CUDA_OK(cudaMemcpyAsync(quat_saved.p, quat[cur].p, quat_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(trans_saved.p, trans[cur].p, trans_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(points_saved.p, points[cur].p, points_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(intr_saved.p, intr.p, intr_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+  }
+  bool restore_state() {
+    if (!quat_saved.p) return false;
+    cudaStream_t s = ctx->stream;
+    B200_CUDA_OK(cudaMemcpyAsync(quat[cur].p, quat_saved.p, quat_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(trans[cur].p, trans_saved.p, trans_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(points[cur].p, points_saved.p, points_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(intr.p, intr_saved.p, intr_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    return true;
+  }
+
+  // -------------------------------------------------------------------------
+  void build_records(int which) {
+    using namespace b200;
+    B200_LAUNCH(ctx, ba_build_records, cdiv(std::max(C, K), 256), 256, 0, C, K, quat[which].p, trans[which].p,
+                cam_intr.p, cam_mask.p, intr.p, intr_model.p, cam_rec.p, intr_rec.p);
+  }
+
+  // robust cost of state `which` -> host (synchronises)
+  double eval_cost(int which, double huber_a) {
+    using namespace b200;
+    build_records(which);
+    B200_CUDA_OK(cudaMemsetAsync(scal.p + 6, 0, sizeof(double), ctx->stream));
+    const int grid = std::min(cdiv(N, 256), 148 * 8);
+    B200_LAUNCH(ctx, ba_cost, grid, 256, 0, view(), cam_rec.p, intr_rec.p, points[which].p, huber_a, scal.p + 6);
+    ctx->allreduce_sum(scal.p + 6, 1);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p + 6, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return ctx->h_scal[0];
+  }
+
+  // Jacobian + Schur blocks at the current state.  Returns (cost, max|g|).
+  void linearize(double huber_a, bool points_var, bool first, bool profile, double& cost, double& gmax) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    build_records(cur);
+    lin.zero(s);
+    B200_CUDA_OK(cudaMemsetAsync(scal.p, 0, 2 * sizeof(double), s));
+    BAView v = view();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (profile) {
+      e0 = timer_lin.next();
+      e1 = timer_lin.next();
+      B200_CUDA_OK(cudaEventRecord(e0, s));
+    }
+    B200_LAUNCH(ctx, ba_linearize_points, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
+                points_var ? 1 : 0, scal.p);
+    if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
+    if (n_segs > 0)
+      B200_LAUNCH(ctx, ba_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p,
+                  points[cur].p, huber_a);
+    // cost travels with U|gc through one all-reduce
+    B200_CUDA_OK(cudaMemcpyAsync(cost_ptr(), scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    ctx->allreduce_sum(lin.p, (size_t)C * 27 + 1);
+    ctx->allreduce_max(scal.p + 1, 1);
+    B200_LAUNCH(ctx, ba_finalize_cams, cdiv(C, 128), 128, 0, C, U(), gc(), cam_mask.p, jscale_c.p, first ? 1 : 0,
+                scal.p);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, cost_ptr(), sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 1, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    cost = ctx->h_scal[0];
+    gmax = ctx->h_scal[1];
+  }
+
+  struct StepResult {
+    double model_cost_change = 0, cand_cost = 0, step_norm = 0, x_norm = 0;
+    int pcg_iters = 0;
+    bool finite = true;
+  };
+
+  // One trust-region step at the current linearisation: damping, preconditioner,
+  // PCG on the reduced camera system, back-substitution, candidate + its cost.
+  StepResult compute_step(const b200sfm_ba_opts& o, double radius, bool points_var, bool set_jscale_p, bool profile) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    BAView v = view();
+    const int nC6 = C * 6;
+    if (points_var) B200_LAUNCH(ctx, ba_damp_points, cdiv(P, 256), 256, 0, P, V.p, jscale_p.p, set_jscale_p ? 1 : 0, radius, Vinv.p);
+    B200_LAUNCH(ctx, ba_damp_cams, cdiv(nC6, 256), 256, 0, C, U(), jscale_c.p, radius, Dc.p);
+    const bool schur_jacobi = points_var && o.preconditioner == 1;
+    if (schur_jacobi) {
+      Sd.zero(s);
+      if (n_segs > 0) B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
+      ctx->allreduce_sum(Sd.p, (size_t)C * 21);
+    }
+    B200_LAUNCH(ctx, ba_build_precond, cdiv(C, 128), 128, 0, C, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
+    // right-hand side b = -(gc - W Vinv gp)
+    if (points_var) {
+      yw.zero(s);
+      B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yw.p, nullptr, nullptr, radius, nullptr);
+      ctx->allreduce_sum(yw.p, nC6);
+    }
+    B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yw.p : nullptr, bvec.p);
+    // ---- PCG ------------------------------------------------------------------
+    const int max_it = std::max(1, o.pcg_max_iterations);
+    if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
+    dots.zero(s);
+    B200_LAUNCH(ctx, pcg_init<6>, cdiv(C, 128), 128, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, pp.p, yw.p, dots.p);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    const double rr0 = ctx->h_scal[2];
+    StepResult res;
+    int it = 0;
+    if (rr0 > 0.0 && std::isfinite(rr0)) {
+      const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * rr0;
+      for (it = 1; it <= max_it; ++it) {
+        double* d_prev = dots.p + (size_t)(it - 1) * 4;
+        double* d_it = dots.p + (size_t)it * 4;
+        if (points_var) {
+          cudaEvent_t e0 = nullptr, e1 = nullptr;
+          if (profile) {
+            e0 = timer_mv.next();
+            e1 = timer_mv.next();
+            B200_CUDA_OK(cudaEventRecord(e0, s));
+          }
+          B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr);
+          if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
+          ctx->allreduce_sum(yw.p, nC6);
+        }
+        B200_LAUNCH(ctx, pcg_apply_diag<6>, cdiv(C, 128), 128, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, d_it);
+        B200_LAUNCH(ctx, pcg_update<6>, cdiv(C, 128), 128, 0, C, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev + 1, d_it);
+        B200_LAUNCH(ctx, pcg_direction<6>, cdiv(nC6, 256), 256, 0, C, pz.p, pp.p, yw.p, d_prev + 1, d_it);
+        B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        const double rr = ctx->h_scal[2];
+        if (!std::isfinite(rr)) { res.finite = false; break; }
+        if (it >= o.pcg_min_iterations && rr <= tol2) break;
+      }
+      if (it > max_it) it = max_it;
+    }
+    res.pcg_iters = it;
+    // ---- back-substitution + candidate ------------------------------------------
+    B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));
+    const int nxt = cur ^ 1;
+    if (points_var) {
+      B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
+                  scal.p + 2);
+    } else {
+      B200_CUDA_OK(cudaMemcpyAsync(points[nxt].p, points[cur].p, points[cur].bytes(), cudaMemcpyDeviceToDevice, s));
+    }
+    B200_LAUNCH(ctx, ba_update_cams, cdiv(C, 128), 128, 0, C, quat[cur].p, trans[cur].p, px.p, gc(), pr.p, Dc.p, jscale_c.p,
+                quat[nxt].p, trans[nxt].p, scal.p + 8);
+    build_records(nxt);
+    const int grid = std::min(cdiv(N, 256), 148 * 8);
+    B200_LAUNCH(ctx, ba_cost, grid, 256, 0, v, cam_rec.p, intr_rec.p, points[nxt].p, o.thres_loss_function, scal.p + 6);
+    ctx->allreduce_sum(scal.p + 2, 5);   // bscal[0..3] + cand cost
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    const double* h = ctx->h_scal;
+    const double g_dot_d = h[8] + h[2];
+    const double dDd = h[10] + h[3];
+    res.model_cost_change = 0.5 * (-g_dot_d + h[9] + dDd);
+    res.cand_cost = h[6];
+    res.step_norm = std::sqrt(h[11] + h[4]);
+    res.x_norm = std::sqrt(h[12] + h[5]);
+    if (!std::isfinite(res.model_cost_change) || !std::isfinite(res.cand_cost)) res.finite = false;
+    return res;
+  }
+
+  // The LM loop, Ceres order of checks (see oracle/ceres_lm.py).
+  int solve(const b200sfm_ba_opts& o, b200sfm_lm_stats* st) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    if (o.optimize_rig_poses) { ctx->err = "optimize_rig_poses: non-trivial rigs are not supported"; return B200SFM_ERR_UNSUPPORTED; }
+    if (o.optimize_intrinsics) { ctx->err = "optimize_intrinsics=1 is not implemented on the device yet"; return B200SFM_ERR_UNSUPPORTED; }
+    const long long launches0 = ctx->launches;
+    timer_lin.reset();
+    timer_mv.reset();
+    cudaEvent_t ev0, ev1;
+    B200_CUDA_OK(cudaEventCreate(&ev0));
+    B200_CUDA_OK(cudaEventCreate(&ev1));
+    B200_CUDA_OK(cudaEventRecord(ev0, s));
+    const bool points_var = o.optimize_points != 0;
+    const bool profile = o.profile_kernels != 0;
+    B200_LAUNCH(ctx, k_eff_mask, cdiv(C, 256), 256, 0, C, cam_mask_base.p, o.optimize_rotations ? 0 : 1,
+                o.optimize_translation ? 0 : 1, cam_mask.p);
+    double cost = 0, gmax = 0;
+    linearize(o.thres_loss_function, points_var, true, profile, cost, gmax);
+    b200sfm_lm_stats local{};
+    local.initial_cost = cost;
+    local.usable = 1;
+    local.num_observations = n_obs_used;
+    double radius = 1e4, decrease = 2.0;
+    int invalid = 0, it = 0, term = B200SFM_TERM_NONE;
+    bool set_jscale_p = true;
+    const bool fixed = o.fixed_num_iterations > 0;
+    const int max_it = fixed ? o.fixed_num_iterations : o.max_num_iterations;
+    if (!fixed && gmax <= o.gradient_tolerance) term = B200SFM_TERM_GRADIENT_TOLERANCE;
+    while (term == B200SFM_TERM_NONE) {
+      if (it >= max_it) { term = B200SFM_TERM_MAX_ITERATIONS; break; }
+      if (radius < 1e-32) { term = B200SFM_TERM_MIN_RADIUS; break; }
+      ++it;
+      StepResult r = compute_step(o, radius, points_var, set_jscale_p, profile);
+      set_jscale_p = false;
+      local.pcg_iterations += r.pcg_iters;
+      if (!r.finite || !(r.model_cost_change > 0.0)) {
+        if (++invalid >= 5) { term = B200SFM_TERM_INVALID_STEPS; local.usable = 0; break; }
+        radius /= decrease;
+        decrease *= 2;
+        continue;
+      }
+      invalid = 0;
+      if (!fixed) {
+        if (r.step_norm <= o.parameter_tolerance * (r.x_norm + o.parameter_tolerance)) { term = B200SFM_TERM_PARAMETER_TOLERANCE; break; }
+        if (std::fabs(cost - r.cand_cost) <= o.function_tolerance * cost) { term = B200SFM_TERM_FUNCTION_TOLERANCE; break; }
+      }
+      const double rel = (cost - r.cand_cost) / r.model_cost_change;
+      if (rel > 1e-3) {
+        cur ^= 1;
+        ++local.num_successful_steps;
+        linearize(o.thres_loss_function, points_var, false, profile, cost, gmax);
+        radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+        decrease = 2.0;
+        if (!fixed && gmax <= o.gradient_tolerance) { term = B200SFM_TERM_GRADIENT_TOLERANCE; break; }
+      } else {
+        radius /= decrease;
+        decrease *= 2;
+      }
+    }
+    B200_CUDA_OK(cudaEventRecord(ev1, s));
+    B200_CUDA_OK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    B200_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    local.iterations = it;
+    local.termination = term;
+    local.final_cost = cost;
+    local.ms_total = ms;
+    for (size_t i = 0; i + 1 < timer_lin.used; i += 2) {
+      float t;
+      B200_CUDA_OK(cudaEventElapsedTime(&t, timer_lin.ev[i], timer_lin.ev[i + 1]));
+      local.ms_linearize += t;
+      ++local.n_linearize;
+    }
+    for (size_t i = 0; i + 1 < timer_mv.used; i += 2) {
+      float t;
+      B200_CUDA_OK(cudaEventElapsedTime(&t, timer_mv.ev[i], timer_mv.ev[i + 1]));
+      local.ms_matvec += t;
+      ++local.n_matvec;
+    }
+    local.kernel_launches = ctx->launches - launches0;
+    if (st) {
+      local.h2d_bytes = st->h2d_bytes; local.d2h_bytes = st->d2h_bytes; local.ms_h2d = st->ms_h2d; local.ms_d2h = st->ms_d2h;
+      local.kernel_launches += st->kernel_launches;
+      *st = local;
+    }
+    return B200SFM_OK;
+  }
+};

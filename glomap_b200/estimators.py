@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference estimator classes over the C ABI.
+
+Same class / option / method names and error behaviour as
+  glomap::BundleAdjuster      glomap/estimators/bundle_adjustment.h:12-51
+  glomap::GlobalPositioner    glomap/estimators/global_positioning.h:9-70
+  glomap::RotationEstimator   glomap/estimators/global_rotation_averaging.h:39-87
+but operating on the flat SoA containers of ``glomap_b200.synthetic`` (what the
+C++ shim builds from the reference's unordered_maps in sorted-id order,
+INTEGRATION.md).  ``Solve`` mutates the container in place and returns a bool
+like the reference.  All arithmetic happens in libb200sfm.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import dataclasses
+
+import numpy as np
+
+from . import _lib
+from ._lib import BAOpts, B200Error, LMStats
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(ct.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One per process and GPU (b200sfm_create / b200sfm_create_dist)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_id: bytes | None = None):
+        self.lib = _lib.load()
+        h = ct.c_void_p()
+        if world_size > 1:
+            buf = ct.create_string_buffer(nccl_id, _lib.NCCL_ID_BYTES)
+            rc = self.lib.b200sfm_create_dist(device, rank, world_size, buf, ct.byref(h))
+        else:
+            rc = self.lib.b200sfm_create(device, ct.byref(h))
+        if rc != 0:
+            raise B200Error(rc, "b200sfm_create failed (is a CUDA device visible? there is no CPU fallback)")
+        self.handle = h
+        self.rank, self.world_size = rank, world_size
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ct.create_string_buffer(_lib.NCCL_ID_BYTES)
+        rc = _lib.load().b200sfm_nccl_unique_id(buf)
+        if rc != 0:
+            raise B200Error(rc, "b200sfm_nccl_unique_id failed")
+        return buf.raw
+
+    def close(self):
+        if self.handle:
+            self.lib.b200sfm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---------------------------------------------------------------------------
+# Bundle adjustment
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass
+class SolverOptions:
+    """The ceres::Solver::Options fields the reference sets
+    (optimization_base.h:18-23) + the PCG knobs of this implementation."""
+    max_num_iterations: int = 100
+    function_tolerance: float = 1e-5
+    gradient_tolerance: float = 1e-10
+    parameter_tolerance: float = 1e-8
+    pcg_max_iterations: int = 500
+    pcg_min_iterations: int = 0
+    pcg_rel_tolerance: float = 1e-2
+    preconditioner: int = 1
+
+
+@dataclasses.dataclass
+class BundleAdjusterOptions:
+    """bundle_adjustment.h:12-37 (defaults identical)."""
+    optimize_rig_poses: bool = False
+    optimize_rotations: bool = True
+    optimize_translation: bool = True
+    optimize_intrinsics: bool = True
+    optimize_principal_point: bool = False
+    optimize_points: bool = True
+    use_gpu: bool = True
+    gpu_index: str = "-1"
+    min_num_images_gpu_solver: int = 50
+    min_num_view_per_track: int = 3
+    thres_loss_function: float = 1.0
+    solver_options: SolverOptions = dataclasses.field(default_factory=lambda: SolverOptions(max_num_iterations=200))
+    # implementation extras
+    profile_kernels: bool = False
+    fixed_num_iterations: int = 0
+
+    def to_c(self) -> BAOpts:
+        o = BAOpts()
+        _lib.load().b200sfm_ba_default_opts(ct.byref(o))
+        for f in ("optimize_rig_poses", "optimize_rotations", "optimize_translation", "optimize_intrinsics",
+                  "optimize_principal_point", "optimize_points", "profile_kernels"):
+            setattr(o, f, int(getattr(self, f)))
+        o.min_num_view_per_track = self.min_num_view_per_track
+        o.thres_loss_function = self.thres_loss_function
+        o.fixed_num_iterations = self.fixed_num_iterations
+        so = self.solver_options
+        for f in ("max_num_iterations", "function_tolerance", "gradient_tolerance", "parameter_tolerance",
+                  "pcg_max_iterations", "pcg_min_iterations", "pcg_rel_tolerance", "preconditioner"):
+            setattr(o, f, getattr(so, f))
+        return o
+
+
+def first_frame_mask(C: int) -> np.ndarray:
+    """The reference holds the first frame (in its map order) constant,
+    bundle_adjustment.cc:261-266; the shim orders frames by id, so index 0."""
+    m = np.zeros(C, dtype=np.uint8)
+    if C:
+        m[0] = 3
+    return m
+
+
+class BAProblem:
+    """Device-resident BA problem (b200sfm_ba_problem_*)."""
+
+    def __init__(self, ctx: Context, scene, min_num_view_per_track: int = 3, cam_const_mask: np.ndarray | None = None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.C, self.P, self.N, self.K = scene.C, scene.P, scene.N, len(scene.intr_model)
+        self._keep = [_c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64),
+                      _c(scene.cam_intr, np.int32), _c(scene.intr_model, np.int32)]
+        mask = first_frame_mask(self.C) if cam_const_mask is None else _c(cam_const_mask, np.uint8)
+        h = ct.c_void_p()
+        rc = self.lib.b200sfm_ba_problem_create(ctx.handle, self.C, self.P, self.N, self.K, *[_ptr(a) for a in self._keep],
+                                                _ptr(mask), min_num_view_per_track, ct.byref(h))
+        _lib.check(ctx.handle, rc)
+        self.handle = h
+
+    def set_state(self, intr_params, quat, trans, points):
+        a = [_c(intr_params, np.float64), _c(quat, np.float64), _c(trans, np.float64), _c(points, np.float64)]
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_set_state(self.handle, *[_ptr(x) for x in a]))
+
+    def get_state(self):
+        intr = np.empty((self.K, _lib.INTR_STRIDE)); quat = np.empty((self.C, 4)); trans = np.empty((self.C, 3))
+        pts = np.empty((self.P, 3))
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_get_state(self.handle, _ptr(intr), _ptr(quat), _ptr(trans), _ptr(pts)))
+        return intr, quat, trans, pts
+
+    def save_state(self):
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_save_state(self.handle))
+
+    def restore_state(self):
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_restore_state(self.handle))
+
+    def solve(self, options: BundleAdjusterOptions) -> LMStats:
+        st = LMStats()
+        o = options.to_c()
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_solve(self.handle, ct.byref(o), ct.byref(st)))
+        return st
+
+    def cost(self, options: BundleAdjusterOptions) -> float:
+        o = options.to_c()
+        c = ct.c_double()
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_cost(self.handle, ct.byref(o), ct.byref(c)))
+        return c.value
+
+    def free(self):
+        if self.handle:
+            self.lib.b200sfm_ba_problem_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BundleAdjuster:
+    """glomap::BundleAdjuster (bundle_adjustment.h:38-51): options are copied
+    at construction and may be mutated through GetOptions() between Solve calls
+    (controllers/global_mapper.cc:204-219)."""
+
+    def __init__(self, options: BundleAdjusterOptions | None = None, ctx: Context | None = None):
+        self.options_ = dataclasses.replace(options) if options else BundleAdjusterOptions()
+        self.ctx = ctx
+        self.summary: LMStats | None = None
+
+    def GetOptions(self) -> BundleAdjusterOptions:
+        return self.options_
+
+    def Solve(self, scene, cam_const_mask: np.ndarray | None = None) -> bool:
+        """One-shot b200sfm_ba_solve with host buffers; poses, points (and
+        intrinsics) of ``scene`` are updated in place.  Returns False on empty
+        input (bundle_adjustment.cc:17-24) or an unusable solution (.cc:105)."""
+        if scene.C == 0 or scene.P == 0 or scene.N == 0:
+            return False
+        ctx = self.ctx or default_context()
+        lib = ctx.lib
+        o = self.options_.to_c()
+        st = LMStats()
+        ptb, cam, xy = _c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64)
+        ci, im = _c(scene.cam_intr, np.int32), _c(scene.intr_model, np.int32)
+        intr, quat = _c(scene.intr_params, np.float64), _c(scene.quat, np.float64)
+        trans, pts = _c(scene.trans, np.float64), _c(scene.points, np.float64)
+        mask = first_frame_mask(scene.C) if cam_const_mask is None else _c(cam_const_mask, np.uint8)
+        rc = lib.b200sfm_ba_solve(ctx.handle, ct.byref(o), scene.C, scene.P, scene.N, len(im), _ptr(ptb), _ptr(cam),
+                                  _ptr(xy), _ptr(ci), _ptr(im), _ptr(intr), _ptr(quat), _ptr(trans), _ptr(mask),
+                                  _ptr(pts), ct.byref(st))
+        self.summary = st
+        if rc == 4:   # B200SFM_ERR_EMPTY
+            return False
+        _lib.check(ctx.handle, rc)
+        scene.intr_params, scene.quat, scene.trans, scene.points = intr, quat, trans, pts
+        return bool(st.usable)

@@ -1,0 +1,185 @@
+/* b200sfm.h -- C ABI of the B200-native global-SfM solver core.
+ *
+ * This is the drop-in boundary for the three numeric hot loops of
+ * colmap/glomap's estimators.  The reference has no FFI layer: the seam is the
+ * public surface of its estimator classes, and each entry point below replaces
+ * the arithmetic behind one of them (paths relative to the reference root):
+ *
+ *   b200sfm_ba_*   <-  glomap::BundleAdjuster::Solve
+ *                      glomap/estimators/bundle_adjustment.h:38-51, .cc:11-106
+ *   b200sfm_gp_*   <-  glomap::GlobalPositioner::Solve
+ *                      glomap/estimators/global_positioning.h:56-70, .cc:28-93
+ *   b200sfm_ra_*   <-  glomap::RotationEstimator::EstimateRotations
+ *                      glomap/estimators/global_rotation_averaging.h:77-87, .cc:40-85
+ *
+ * Conventions: plain pointers and sizes only (no C++/torch types), caller-owned
+ * HOST buffers unless a parameter is documented as a device pointer, FP64
+ * values, int32 indices (int64 CSR offsets), return 0 on success or a
+ * b200sfm_status code; b200sfm_last_error() gives the message.  A context is
+ * thread-compatible (one thread at a time), distinct contexts are independent
+ * -- the same contract as the reference estimators.
+ * There is no CPU fallback behind any of these calls.
+ */
+#ifndef B200SFM_H_
+#define B200SFM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SFM_VERSION 100
+/* doubles reserved per intrinsics block (colmap Camera::params, un-vendored) */
+#define B200SFM_INTR_STRIDE 12
+#define B200SFM_NCCL_ID_BYTES 128
+
+typedef enum {
+  B200SFM_OK = 0,
+  B200SFM_ERR_INVALID_ARG = 1,
+  B200SFM_ERR_CUDA = 2,
+  B200SFM_ERR_NCCL = 3,
+  B200SFM_ERR_EMPTY = 4,        /* reference returns false: no images / no tracks */
+  B200SFM_ERR_UNSUPPORTED = 5,
+  B200SFM_ERR_NUMERIC = 6       /* NaN encountered (reference: LOG(ERROR) + false) */
+} b200sfm_status;
+
+/* COLMAP camera model ids supported on the device (colmap/sensor/models.h). */
+typedef enum {
+  B200SFM_SIMPLE_PINHOLE = 0,   /* f, cx, cy */
+  B200SFM_PINHOLE = 1,          /* fx, fy, cx, cy */
+  B200SFM_SIMPLE_RADIAL = 2,    /* f, cx, cy, k */
+  B200SFM_RADIAL = 3            /* f, cx, cy, k1, k2 */
+} b200sfm_camera_model;
+
+typedef enum {
+  B200SFM_TERM_NONE = 0,
+  B200SFM_TERM_FUNCTION_TOLERANCE = 1,
+  B200SFM_TERM_PARAMETER_TOLERANCE = 2,
+  B200SFM_TERM_GRADIENT_TOLERANCE = 3,
+  B200SFM_TERM_MAX_ITERATIONS = 4,
+  B200SFM_TERM_MIN_RADIUS = 5,
+  B200SFM_TERM_INVALID_STEPS = 6
+} b200sfm_termination;
+
+typedef struct b200sfm_ctx b200sfm_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+int b200sfm_version(void);
+/* One context per process and GPU.  `device` is the CUDA ordinal
+ * (reference: colmap::SetBestCudaDevice(gpu_indices[0]),
+ * bundle_adjustment.cc:79-84). */
+int b200sfm_create(int device, b200sfm_ctx** out);
+/* Multi-GPU: one process per GPU; rank 0 obtains an id with
+ * b200sfm_nccl_unique_id and the host distributes it (torch.distributed /
+ * MPI / file).  Points (with all their observations) or edges are sharded
+ * across ranks by the caller; camera-sized vectors are replicated and
+ * all-reduced over NCCL inside the solver. */
+int b200sfm_nccl_unique_id(void* out_id /* B200SFM_NCCL_ID_BYTES */);
+int b200sfm_create_dist(int device, int rank, int world_size, const void* nccl_id, b200sfm_ctx** out);
+void b200sfm_destroy(b200sfm_ctx* ctx);
+const char* b200sfm_last_error(const b200sfm_ctx* ctx);
+int b200sfm_rank(const b200sfm_ctx* ctx);
+int b200sfm_world_size(const b200sfm_ctx* ctx);
+
+/* ---- statistics common to the LM-based solvers (BA, GP) ------------------ */
+typedef struct {
+  int32_t iterations;            /* LM iterations (successful + unsuccessful) == ceres summary.iterations - 1 */
+  int32_t num_successful_steps;
+  int32_t termination;           /* b200sfm_termination */
+  int32_t usable;                /* summary.IsSolutionUsable() */
+  double initial_cost;
+  double final_cost;
+  int64_t num_observations;      /* residual blocks actually used (this rank) */
+  int64_t pcg_iterations;        /* total PCG iterations (mat-vecs) */
+  int64_t kernel_launches;       /* kernels of this library launched by the call */
+  double ms_total;               /* device time of the whole solve (CUDA events) */
+  double ms_linearize;           /* accumulated time of the Jacobian+Schur kernel */
+  int64_t n_linearize;
+  double ms_matvec;              /* accumulated time of the implicit-Schur mat-vec kernel */
+  int64_t n_matvec;
+  double ms_h2d;                 /* host->device copies inside the call */
+  double ms_d2h;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} b200sfm_lm_stats;
+
+/* ---- (iii) bundle adjustment --------------------------------------------- */
+/* Field-for-field mirror of BundleAdjusterOptions (bundle_adjustment.h:12-37)
+ * + the inherited ceres::Solver::Options the reference sets
+ * (optimization_base.h:18-23), + the PCG knobs of this implementation. */
+typedef struct {
+  int32_t optimize_rig_poses;        /* must be 0: non-trivial rigs unsupported (B200SFM_ERR_UNSUPPORTED) */
+  int32_t optimize_rotations;        /* default 1 */
+  int32_t optimize_translation;      /* default 1 */
+  int32_t optimize_intrinsics;       /* default 1 in the reference */
+  int32_t optimize_principal_point;  /* default 0 */
+  int32_t optimize_points;           /* default 1 */
+  int32_t min_num_view_per_track;    /* default 3 */
+  int32_t max_num_iterations;        /* default 200 */
+  double thres_loss_function;        /* Huber threshold, default 1.0 px */
+  double function_tolerance;         /* default 1e-5 */
+  double gradient_tolerance;         /* Ceres default 1e-10 */
+  double parameter_tolerance;        /* Ceres default 1e-8 */
+  /* implementation knobs (no reference counterpart: the reference factors
+   * the reduced camera system with CHOLMOD, bundle_adjustment.cc:94-96) */
+  int32_t pcg_max_iterations;        /* default 500 */
+  int32_t pcg_min_iterations;        /* default 0 */
+  double pcg_rel_tolerance;          /* ||r_k|| <= tol * ||r_0||, default 1e-2 */
+  int32_t preconditioner;            /* 0 = block-Jacobi on U, 1 = Schur-Jacobi (default) */
+  int32_t profile_kernels;           /* 1: time linearize / mat-vec kernels with CUDA events */
+  int32_t fixed_num_iterations;      /* >0: run exactly this many LM iterations (bench), ignore tolerances */
+  int32_t reserved0;
+} b200sfm_ba_opts;
+
+void b200sfm_ba_default_opts(b200sfm_ba_opts* opts);
+
+/* One-shot solve with host buffers: uploads, solves, writes the results back
+ * in place (the estimator mutates frames/tracks/cameras in place,
+ * bundle_adjustment.cc:140-146).
+ *   C cameras (frames with trivial rigs), P points (tracks), N observations,
+ *   K intrinsics blocks.
+ *   pt_obs_begin [P+1]  CSR by point over the observation arrays
+ *   obs_cam      [N]    camera index of each observation
+ *   obs_xy       [N][2] observed (distorted) pixel, Image::features
+ *   cam_intr     [C]    intrinsics block of each camera
+ *   intr_model   [K]    b200sfm_camera_model
+ *   intr_params  [K][B200SFM_INTR_STRIDE]   in/out
+ *   quat_xyzw    [C][4] cam_from_world rotation, Eigen coeffs order, in/out
+ *   trans        [C][3] cam_from_world translation, in/out
+ *   cam_const_mask [C]  bit0: rotation constant, bit1: translation constant.
+ *                       The shim sets 3 on the first frame
+ *                       (bundle_adjustment.cc:261-266).  May be NULL.
+ *   points       [P][3] in/out
+ * In a distributed context every rank passes its own shard of points and
+ * observations and the same cameras/intrinsics. */
+int b200sfm_ba_solve(b200sfm_ctx* ctx, const b200sfm_ba_opts* opts, int32_t C, int32_t P, int64_t N, int32_t K,
+                     const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_xy,
+                     const int32_t* cam_intr, const int32_t* intr_model, double* intr_params,
+                     double* quat_xyzw, double* trans, const uint8_t* cam_const_mask, double* points,
+                     b200sfm_lm_stats* stats);
+
+/* Resident problem: upload once, solve many times (GlobalMapper re-solves the
+ * same BundleAdjuster after flipping GetOptions().optimize_rotations,
+ * controllers/global_mapper.cc:204-221). */
+typedef struct b200sfm_ba_problem b200sfm_ba_problem;
+int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, int32_t K,
+                              const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_xy,
+                              const int32_t* cam_intr, const int32_t* intr_model, const uint8_t* cam_const_mask,
+                              int32_t min_num_view_per_track, b200sfm_ba_problem** out);
+int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
+                                 const double* trans, const double* points);
+int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr_params, double* quat_xyzw, double* trans,
+                                 double* points);
+/* device-side snapshot / restore of the state (benchmark loops) */
+int b200sfm_ba_problem_save_state(b200sfm_ba_problem* p);
+int b200sfm_ba_problem_restore_state(b200sfm_ba_problem* p);
+int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, b200sfm_lm_stats* stats);
+/* robust cost 1/2 sum rho(|r|^2) of the current state (all ranks) */
+int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, double* cost);
+void b200sfm_ba_problem_free(b200sfm_ba_problem* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SFM_H_ */
