@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: observations/s per BA LM-iteration on the
+10k-camera / 2M-point / 20M-observation synthetic global BA (config 4), points
+sharded across N GPUs (one process per GPU, NCCL all-reduce inside the solver).
+
+  python bench.py --gpus 1 --steps 3 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      (CPU arm: the oracle port on host cores)
+
+One "step" = one BundleAdjuster solve (cap of --lm-iters LM iterations, natural
+Ceres termination) from the same perturbed start; `value` = observations x LM
+iterations / device time with the problem resident in HBM; `e2e` = the same
+through the one-shot C-ABI call b200sfm_ba_solve with pinned HOST buffers
+(upload, structure build, solve, download inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (C, P, mean track len, chunk)
+    "config4": (10_000, 2_000_000, 10.0, 50_000),   # 10k cams / 2M pts / 20M obs  (the metric's config)
+    "config2": (1_000, 200_000, 10.0, 25_000),      # 1k cams / 200k pts / 2M obs
+    "tiny": (200, 20_000, 8.0, 2_500),
+}
+CPU_SAMPLE = "config2"   # bounded sample for the CPU baseline: 1/10 of the cameras and points
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shard_range(P, chunk, rank, world):
+    nchunks = (P + chunk - 1) // chunk
+    a = (nchunks * rank) // world
+    b = (nchunks * (rank + 1)) // world
+    return a * chunk, min(P, b * chunk)
+
+
+def cpu_baseline(steps: int, lm_iters: int):
+    """The oracle port (C/OpenMP + LAPACK Cholesky) on a bounded sample."""
+    from glomap_b200 import synthetic as S
+    from oracle import ba_oracle as B, ba_oracle_fast as F
+    C, P, L, chunk = WORKLOADS[CPU_SAMPLE]
+    sc = S.make_scene(C, P, L, seed=1, pixel_sigma=0.5, chunk=chunk)
+    init = S.perturb_scene(sc, chunk=chunk)
+    mask = np.zeros(C, np.uint8); mask[0] = 3
+    tot_t, tot_it = 0.0, 0
+    times = {}
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, summ = F.solve_ba_fast(init.quat, init.trans, init.points, sc.pt_obs_begin, sc.obs_cam, sc.obs_xy, sc.cam_intr,
+                                  sc.intr_model, sc.intr_params, B.BAOptions(), mask, fixed_num_iterations=lm_iters)
+        tot_t += time.perf_counter() - t0
+        tot_it += summ.iterations
+        times = summ.times
+    n_used = int((np.diff(sc.pt_obs_begin)[np.diff(sc.pt_obs_begin) >= 3]).sum())
+    return {"value": n_used * tot_it / tot_t, "unit": "observations/s per LM iteration", "cores": F.num_threads(),
+            "kind": "port",
+            "sample": f"{CPU_SAMPLE}-shaped sample ({C} cams / {P} pts / {sc.N} obs, 1/10 of the workload), "
+                      f"{tot_it} LM iterations, explicit Schur + dense LAPACK Cholesky (CPU restatement, not Ceres)",
+            "seconds": tot_t, "phase_seconds_last_step": times}, tot_t / max(steps, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C, P, L, chunk = WORKLOADS[args.workload]
+    steps = max(1, args.steps)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(1, 1)
+    cb, sec_per_step = cpu_baseline(steps, args.cpu_lm_iters)
+    line = {"impl": "reference", "metric": "observations/sec per BA LM-iteration", "value": cb["value"],
+            "unit": "observations/s per LM iteration", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {C} cams / {P} pts BA; CPU arm times a bounded sample: {cb['sample']}"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from glomap_b200 import _lib, estimators as E, synthetic as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        obj = [E.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+    ctx = E.Context(local, rank, world, nccl_id)
+    lib = ctx.lib
+    stream = torch.cuda.ExternalStream(lib.b200sfm_cuda_stream(ctx.handle), device=torch.device("cuda", local))
+
+    C, P, L, chunk = WORKLOADS[args.workload]
+    a, b = shard_range(P, chunk, rank, world)
+    t0 = time.time()
+    sc = S.make_scene(C, P, L, seed=1, pixel_sigma=0.5, chunk=chunk, point_range=(a, b))
+    init = S.perturb_scene(sc, chunk=chunk, point_offset=a)
+    gen_s = time.time() - t0
+    lens = np.diff(sc.pt_obs_begin)
+    n_local = int(lens[lens >= 3].sum())
+    tot = torch.tensor([n_local, sc.P, sc.N], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    n_global, p_global, nraw_global = (int(x) for x in tot.tolist())
+    mask = E.first_frame_mask(C)
+
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=False, profile_kernels=True)
+    opts.solver_options.max_num_iterations = args.lm_iters
+    opts.solver_options.pcg_rel_tolerance = args.pcg_tol
+    opts.solver_options.pcg_max_iterations = args.pcg_max
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident leg: `value` ----------------------------------------------------
+    prob = E.BAProblem(ctx, sc, 3, mask)
+    prob.set_state(init.intr_params, init.quat, init.trans, init.points)
+    prob.save_state()
+    stats = []
+    for _ in range(args.warmup):
+        prob.restore_state()
+        prob.solve(opts)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        prob.restore_state()
+        stats.append(prob.solve(opts).as_dict())
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = maxr(e0.elapsed_time(e1))
+    wall = maxr(wall)
+    lm_its = sum(s["iterations"] for s in stats)
+    pcg_its = sum(s["pcg_iterations"] for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats)
+    value = n_global * lm_its / (dev_ms * 1e-3)
+    # kernel roofline (this rank's shard)
+    peak, peak_src = peaks()
+    n_mv = sum(s["n_matvec"] for s in stats); ms_mv = sum(s["ms_matvec"] for s in stats)
+    n_li = sum(s["n_linearize"] for s in stats); ms_li = sum(s["ms_linearize"] for s in stats)
+    mv_bytes = 152 * sc.N + 56 * sc.P + 96 * C
+    li_bytes = 168 * sc.N + 96 * sc.P + 64 * C
+    roof_mv = {"kernel": "ba_schur_pass<0> (implicit-Schur mat-vec)", "bound": "hbm",
+               "achieved": mv_bytes / (ms_mv / max(n_mv, 1) * 1e-3) / 1e9 if n_mv else None, "peak": peak, "unit": "GB/s",
+               "traffic": None, "peak_source": peak_src, "launches_timed": n_mv, "avg_ms": ms_mv / max(n_mv, 1),
+               "bytes_model": "152*N + 56*P + 96*C per launch"}
+    roof_li = {"kernel": "ba_linearize_points (Jacobian + point Schur blocks)", "bound": "hbm",
+               "achieved": li_bytes / (ms_li / max(n_li, 1) * 1e-3) / 1e9 if n_li else None, "peak": peak, "unit": "GB/s",
+               "traffic": None, "peak_source": peak_src, "launches_timed": n_li, "avg_ms": ms_li / max(n_li, 1),
+               "bytes_model": "168*N + 96*P + 64*C per launch"}
+    for r in (roof_mv, roof_li):
+        r["frac"] = r["achieved"] / peak if r["achieved"] else None
+    final_cost, init_cost = stats[-1]["final_cost"], stats[-1]["initial_cost"]
+    prob.free()
+
+    # ---- end-to-end leg: one-shot C-ABI call with pinned host buffers ----------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    keep = []
+    host = S.Scene(*[None] * 9)
+    for f in ("pt_obs_begin", "obs_cam", "obs_xy", "cam_intr", "intr_model"):
+        arr, t = pinned(getattr(sc, f)); keep.append(t); setattr(host, f, arr)
+    state0 = {}
+    for f in ("quat", "trans", "points", "intr_params"):
+        arr, t = pinned(getattr(init, f)); keep.append(t); setattr(host, f, arr)
+        state0[f] = np.array(arr, copy=True)
+    opts_e = E.BundleAdjusterOptions(optimize_intrinsics=False)
+    opts_e.solver_options.max_num_iterations = args.lm_iters
+    opts_e.solver_options.pcg_rel_tolerance = args.pcg_tol
+    opts_e.solver_options.pcg_max_iterations = args.pcg_max
+    ba = E.BundleAdjuster(opts_e, ctx)
+    e2e_stats = []
+
+    def e2e_step():
+        for f in state0:
+            getattr(host, f)[...] = state0[f]
+        ok = ba.Solve(host, mask)
+        assert ok
+        return ba.summary.as_dict()
+
+    for _ in range(min(args.warmup, 1) if args.workload == "config4" else args.warmup):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_stats.append(e2e_step())
+    barrier()
+    e2e_wall = maxr(time.perf_counter() - w0)
+    e2e_its = sum(s["iterations"] for s in e2e_stats)
+    e2e = {"value": n_global * e2e_its / e2e_wall, "unit": "observations/s per LM iteration",
+           "h2d_bytes_per_step": int(e2e_stats[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(e2e_stats[-1]["d2h_bytes"]),
+           "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_wall / args.e2e_steps,
+           "lm_iterations_per_step": e2e_its / args.e2e_steps,
+           "ms_h2d_upload": e2e_stats[-1]["ms_h2d"], "ms_d2h": e2e_stats[-1]["ms_d2h"],
+           "timed": "host wall clock around b200sfm_ba_solve with pinned host buffers, max over ranks"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(1, args.cpu_lm_iters)
+
+    if rank == 0:
+        line = {
+            "metric": "observations/sec per BA LM-iteration", "value": value, "unit": "observations/s per LM iteration",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {C} cameras / {p_global} points / {nraw_global} observations "
+                                   f"({n_global} in tracks >= 3 views) global BA, SIMPLE_PINHOLE, intrinsics constant, "
+                                   f"0.5 px noise, start = GT perturbed 0.5 deg / 1% / 1%",
+                       "parallelism": f"points sharded over {world} GPU(s), cameras replicated, NCCL all-reduce per PCG mat-vec",
+                       "lm_iterations_per_step": lm_its / args.steps, "pcg_iterations_per_lm_iteration": pcg_its / max(lm_its, 1),
+                       "pcg_rel_tolerance": args.pcg_tol, "preconditioner": "schur-jacobi",
+                       "l2_policy": "inputs_exceed_L2 (W alone is 144 B x N >> 126 MB)",
+                       "cost": [init_cost, final_cost], "wall_ms_per_step": 1e3 * wall / args.steps,
+                       "scene_generation_s": gen_s},
+            "roofline": roof_mv, "roofline_linearize": roof_li,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cb:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config4", choices=list(WORKLOADS))
+    ap.add_argument("--lm-iters", type=int, default=20, help="cap on LM iterations per solve (natural termination)")
+    ap.add_argument("--pcg-tol", type=float, default=0.1, help="PCG forcing tolerance (Ceres eta default 0.1)")
+    ap.add_argument("--pcg-max", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-lm-iters", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

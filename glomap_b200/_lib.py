@@ -52,6 +52,8 @@ PROTOTYPES = {
     "b200sfm_last_error": (ct.c_char_p, [c_void_p]),
     "b200sfm_rank": (c_int32, [c_void_p]),
     "b200sfm_world_size": (c_int32, [c_void_p]),
+    "b200sfm_cuda_stream": (c_void_p, [c_void_p]),
+    "b200sfm_kernel_launches": (c_int64, [c_void_p]),
     "b200sfm_ba_default_opts": (None, [P(BAOpts)]),
     "b200sfm_ba_solve": (c_int32, [c_void_p, P(BAOpts), c_int32, c_int32, c_int64, c_int32] + [c_void_p] * 10 + [P(LMStats)]),
     "b200sfm_ba_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32] + [c_void_p] * 6 + [c_int32, P(c_void_p)]),

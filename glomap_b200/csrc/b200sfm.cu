@@ -94,6 +94,8 @@ void b200sfm_destroy(b200sfm_ctx* ctx) {
 const char* b200sfm_last_error(const b200sfm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int b200sfm_rank(const b200sfm_ctx* ctx) { return ctx ? ctx->rank : -1; }
 int b200sfm_world_size(const b200sfm_ctx* ctx) { return ctx ? ctx->world : -1; }
+void* b200sfm_cuda_stream(const b200sfm_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int64_t b200sfm_kernel_launches(const b200sfm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- BA ----------------------------------------------------------------------
 void b200sfm_ba_default_opts(b200sfm_ba_opts* o) {

@@ -98,25 +98,18 @@ def _look_at_rotations(centers: np.ndarray, rng, jitter_deg: float) -> np.ndarra
     return R
 
 
-def make_scene(C: int, P: int, mean_track_len: float = 10.0, seed: int = 1, pixel_sigma: float = 0.0,
-               model: int = SIMPLE_PINHOLE, focal: float = 1000.0, image_size: int = 1000,
-               num_intrinsics: int = 1, candidates_mult: int = 3, ragged: bool = True,
-               jitter_deg: float = 10.0, chunk: int = 200_000) -> Scene:
-    """Cameras on a shell r in [8,12] looking at the origin (+-jitter), points
-    uniform in a ball of radius 3, each point observed by the cameras (of a
-    random candidate set) with the smallest off-axis angle.  Track lengths are
-    3 + Poisson(mean-3) when ``ragged`` else constant."""
-    rng = np.random.default_rng(seed)
+def make_cameras(C: int, seed: int = 1, jitter_deg: float = 10.0):
+    """Camera poses only (identical on every rank)."""
+    rng = np.random.default_rng([seed, 0])
     d = rng.normal(size=(C, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     centers = d * rng.uniform(8, 12, size=(C, 1))
     R = _look_at_rotations(centers, rng, jitter_deg)
     t = -np.einsum("nij,nj->ni", R, centers)
+    return R, t
 
-    pts = rng.normal(size=(P, 3))
-    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
-    pts *= 3.0 * rng.uniform(0, 1, size=(P, 1)) ** (1 / 3)
 
+def make_intrinsics(C: int, model: int, focal: float, image_size: int, num_intrinsics: int):
     K = num_intrinsics
     intr_model = np.full(K, model, dtype=np.int32)
     intr_params = np.zeros((K, INTR_STRIDE))
@@ -131,19 +124,46 @@ def make_scene(C: int, P: int, mean_track_len: float = 10.0, seed: int = 1, pixe
             intr_params[k, :4] = [f, half, half, 0.02]
         elif model == RADIAL:
             intr_params[k, :5] = [f, half, half, 0.02, -0.005]
+        else:
+            raise ValueError(f"unsupported camera model {model}")
     cam_intr = (np.arange(C) % K).astype(np.int32)
+    return cam_intr, intr_model, intr_params
 
-    if ragged:
-        lens = 3 + rng.poisson(max(mean_track_len - 3, 0), size=P)
-    else:
-        lens = np.full(P, int(round(mean_track_len)))
-    lens = np.minimum(lens, C).astype(np.int64)
-    M = int(min(C, max(lens.max(), int(candidates_mult * mean_track_len))))
 
-    obs_cam_chunks, obs_xy_chunks, final_lens = [], [], np.zeros(P, dtype=np.int64)
-    for s in range(0, P, chunk):
+def make_scene(C: int, P: int, mean_track_len: float = 10.0, seed: int = 1, pixel_sigma: float = 0.0,
+               model: int = SIMPLE_PINHOLE, focal: float = 1000.0, image_size: int = 1000,
+               num_intrinsics: int = 1, candidates_mult: int = 3, ragged: bool = True,
+               jitter_deg: float = 10.0, chunk: int = 100_000, point_range: tuple[int, int] | None = None) -> Scene:
+    """Cameras on a shell r in [8,12] looking at the origin (+-jitter), points
+    uniform in a ball of radius 3, each point observed by the cameras (of a
+    random candidate set) with the smallest off-axis angle.  Track lengths are
+    3 + Poisson(mean-3) when ``ragged`` else constant.
+
+    Points are generated in chunks of ``chunk`` with one RNG stream per chunk,
+    so ``point_range=(a, b)`` (multiples of ``chunk``) yields exactly the
+    points [a, b) of the full scene -- how the multi-GPU bench shards."""
+    R, t = make_cameras(C, seed, jitter_deg)
+    cam_intr, intr_model, intr_params = make_intrinsics(C, model, focal, image_size, num_intrinsics)
+    K = num_intrinsics
+    a, b = point_range if point_range is not None else (0, P)
+    assert a % chunk == 0 and (b % chunk == 0 or b == P), "point_range must align with chunk"
+    M = int(min(C, max(int(candidates_mult * mean_track_len), 8)))
+    R32, t32 = R.astype(np.float32), t.astype(np.float32)
+    tan_half = 0.48 * image_size / focal
+
+    pts_chunks, obs_cam_chunks, obs_xy_chunks, len_chunks = [], [], [], []
+    for s in range(a, b, chunk):
         e = min(P, s + chunk)
         n = e - s
+        rng = np.random.default_rng([seed, 1 + s // chunk])
+        pts = rng.normal(size=(n, 3))
+        pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+        pts *= 3.0 * rng.uniform(0, 1, size=(n, 1)) ** (1 / 3)
+        if ragged:
+            lens = 3 + rng.poisson(max(mean_track_len - 3, 0), size=n)
+        else:
+            lens = np.full(n, int(round(mean_track_len)))
+        lens = np.minimum(lens, M).astype(np.int64)
         if M >= C:
             cand = np.tile(np.arange(C), (n, 1))
         else:
@@ -151,46 +171,49 @@ def make_scene(C: int, P: int, mean_track_len: float = 10.0, seed: int = 1, pixe
             cand.sort(axis=1)
         dup = np.zeros_like(cand, dtype=bool)
         dup[:, 1:] = cand[:, 1:] == cand[:, :-1]
-        Xc = np.einsum("nmij,nj->nmi", R[cand], pts[s:e]) + t[cand]
+        # candidate scoring in float32 (only the ranking matters)
+        Xc = np.einsum("nmij,nj->nmi", R32[cand], pts.astype(np.float32)) + t32[cand]
         z = Xc[..., 2]
         cosang = z / np.linalg.norm(Xc, axis=-1)
         with np.errstate(divide="ignore", invalid="ignore"):
             u = Xc[..., 0] / z
             v = Xc[..., 1] / z
-        vis = (z > 0.1) & (np.abs(u) < 0.48 * image_size / focal) & (np.abs(v) < 0.48 * image_size / focal) & ~dup
+        vis = (z > 0.1) & (np.abs(u) < tan_half) & (np.abs(v) < tan_half) & ~dup
         score = np.where(vis, -cosang, np.inf)
         order = np.argsort(score, axis=1, kind="stable")
-        nvis = vis.sum(1)
-        ln = np.minimum(lens[s:e], nvis)
-        final_lens[s:e] = ln
+        ln = np.minimum(lens, vis.sum(1))
         take = np.arange(M)[None, :] < ln[:, None]
         sel_cam = np.take_along_axis(cand, order, axis=1)[take]
         pidx = np.repeat(np.arange(n), ln)
-        Xs = np.einsum("nij,nj->ni", R[sel_cam], pts[s:e][pidx]) + t[sel_cam]
+        Xs = np.einsum("nij,nj->ni", R[sel_cam], pts[pidx]) + t[sel_cam]
         xy = np.empty((len(sel_cam), 2))
         ci = cam_intr[sel_cam]
         for k in range(K):
-            mk = ci == k
-            if mk.any():
-                xy[mk] = project(int(intr_model[k]), intr_params[k], Xs[mk])
+            mk = ci == k if K > 1 else slice(None)
+            xy[mk] = project(int(intr_model[k]), intr_params[k], Xs[mk])
+        if pixel_sigma > 0:
+            xy += rng.normal(scale=pixel_sigma, size=xy.shape)
+        pts_chunks.append(pts)
         obs_cam_chunks.append(sel_cam.astype(np.int32))
         obs_xy_chunks.append(xy)
+        len_chunks.append(ln)
+    points = np.concatenate(pts_chunks)
     obs_cam = np.concatenate(obs_cam_chunks)
     obs_xy = np.concatenate(obs_xy_chunks)
-    if pixel_sigma > 0:
-        obs_xy = obs_xy + rng.normal(scale=pixel_sigma, size=obs_xy.shape)
-    pt_obs_begin = np.zeros(P + 1, dtype=np.int64)
+    final_lens = np.concatenate(len_chunks)
+    pt_obs_begin = np.zeros(len(points) + 1, dtype=np.int64)
     np.cumsum(final_lens, out=pt_obs_begin[1:])
     quat = geo.rotmat_to_quat_xyzw_fast(R)
-    return Scene(quat, t, pts, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, intr_params)
+    return Scene(quat, t, points, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, intr_params)
 
 
 def perturb_scene(scene: Scene, rot_deg: float = 0.5, center_frac: float = 0.01, point_frac: float = 0.01,
-                  seed: int = 2, extent: float = 10.0) -> Scene:
+                  seed: int = 2, extent: float = 10.0, chunk: int = 100_000, point_offset: int = 0) -> Scene:
     """BA initial state: ground truth perturbed by ``rot_deg`` degrees,
     ``center_frac``*extent camera-centre noise, ``point_frac``*3 point noise
-    (SURVEY.md 8(d) config 4)."""
-    rng = np.random.default_rng(seed)
+    (SURVEY.md 8(d) config 4).  Point noise uses one RNG stream per chunk of
+    the global point index (``point_offset`` = first global index of a shard)."""
+    rng = np.random.default_rng([seed, 0])
     out = scene.copy()
     R = geo.quat_xyzw_to_rotmat(scene.quat)
     c = geo.centers_from_pose(R, scene.trans)
@@ -199,7 +222,11 @@ def perturb_scene(scene: Scene, rot_deg: float = 0.5, center_frac: float = 0.01,
     cn = c + rng.normal(size=c.shape) * center_frac * extent / np.sqrt(3)
     out.quat = geo.rotmat_to_quat_xyzw_fast(Rn)
     out.trans = -np.einsum("nij,nj->ni", Rn, cn)
-    out.points = scene.points + rng.normal(size=scene.points.shape) * point_frac * 3.0 / np.sqrt(3)
+    assert point_offset % chunk == 0
+    for s in range(0, scene.P, chunk):
+        e = min(scene.P, s + chunk)
+        prng = np.random.default_rng([seed, 1 + (point_offset + s) // chunk])
+        out.points[s:e] = scene.points[s:e] + prng.normal(size=(e - s, 3)) * point_frac * 3.0 / np.sqrt(3)
     return out
 
 

@@ -81,6 +81,10 @@ void b200sfm_destroy(b200sfm_ctx* ctx);
 const char* b200sfm_last_error(const b200sfm_ctx* ctx);
 int b200sfm_rank(const b200sfm_ctx* ctx);
 int b200sfm_world_size(const b200sfm_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the host) */
+void* b200sfm_cuda_stream(const b200sfm_ctx* ctx);
+/* kernels launched by this context so far */
+int64_t b200sfm_kernel_launches(const b200sfm_ctx* ctx);
 
 /* ---- statistics common to the LM-based solvers (BA, GP) ------------------ */
 typedef struct {

@@ -1,0 +1,50 @@
+"""CPU checks of the drop-in boundary: the C-ABI library is built, loads, and
+exports every symbol include/b200sfm.h declares (no compute calls: no GPU)."""
+import ctypes as ct
+import os
+import re
+
+from glomap_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200sfm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200sfm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200sfm.h but not exported"
+
+
+def test_python_prototypes_cover_header():
+    assert set(declared_symbols()) == set(_lib.PROTOTYPES), set(declared_symbols()) ^ set(_lib.PROTOTYPES)
+
+
+def test_version_and_struct_sizes():
+    lib = _lib.load()
+    assert lib.b200sfm_version() == 100
+    o = _lib.BAOpts()
+    lib.b200sfm_ba_default_opts(ct.byref(o))
+    # defaults mirror bundle_adjustment.h:14-32 / optimization_base.h:18-23
+    assert (o.optimize_rotations, o.optimize_translation, o.optimize_intrinsics, o.optimize_principal_point,
+            o.optimize_points, o.optimize_rig_poses) == (1, 1, 1, 0, 1, 0)
+    assert o.min_num_view_per_track == 3 and o.max_num_iterations == 200
+    assert o.thres_loss_function == 1.0 and o.function_tolerance == 1e-5
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the context creation must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = _lib.load()
+    h = ct.c_void_p()
+    assert lib.b200sfm_create(0, ct.byref(h)) != 0
+    assert not h.value
