@@ -6,7 +6,7 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sfm.so")
+LIB_PATH = os.environ.get("B200SFM_LIB", os.path.join(_HERE, "libb200sfm.so"))   # env override: kernel-tuning sweeps only
 
 INTR_STRIDE = 12
 NCCL_ID_BYTES = 128

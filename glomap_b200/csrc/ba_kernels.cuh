@@ -201,11 +201,14 @@ __global__ void ba_build_records(int C, int K, const double* __restrict__ quat, 
 // ---------------------------------------------------------------------------
 struct K1Smem {
   alignas(128) double Wt[kTile * kWDoubles];
-  double red[9][kTile];
+  double red[9][kTile + 1];  // +1: rows land in different banks for the (point, component) reduction
+  double acc[9][kTilePts + 1];   // per-point sums (V packed 6 + g 3)
+  unsigned pb[kTilePts + 1]; // observation range of each point of the tile
+  double X[3][kTilePts + 1]; // the tile's points
   double scratch[32];
 };
 
-__global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const double* __restrict__ cam_rec,
+__global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(BAView v, const double* __restrict__ cam_rec,
                                                              const double* __restrict__ intr_rec,
                                                              const double* __restrict__ points, double huber_a,
                                                              int points_var, double* __restrict__ scal) {
@@ -217,17 +220,21 @@ __global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const dou
   const int n = (int)(o1 - o0);
   const int tid = threadIdx.x;
   const int npts = p1 - p0;
-  // per-point accumulators (thread j <-> point p0 + j)
-  double acc[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  // per-point accumulators live in shared memory (thread j <-> point p0 + j)
   unsigned pb = 0, pe = 0;
   bool pvalid = false;
   if (tid < npts) {
     pb = v.pt_begin[p0 + tid];
     pe = v.pt_begin[p0 + tid + 1];
     pvalid = (int)(pe - pb) >= v.min_views;
+    sm.pb[tid] = pb;
+    if (tid == npts - 1) sm.pb[npts] = pe;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sm.X[k][tid] = points[3 * (size_t)(p0 + tid) + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sm.acc[k][tid] = 0.0;
   }
+  __syncthreads();
   double cost = 0.0;
   for (int c0 = 0; c0 < n; c0 += kTile) {
     const int nc = min(kTile, n - c0);
@@ -236,12 +243,12 @@ __global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const dou
     bool use = false;
     if (active) {
       const unsigned oi = o0 + c0 + tid;
-      const int pt = v.obs_pt[oi];
-      use = (int)(v.pt_begin[pt + 1] - v.pt_begin[pt]) >= v.min_views;
+      const int cam = v.obs_cam[oi];
+      const double2 xy = v.obs_xy[oi];
+      const int pl = v.obs_pt[oi] - p0;     // point index within the tile: X and validity come from smem
+      use = (int)(sm.pb[pl + 1] - sm.pb[pl]) >= v.min_views;
       if (use) {
-        const int cam = v.obs_cam[oi];
-        const double2 xy = v.obs_xy[oi];
-        const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+        const double X0 = sm.X[0][pl], X1 = sm.X[1][pl], X2 = sm.X[2][pl];
         linearize_obs(cam_rec, intr_rec, cam, X0, X1, X2, xy, huber_a, o);
         cost += 0.5 * o.rho0;
       }
@@ -277,12 +284,13 @@ __global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const dou
         tma_store_1d(v.W + (size_t)(o0 + c0) * kWDoubles, sm.Wt, (uint32_t)nc * kWBytes);
         tma_store_commit();
       }
-      if (tid < npts && pvalid) {
-        const int lo = max((int)pb - (int)(o0 + c0), 0), hi = min((int)pe - (int)(o0 + c0), nc);
-        for (int i = lo; i < hi; ++i) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) acc[k] += sm.red[k][i];
-        }
+      // per-point sums: thread -> (point j, component k), 9 threads per point
+      for (int item = tid; item < npts * 9; item += kTile) {
+        const int j = item / 9, k = item - 9 * j;
+        const int lo = max((int)sm.pb[j] - (int)(o0 + c0), 0), hi = min((int)sm.pb[j + 1] - (int)(o0 + c0), nc);
+        double a = 0.0;
+        for (int i = lo; i < hi; ++i) a += sm.red[k][i];
+        sm.acc[k][j] += a;
       }
       if (tid == 0) tma_store_wait_read();
       __syncthreads();
@@ -293,11 +301,12 @@ __global__ void __launch_bounds__(kTile) ba_linearize_points(BAView v, const dou
     const size_t p = (size_t)(p0 + tid);
     if (pvalid) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) v.V[6 * p + k] = acc[k];
+      for (int k = 0; k < 6; ++k) v.V[6 * p + k] = sm.acc[k][tid];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        v.gp[3 * p + k] = acc[6 + k];
-        gmax = fmax(gmax, fabs(acc[6 + k]));
+        const double gk = sm.acc[6 + k][tid];
+        v.gp[3 * p + k] = gk;
+        gmax = fmax(gmax, fabs(gk));
       }
     } else {
 #pragma unroll
@@ -521,17 +530,18 @@ __global__ void ba_build_precond(int C, const double* __restrict__ U, const doub
 // ---------------------------------------------------------------------------
 struct K3Smem {
   alignas(128) double Wt[kTile * kWDoubles];
-  double t[3][kTile];
-  double z[3][kTile];
+  double t[3][kTile + 1];
+  double z[3][kTilePts + 1];     // s_p while accumulating, then z_p
+  unsigned pb[kTilePts + 1];
   double scratch[32];
   alignas(8) uint64_t mbar;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* __restrict__ x, double* __restrict__ y,
-                                                       const double* __restrict__ points,
-                                                       double* __restrict__ points_new, double radius,
-                                                       double* __restrict__ bscal) {
+__global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView v, const double* __restrict__ x, double* __restrict__ y,
+                                                          const double* __restrict__ points,
+                                                          double* __restrict__ points_new, double radius,
+                                                          double* __restrict__ bscal) {
   extern __shared__ unsigned char smem_raw[];
   K3Smem& sm = *reinterpret_cast<K3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int tile = blockIdx.x;
@@ -545,19 +555,14 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
     mbar_init(&sm.mbar, 1);
     fence_mbar_init();
   }
+  if (tid < npts) {
+    sm.pb[tid] = v.pt_begin[p0 + tid];
+    if (tid == npts - 1) sm.pb[npts] = o1;
+    sm.z[0][tid] = sm.z[1][tid] = sm.z[2][tid] = 0.0;
+  }
   __syncthreads();
   uint32_t phase = 0;
-  unsigned pb = 0, pe = 0;
-  bool pvalid = false;
-  if (tid < npts) {
-    pb = v.pt_begin[p0 + tid];
-    pe = v.pt_begin[p0 + tid + 1];
-    pvalid = (int)(pe - pb) >= v.min_views;
-  }
-  double s[3] = {0.0, 0.0, 0.0};
-  double w[18];
-  int cam = 0;
-  // ---- phase A: s_p ----------------------------------------------------------
+  // ---- phase A: s_p = sum_o W_o^T x_cam(o) (accumulated in sm.z) --------------------
   if (MODE != 1) {
     for (int ch = 0; ch < nchunks; ++ch) {
       const int c0 = ch * kTile;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
       double xc[6] = {0, 0, 0, 0, 0, 0};
       const bool active = tid < nc;
       if (active) {
-        cam = v.obs_cam[o0 + c0 + tid];
+        const int cam = v.obs_cam[o0 + c0 + tid];
         const double2* xp = reinterpret_cast<const double2*>(x + (size_t)cam * 6);
         const double2 a = xp[0], b = xp[1], c = xp[2];
         xc[0] = a.x; xc[1] = a.y; xc[2] = b.x; xc[3] = b.y; xc[4] = c.x; xc[5] = c.y;
@@ -580,39 +585,37 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
       if (active) {
         const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const double2 q = wr[k];
-          w[2 * k] = q.x;
-          w[2 * k + 1] = q.y;
-        }
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          t0 += w[3 * r] * xc[r];
-          t1 += w[3 * r + 1] * xc[r];
-          t2 += w[3 * r + 2] * xc[r];
+        for (int r = 0; r < 6; r += 2) {
+          const double2 q0 = wr[(3 * r) / 2], q1 = wr[(3 * r) / 2 + 1], q2 = wr[(3 * r) / 2 + 2];
+          // rows r (q0.x q0.y q1.x) and r+1 (q1.y q2.x q2.y)
+          t0 += q0.x * xc[r] + q1.y * xc[r + 1];
+          t1 += q0.y * xc[r] + q2.x * xc[r + 1];
+          t2 += q1.x * xc[r] + q2.y * xc[r + 1];
         }
       }
       sm.t[0][tid] = t0;
       sm.t[1][tid] = t1;
       sm.t[2][tid] = t2;
       __syncthreads();
-      if (tid < npts && pvalid) {
-        const int lo = max((int)pb - (int)(o0 + c0), 0), hi = min((int)pe - (int)(o0 + c0), nc);
-        for (int i = lo; i < hi; ++i) {
-          s[0] += sm.t[0][i];
-          s[1] += sm.t[1][i];
-          s[2] += sm.t[2][i];
-        }
+      // per-point partial sums: thread -> (point j, component k)
+      for (int item = tid; item < npts * 3; item += kTile) {
+        const int j = item / 3, k = item - 3 * j;
+        const int lo = max((int)sm.pb[j] - (int)(o0 + c0), 0), hi = min((int)sm.pb[j + 1] - (int)(o0 + c0), nc);
+        double a = 0.0;
+        for (int i = lo; i < hi; ++i) a += sm.t[k][i];
+        sm.z[k][j] += a;
       }
-      if (nchunks > 1) __syncthreads();
+      __syncthreads();
     }
   }
-  // ---- z_p -------------------------------------------------------------------
+  // ---- z_p = Vinv_p s_p -----------------------------------------------------------
   double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
   if (tid < npts) {
+    const size_t p = (size_t)(p0 + tid);
+    const bool pvalid = (int)(sm.pb[tid + 1] - sm.pb[tid]) >= v.min_views;
     double z[3] = {0.0, 0.0, 0.0};
     if (pvalid) {
-      const size_t p = (size_t)(p0 + tid);
+      double s[3] = {sm.z[0][tid], sm.z[1][tid], sm.z[2][tid]};
       double g[3] = {0, 0, 0};
       if (MODE != 0) {
         g[0] = v.gp[3 * p];
@@ -645,13 +648,14 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
         }
       }
     } else if (MODE == 2) {
-      const size_t p = (size_t)(p0 + tid);
 #pragma unroll
       for (int k = 0; k < 3; ++k) points_new[3 * p + k] = points[3 * p + k];
     }
-    sm.z[0][tid] = z[0];
-    sm.z[1][tid] = z[1];
-    sm.z[2][tid] = z[2];
+    if (MODE != 2) {
+      sm.z[0][tid] = z[0];
+      sm.z[1][tid] = z[1];
+      sm.z[2][tid] = z[2];
+    }
   }
   if (MODE == 2) {
     b0 = block_sum(b0, sm.scratch);
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
     return;
   }
   __syncthreads();
-  // ---- phase B: y_cam -= W_o z_p ---------------------------------------------
+  // ---- phase B: y_cam -= W_o z_p (W re-read from the shared-memory tile) --------------
   for (int ch = 0; ch < nchunks; ++ch) {
     const int c0 = ch * kTile;
     const int nc = min(kTile, n - c0);
@@ -683,24 +687,17 @@ __global__ void __launch_bounds__(kTile) ba_schur_pass(BAView v, const double* _
     }
     if (tid < nc) {
       const unsigned oi = o0 + c0 + tid;
-      if (reload) {
-        cam = v.obs_cam[oi];
-        const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const double2 q = wr[k];
-          w[2 * k] = q.x;
-          w[2 * k + 1] = q.y;
-        }
-      }
+      const int cam = v.obs_cam[oi];
       const int pl = v.obs_pt[oi] - p0;
       const double z0 = sm.z[0][pl], z1 = sm.z[1][pl], z2 = sm.z[2][pl];
       if (z0 != 0.0 || z1 != 0.0 || z2 != 0.0) {
+        const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);
         double* yc = y + (size_t)cam * 6;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double val = w[3 * r] * z0 + w[3 * r + 1] * z1 + w[3 * r + 2] * z2;
-          atomicAdd(&yc[r], -val);
+        for (int r = 0; r < 6; r += 2) {
+          const double2 q0 = wr[(3 * r) / 2], q1 = wr[(3 * r) / 2 + 1], q2 = wr[(3 * r) / 2 + 2];
+          atomicAdd(&yc[r], -(q0.x * z0 + q0.y * z1 + q1.x * z2));
+          atomicAdd(&yc[r + 1], -(q1.y * z0 + q2.x * z1 + q2.y * z2));
         }
       }
     }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "ba_kernels.cuh"
@@ -144,7 +145,7 @@ struct b200sfm_ba_problem {
       ptb[p] = (unsigned)h_pt_begin[p];
       const long long len = h_pt_begin[p + 1] - h_pt_begin[p];
       if (len >= min_views) n_obs_used += len;
-      if (tile_pts > 0 && (tile_obs + len > kTile || tile_pts >= kTile)) {
+      if (tile_pts > 0 && (tile_obs + len > kTile || tile_pts >= kTilePts)) {
         tiles.push_back(p);
         tile_obs = 0;
         tile_pts = 0;
@@ -223,6 +224,12 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
+    // several 50-KB CTAs per SM: ask for the full shared-memory carve-out
+    const int carve = getenv("B200SFM_CARVEOUT") ? atoi(getenv("B200SFM_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaStreamSynchronize(s));   // temporaries go out of scope
   }
 

@@ -8,7 +8,18 @@
 
 namespace b200 {
 
-constexpr int kTile = 256;       // observations per point-order tile == threads per CTA
+// Tunables of the point-order kernels (overridable with -D for sweeps)
+#ifndef B200_TILE
+#define B200_TILE 128
+#endif
+#ifndef B200_K1_MIN_CTAS
+#define B200_K1_MIN_CTAS 5
+#endif
+#ifndef B200_K3_MIN_CTAS
+#define B200_K3_MIN_CTAS 8
+#endif
+constexpr int kTile = B200_TILE; // observations per point-order tile == threads per CTA
+constexpr int kTilePts = 64;     // max points per tile (bounds the per-point shared-memory arrays)
 constexpr int kWDoubles = 18;    // W block of one observation: 6x3 doubles, row-major
 constexpr int kWBytes = kWDoubles * 8;
 
