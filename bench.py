@@ -94,10 +94,8 @@ class ClockSampler:
 
 
 def shard_range(P, chunk, rank, world):
-    nchunks = (P + chunk - 1) // chunk
-    a = (nchunks * rank) // world
-    b = (nchunks * (rank + 1)) // world
-    return a * chunk, min(P, b * chunk)
+    from glomap_b200.dist import shard_range as sr
+    return sr(P, chunk, rank, world)
 
 
 def cpu_baseline(steps: int, lm_iters: int):

@@ -1,0 +1,54 @@
+"""Run under torchrun on >= 2 GPUs (not collected by pytest): the sharded BA
+must reproduce the single-GPU BA.  Usage:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_ba_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from glomap_b200 import dist as D, estimators as E, synthetic as S  # noqa: E402
+
+
+def main():
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = E.Context(local, rank, world, D.broadcast_nccl_id(E.Context.nccl_unique_id, rank, world))
+    full = S.make_scene(60, 6000, 7, seed=5, pixel_sigma=0.5, chunk=500)
+    init = S.perturb_scene(full, chunk=500)
+    mask = E.first_frame_mask(full.C)
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=False)
+    opts.solver_options.pcg_rel_tolerance = 1e-12
+    opts.solver_options.pcg_max_iterations = 2000
+    shard, (a, b) = D.shard_scene(init, rank, world, chunk=500)
+    ba = E.BundleAdjuster(opts, ctx)
+    assert ba.Solve(shard, mask)
+    st = ba.summary
+    ok = True
+    if rank == 0:
+        ref = init.copy()
+        ba1 = E.BundleAdjuster(opts, E.Context(local))
+        assert ba1.Solve(ref, mask)
+        s1 = ba1.summary
+        dq = np.abs(ref.quat - shard.quat).max()
+        dt = np.abs(ref.trans - shard.trans).max()
+        dp = np.abs(ref.points[a:b] - shard.points).max()
+        print(f"multi-GPU({world}) vs single: its {st.iterations}/{s1.iterations} cost {st.final_cost:.10e}/{s1.final_cost:.10e} "
+              f"dq {dq:.2e} dt {dt:.2e} dp {dp:.2e}")
+        ok = st.iterations == s1.iterations and abs(st.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost and dq < 1e-8 and dt < 1e-7 and dp < 1e-6
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ctx.close()
+    dist.destroy_process_group()
+    if flag.item() < 1:
+        raise SystemExit("multi-GPU parity FAILED")
+    if rank == 0:
+        print("multi-GPU parity OK")
+
+
+if __name__ == "__main__":
+    main()
