@@ -106,7 +106,7 @@ struct b200sfm_ba_problem {
   // linear system
   DevBuf<double> W, V, Vinv, gp, lin /* U | gc | cost */, Sd, Minv, jscale_c, jscale_p, Dc;
   // pcg
-  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dots;
+  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dots, part;
   DevBuf<double> scal;   // [0] cost [1] gmax | [2..5] bscal | [6] cand cost | [8..12] cscal
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_k1 = 0, smem_k3 = 0;
@@ -357,9 +357,14 @@ struct b200sfm_ba_problem {
     B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yw.p : nullptr, bvec.p);
     // ---- PCG ------------------------------------------------------------------
     const int max_it = std::max(1, o.pcg_max_iterations);
+    const int nblk = cdiv(C, kPcgThreads);
     if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
-    dots.zero(s);
-    B200_LAUNCH(ctx, pcg_init<6>, cdiv(C, 128), 128, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, pp.p, yw.p, dots.p);
+    if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
+    double* part_pq = part.p;
+    double* part_rz = part.p + nblk;
+    double* part_rr = part.p + 2 * (size_t)nblk;
+    B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
+    B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     const double rr0 = ctx->h_scal[2];
@@ -381,9 +386,10 @@ struct b200sfm_ba_problem {
           if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
           ctx->allreduce_sum(yw.p, nC6);
         }
-        B200_LAUNCH(ctx, pcg_apply_diag<6>, cdiv(C, 128), 128, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, d_it);
-        B200_LAUNCH(ctx, pcg_update<6>, cdiv(C, 128), 128, 0, C, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev + 1, d_it);
-        B200_LAUNCH(ctx, pcg_direction<6>, cdiv(nC6, 256), 256, 0, C, pz.p, pp.p, yw.p, d_prev + 1, d_it);
+        B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, part_pq);
+        B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq,
+                    part_rz, part_rr, d_it);
+        B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, C, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
         B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
         B200_CUDA_OK(cudaStreamSynchronize(s));
         const double rr = ctx->h_scal[2];
@@ -407,10 +413,14 @@ struct b200sfm_ba_problem {
     build_records(nxt);
     const int grid = std::min(cdiv(N, 256), 148 * 8);
     B200_LAUNCH(ctx, ba_cost, grid, 256, 0, v, cam_rec.p, intr_rec.p, points[nxt].p, o.thres_loss_function, scal.p + 6);
-    ctx->allreduce_sum(scal.p + 2, 5);   // bscal[0..3] + cand cost
+    // bscal[0..3] + cand cost are per-shard partial sums; cscal[8..12] is replicated but summed
+    // with atomics (rank-dependent rounding): all-reduce everything and average the replicated
+    // part so that every rank takes bit-identical accept/reject decisions.
+    ctx->allreduce_sum(scal.p + 2, 11);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
-    const double* h = ctx->h_scal;
+    double* h = ctx->h_scal;
+    for (int k = 8; k <= 12; ++k) h[k] /= (double)ctx->world;
     const double g_dot_d = h[8] + h[2];
     const double dDd = h[10] + h[3];
     res.model_cost_change = 0.5 * (-g_dot_d + h[9] + dDd);

@@ -4,22 +4,48 @@
 // (bundle_adjustment.cc:94-96, global_positioning.cc:551-559); north_star
 // mandates PCG with one all-reduce per mat-vec.
 //
-// Scalars live in a device array dots[it][4] = {p.q, r.z (next), r.r (next), -}
-// indexed by iteration so that no kernel ever resets a value another kernel of
-// the same iteration still reads.
+// All inner products are DETERMINISTIC: every CTA writes its partial sum to
+// part[which][blockIdx.x] and the consuming kernel re-sums the partials in a
+// fixed order.  With replicated camera-sized vectors this makes alpha, beta and
+// the convergence test bit-identical on every rank, so all ranks take the same
+// control-flow decisions without an extra collective.
+//
+// Scalars: dots[it][0] = p.q, dots[it][1] = r.z after iteration it,
+// dots[it][2] = r.r after iteration it (it = 0: initial values).
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-// q_c = (A_c + diag(D_c)) p_c + yw_c ; dots[it][0] += p.q
-//   A packed symmetric B x B per block, yw = the (negative) Schur part already
-//   accumulated by the mat-vec kernel (and all-reduced).
+constexpr int kPcgThreads = 128;
+
+// fixed-order sum of n partials by the first warp of the CTA; result broadcast
+// through shared memory to all threads.
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int n, double* sh) {
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += part[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *sh = s;
+  }
+  __syncthreads();
+  return *sh;
+}
+// CTA-level deterministic sum -> part[blockIdx.x]
+__device__ __forceinline__ void write_partial(double v, double* __restrict__ part, double* scratch) {
+  v = block_sum(v, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+
+// q_c = (A_c + diag(D_c)) p_c + yw_c ; part_pq[blk] = partial p.q
 template <int B>
-__global__ void pcg_apply_diag(int nb, const double* __restrict__ A, const double* __restrict__ D,
-                               const double* __restrict__ p, const double* __restrict__ yw, double* __restrict__ q,
-                               double* __restrict__ dots_it) {
+__global__ void __launch_bounds__(kPcgThreads) pcg_apply_diag(int nb, const double* __restrict__ A,
+                                                              const double* __restrict__ D,
+                                                              const double* __restrict__ p,
+                                                              const double* __restrict__ yw, double* __restrict__ q,
+                                                              double* __restrict__ part_pq) {
   constexpr int NP = B * (B + 1) / 2;
+  __shared__ double scratch[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double pq = 0.0;
   if (c < nb) {
@@ -36,20 +62,26 @@ __global__ void pcg_apply_diag(int nb, const double* __restrict__ A, const doubl
       pq += qv * pv[k];
     }
   }
-  pq = warp_sum(pq);
-  if ((threadIdx.x & 31) == 0 && pq != 0.0) atomicAdd(&dots_it[0], pq);
+  write_partial(pq, part_pq, scratch);
 }
 
-// alpha = rz / pq; x += alpha p; r -= alpha q; z = Minv r; dots[it][1] += r.z; dots[it][2] += r.r
+// alpha = rz / pq; x += alpha p; r -= alpha q; z = Minv r; partial r.z, r.r
 template <int B>
-__global__ void pcg_update(int nb, const double* __restrict__ Minv, const double* __restrict__ p,
-                           const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r,
-                           double* __restrict__ z, const double* __restrict__ rz_ptr, double* __restrict__ dots_it) {
+__global__ void __launch_bounds__(kPcgThreads) pcg_update(int nb, int nblk, const double* __restrict__ Minv,
+                                                          const double* __restrict__ p, const double* __restrict__ q,
+                                                          double* __restrict__ x, double* __restrict__ r,
+                                                          double* __restrict__ z, const double* __restrict__ dots_prev,
+                                                          const double* __restrict__ part_pq,
+                                                          double* __restrict__ part_rz, double* __restrict__ part_rr,
+                                                          double* __restrict__ dots_it) {
   constexpr int NP = B * (B + 1) / 2;
+  __shared__ double scratch[32];
+  __shared__ double sh;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const double pq = dots_it[0];
-  const double rz = *rz_ptr;
+  const double pq = sum_partials(part_pq, nblk, &sh);
+  const double rz = dots_prev[1];
   const double alpha = (pq > 0.0) ? rz / pq : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) dots_it[0] = pq;
   double rzn = 0.0, rr = 0.0;
   if (c < nb) {
     double m[NP], rv[B], zv[B];
@@ -70,32 +102,50 @@ __global__ void pcg_update(int nb, const double* __restrict__ Minv, const double
       rzn += rv[k] * zv[k];
     }
   }
-  rzn = warp_sum(rzn);
-  rr = warp_sum(rr);
-  if ((threadIdx.x & 31) == 0) {
-    if (rzn != 0.0) atomicAdd(&dots_it[1], rzn);
-    if (rr != 0.0) atomicAdd(&dots_it[2], rr);
+  write_partial(rzn, part_rz, scratch);
+  write_partial(rr, part_rr, scratch);
+}
+
+// beta = rz_new / rz; p = z + beta p; clears the mat-vec accumulator yw;
+// CTA 0 publishes dots[it][1] = r.z, dots[it][2] = r.r
+template <int B>
+__global__ void __launch_bounds__(kPcgThreads) pcg_direction(int nb, int nblk, const double* __restrict__ z,
+                                                             double* __restrict__ p, double* __restrict__ yw,
+                                                             const double* __restrict__ dots_prev,
+                                                             const double* __restrict__ part_rz,
+                                                             const double* __restrict__ part_rr,
+                                                             double* __restrict__ dots_it) {
+  __shared__ double sh, sh2;
+  const double rzn = sum_partials(part_rz, nblk, &sh);
+  if (blockIdx.x == 0) {
+    const double rr = sum_partials(part_rr, nblk, &sh2);
+    if (threadIdx.x == 0) {
+      dots_it[1] = rzn;
+      dots_it[2] = rr;
+    }
+  }
+  const double rz = dots_prev[1];
+  const double beta = (rz > 0.0) ? rzn / rz : 0.0;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nb) {
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const size_t i = (size_t)c * B + k;
+      p[i] = z[i] + beta * p[i];
+      if (yw) yw[i] = 0.0;
+    }
   }
 }
 
-// beta = rz_new / rz; p = z + beta p; also clears the mat-vec accumulator yw
+// x = 0; r = b; z = Minv r; p = z; yw = 0; partial r.z, r.r
 template <int B>
-__global__ void pcg_direction(int nb, const double* __restrict__ z, double* __restrict__ p, double* __restrict__ yw,
-                              const double* __restrict__ rz_ptr, const double* __restrict__ dots_it) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb * B) return;
-  const double rz = *rz_ptr;
-  const double beta = (rz > 0.0) ? dots_it[1] / rz : 0.0;
-  p[i] = z[i] + beta * p[i];
-  if (yw) yw[i] = 0.0;
-}
-
-// x = 0; r = b; z = Minv r; p = z; init[1] = r.z; init[2] = r.r; yw = 0
-template <int B>
-__global__ void pcg_init(int nb, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x,
-                         double* __restrict__ r, double* __restrict__ z, double* __restrict__ p,
-                         double* __restrict__ yw, double* __restrict__ dots0) {
+__global__ void __launch_bounds__(kPcgThreads) pcg_init(int nb, const double* __restrict__ Minv,
+                                                        const double* __restrict__ b, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ z,
+                                                        double* __restrict__ p, double* __restrict__ yw,
+                                                        double* __restrict__ part_rz, double* __restrict__ part_rr) {
   constexpr int NP = B * (B + 1) / 2;
+  __shared__ double scratch[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double rz = 0.0, rr = 0.0;
   if (c < nb) {
@@ -120,11 +170,21 @@ __global__ void pcg_init(int nb, const double* __restrict__ Minv, const double* 
       rz += rv[k] * zv[k];
     }
   }
-  rz = warp_sum(rz);
-  rr = warp_sum(rr);
-  if ((threadIdx.x & 31) == 0) {
-    if (rz != 0.0) atomicAdd(&dots0[1], rz);
-    if (rr != 0.0) atomicAdd(&dots0[2], rr);
+  write_partial(rz, part_rz, scratch);
+  write_partial(rr, part_rr, scratch);
+}
+
+// dots0[1] = sum part_rz, dots0[2] = sum part_rr   (single CTA)
+__global__ void __launch_bounds__(kPcgThreads) pcg_publish_init(int nblk, const double* __restrict__ part_rz,
+                                                                const double* __restrict__ part_rr,
+                                                                double* __restrict__ dots0) {
+  __shared__ double sh, sh2;
+  const double rz = sum_partials(part_rz, nblk, &sh);
+  const double rr = sum_partials(part_rr, nblk, &sh2);
+  if (threadIdx.x == 0) {
+    dots0[0] = 0.0;
+    dots0[1] = rz;
+    dots0[2] = rr;
   }
 }
 
