@@ -42,6 +42,19 @@ class BAOpts(ct.Structure):
     ]
 
 
+class GPOpts(ct.Structure):
+    _fields_ = [
+        ("optimize_positions", c_int32), ("optimize_points", c_int32), ("optimize_scales", c_int32),
+        ("min_num_view_per_track", c_int32), ("max_num_iterations", c_int32),
+        ("max_num_line_search_step_size_iterations", c_int32),
+        ("thres_loss_function", c_double), ("function_tolerance", c_double), ("gradient_tolerance", c_double),
+        ("parameter_tolerance", c_double),
+        ("pcg_max_iterations", c_int32), ("pcg_min_iterations", c_int32), ("pcg_rel_tolerance", c_double),
+        ("preconditioner", c_int32), ("profile_kernels", c_int32), ("fixed_num_iterations", c_int32),
+        ("reserved0", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b200sfm.h declares
 PROTOTYPES = {
     "b200sfm_version": (c_int32, []),
@@ -64,6 +77,15 @@ PROTOTYPES = {
     "b200sfm_ba_problem_solve": (c_int32, [c_void_p, P(BAOpts), P(LMStats)]),
     "b200sfm_ba_problem_cost": (c_int32, [c_void_p, P(BAOpts), P(c_double)]),
     "b200sfm_ba_problem_free": (None, [c_void_p]),
+    "b200sfm_gp_default_opts": (None, [P(GPOpts)]),
+    "b200sfm_gp_solve": (c_int32, [c_void_p, P(GPOpts), c_int32, c_int32, c_int64] + [c_void_p] * 8 + [P(LMStats)]),
+    "b200sfm_gp_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 5 + [c_int32, P(c_void_p)]),
+    "b200sfm_gp_problem_set_state": (c_int32, [c_void_p] * 4),
+    "b200sfm_gp_problem_get_state": (c_int32, [c_void_p] * 4),
+    "b200sfm_gp_problem_save_state": (c_int32, [c_void_p]),
+    "b200sfm_gp_problem_restore_state": (c_int32, [c_void_p]),
+    "b200sfm_gp_problem_solve": (c_int32, [c_void_p, P(GPOpts), P(LMStats)]),
+    "b200sfm_gp_problem_free": (None, [c_void_p]),
 }
 
 _lib = None

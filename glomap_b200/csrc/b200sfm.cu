@@ -5,6 +5,7 @@
 
 #include "ba_solver.cuh"
 #include "context.cuh"
+#include "gp_solver.cuh"
 
 namespace {
 
@@ -267,6 +268,136 @@ int b200sfm_ba_solve(b200sfm_ctx* ctx, const b200sfm_ba_opts* opts, int32_t C, i
   if (p) b200sfm_ba_problem_free(p);
   for (cudaEvent_t e : {e0, e1, e2, e3})
     if (e) cudaEventDestroy(e);
+  if (stats) *stats = st;
+  return rc;
+}
+
+// ---- GP ----------------------------------------------------------------------
+void b200sfm_gp_default_opts(b200sfm_gp_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // global_positioning.h:22-49, optimization_base.h:18-23
+  o->optimize_positions = 1;
+  o->optimize_points = 1;
+  o->optimize_scales = 1;
+  o->min_num_view_per_track = 3;
+  o->max_num_iterations = 100;
+  o->max_num_line_search_step_size_iterations = 20;
+  o->thres_loss_function = 0.1;
+  o->function_tolerance = 1e-5;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->pcg_max_iterations = 1000;
+  o->pcg_min_iterations = 0;
+  o->pcg_rel_tolerance = 1e-2;
+  o->preconditioner = 1;
+}
+
+int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, const int64_t* pt_obs_begin,
+                              const int32_t* obs_cam, const double* obs_dir, const uint8_t* cam_calibrated,
+                              const uint8_t* cam_const_mask, int32_t min_num_view_per_track, b200sfm_gp_problem** out) {
+  if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (C <= 0 || P <= 0 || N <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
+  if (!pt_obs_begin || !obs_cam || !obs_dir) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
+  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+  return guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    auto* p = new b200sfm_gp_problem();
+    try {
+      p->create(ctx, C, P, N, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, cam_const_mask, min_num_view_per_track);
+    } catch (...) {
+      delete p;
+      throw;
+    }
+    *out = p;
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* centers, const double* points, const double* scales) {
+  if (!p || !centers || !points || !scales) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->set_state(centers, points, scales);
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* centers, double* points, double* scales) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->get_state(centers, points, scales);
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->save_state();
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    if (!p->restore_state()) { p->ctx->err = "no saved state"; return (int)B200SFM_ERR_INVALID_ARG; }
+    B200_CUDA_OK(cudaStreamSynchronize(p->ctx->stream));
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* opts, b200sfm_lm_stats* stats) {
+  if (!p || !opts) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    if (opts->min_num_view_per_track != p->min_views) {
+      p->ctx->err = "min_num_view_per_track differs from the value the problem was created with";
+      return (int)B200SFM_ERR_INVALID_ARG;
+    }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    return p->solve(*opts, stats);
+  });
+}
+
+void b200sfm_gp_problem_free(b200sfm_gp_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  delete p;
+}
+
+int b200sfm_gp_solve(b200sfm_ctx* ctx, const b200sfm_gp_opts* opts, int32_t C, int32_t P, int64_t N,
+                     const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_dir,
+                     const uint8_t* cam_calibrated, const uint8_t* cam_const_mask, double* centers, double* points,
+                     double* scales, b200sfm_lm_stats* stats) {
+  if (!ctx || !opts || !centers || !points || !scales) return B200SFM_ERR_INVALID_ARG;
+  b200sfm_gp_problem* p = nullptr;
+  b200sfm_lm_stats st{};
+  const long long launches0 = ctx->launches;
+  int rc = b200sfm_gp_problem_create(ctx, C, P, N, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, cam_const_mask,
+                                     opts->min_num_view_per_track, &p);
+  if (rc == B200SFM_OK) {
+    rc = guarded(ctx, [&]() {
+      p->set_state(centers, points, scales);
+      int r = p->solve(*opts, &st);
+      if (r != B200SFM_OK) return r;
+      p->get_state(centers, points, scales);
+      st.kernel_launches = ctx->launches - launches0;
+      st.h2d_bytes = N * 36 + ((long long)P + 1) * 4 + ((long long)C + P) * 24;
+      st.d2h_bytes = N * 8 + ((long long)C + P) * 24;
+      return (int)B200SFM_OK;
+    });
+  }
+  if (p) b200sfm_gp_problem_free(p);
   if (stats) *stats = st;
   return rc;
 }

@@ -60,6 +60,10 @@ __global__ void k_gather_camorder(int Nv, const int* __restrict__ camord_obs, co
   pt_c[i] = obs_pt[o];
   xy_c[i] = obs_xy[o];
 }
+__global__ void k_gather_int(int n, const int* __restrict__ idx, const int* __restrict__ src, int* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
 __global__ void k_eff_mask(int C, const unsigned char* __restrict__ base, int fix_rot, int fix_trn,
                            unsigned char* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;

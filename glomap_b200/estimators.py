@@ -227,3 +227,128 @@ class BundleAdjuster:
         _lib.check(ctx.handle, rc)
         scene.intr_params, scene.quat, scene.trans, scene.points = intr, quat, trans, pts
         return bool(st.usable)
+
+
+# ---------------------------------------------------------------------------
+# Global positioning (BATA)
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass
+class GlobalPositionerOptions:
+    """global_positioning.h:9-54 (defaults identical).  Only ONLY_POINTS is
+    implemented -- the constraint type the mapper enforces
+    (controllers/global_mapper.cc:145-149)."""
+    ONLY_POINTS = 0
+    generate_random_positions: bool = True
+    generate_random_points: bool = True
+    generate_scales: bool = True
+    optimize_positions: bool = True
+    optimize_points: bool = True
+    optimize_scales: bool = True
+    use_gpu: bool = True
+    gpu_index: str = "-1"
+    min_num_images_gpu_solver: int = 50
+    min_num_view_per_track: int = 3
+    seed: int = 1
+    constraint_type: int = 0
+    thres_loss_function: float = 1e-1
+    solver_options: SolverOptions = dataclasses.field(default_factory=lambda: SolverOptions(max_num_iterations=100, pcg_max_iterations=1000))
+    profile_kernels: bool = False
+    fixed_num_iterations: int = 0
+
+    def to_c(self) -> _lib.GPOpts:
+        o = _lib.GPOpts()
+        _lib.load().b200sfm_gp_default_opts(ct.byref(o))
+        for f in ("optimize_positions", "optimize_points", "optimize_scales", "profile_kernels"):
+            setattr(o, f, int(getattr(self, f)))
+        o.min_num_view_per_track = self.min_num_view_per_track
+        o.thres_loss_function = self.thres_loss_function
+        o.fixed_num_iterations = self.fixed_num_iterations
+        so = self.solver_options
+        for f in ("max_num_iterations", "function_tolerance", "gradient_tolerance", "parameter_tolerance",
+                  "pcg_max_iterations", "pcg_min_iterations", "pcg_rel_tolerance", "preconditioner"):
+            setattr(o, f, getattr(so, f))
+        return o
+
+
+@dataclasses.dataclass
+class PositioningProblem:
+    """Flat GP input (what the shim builds from frames/images/tracks):
+    rotations are known (from rotation averaging), bearings are
+    Image::features_undist (scene/image.h:31)."""
+    quat: np.ndarray           # [C,4] cam_from_world rotations (fixed during GP)
+    pt_obs_begin: np.ndarray   # [P+1]
+    obs_cam: np.ndarray        # [N]
+    bearings: np.ndarray       # [N,3] unit bearings in the camera frame
+    cam_calibrated: np.ndarray | None = None   # [C] has_prior_focal_length
+    centers: np.ndarray | None = None          # [C,3] filled by Solve (or initial values)
+    points: np.ndarray | None = None           # [P,3]
+    scales: np.ndarray | None = None           # [N]
+    trans: np.ndarray | None = None            # [C,3] cam_from_world translations, written by Solve
+
+    @property
+    def C(self):
+        return len(self.quat)
+
+    @property
+    def P(self):
+        return len(self.pt_obs_begin) - 1
+
+    @property
+    def N(self):
+        return len(self.obs_cam)
+
+
+def world_bearings(quat, bearings_cam, obs_cam):
+    """t_obs = R_cw^T * bearing (global_positioning.cc:294-296) -- host-side input prep."""
+    from . import geometry as geo
+    R = geo.quat_xyzw_to_rotmat(np.asarray(quat, dtype=np.float64))[np.asarray(obs_cam)]
+    return np.einsum("nji,nj->ni", R, bearings_cam)
+
+
+class GlobalPositioner:
+    """glomap::GlobalPositioner (global_positioning.h:56-70)."""
+
+    def __init__(self, options: GlobalPositionerOptions | None = None, ctx: Context | None = None):
+        self.options_ = dataclasses.replace(options) if options else GlobalPositionerOptions()
+        self.ctx = ctx
+        self.rng = np.random.default_rng(self.options_.seed)    # reference: std::mt19937(seed), .cc:23-26
+        self.summary: LMStats | None = None
+
+    def GetOptions(self) -> GlobalPositionerOptions:
+        return self.options_
+
+    def Solve(self, prob: PositioningProblem) -> bool:
+        """Returns False on empty input (global_positioning.cc:37-50) or an
+        unusable solution; on success ``prob.centers/points/scales`` hold the
+        optimum and ``prob.trans = -R c`` (ConvertResults, .cc:562-572)."""
+        o = self.options_
+        if o.constraint_type != GlobalPositionerOptions.ONLY_POINTS:
+            raise NotImplementedError("only ONLY_POINTS is implemented (controllers/global_mapper.cc:145-149)")
+        if prob.C == 0 or prob.P == 0 or prob.N == 0:
+            return False
+        ctx = self.ctx or default_context()
+        lib = ctx.lib
+        # InitializeRandomPositions (.cc:123-165) / random points (.cc:261-264): 100 * U(-1,1)^3
+        if o.generate_random_positions and o.optimize_positions or prob.centers is None:
+            prob.centers = 100.0 * self.rng.uniform(-1, 1, size=(prob.C, 3))
+        if o.generate_random_points and o.optimize_points or prob.points is None:
+            prob.points = 100.0 * self.rng.uniform(-1, 1, size=(prob.P, 3))
+        if o.generate_scales or prob.scales is None:
+            prob.scales = np.ones(prob.N)                               # .cc:298
+        t_obs = _c(world_bearings(prob.quat, prob.bearings, prob.obs_cam), np.float64)
+        ptb, cam = _c(prob.pt_obs_begin, np.int64), _c(prob.obs_cam, np.int32)
+        cal = None if prob.cam_calibrated is None else _c(prob.cam_calibrated, np.uint8)
+        cen, pts, sc = _c(prob.centers, np.float64), _c(prob.points, np.float64), _c(prob.scales, np.float64)
+        co = o.to_c()
+        st = LMStats()
+        rc = lib.b200sfm_gp_solve(ctx.handle, ct.byref(co), prob.C, prob.P, prob.N, _ptr(ptb), _ptr(cam), _ptr(t_obs),
+                                  _ptr(cal), None, _ptr(cen), _ptr(pts), _ptr(sc), ct.byref(st))
+        self.summary = st
+        if rc == 4:
+            return False
+        _lib.check(ctx.handle, rc)
+        prob.centers, prob.points, prob.scales = cen, pts, sc
+        from . import geometry as geo
+        R = geo.quat_xyzw_to_rotmat(prob.quat)
+        prob.trans = -np.einsum("nij,nj->ni", R, cen)                   # ConvertResults .cc:566-568
+        return bool(st.usable)

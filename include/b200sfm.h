@@ -183,6 +183,61 @@ int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts,
 int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, double* cost);
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p);
 
+/* ---- (ii) global positioning (BATA) ----------------------------------------- */
+/* Mirror of GlobalPositionerOptions (global_positioning.h:9-54) + inherited
+ * solver options (optimization_base.h:18-23) + PCG knobs.  Only the
+ * ONLY_POINTS constraint type is implemented (the mapper enforces it,
+ * controllers/global_mapper.cc:145-149); random initialisation
+ * (generate_random_positions / points, seed) is done by the host shim. */
+typedef struct {
+  int32_t optimize_positions;        /* default 1 */
+  int32_t optimize_points;           /* default 1 */
+  int32_t optimize_scales;           /* default 1 */
+  int32_t min_num_view_per_track;    /* default 3 */
+  int32_t max_num_iterations;        /* default 100 */
+  int32_t max_num_line_search_step_size_iterations;  /* Ceres default 20 (bounded problems) */
+  double thres_loss_function;        /* Huber threshold, default 0.1 */
+  double function_tolerance;         /* 1e-5 */
+  double gradient_tolerance;         /* 1e-10 */
+  double parameter_tolerance;        /* 1e-8 */
+  int32_t pcg_max_iterations;        /* default 1000 */
+  int32_t pcg_min_iterations;
+  double pcg_rel_tolerance;          /* default 1e-2 */
+  int32_t preconditioner;            /* 0 block-Jacobi, 1 Schur-Jacobi (default) */
+  int32_t profile_kernels;
+  int32_t fixed_num_iterations;
+  int32_t reserved0;
+} b200sfm_gp_opts;
+
+void b200sfm_gp_default_opts(b200sfm_gp_opts* opts);
+
+/* One-shot solve with host buffers (results written back in place):
+ *   pt_obs_begin [P+1], obs_cam [N]  as for BA
+ *   obs_dir      [N][3]  unit bearing rotated into the world frame,
+ *                        R_cw^T * features_undist (global_positioning.cc:294-296)
+ *   cam_calibrated [C]   1: Huber loss, 0: ScaledLoss(Huber, 0.5) (.cc:313-316); NULL = all calibrated
+ *   cam_const_mask [C]   nonzero: centre held constant; may be NULL
+ *   centers [C][3]       camera centres (the reference keeps them in
+ *                        RigFromWorld().translation during the solve), in/out
+ *   points  [P][3]       in/out
+ *   scales  [N]          one per observation, in/out (initialise to 1, .cc:298);
+ *                        lower bound 1e-5 (.cc:373); the first scale of rank 0 is constant (.cc:484-489) */
+int b200sfm_gp_solve(b200sfm_ctx* ctx, const b200sfm_gp_opts* opts, int32_t C, int32_t P, int64_t N,
+                     const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_dir,
+                     const uint8_t* cam_calibrated, const uint8_t* cam_const_mask, double* centers, double* points,
+                     double* scales, b200sfm_lm_stats* stats);
+
+typedef struct b200sfm_gp_problem b200sfm_gp_problem;
+int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, const int64_t* pt_obs_begin,
+                              const int32_t* obs_cam, const double* obs_dir, const uint8_t* cam_calibrated,
+                              const uint8_t* cam_const_mask, int32_t min_num_view_per_track, b200sfm_gp_problem** out);
+int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* centers, const double* points, const double* scales);
+int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* centers, double* points, double* scales);
+int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p);
+int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p);
+int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* opts, b200sfm_lm_stats* stats);
+void b200sfm_gp_problem_free(b200sfm_gp_problem* p);
+
 #ifdef __cplusplus
 }
 #endif

