@@ -55,6 +55,27 @@ class GPOpts(ct.Structure):
     ]
 
 
+class RAOpts(ct.Structure):
+    _fields_ = [
+        ("max_num_l1_iterations", c_int32), ("max_num_irls_iterations", c_int32), ("weight_type", c_int32),
+        ("use_weight", c_int32), ("l1_step_convergence_threshold", c_double),
+        ("irls_step_convergence_threshold", c_double), ("irls_loss_parameter_sigma", c_double),
+        ("l1_max_admm_iterations", c_int32), ("reserved0", c_int32), ("l1_rho", c_double),
+        ("l1_absolute_tolerance", c_double), ("l1_relative_tolerance", c_double),
+        ("pcg_max_iterations", c_int32), ("reserved1", c_int32), ("pcg_rel_tolerance", c_double),
+    ]
+
+
+class RAStats(ct.Structure):
+    _fields_ = [
+        ("l1_iterations", c_int32), ("irls_iterations", c_int32), ("admm_iterations", c_int32), ("usable", c_int32),
+        ("num_edges", c_int64), ("pcg_iterations", c_int64), ("kernel_launches", c_int64), ("ms_total", c_double),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
 # name -> (restype, argtypes); every symbol include/b200sfm.h declares
 PROTOTYPES = {
     "b200sfm_version": (c_int32, []),
@@ -86,6 +107,8 @@ PROTOTYPES = {
     "b200sfm_gp_problem_restore_state": (c_int32, [c_void_p]),
     "b200sfm_gp_problem_solve": (c_int32, [c_void_p, P(GPOpts), P(LMStats)]),
     "b200sfm_gp_problem_free": (None, [c_void_p]),
+    "b200sfm_ra_default_opts": (None, [P(RAOpts)]),
+    "b200sfm_ra_solve": (c_int32, [c_void_p, P(RAOpts), c_int32, c_int64] + [c_void_p] * 4 + [c_int32, c_void_p, P(RAStats)]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@
 #include "ba_solver.cuh"
 #include "context.cuh"
 #include "gp_solver.cuh"
+#include "ra_solver.cuh"
 
 namespace {
 
@@ -398,6 +399,50 @@ int b200sfm_gp_solve(b200sfm_ctx* ctx, const b200sfm_gp_opts* opts, int32_t C, i
     });
   }
   if (p) b200sfm_gp_problem_free(p);
+  if (stats) *stats = st;
+  return rc;
+}
+
+// ---- RA ----------------------------------------------------------------------
+void b200sfm_ra_default_opts(b200sfm_ra_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // global_rotation_averaging.h:41-71
+  o->max_num_l1_iterations = 5;
+  o->max_num_irls_iterations = 100;
+  o->weight_type = 0;
+  o->use_weight = 0;
+  o->l1_step_convergence_threshold = 1e-3;
+  o->irls_step_convergence_threshold = 1e-3;
+  o->irls_loss_parameter_sigma = 5.0;
+  o->l1_max_admm_iterations = 10;   // .cc:484
+  o->l1_rho = 1.0;
+  o->l1_absolute_tolerance = 1e-4;
+  o->l1_relative_tolerance = 1e-2;
+  o->pcg_max_iterations = 5000;
+  o->pcg_rel_tolerance = 1e-8;
+}
+
+int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int64_t n_edges,
+                     const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
+                     int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats) {
+  if (!ctx || !opts || !theta) return B200SFM_ERR_INVALID_ARG;
+  if (n_frames <= 0) { ctx->err = "no frames"; return B200SFM_ERR_EMPTY; }
+  if (n_edges < 0 || (n_edges > 0 && (!ei || !ej || !R_rel))) { ctx->err = "null edge array"; return B200SFM_ERR_INVALID_ARG; }
+  if (fixed_frame < 0 || fixed_frame >= n_frames) { ctx->err = "fixed_frame out of range"; return B200SFM_ERR_INVALID_ARG; }
+  for (int64_t e = 0; e < n_edges; ++e)
+    if (ei[e] < 0 || ei[e] >= n_frames || ej[e] < 0 || ej[e] >= n_frames) { ctx->err = "edge index out of range"; return B200SFM_ERR_INVALID_ARG; }
+  b200sfm_ra_stats st{};
+  int rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    b200sfm_ra_problem p;
+    p.create(ctx, n_frames, n_edges, ei, ej, R_rel, edge_w, opts->use_weight, fixed_frame, theta);
+    int r = p.solve(*opts, &st);
+    if (r != B200SFM_OK) return r;
+    p.theta.download(theta, (size_t)n_frames * 3, ctx->stream);
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return (int)B200SFM_OK;
+  });
   if (stats) *stats = st;
   return rc;
 }

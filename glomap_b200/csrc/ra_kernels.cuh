@@ -1,0 +1,334 @@
+// ra_kernels.cuh -- rotation-averaging kernels (sm_100a).
+//
+// Replaces the arithmetic of glomap::RotationEstimator
+// (reference: glomap/estimators/global_rotation_averaging.cc:479-772, 3-DoF
+// frames with trivial rigs): per-edge SO(3) residual, IRLS / L1-ADMM weights,
+// and the normal equations A^T W A, which for the reference's first-order
+// A (rows -I at image 1, +I at image 2, .cc:396-415) are the weighted graph
+// Laplacian (x) I3 plus the gauge block -- solved here by PCG with one
+// edge-parallel Laplacian mat-vec per iteration instead of CHOLMOD (.cc:547-611).
+//
+// Layout: edges SoA  ei[E], ej[E] (int32), Rrel[E][9], w_edge[E]; the 3 gauge
+// rows (.cc:455-460) are carried as one pseudo-edge with ei = -1 (identity, no
+// scatter), ej = fixed frame, Rrel = R_fixed(initial), weight 1.
+// Node vectors [n][3] are replicated on every rank; edges are sharded.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr double kRaEps = 1e-12;   // glomap/types.h EPS
+
+struct RAView {
+  int n;
+  long long E;            // local edges including the gauge pseudo-edge (rank 0)
+  const int* ei;
+  const int* ej;
+  const double* Rrel;     // [E][9] row-major
+  const double* w_edge;   // [E] weights_ (.cc:466-472)
+};
+
+// AngleAxisToRotation (math/rigid3d.cc:45-63): first-order fallback below EPS
+__device__ __forceinline__ void aa_to_R(const double v[3], double R[9]) {
+  const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (n > kRaEps) {
+    const double inv = 1.0 / n;
+    const double x = v[0] * inv, y = v[1] * inv, z = v[2] * inv;
+    double s, c;
+    sincos(n, &s, &c);
+    const double t = 1.0 - c;
+    // Eigen AngleAxis::toRotationMatrix
+    R[0] = t * x * x + c;
+    R[1] = t * x * y - s * z;
+    R[2] = t * x * z + s * y;
+    R[3] = t * x * y + s * z;
+    R[4] = t * y * y + c;
+    R[5] = t * y * z - s * x;
+    R[6] = t * x * z - s * y;
+    R[7] = t * y * z + s * x;
+    R[8] = t * z * z + c;
+  } else {
+    R[0] = 1; R[1] = -v[2]; R[2] = v[1];
+    R[3] = v[2]; R[4] = 1; R[5] = -v[0];
+    R[6] = -v[1]; R[7] = v[0]; R[8] = 1;
+  }
+}
+
+// RotationToAngleAxis (math/rigid3d.cc:39-43): Eigen Matrix3 -> Quaternion -> AngleAxis
+__device__ __forceinline__ void R_to_aa(const double R[9], double v[3]) {
+  double q[4];   // x y z w
+  const double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    double tt = sqrt(t + 1.0);
+    q[3] = 0.5 * tt;
+    tt = 0.5 / tt;
+    q[0] = (R[7] - R[5]) * tt;
+    q[1] = (R[2] - R[6]) * tt;
+    q[2] = (R[3] - R[1]) * tt;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double tt = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * tt;
+    tt = 0.5 / tt;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * tt;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * tt;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * tt;
+  }
+  const double nv = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (nv > 0.0) {
+    const double ang = 2.0 * atan2(nv, fabs(q[3]));
+    const double f = (q[3] < 0.0 ? -ang : ang) / nv;
+    v[0] = q[0] * f;
+    v[1] = q[1] * f;
+    v[2] = q[2] * f;
+  } else {
+    v[0] = v[1] = v[2] = 0.0;
+  }
+}
+
+__device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_tmul(const double A[9], const double B[9], double C[9]) {   // A^T B
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+
+// ComputeResiduals (.cc:696-756) + the weight of each edge for the next solve.
+//   mode 0: w_out = w_edge                       (L1 stage rows, .cc:488-489,506)
+//   mode 1: w_out = w_edge * sigma^2/(e^2+sigma^2)^2   GEMAN_MCCLURE (.cc:583-585)
+//   mode 2: w_out = w_edge * (e^2)^(-0.75)              HALF_NORM (.cc:587)
+// flags[0] |= 1 on NaN weight (.cc:590-593)
+__global__ void ra_residuals(RAView v, const double* __restrict__ theta, int mode, double sigma2,
+                             double* __restrict__ res, double* __restrict__ w_out, int* __restrict__ flags) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.E) return;
+  const int i = v.ei[e], j = v.ej[e];
+  double Rrel[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rrel[k] = v.Rrel[9 * e + k];
+  double Rj[9], T[9], M[9], r[3];
+  const double tj[3] = {theta[3 * (size_t)j], theta[3 * (size_t)j + 1], theta[3 * (size_t)j + 2]};
+  aa_to_R(tj, Rj);
+  if (i >= 0) {
+    const double ti[3] = {theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2]};
+    double Ri[9];
+    aa_to_R(ti, Ri);
+    mat3_mul(Rrel, Ri, T);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) T[k] = Rrel[k];
+  }
+  mat3_tmul(Rj, T, M);      // R_j^T R_rel R_i
+  R_to_aa(M, r);
+  res[3 * e] = -r[0];
+  res[3 * e + 1] = -r[1];
+  res[3 * e + 2] = -r[2];
+  double w = v.w_edge[e];
+  if (i >= 0 && mode != 0) {
+    const double e2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double wi;
+    if (mode == 1) {
+      const double tmp = e2 + sigma2;
+      wi = sigma2 / (tmp * tmp);
+    } else {
+      wi = pow(e2, (0.5 - 2.0) / 2.0);
+    }
+    if (isnan(wi)) atomicOr(flags, 1);
+    w *= wi;
+  }
+  w_out[e] = w;
+}
+
+// out += A^T diag(w^p) vec  (p = 1 or 2); deg += w^p at both ends (Laplacian diagonal)
+__global__ void ra_scatter(RAView v, const double* __restrict__ w, int square, const double* __restrict__ vec,
+                           double* __restrict__ out, double* __restrict__ deg) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.E) return;
+  const int i = v.ei[e], j = v.ej[e];
+  double we = w[e];
+  if (square) we *= we;
+  const double a0 = we * vec[3 * e], a1 = we * vec[3 * e + 1], a2 = we * vec[3 * e + 2];
+  atomicAdd(&out[3 * (size_t)j], a0);
+  atomicAdd(&out[3 * (size_t)j + 1], a1);
+  atomicAdd(&out[3 * (size_t)j + 2], a2);
+  if (deg) atomicAdd(&deg[j], we);
+  if (i >= 0) {
+    atomicAdd(&out[3 * (size_t)i], -a0);
+    atomicAdd(&out[3 * (size_t)i + 1], -a1);
+    atomicAdd(&out[3 * (size_t)i + 2], -a2);
+    if (deg) atomicAdd(&deg[i], we);
+  }
+}
+
+// y += L(w^p) x :  t = w (x_j - x_i); y_j += t; y_i -= t
+__global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square, const double* __restrict__ x,
+                             double* __restrict__ y) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.E) return;
+  const int i = v.ei[e], j = v.ej[e];
+  double we = w[e];
+  if (square) we *= we;
+  double t0 = x[3 * (size_t)j], t1 = x[3 * (size_t)j + 1], t2 = x[3 * (size_t)j + 2];
+  if (i >= 0) {
+    t0 -= x[3 * (size_t)i];
+    t1 -= x[3 * (size_t)i + 1];
+    t2 -= x[3 * (size_t)i + 2];
+  }
+  t0 *= we; t1 *= we; t2 *= we;
+  atomicAdd(&y[3 * (size_t)j], t0);
+  atomicAdd(&y[3 * (size_t)j + 1], t1);
+  atomicAdd(&y[3 * (size_t)j + 2], t2);
+  if (i >= 0) {
+    atomicAdd(&y[3 * (size_t)i], -t0);
+    atomicAdd(&y[3 * (size_t)i + 1], -t1);
+    atomicAdd(&y[3 * (size_t)i + 2], -t2);
+  }
+}
+
+// Minv (packed 3x3 diagonal) = 1/deg ; nodes without edges get identity
+__global__ void ra_build_precond(int n, const double* __restrict__ deg, double* __restrict__ Minv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = deg[i];
+  const double inv = d > 0.0 ? 1.0 / d : 1.0;
+  double* m = Minv + 6 * (size_t)i;
+  m[0] = inv; m[1] = 0; m[2] = 0; m[3] = inv; m[4] = 0; m[5] = inv;
+}
+
+// b = w * r  (row-weighted residual of the L1 stage); norms[0] += |b|^2
+__global__ void ra_weighted_rhs(RAView v, const double* __restrict__ w, const double* __restrict__ res,
+                                double* __restrict__ b, double* __restrict__ norms) {
+  __shared__ double scratch[32];
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (e < v.E) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double t = w[e] * res[3 * e + k];
+      b[3 * e + k] = t;
+      s += t * t;
+    }
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(&norms[0], s);
+}
+
+// One ADMM iteration after the x-update (colmap LeastAbsoluteDeviationSolver,
+// rho = alpha = 1):  a = A_w x; z = shrink(a - b + u, 1/rho); u += a - z - b;
+//   norms[1] += |a - z - b|^2, norms[2] += |a|^2, norms[3] += |z|^2
+//   rhs  += A_w^T (b + z - u)      (next x-update)
+//   svec += A_w^T (z - z_old)      (dual residual)
+//   uvec += A_w^T u                (dual tolerance)
+__global__ void ra_admm_step(RAView v, const double* __restrict__ w, const double* __restrict__ x,
+                             const double* __restrict__ b, double* __restrict__ z, double* __restrict__ u, double rho,
+                             double* __restrict__ rhs, double* __restrict__ svec, double* __restrict__ uvec,
+                             double* __restrict__ norms) {
+  __shared__ double scratch[32];
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double n1 = 0, n2 = 0, n3 = 0;
+  if (e < v.E) {
+    const int i = v.ei[e], j = v.ej[e];
+    const double we = w[e];
+    const double kappa = 1.0 / rho;
+    double r3[3], s3[3], u3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double a = x[3 * (size_t)j + k];
+      if (i >= 0) a -= x[3 * (size_t)i + k];
+      a *= we;
+      const double bo = b[3 * e + k], zo = z[3 * e + k], uo = u[3 * e + k];
+      const double vv = a - bo + uo;
+      const double zn = fmax(0.0, vv - kappa) - fmax(0.0, -vv - kappa);
+      const double un = uo + a - zn - bo;
+      z[3 * e + k] = zn;
+      u[3 * e + k] = un;
+      const double pr = a - zn - bo;
+      n1 += pr * pr;
+      n2 += a * a;
+      n3 += zn * zn;
+      r3[k] = we * (bo + zn - un);
+      s3[k] = we * (zn - zo);
+      u3[k] = we * un;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicAdd(&rhs[3 * (size_t)j + k], r3[k]);
+      atomicAdd(&svec[3 * (size_t)j + k], s3[k]);
+      atomicAdd(&uvec[3 * (size_t)j + k], u3[k]);
+      if (i >= 0) {
+        atomicAdd(&rhs[3 * (size_t)i + k], -r3[k]);
+        atomicAdd(&svec[3 * (size_t)i + k], -s3[k]);
+        atomicAdd(&uvec[3 * (size_t)i + k], -u3[k]);
+      }
+    }
+  }
+  n1 = block_sum(n1, scratch);
+  n2 = block_sum(n2, scratch);
+  n3 = block_sum(n3, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&norms[1], n1);
+    atomicAdd(&norms[2], n2);
+    atomicAdd(&norms[3], n3);
+  }
+}
+
+// UpdateGlobalRotations (.cc:631-640): theta <- log(exp(theta) exp(-step));
+// sums[0] += |step_i| (ComputeAverageStepSize .cc:758-772), sums[1] += |step|^2,
+// sums[2] = NaN flag
+__global__ void ra_update(int n, double* __restrict__ theta, const double* __restrict__ step, double* __restrict__ sums) {
+  __shared__ double scratch[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0, s2 = 0, bad = 0;
+  if (i < n) {
+    const double d[3] = {step[3 * (size_t)i], step[3 * (size_t)i + 1], step[3 * (size_t)i + 2]};
+    const double nd[3] = {-d[0], -d[1], -d[2]};
+    const double t[3] = {theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2]};
+    double R[9], Rd[9], M[9], out[3];
+    aa_to_R(t, R);
+    aa_to_R(nd, Rd);
+    mat3_mul(R, Rd, M);
+    R_to_aa(M, out);
+    theta[3 * (size_t)i] = out[0];
+    theta[3 * (size_t)i + 1] = out[1];
+    theta[3 * (size_t)i + 2] = out[2];
+    const double sq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    s1 = sqrt(sq);
+    s2 = sq;
+    if (isnan(sq)) bad = 1.0;
+  }
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  bad = block_sum(bad, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s1);
+    atomicAdd(&sums[1], s2);
+    if (bad > 0) atomicAdd(&sums[2], bad);
+  }
+}
+
+// |vec|^2 of a node vector -> out[0] (single CTA, deterministic)
+__global__ void ra_norm2(int n3, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double s0 = 0, s1 = 0;
+  for (int i = threadIdx.x; i < n3; i += blockDim.x) {
+    s0 += a[i] * a[i];
+    if (b) s1 += b[i] * b[i];
+  }
+  s0 = block_sum(s0, scratch);
+  s1 = block_sum(s1, scratch);
+  if (threadIdx.x == 0) {
+    out[0] = s0;
+    out[1] = s1;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,250 @@
+// ra_solver.cuh -- host-side driver of the device rotation averaging
+// (reference: glomap/estimators/global_rotation_averaging.cc:40-85, the
+// SetupLinearSystem / SolveL1Regression / SolveIRLS sequence; the L1 solver is
+// colmap::LeastAbsoluteDeviationSolver restated in oracle/ra_oracle.py).
+#pragma once
+#include "context.cuh"
+#include "pcg.cuh"
+#include "ra_kernels.cuh"
+
+struct b200sfm_ra_problem {
+  template <class T>
+  using DevBuf = b200::DevBuf<T>;
+  b200sfm_ctx* ctx = nullptr;
+  int n = 0;
+  long long E = 0;        // local edges (+1 gauge pseudo-edge on rank 0)
+  long long E_real = 0;
+  long long E_total = 0;  // valid edges over all ranks
+  int fixed = 0;
+  DevBuf<int> ei, ej, flags;
+  DevBuf<double> Rrel, w_edge, theta, res, w, b, z, u;
+  DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, dots, part, scal;
+
+  b200::RAView view() {
+    b200::RAView v;
+    v.n = n; v.E = E; v.ei = ei.p; v.ej = ej.p; v.Rrel = Rrel.p; v.w_edge = w_edge.p;
+    return v;
+  }
+
+  void create(b200sfm_ctx* c, int n_, long long E_, const int32_t* h_ei, const int32_t* h_ej, const double* h_Rrel,
+              const double* h_w, int use_weight, int fixed_, const double* h_theta) {
+    using namespace b200;
+    ctx = c; n = n_; E_real = E_; fixed = fixed_;
+    cudaStream_t s = ctx->stream;
+    const bool gauge_here = ctx->rank == 0;
+    E = E_real + (gauge_here ? 1 : 0);
+    std::vector<int> hi(h_ei, h_ei + E_real), hj(h_ej, h_ej + E_real);
+    std::vector<double> hr(h_Rrel, h_Rrel + 9 * E_real), hw((size_t)E_real, 1.0);
+    if (use_weight && h_w)
+      for (long long e = 0; e < E_real; ++e) hw[e] = h_w[e] >= 0 ? h_w[e] : 1.0;   // .cc:390-393,417-421
+    if (gauge_here) {
+      // gauge rows (.cc:455-460): pseudo-edge (identity -> fixed frame) with R_rel = R_fixed(initial)
+      hi.push_back(-1);
+      hj.push_back(fixed);
+      const double* t = h_theta + 3 * (size_t)fixed;
+      const double nn = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+      double R[9];
+      if (nn > 1e-12) {
+        const double x = t[0] / nn, y = t[1] / nn, zc = t[2] / nn, sn = std::sin(nn), cs = std::cos(nn), tt = 1 - cs;
+        const double Rm[9] = {tt * x * x + cs, tt * x * y - sn * zc, tt * x * zc + sn * y,
+                              tt * x * y + sn * zc, tt * y * y + cs, tt * y * zc - sn * x,
+                              tt * x * zc - sn * y, tt * y * zc + sn * x, tt * zc * zc + cs};
+        std::copy(Rm, Rm + 9, R);
+      } else {
+        const double Rm[9] = {1, -t[2], t[1], t[2], 1, -t[0], -t[1], t[0], 1};
+        std::copy(Rm, Rm + 9, R);
+      }
+      hr.insert(hr.end(), R, R + 9);
+      hw.push_back(1.0);
+    }
+    const size_t Ea = (size_t)std::max<long long>(E, 1);
+    ei.alloc(Ea); ej.alloc(Ea); Rrel.alloc(Ea * 9); w_edge.alloc(Ea); flags.alloc(4);
+    ei.upload(hi.data(), E, s); ej.upload(hj.data(), E, s); Rrel.upload(hr.data(), (size_t)E * 9, s); w_edge.upload(hw.data(), E, s);
+    theta.alloc((size_t)n * 3);
+    theta.upload(h_theta, (size_t)n * 3, s);
+    res.alloc(Ea * 3); w.alloc(Ea); b.alloc(Ea * 3); z.alloc(Ea * 3); u.alloc(Ea * 3);
+    deg.alloc(n); Minv.alloc((size_t)n * 6); Azero.alloc((size_t)n * 6); Dzero.alloc((size_t)n * 3);
+    rhs.alloc((size_t)n * 9);   // rhs | svec | uvec contiguous for one all-reduce
+    px.alloc((size_t)n * 3); pr.alloc((size_t)n * 3); pz.alloc((size_t)n * 3); pp.alloc((size_t)n * 3);
+    pq.alloc((size_t)n * 3); yw.alloc((size_t)n * 3); scal.alloc(16);
+    Azero.zero(s); Dzero.zero(s);
+    {
+      const double cnt = (double)E_real;
+      B200_CUDA_OK(cudaMemcpyAsync(scal.p, &cnt, sizeof(double), cudaMemcpyHostToDevice, s));
+      ctx->allreduce_sum(scal.p, 1);
+      double tot = 0;
+      B200_CUDA_OK(cudaMemcpyAsync(&tot, scal.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      E_total = (long long)(tot + 0.5);
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(s));   // host vectors go out of scope
+  }
+
+  // x = L(w^p)^-1 rhs_vec by PCG (result in px); returns iterations
+  int pcg_solve(const b200sfm_ra_opts& o, int square, const double* rhs_vec, bool& finite) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    RAView v = view();
+    const int nblk = cdiv(n, kPcgThreads);
+    const int max_it = std::max(1, o.pcg_max_iterations);
+    if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
+    if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
+    double *part_pq = part.p, *part_rz = part.p + nblk, *part_rr = part.p + 2 * (size_t)nblk;
+    const int egrid = cdiv(std::max<long long>(E, 1), 256);
+    B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
+    B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    const double rr0 = ctx->h_scal[2];
+    int it = 0;
+    finite = std::isfinite(rr0);
+    if (!(rr0 > 0.0) || !finite) return 0;
+    const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * rr0;
+    const int check_every = 4;   // convergence is polled every few iterations (host sync)
+    for (it = 1; it <= max_it; ++it) {
+      double* d_prev = dots.p + (size_t)(it - 1) * 4;
+      double* d_it = dots.p + (size_t)it * 4;
+      if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, pp.p, yw.p);
+      ctx->allreduce_sum(yw.p, (size_t)n * 3);
+      B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq);
+      B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq, part_rz,
+                  part_rr, d_it);
+      B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
+      if (it % check_every == 0 || it == max_it) {
+        B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        const double rr = ctx->h_scal[2];
+        if (!std::isfinite(rr)) { finite = false; break; }
+        if (rr <= tol2) break;
+      }
+    }
+    return std::min(it, max_it);
+  }
+
+  // weights w -> Laplacian diagonal + preconditioner, rhs = A^T diag(w^p) vec
+  void prepare_system(int square, const double* vec) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    RAView v = view();
+    deg.zero(s);
+    B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 3 * sizeof(double), s));
+    if (E > 0) B200_LAUNCH(ctx, ra_scatter, cdiv(E, 256), 256, 0, v, w.p, square, vec, rhs.p, deg.p);
+    ctx->allreduce_sum(rhs.p, (size_t)n * 3);
+    ctx->allreduce_sum(deg.p, n);
+    B200_LAUNCH(ctx, ra_build_precond, cdiv(n, 256), 256, 0, n, deg.p, Minv.p);
+  }
+
+  // theta <- theta (+) step(px); returns (avg step, |step|, nan?)
+  void apply_step(double& avg, double& norm, bool& bad) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    B200_CUDA_OK(cudaMemsetAsync(scal.p + 8, 0, 4 * sizeof(double), s));
+    B200_LAUNCH(ctx, ra_update, cdiv(n, 256), 256, 0, n, theta.p, px.p, scal.p + 8);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, scal.p + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    avg = ctx->h_scal[8] / n;
+    norm = std::sqrt(ctx->h_scal[9]);
+    bad = ctx->h_scal[10] > 0 || !std::isfinite(ctx->h_scal[9]);
+  }
+
+  int solve(const b200sfm_ra_opts& o, b200sfm_ra_stats* st) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    const long long launches0 = ctx->launches;
+    cudaEvent_t ev0, ev1;
+    B200_CUDA_OK(cudaEventCreate(&ev0));
+    B200_CUDA_OK(cudaEventCreate(&ev1));
+    B200_CUDA_OK(cudaEventRecord(ev0, s));
+    RAView v = view();
+    const int egrid = cdiv(std::max<long long>(E, 1), 256);
+    b200sfm_ra_stats local{};
+    local.usable = 1;
+    local.num_edges = E_real;
+    flags.zero(s);
+    bool failed = false;
+    // ---- L1 (.cc:479-541) ----------------------------------------------------------
+    if (o.max_num_l1_iterations > 0) {
+      if (E > 0) B200_LAUNCH(ctx, ra_residuals, egrid, 256, 0, v, theta.p, 0, 0.0, res.p, w.p, flags.p);
+      double last_norm = 0, curr_norm = 0;
+      for (int it = 0; it < o.max_num_l1_iterations && !failed; ++it) {
+        last_norm = curr_norm;
+        // b = W r ; ADMM on |A_w x - b|_1, A_w^T A_w = L(w^2)
+        B200_CUDA_OK(cudaMemsetAsync(scal.p, 0, 8 * sizeof(double), s));
+        if (E > 0) B200_LAUNCH(ctx, ra_weighted_rhs, egrid, 256, 0, v, w.p, res.p, b.p, scal.p);
+        ctx->allreduce_sum(scal.p, 1);   // |b|^2 over all ranks
+        z.zero(s);
+        u.zero(s);
+        prepare_system(1, res.p);   // rhs = A^T W^2 r = A_w^T b ; deg = sum w^2
+        double b_norm2 = 0;
+        const double eps_pri_thr = std::sqrt(3.0 * (double)(E_total + 1)) * o.l1_absolute_tolerance;   // sqrt(rows)
+        const double eps_dual_thr = std::sqrt(3.0 * n) * o.l1_absolute_tolerance;
+        for (int k = 0; k < o.l1_max_admm_iterations; ++k) {
+          bool finite = true;
+          local.pcg_iterations += pcg_solve(o, 1, rhs.p, finite);
+          ++local.admm_iterations;
+          if (!finite) { failed = true; break; }
+          B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 9 * sizeof(double), s));
+          B200_CUDA_OK(cudaMemsetAsync(scal.p + 1, 0, 3 * sizeof(double), s));
+          if (E > 0)
+            B200_LAUNCH(ctx, ra_admm_step, egrid, 256, 0, v, w.p, px.p, b.p, z.p, u.p, o.l1_rho, rhs.p, rhs.p + (size_t)n * 3,
+                        rhs.p + (size_t)n * 6, scal.p);
+          ctx->allreduce_sum(rhs.p, (size_t)n * 9);
+          ctx->allreduce_sum(scal.p + 1, 3);
+          B200_LAUNCH(ctx, ra_norm2, 1, 256, 0, n * 3, rhs.p + (size_t)n * 3, rhs.p + (size_t)n * 6, scal.p + 4);
+          B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+          B200_CUDA_OK(cudaStreamSynchronize(s));
+          const double* h = ctx->h_scal;
+          b_norm2 = h[0];
+          const double r_norm = std::sqrt(h[1]), s_norm = o.l1_rho * std::sqrt(h[4]);
+          const double eps_pri = eps_pri_thr + o.l1_relative_tolerance * std::sqrt(std::max(b_norm2, std::max(h[2], h[3])));
+          const double eps_dual = eps_dual_thr + o.l1_relative_tolerance * o.l1_rho * std::sqrt(h[5]);
+          if (r_norm < eps_pri && s_norm < eps_dual) break;
+        }
+        if (failed) break;
+        double avg, norm;
+        bool bad;
+        apply_step(avg, norm, bad);                                    // UpdateGlobalRotations (.cc:523)
+        if (bad) { failed = true; break; }                             // .cc:508-512
+        curr_norm = norm;
+        if (E > 0) B200_LAUNCH(ctx, ra_residuals, egrid, 256, 0, v, theta.p, 0, 0.0, res.p, w.p, flags.p);   // .cc:524
+        ++local.l1_iterations;
+        if (avg < o.l1_step_convergence_threshold || std::fabs(last_norm - curr_norm) < kRaEps) break;   // .cc:528-535
+      }
+    }
+    // ---- IRLS (.cc:543-625) --------------------------------------------------------
+    if (!failed && o.max_num_irls_iterations > 0) {
+      const double sigma = o.irls_loss_parameter_sigma * M_PI / 180.0;
+      const int mode = (o.weight_type == 1) ? 2 : 1;
+      for (int it = 0; it < o.max_num_irls_iterations; ++it) {
+        if (E > 0) B200_LAUNCH(ctx, ra_residuals, egrid, 256, 0, v, theta.p, mode, sigma * sigma, res.p, w.p, flags.p);
+        {
+          int hflag = 0;
+          B200_CUDA_OK(cudaMemcpyAsync(&hflag, flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+          B200_CUDA_OK(cudaStreamSynchronize(s));
+          if (hflag) { failed = true; break; }                         // "nan weight!" .cc:590-593
+        }
+        prepare_system(0, res.p);                                      // A^T W A, A^T W r (.cc:603-611)
+        bool finite = true;
+        local.pcg_iterations += pcg_solve(o, 0, rhs.p, finite);
+        if (!finite) { failed = true; break; }
+        double avg, norm;
+        bool bad;
+        apply_step(avg, norm, bad);
+        if (bad) { failed = true; break; }
+        ++local.irls_iterations;
+        if (avg < o.irls_step_convergence_threshold) break;            // .cc:616-620
+      }
+    }
+    B200_CUDA_OK(cudaEventRecord(ev1, s));
+    B200_CUDA_OK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    B200_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    local.ms_total = ms;
+    local.usable = failed ? 0 : 1;
+    local.kernel_launches = ctx->launches - launches0;
+    if (st) *st = local;
+    return B200SFM_OK;
+  }
+};

@@ -352,3 +352,98 @@ class GlobalPositioner:
         R = geo.quat_xyzw_to_rotmat(prob.quat)
         prob.trans = -np.einsum("nij,nj->ni", R, cen)                   # ConvertResults .cc:566-568
         return bool(st.usable)
+
+
+# ---------------------------------------------------------------------------
+# Rotation averaging
+# ---------------------------------------------------------------------------
+@dataclasses.dataclass
+class RotationEstimatorOptions:
+    """global_rotation_averaging.h:39-75 (defaults identical).  use_gravity
+    (1-DoF frames) is not implemented on the device yet."""
+    GEMAN_MCCLURE = 0
+    HALF_NORM = 1
+    max_num_l1_iterations: int = 5
+    l1_step_convergence_threshold: float = 0.001
+    max_num_irls_iterations: int = 100
+    irls_step_convergence_threshold: float = 0.001
+    irls_loss_parameter_sigma: float = 5.0
+    weight_type: int = 0
+    skip_initialization: bool = False
+    use_weight: bool = False
+    use_gravity: bool = False
+    pcg_max_iterations: int = 5000
+    pcg_rel_tolerance: float = 1e-8
+
+    def to_c(self) -> _lib.RAOpts:
+        o = _lib.RAOpts()
+        _lib.load().b200sfm_ra_default_opts(ct.byref(o))
+        for f in ("max_num_l1_iterations", "l1_step_convergence_threshold", "max_num_irls_iterations",
+                  "irls_step_convergence_threshold", "irls_loss_parameter_sigma", "weight_type", "pcg_max_iterations",
+                  "pcg_rel_tolerance"):
+            setattr(o, f, getattr(self, f))
+        o.use_weight = int(self.use_weight)
+        return o
+
+
+def initialize_from_maximum_spanning_tree(vg, R_init: np.ndarray | None = None) -> np.ndarray:
+    """Host-side InitializeFromMaximumSpanningTree
+    (global_rotation_averaging.cc:87-138 + math/tree.cc:78-170): Kruskal on
+    (max_weight - weight), BFS from index 0, compose R_child from the parent
+    along tree edges.  O(E log E), stays on the host."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
+    n = vg.n_images
+    wmax = float(vg.weight.max()) if vg.E else 0.0
+    cost = (wmax - vg.weight) + 1e-9 * (1 + np.arange(vg.E) / max(vg.E, 1))   # strictly positive, stable tie order
+    G = sp.coo_matrix((cost, (vg.ei, vg.ej)), shape=(n, n)).tocsr()
+    G = G.maximum(G.T)
+    T = minimum_spanning_tree(G)
+    T = T.maximum(T.T).tocsr()
+    order, pred = breadth_first_order(T, 0, directed=False)
+    R = np.tile(np.eye(3), (n, 1, 1)) if R_init is None else np.array(R_init, copy=True)
+    lut = {}
+    for e in range(vg.E):
+        lut[(int(vg.ei[e]), int(vg.ej[e]))] = e
+    for node in order[1:]:
+        par = int(pred[node])
+        if (int(node), par) in lut:          # image_id1 == curr: R_curr = R_rel^T R_parent   (.cc:125-129)
+            R[node] = vg.R_rel[lut[(int(node), par)]].T @ R[par]
+        else:                                # R_curr = R_rel R_parent                          (.cc:130-134)
+            R[node] = vg.R_rel[lut[(par, int(node))]] @ R[par]
+    return R
+
+
+class RotationEstimator:
+    """glomap::RotationEstimator (global_rotation_averaging.h:77-87)."""
+
+    def __init__(self, options: RotationEstimatorOptions | None = None, ctx: Context | None = None):
+        self.options_ = options or RotationEstimatorOptions()     # the reference keeps a const& (.h:140)
+        self.ctx = ctx
+        self.summary: _lib.RAStats | None = None
+
+    def EstimateRotations(self, vg, R_init: np.ndarray | None = None, fixed: int = 0):
+        """Returns (ok, R [n,3,3] cam_from_world rotations).  False on a NaN
+        step/weight (.cc:508-512,590-593) or when gravity is requested."""
+        from . import geometry as geo
+        o = self.options_
+        if o.use_gravity:
+            raise NotImplementedError("gravity-aligned (1-DoF) rotation averaging is not implemented on the device")
+        n = vg.n_images
+        if not o.skip_initialization:
+            R0 = initialize_from_maximum_spanning_tree(vg, R_init)
+        else:
+            R0 = np.tile(np.eye(3), (n, 1, 1)) if R_init is None else np.asarray(R_init)
+        theta = _c(geo.so3_log(R0), np.float64)
+        ctx = self.ctx or default_context()
+        co = o.to_c()
+        st = _lib.RAStats()
+        ei, ej = _c(vg.ei, np.int32), _c(vg.ej, np.int32)
+        Rr, w = _c(vg.R_rel.reshape(-1, 9), np.float64), _c(vg.weight, np.float64)
+        rc = ctx.lib.b200sfm_ra_solve(ctx.handle, ct.byref(co), n, vg.E, _ptr(ei), _ptr(ej), _ptr(Rr), _ptr(w), fixed,
+                                      _ptr(theta), ct.byref(st))
+        self.summary = st
+        if rc == 4:
+            return False, None
+        _lib.check(ctx.handle, rc)
+        return bool(st.usable), geo.so3_exp(theta)

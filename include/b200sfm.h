@@ -238,6 +238,57 @@ int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p);
 int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* opts, b200sfm_lm_stats* stats);
 void b200sfm_gp_problem_free(b200sfm_gp_problem* p);
 
+/* ---- (i) rotation averaging --------------------------------------------------- */
+/* Mirror of RotationEstimatorOptions (global_rotation_averaging.h:39-75) for
+ * 3-DoF frames with trivial rigs.  skip_initialization / use_gravity / axis are
+ * host-side concerns (the maximum-spanning-tree initialisation, math/tree.cc:78,
+ * stays on the host: O(E log E)).  The l1_* fields are
+ * the colmap::LeastAbsoluteDeviationSolver options the reference uses
+ * (global_rotation_averaging.cc:483-486 + COLMAP defaults). */
+typedef struct {
+  int32_t max_num_l1_iterations;           /* 5 */
+  int32_t max_num_irls_iterations;         /* 100 */
+  int32_t weight_type;                     /* 0 GEMAN_MCCLURE (default), 1 HALF_NORM */
+  int32_t use_weight;                      /* 0 */
+  double l1_step_convergence_threshold;    /* 1e-3 */
+  double irls_step_convergence_threshold;  /* 1e-3 */
+  double irls_loss_parameter_sigma;        /* 5 degrees */
+  int32_t l1_max_admm_iterations;          /* 10 (.cc:484) */
+  int32_t reserved0;
+  double l1_rho;                           /* 1.0 */
+  double l1_absolute_tolerance;            /* 1e-4 */
+  double l1_relative_tolerance;            /* 1e-2 */
+  /* PCG replaces the reference's CHOLMOD factorisations (.cc:491,547-611) */
+  int32_t pcg_max_iterations;              /* 5000 */
+  int32_t reserved1;
+  double pcg_rel_tolerance;                /* 1e-8 */
+} b200sfm_ra_opts;
+
+typedef struct {
+  int32_t l1_iterations;
+  int32_t irls_iterations;
+  int32_t admm_iterations;
+  int32_t usable;                 /* 0: NaN encountered -> EstimateRotations returns false */
+  int64_t num_edges;
+  int64_t pcg_iterations;         /* Laplacian mat-vecs */
+  int64_t kernel_launches;
+  double ms_total;
+} b200sfm_ra_stats;
+
+void b200sfm_ra_default_opts(b200sfm_ra_opts* opts);
+
+/*   n_frames          registered frames (unknown blocks of 3)
+ *   ei, ej [E]        image/frame indices of each valid pair (image_id1, image_id2)
+ *   R_rel  [E][9]     row-major cam2_from_cam1 rotation (ImagePairTempInfo::R_rel, .h:29)
+ *   edge_w [E]        ImagePair::weight (used when use_weight; <0 -> 1); may be NULL
+ *   fixed_frame       gauge frame (fixed_camera_id_, .cc:248-256)
+ *   theta  [n][3]     angle-axis of every frame: in = initial estimate, out = result.
+ * In a distributed context every rank passes its own shard of edges and the
+ * same theta. */
+int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int64_t n_edges,
+                     const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
+                     int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif
