@@ -1,0 +1,375 @@
+// estimators_shim.h -- C++ drop-in for glomap's three estimator classes over
+// the C ABI (include/b200sfm.h).  Same class names, constructor / method
+// signatures, option fields and bool-return error behaviour as
+//   glomap::RotationEstimator   glomap/estimators/global_rotation_averaging.h:39-87
+//   glomap::GlobalPositioner    glomap/estimators/global_positioning.h:9-70
+//   glomap::BundleAdjuster      glomap/estimators/bundle_adjustment.h:12-51
+// Each Solve flattens the unordered_map world into SoA in SORTED-ID order
+// (deterministic, unlike the reference's hash-map order), calls the GPU solver
+// and scatters the results back in place.  Trivial rigs only (one image per
+// frame); anything else returns false with a message on stderr.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sfm.h"
+#include "scene_min.h"
+
+namespace b200sfm_shim {
+using namespace b200host;
+
+inline b200sfm_ctx* DefaultContext(int device = 0) {
+  static b200sfm_ctx* ctx = nullptr;
+  if (!ctx && b200sfm_create(device, &ctx) != B200SFM_OK) {
+    std::fprintf(stderr, "b200sfm: no CUDA device / context creation failed (there is no CPU fallback)\n");
+    ctx = nullptr;
+  }
+  return ctx;
+}
+
+inline void QuatToR(const double* q, double R[9]) {
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// ---------------------------------------------------------------------------
+struct OptimizationBaseOptions {                 // optimization_base.h:10-24
+  double thres_loss_function = 1e-1;
+  struct SolverOptions {
+    int max_num_iterations = 100;
+    double function_tolerance = 1e-5;
+    double gradient_tolerance = 1e-10;
+    double parameter_tolerance = 1e-8;
+  } solver_options;
+};
+
+struct BundleAdjusterOptions : public OptimizationBaseOptions {   // bundle_adjustment.h:12-37
+  bool optimize_rig_poses = false;
+  bool optimize_rotations = true;
+  bool optimize_translation = true;
+  bool optimize_intrinsics = true;
+  bool optimize_principal_point = false;
+  bool optimize_points = true;
+  bool use_gpu = true;
+  std::string gpu_index = "-1";
+  int min_num_images_gpu_solver = 50;
+  int min_num_view_per_track = 3;
+  // PCG knobs of this implementation
+  double pcg_rel_tolerance = 1e-2;
+  int pcg_max_iterations = 500;
+  BundleAdjusterOptions() {
+    thres_loss_function = 1.;
+    solver_options.max_num_iterations = 200;
+  }
+};
+
+class BundleAdjuster {
+ public:
+  BundleAdjuster(const BundleAdjusterOptions& options) : options_(options) {}
+  BundleAdjusterOptions& GetOptions() { return options_; }
+  b200sfm_lm_stats summary{};
+
+  // bundle_adjustment.cc:11-106
+  bool Solve(std::unordered_map<rig_t, Rig>& rigs, std::unordered_map<camera_t, Camera>& cameras,
+             std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images,
+             std::unordered_map<track_t, Track>& tracks) {
+    (void)rigs;
+    if (images.empty()) { std::fprintf(stderr, "Number of images = 0\n"); return false; }     // .cc:17-20
+    if (tracks.empty()) { std::fprintf(stderr, "Number of tracks = 0\n"); return false; }     // .cc:21-24
+    b200sfm_ctx* ctx = DefaultContext();
+    if (!ctx) return false;
+    // frames / cameras / tracks in sorted-id order
+    std::map<frame_t, Frame*> fsorted;
+    for (auto& [id, f] : frames) fsorted[id] = &f;
+    std::map<frame_t, int> fidx;
+    for (auto& [id, f] : fsorted) { const int i = (int)fidx.size(); fidx[id] = i; }
+    std::map<camera_t, Camera*> csorted;
+    for (auto& [id, c] : cameras) csorted[id] = &c;
+    std::map<camera_t, int> cidx;
+    for (auto& [id, c] : csorted) { const int i = (int)cidx.size(); cidx[id] = i; }
+    const int C = (int)fsorted.size(), K = (int)csorted.size();
+    std::vector<double> quat(4 * (size_t)C), trans(3 * (size_t)C), intr((size_t)K * B200SFM_INTR_STRIDE, 0.0);
+    std::vector<int32_t> cam_intr(C, 0), intr_model(K);
+    std::vector<uint8_t> mask(C, 0);
+    for (auto& [id, f] : fsorted) {
+      const int i = fidx[id];
+      for (int k = 0; k < 4; ++k) quat[4 * i + k] = f->RigFromWorld().rotation.coeffs_data()[k];
+      for (int k = 0; k < 3; ++k) trans[3 * i + k] = f->RigFromWorld().translation[k];
+    }
+    if (C > 0) mask[0] = 3;                                                                   // .cc:261-266 (first frame)
+    for (auto& [id, c] : csorted) {
+      const int k = cidx[id];
+      intr_model[k] = c->model_id;
+      for (size_t j = 0; j < c->params.size() && j < B200SFM_INTR_STRIDE; ++j) intr[(size_t)k * B200SFM_INTR_STRIDE + j] = c->params[j];
+    }
+    for (auto& [id, im] : images) {
+      if (!im.HasTrivialFrame()) { std::fprintf(stderr, "b200sfm: non-trivial rigs are not supported\n"); return false; }
+      cam_intr[fidx[im.frame_id]] = cidx[im.camera_id];
+    }
+    std::map<track_t, Track*> tsorted;
+    for (auto& [id, t] : tracks) tsorted[id] = &t;
+    const int P = (int)tsorted.size();
+    std::vector<int64_t> ptb(1, 0);
+    std::vector<int32_t> obs_cam;
+    std::vector<double> obs_xy, points(3 * (size_t)P);
+    int p = 0;
+    for (auto& [id, t] : tsorted) {
+      for (const auto& ob : t->observations) {
+        auto it = images.find(ob.first);
+        if (it == images.end()) continue;                                                     // .cc:125
+        obs_cam.push_back(fidx[it->second.frame_id]);
+        obs_xy.push_back(it->second.features[ob.second][0]);
+        obs_xy.push_back(it->second.features[ob.second][1]);
+      }
+      ptb.push_back((int64_t)obs_cam.size());
+      for (int k = 0; k < 3; ++k) points[3 * (size_t)p + k] = t->xyz[k];
+      ++p;
+    }
+    b200sfm_ba_opts o;
+    b200sfm_ba_default_opts(&o);
+    o.optimize_rig_poses = options_.optimize_rig_poses; o.optimize_rotations = options_.optimize_rotations;
+    o.optimize_translation = options_.optimize_translation; o.optimize_intrinsics = options_.optimize_intrinsics;
+    o.optimize_principal_point = options_.optimize_principal_point; o.optimize_points = options_.optimize_points;
+    o.min_num_view_per_track = options_.min_num_view_per_track;
+    o.max_num_iterations = options_.solver_options.max_num_iterations;
+    o.thres_loss_function = options_.thres_loss_function;
+    o.function_tolerance = options_.solver_options.function_tolerance;
+    o.gradient_tolerance = options_.solver_options.gradient_tolerance;
+    o.parameter_tolerance = options_.solver_options.parameter_tolerance;
+    o.pcg_rel_tolerance = options_.pcg_rel_tolerance; o.pcg_max_iterations = options_.pcg_max_iterations;
+    const int rc = b200sfm_ba_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), K, ptb.data(), obs_cam.data(), obs_xy.data(),
+                                    cam_intr.data(), intr_model.data(), intr.data(), quat.data(), trans.data(), mask.data(),
+                                    points.data(), &summary);
+    if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ba_solve: %s\n", b200sfm_last_error(ctx)); return false; }
+    for (auto& [id, f] : fsorted) {                                                           // results in place (.cc:140-146)
+      const int i = fidx[id];
+      for (int k = 0; k < 4; ++k) f->RigFromWorld().rotation.coeffs_data()[k] = quat[4 * i + k];
+      for (int k = 0; k < 3; ++k) f->RigFromWorld().translation[k] = trans[3 * i + k];
+    }
+    p = 0;
+    for (auto& [id, t] : tsorted) { for (int k = 0; k < 3; ++k) t->xyz[k] = points[3 * (size_t)p + k]; ++p; }
+    for (auto& [id, c] : csorted)
+      for (size_t j = 0; j < c->params.size() && j < B200SFM_INTR_STRIDE; ++j) c->params[j] = intr[(size_t)cidx[id] * B200SFM_INTR_STRIDE + j];
+    return summary.usable != 0;                                                               // .cc:105
+  }
+
+ private:
+  BundleAdjusterOptions options_;
+};
+
+// ---------------------------------------------------------------------------
+struct GlobalPositionerOptions : public OptimizationBaseOptions {   // global_positioning.h:9-54
+  enum ConstraintType { ONLY_POINTS, ONLY_CAMERAS, POINTS_AND_CAMERAS_BALANCED, POINTS_AND_CAMERAS };
+  bool generate_random_positions = true, generate_random_points = true, generate_scales = true;
+  bool optimize_positions = true, optimize_points = true, optimize_scales = true;
+  bool use_gpu = true;
+  std::string gpu_index = "-1";
+  int min_num_images_gpu_solver = 50;
+  int min_num_view_per_track = 3;
+  unsigned seed = 1;
+  ConstraintType constraint_type = ONLY_POINTS;
+  double constraint_reweight_scale = 1.0;
+  double pcg_rel_tolerance = 1e-2;
+  int pcg_max_iterations = 1000;
+  GlobalPositionerOptions() { thres_loss_function = 1e-1; }
+};
+
+class GlobalPositioner {
+ public:
+  GlobalPositioner(const GlobalPositionerOptions& options) : options_(options) { random_generator_.seed(options_.seed); }
+  GlobalPositionerOptions& GetOptions() { return options_; }
+  b200sfm_lm_stats summary{};
+
+  // global_positioning.cc:28-93 (ONLY_POINTS, trivial rigs)
+  bool Solve(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
+             std::unordered_map<camera_t, Camera>& cameras, std::unordered_map<frame_t, Frame>& frames,
+             std::unordered_map<image_t, Image>& images, std::unordered_map<track_t, Track>& tracks) {
+    (void)view_graph; (void)rigs;
+    if (images.empty()) { std::fprintf(stderr, "Number of images = 0\n"); return false; }     // .cc:37-40
+    if (tracks.empty()) { std::fprintf(stderr, "Number of tracks = 0\n"); return false; }     // .cc:46-50
+    if (options_.constraint_type != GlobalPositionerOptions::ONLY_POINTS) {
+      std::fprintf(stderr, "b200sfm: only ONLY_POINTS is implemented\n");
+      return false;
+    }
+    b200sfm_ctx* ctx = DefaultContext();
+    if (!ctx) return false;
+    std::map<frame_t, Frame*> fsorted;
+    for (auto& [id, f] : frames) fsorted[id] = &f;
+    std::map<frame_t, int> fidx;
+    for (auto& [id, f] : fsorted) { const int i = (int)fidx.size(); fidx[id] = i; }
+    const int C = (int)fsorted.size();
+    std::uniform_real_distribution<double> U(-1, 1);
+    std::vector<double> centers(3 * (size_t)C), Rm(9 * (size_t)C);
+    std::vector<uint8_t> calibrated(C, 1);
+    for (auto& [id, f] : fsorted) {
+      const int i = fidx[id];
+      QuatToR(f->RigFromWorld().rotation.coeffs_data(), &Rm[9 * (size_t)i]);
+      for (int k = 0; k < 3; ++k) {
+        if (options_.generate_random_positions && options_.optimize_positions) {
+          centers[3 * i + k] = 100.0 * U(random_generator_);                                  // .cc:158-159
+        } else {                                                                              // CenterFromPose: -R^T t
+          const double* R = &Rm[9 * (size_t)i];
+          const auto& t = f->RigFromWorld().translation;
+          centers[3 * i + k] = -(R[k] * t[0] + R[3 + k] * t[1] + R[6 + k] * t[2]);
+        }
+      }
+    }
+    for (auto& [id, im] : images) calibrated[fidx[im.frame_id]] = cameras[im.camera_id].has_prior_focal_length ? 1 : 0;
+    std::map<track_t, Track*> tsorted;
+    for (auto& [id, t] : tracks) tsorted[id] = &t;
+    const int P = (int)tsorted.size();
+    std::vector<int64_t> ptb(1, 0);
+    std::vector<int32_t> obs_cam;
+    std::vector<double> obs_dir, points(3 * (size_t)P);
+    int p = 0;
+    for (auto& [id, t] : tsorted) {
+      for (const auto& ob : t->observations) {
+        auto it = images.find(ob.first);
+        if (it == images.end() || !it->second.IsRegistered()) continue;                      // .cc:279-282
+        const auto& b = it->second.features_undist[ob.second];
+        if (std::isnan(b[0]) || std::isnan(b[1]) || std::isnan(b[2])) continue;               // .cc:286-292
+        const int ci = fidx[it->second.frame_id];
+        const double* R = &Rm[9 * (size_t)ci];
+        for (int k = 0; k < 3; ++k) obs_dir.push_back(R[k] * b[0] + R[3 + k] * b[1] + R[6 + k] * b[2]);   // R^T b (.cc:294-296)
+        obs_cam.push_back(ci);
+      }
+      ptb.push_back((int64_t)obs_cam.size());
+      const bool rnd = options_.optimize_points && options_.generate_random_points &&
+                       (int)t->observations.size() >= options_.min_num_view_per_track;
+      for (int k = 0; k < 3; ++k) points[3 * (size_t)p + k] = rnd ? 100.0 * U(random_generator_) : t->xyz[k];   // .cc:261-264
+      if (rnd) t->is_initialized = true;
+      ++p;
+    }
+    std::vector<double> scales(obs_cam.size(), 1.0);                                          // .cc:298
+    b200sfm_gp_opts o;
+    b200sfm_gp_default_opts(&o);
+    o.optimize_positions = options_.optimize_positions; o.optimize_points = options_.optimize_points;
+    o.optimize_scales = options_.optimize_scales; o.min_num_view_per_track = options_.min_num_view_per_track;
+    o.max_num_iterations = options_.solver_options.max_num_iterations;
+    o.thres_loss_function = options_.thres_loss_function;
+    o.function_tolerance = options_.solver_options.function_tolerance;
+    o.pcg_rel_tolerance = options_.pcg_rel_tolerance; o.pcg_max_iterations = options_.pcg_max_iterations;
+    const int rc = b200sfm_gp_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),
+                                    calibrated.data(), nullptr, centers.data(), points.data(), scales.data(), &summary);
+    if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_gp_solve: %s\n", b200sfm_last_error(ctx)); return false; }
+    for (auto& [id, f] : fsorted) {                                                           // ConvertResults: t = -R c (.cc:566-568)
+      const int i = fidx[id];
+      const double* R = &Rm[9 * (size_t)i];
+      for (int k = 0; k < 3; ++k)
+        f->RigFromWorld().translation[k] = -(R[3 * k] * centers[3 * i] + R[3 * k + 1] * centers[3 * i + 1] + R[3 * k + 2] * centers[3 * i + 2]);
+    }
+    p = 0;
+    for (auto& [id, t] : tsorted) { for (int k = 0; k < 3; ++k) t->xyz[k] = points[3 * (size_t)p + k]; ++p; }
+    return summary.usable != 0;
+  }
+
+ private:
+  GlobalPositionerOptions options_;
+  std::mt19937 random_generator_;
+};
+
+// ---------------------------------------------------------------------------
+struct RotationEstimatorOptions {   // global_rotation_averaging.h:39-75
+  int max_num_l1_iterations = 5;
+  double l1_step_convergence_threshold = 0.001;
+  int max_num_irls_iterations = 100;
+  double irls_step_convergence_threshold = 0.001;
+  double irls_loss_parameter_sigma = 5.0;
+  enum WeightType { GEMAN_MCCLURE, HALF_NORM } weight_type = GEMAN_MCCLURE;
+  bool skip_initialization = false;
+  bool use_weight = false;
+  bool use_gravity = false;
+  double pcg_rel_tolerance = 1e-8;
+};
+
+class RotationEstimator {
+ public:
+  explicit RotationEstimator(const RotationEstimatorOptions& options) : options_(options) {}
+  b200sfm_ra_stats summary{};
+
+  // global_rotation_averaging.cc:40-85 (3-DoF frames, trivial rigs).  The
+  // spanning-tree initialisation is expected from the caller when
+  // skip_initialization is false (host-side, math/tree.cc).
+  bool EstimateRotations(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
+                         std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images) {
+    (void)rigs;
+    if (options_.use_gravity) { std::fprintf(stderr, "b200sfm: gravity-aligned rotation averaging is not implemented\n"); return false; }
+    b200sfm_ctx* ctx = DefaultContext();
+    if (!ctx) return false;
+    std::map<frame_t, Frame*> fsorted;
+    for (auto& [id, f] : frames)
+      if (f.is_registered) fsorted[id] = &f;
+    std::map<frame_t, int> fidx;
+    for (auto& [id, f] : fsorted) { const int i = (int)fidx.size(); fidx[id] = i; }
+    const int n = (int)fsorted.size();
+    if (n == 0) return false;
+    std::vector<double> theta(3 * (size_t)n);
+    for (auto& [id, f] : fsorted) QuatToAngleAxis(f->RigFromWorld().rotation.coeffs_data(), &theta[3 * (size_t)fidx[id]]);   // .cc:223-224
+    std::map<image_pair_t, const ImagePair*> psorted;
+    for (const auto& [id, pr] : view_graph.image_pairs)
+      if (pr.is_valid) psorted[id] = &pr;
+    std::vector<int32_t> ei, ej;
+    std::vector<double> Rrel, w;
+    for (const auto& [id, pr] : psorted) {
+      const auto i1 = images.find(pr->image_id1), i2 = images.find(pr->image_id2);
+      if (i1 == images.end() || i2 == images.end()) continue;
+      const auto f1 = fidx.find(i1->second.frame_id), f2 = fidx.find(i2->second.frame_id);
+      if (f1 == fidx.end() || f2 == fidx.end()) continue;                                     // .cc:365-368
+      ei.push_back(f1->second);
+      ej.push_back(f2->second);
+      double R[9];
+      QuatToR(pr->cam2_from_cam1.rotation.coeffs_data(), R);                                  // .cc:306-309 (trivial rigs)
+      Rrel.insert(Rrel.end(), R, R + 9);
+      w.push_back(pr->weight);
+    }
+    b200sfm_ra_opts o;
+    b200sfm_ra_default_opts(&o);
+    o.max_num_l1_iterations = options_.max_num_l1_iterations; o.max_num_irls_iterations = options_.max_num_irls_iterations;
+    o.l1_step_convergence_threshold = options_.l1_step_convergence_threshold;
+    o.irls_step_convergence_threshold = options_.irls_step_convergence_threshold;
+    o.irls_loss_parameter_sigma = options_.irls_loss_parameter_sigma;
+    o.weight_type = options_.weight_type == RotationEstimatorOptions::HALF_NORM ? 1 : 0;
+    o.use_weight = options_.use_weight; o.pcg_rel_tolerance = options_.pcg_rel_tolerance;
+    const int rc = b200sfm_ra_solve(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), 0, theta.data(), &summary);
+    if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ra_solve: %s\n", b200sfm_last_error(ctx)); return false; }
+    if (!summary.usable) return false;                                                        // NaN (.cc:508-512,590-593)
+    for (auto& [id, f] : fsorted) {                                                           // ConvertResults (.cc:795-798)
+      AngleAxisToQuat(&theta[3 * (size_t)fidx[id]], f->RigFromWorld().rotation.coeffs_data());
+      f->RigFromWorld().translation = {{0, 0, 0}};
+    }
+    return true;
+  }
+
+  static void QuatToAngleAxis(const double* q, double* v) {
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (n > 0) {
+      const double ang = 2 * std::atan2(n, std::fabs(q[3]));
+      const double f = (q[3] < 0 ? -ang : ang) / n;
+      v[0] = q[0] * f; v[1] = q[1] * f; v[2] = q[2] * f;
+    } else {
+      v[0] = v[1] = v[2] = 0;
+    }
+  }
+  static void AngleAxisToQuat(const double* v, double* q) {
+    const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (n > 0) {
+      const double s = std::sin(n / 2) / n;
+      q[0] = v[0] * s; q[1] = v[1] * s; q[2] = v[2] * s; q[3] = std::cos(n / 2);
+    } else {
+      q[0] = q[1] = q[2] = 0; q[3] = 1;
+    }
+  }
+
+ private:
+  const RotationEstimatorOptions& options_;   // the reference stores a const& too (.h:140)
+};
+
+}  // namespace b200sfm_shim

@@ -1,0 +1,87 @@
+// scene_min.h -- minimal stand-ins for the glomap / COLMAP scene types the
+// estimator shim touches (the real ones need COLMAP + Eigen, absent here).
+// Field and accessor names follow the reference so that estimators_shim.h
+// compiles unchanged against either:
+//   glomap/scene/image.h:10-45, frame.h:11-27, track.h:12-24, camera.h:12,
+//   image_pair.h:13-40, view_graph.h:12, types.h:32-40; colmap Rigid3d.
+// Define B200SFM_WITH_GLOMAP to use the real headers instead.
+#pragma once
+#ifdef B200SFM_WITH_GLOMAP
+#include "glomap/scene/types_sfm.h"
+namespace b200host = glomap;
+#else
+#include <array>
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+namespace b200host {
+
+using image_t = uint32_t;
+using camera_t = uint32_t;
+using frame_t = uint32_t;
+using rig_t = uint32_t;
+using track_t = uint64_t;
+using image_pair_t = uint64_t;
+using feature_t = uint32_t;
+
+struct Quaternion {   // Eigen::Quaterniond: coeffs() is (x, y, z, w)
+  double c[4] = {0, 0, 0, 1};
+  double* coeffs_data() { return c; }
+  const double* coeffs_data() const { return c; }
+};
+struct Rigid3d {
+  Quaternion rotation;
+  std::array<double, 3> translation{{0, 0, 0}};
+};
+struct Camera {
+  camera_t camera_id = 0;
+  int model_id = 0;                  // colmap::CameraModelId
+  std::vector<double> params;
+  bool has_prior_focal_length = true;
+};
+struct Rig {};
+struct Frame {
+  frame_t frame_id = 0;
+  rig_t rig_id = 0;
+  bool is_registered = true;
+  Rigid3d rig_from_world;
+  Rigid3d& RigFromWorld() { return rig_from_world; }
+  const Rigid3d& RigFromWorld() const { return rig_from_world; }
+  bool HasPose() const { return true; }
+};
+struct Image {
+  image_t image_id = 0;
+  camera_t camera_id = 0;
+  frame_t frame_id = 0;
+  std::string file_name;
+  Frame* frame_ptr = nullptr;
+  std::vector<std::array<double, 2>> features;          // distorted pixels (scene/image.h:29)
+  std::vector<std::array<double, 3>> features_undist;   // unit bearings (scene/image.h:31)
+  bool IsRegistered() const { return frame_ptr && frame_ptr->is_registered; }
+  bool HasTrivialFrame() const { return true; }
+};
+struct Track {
+  track_t track_id = 0;
+  std::array<double, 3> xyz{{0, 0, 0}};
+  std::vector<std::pair<image_t, feature_t>> observations;
+  bool is_initialized = false;
+};
+struct ImagePair {
+  image_t image_id1 = 0, image_id2 = 0;
+  bool is_valid = true;
+  double weight = -1;
+  Rigid3d cam2_from_cam1;
+};
+struct ViewGraph {
+  std::unordered_map<image_pair_t, ImagePair> image_pairs;
+};
+inline image_pair_t ImagePairToPairId(image_t a, image_t b) {   // colmap::ImagePairToPairId
+  if (a > b) std::swap(a, b);
+  return (image_pair_t)a * 2147483647ull + b;
+}
+
+}  // namespace b200host
+#endif

@@ -418,3 +418,35 @@ def write_global_rotation_file(path: str, names, R: np.ndarray) -> None:
     with open(path, "w") as f:
         for i, nm in enumerate(names):
             f.write(f"{nm} {q[i,3]:.6g} {q[i,0]:.6g} {q[i,1]:.6g} {q[i,2]:.6g}\n")
+
+
+# ---------------------------------------------------------------------------
+# Flat binary problem file (glomap_b200/host/b200sfm_cli.cc)
+# ---------------------------------------------------------------------------
+def write_flat_problem(path: str, scene: Scene, bearings: np.ndarray | None = None) -> None:
+    """int64 {C,P,N,K}; int64 pt_obs_begin[P+1]; int32 obs_cam[N]; f64 obs_xy[2N]; f64 bearings[3N];
+    int32 cam_intr[C]; int32 intr_model[K]; f64 intr[K*12]; f64 quat[4C]; f64 trans[3C]; f64 points[3P]."""
+    b = bearings_from_scene(scene) if bearings is None else bearings
+    with open(path, "wb") as f:
+        np.array([scene.C, scene.P, scene.N, len(scene.intr_model)], np.int64).tofile(f)
+        for arr, dt in ((scene.pt_obs_begin, np.int64), (scene.obs_cam, np.int32), (scene.obs_xy, np.float64),
+                        (b, np.float64), (scene.cam_intr, np.int32), (scene.intr_model, np.int32),
+                        (scene.intr_params, np.float64), (scene.quat, np.float64), (scene.trans, np.float64),
+                        (scene.points, np.float64)):
+            np.ascontiguousarray(arr, dtype=dt).tofile(f)
+
+
+def read_flat_problem(path: str) -> Scene:
+    with open(path, "rb") as f:
+        C, P, N, K = (int(x) for x in np.fromfile(f, np.int64, 4))
+        ptb = np.fromfile(f, np.int64, P + 1)
+        cam = np.fromfile(f, np.int32, N)
+        xy = np.fromfile(f, np.float64, 2 * N).reshape(N, 2)
+        np.fromfile(f, np.float64, 3 * N)
+        ci = np.fromfile(f, np.int32, C)
+        im = np.fromfile(f, np.int32, K)
+        intr = np.fromfile(f, np.float64, K * INTR_STRIDE).reshape(K, INTR_STRIDE)
+        quat = np.fromfile(f, np.float64, 4 * C).reshape(C, 4)
+        trans = np.fromfile(f, np.float64, 3 * C).reshape(C, 3)
+        pts = np.fromfile(f, np.float64, 3 * P).reshape(P, 3)
+    return Scene(quat, trans, pts, ptb, cam, xy, ci, im, intr)
