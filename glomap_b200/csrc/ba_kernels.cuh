@@ -25,6 +25,7 @@ constexpr int kCamRec = 8;    // q(4) t(3) packed{mask, intr idx}
 constexpr int kIntrRec = 8;   // fx fy cx cy k1 k2 model pad
 constexpr double kZEps = 1e-12;
 constexpr int kSeg = 256;     // observations per camera-order segment (one warp)
+constexpr int kIntrSmem = 16; // intrinsics blocks cached in shared memory by the point-order kernels
 
 struct BAView {
   int C, P, K;
@@ -38,6 +39,7 @@ struct BAView {
   const double2* obs_xy;
   const unsigned* pt_begin;     // [P+1]
   const int* tile_pt_begin;     // [n_tiles+1]
+  const int4* tile_desc;        // [n_tiles] {first point, #points, first observation, #observations}
   const int* camord_obs;        // [Nv] observation ids sorted by camera
   const int* pt_c;              // [Nv]
   const double2* xy_c;          // [Nv]
@@ -108,14 +110,13 @@ struct ObsLin {
   bool valid;
 };
 
-__device__ __forceinline__ void linearize_obs(const double* __restrict__ cam_rec, const double* __restrict__ intr_rec,
-                                              int cam, double X0, double X1, double X2, double2 xy, double huber_a,
-                                              ObsLin& o) {
-  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+__device__ __forceinline__ int cam_rec_intr(const double4& t4) { return (int)(__double_as_longlong(t4.w) >> 8); }
+
+// q4/t4 = the camera record (already loaded), ir = the intrinsics record of that camera
+__device__ __forceinline__ void linearize_obs(const double4& q4, const double4& t4, const double* __restrict__ ir,
+                                              double X0, double X1, double X2, double2 xy, double huber_a, ObsLin& o) {
   const long long packed = __double_as_longlong(t4.w);
   const int mask = (int)(packed & 0xff);
-  const int intr = (int)(packed >> 8);
   const double q[4] = {q4.x, q4.y, q4.z, q4.w};
   double R[9];
   quat_to_R(q, R);
@@ -132,7 +133,7 @@ __device__ __forceinline__ void linearize_obs(const double* __restrict__ cam_rec
     return;
   }
   double px, py, J[6];
-  project_jac(intr_rec + (size_t)intr * kIntrRec, xc, yc, zc, px, py, J);
+  project_jac(ir, xc, yc, zc, px, py, J);
   const double r0 = px - xy.x, r1 = py - xy.y;
   double rho1;
   huber(r0 * r0 + r1 * r1, huber_a, o.rho0, rho1);
@@ -205,6 +206,7 @@ struct K1Smem {
   double acc[9][kTilePts + 1];   // per-point sums (V packed 6 + g 3)
   unsigned pb[kTilePts + 1]; // observation range of each point of the tile
   double X[3][kTilePts + 1]; // the tile's points
+  double intr[kIntrSmem][kIntrRec];   // intrinsics table (first kIntrSmem blocks)
   double scratch[32];
 };
 
@@ -215,11 +217,23 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
   extern __shared__ unsigned char smem_raw[];
   K1Smem& sm = *reinterpret_cast<K1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int tile = blockIdx.x;
-  const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
-  const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
-  const int n = (int)(o1 - o0);
   const int tid = threadIdx.x;
-  const int npts = p1 - p0;
+  // one 16-B descriptor per tile: the dependent-load chain is descriptor -> {observations, points} -> camera record
+  const int4 td = v.tile_desc[tile];
+  const int p0 = td.x, npts = td.y, n = td.w;
+  const unsigned o0 = (unsigned)td.z;
+  // prefetch the first chunk's observation + its camera record before the shared-memory fill / barrier
+  int cam_pf = 0, pt_pf = 0;
+  double2 xy_pf = make_double2(0.0, 0.0);
+  double4 q4_pf = make_double4(0, 0, 0, 1), t4_pf = make_double4(0, 0, 0, 0);
+  if (tid < n) {
+    cam_pf = v.obs_cam[o0 + tid];
+    xy_pf = v.obs_xy[o0 + tid];
+    pt_pf = v.obs_pt[o0 + tid];
+    q4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec);
+    t4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec + 4);
+  }
+  for (int i = tid; i < min(v.K, kIntrSmem) * kIntrRec; i += kTile) (&sm.intr[0][0])[i] = intr_rec[i];
   // per-point accumulators live in shared memory (thread j <-> point p0 + j)
   unsigned pb = 0, pe = 0;
   bool pvalid = false;
@@ -242,14 +256,21 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
     ObsLin o;
     bool use = false;
     if (active) {
-      const unsigned oi = o0 + c0 + tid;
-      const int cam = v.obs_cam[oi];
-      const double2 xy = v.obs_xy[oi];
-      const int pl = v.obs_pt[oi] - p0;     // point index within the tile: X and validity come from smem
+      if (c0 > 0) {   // multi-chunk tiles (one track longer than the tile) reload per chunk
+        const unsigned oi = o0 + c0 + tid;
+        cam_pf = v.obs_cam[oi];
+        xy_pf = v.obs_xy[oi];
+        pt_pf = v.obs_pt[oi];
+        q4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec);
+        t4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec + 4);
+      }
+      const int pl = pt_pf - p0;     // point index within the tile: X and validity come from smem
       use = (int)(sm.pb[pl + 1] - sm.pb[pl]) >= v.min_views;
       if (use) {
         const double X0 = sm.X[0][pl], X1 = sm.X[1][pl], X2 = sm.X[2][pl];
-        linearize_obs(cam_rec, intr_rec, cam, X0, X1, X2, xy, huber_a, o);
+        const int intr = cam_rec_intr(t4_pf);
+        const double* ir = intr < kIntrSmem ? sm.intr[intr] : intr_rec + (size_t)intr * kIntrRec;
+        linearize_obs(q4_pf, t4_pf, ir, X0, X1, X2, xy_pf, huber_a, o);
         cost += 0.5 * o.rho0;
       }
     }
@@ -333,6 +354,9 @@ __global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double*
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
+  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double* irc = intr_rec + (size_t)cam_rec_intr(t4c) * kIntrRec;
   double U[21], g[6];
 #pragma unroll
   for (int k = 0; k < 21; ++k) U[k] = 0.0;
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double*
     const double2 xy = v.xy_c[i];
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
     ObsLin o;
-    linearize_obs(cam_rec, intr_rec, cam, X0, X1, X2, xy, huber_a, o);
+    linearize_obs(q4c, t4c, irc, X0, X1, X2, xy, huber_a, o);
     double Jc[2][6];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -545,15 +569,30 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView 
   extern __shared__ unsigned char smem_raw[];
   K3Smem& sm = *reinterpret_cast<K3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int tile = blockIdx.x;
-  const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
-  const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
-  const int n = (int)(o1 - o0);
   const int tid = threadIdx.x;
-  const int npts = p1 - p0;
+  const int4 td = v.tile_desc[tile];
+  const int p0 = td.x, npts = td.y, n = td.w;
+  const unsigned o0 = (unsigned)td.z, o1 = o0 + (unsigned)n;
   const int nchunks = (n + kTile - 1) / kTile;
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
     fence_mbar_init();
+    if (MODE != 1 && n > 0) {   // first W tile is requested before anything else
+      const int nc0 = min(kTile, n);
+      mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc0 * kWBytes);
+      tma_load_1d(sm.Wt, v.W + (size_t)o0 * kWDoubles, (uint32_t)nc0 * kWBytes, &sm.mbar);
+    }
+  }
+  // prefetch the first chunk's camera index + x block before the barrier
+  int cam_pf = 0, pt_pf = 0;
+  double2 xa_pf = make_double2(0, 0), xb_pf = xa_pf, xc_pf = xa_pf;
+  if (MODE != 1 && tid < n) {
+    cam_pf = v.obs_cam[o0 + tid];
+    if (MODE == 0) pt_pf = v.obs_pt[o0 + tid];
+    const double2* xp = reinterpret_cast<const double2*>(x + (size_t)cam_pf * 6);
+    xa_pf = xp[0];
+    xb_pf = xp[1];
+    xc_pf = xp[2];
   }
   if (tid < npts) {
     sm.pb[tid] = v.pt_begin[p0 + tid];
@@ -567,17 +606,21 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView 
     for (int ch = 0; ch < nchunks; ++ch) {
       const int c0 = ch * kTile;
       const int nc = min(kTile, n - c0);
-      if (tid == 0) {
+      if (tid == 0 && ch > 0) {
         mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kWBytes);
         tma_load_1d(sm.Wt, v.W + (size_t)(o0 + c0) * kWDoubles, (uint32_t)nc * kWBytes, &sm.mbar);
       }
       double xc[6] = {0, 0, 0, 0, 0, 0};
       const bool active = tid < nc;
       if (active) {
-        const int cam = v.obs_cam[o0 + c0 + tid];
-        const double2* xp = reinterpret_cast<const double2*>(x + (size_t)cam * 6);
-        const double2 a = xp[0], b = xp[1], c = xp[2];
-        xc[0] = a.x; xc[1] = a.y; xc[2] = b.x; xc[3] = b.y; xc[4] = c.x; xc[5] = c.y;
+        if (ch > 0) {
+          cam_pf = v.obs_cam[o0 + c0 + tid];
+          const double2* xp = reinterpret_cast<const double2*>(x + (size_t)cam_pf * 6);
+          xa_pf = xp[0];
+          xb_pf = xp[1];
+          xc_pf = xp[2];
+        }
+        xc[0] = xa_pf.x; xc[1] = xa_pf.y; xc[2] = xb_pf.x; xc[3] = xb_pf.y; xc[4] = xc_pf.x; xc[5] = xc_pf.y;
       }
       mbar_wait(&sm.mbar, phase);
       phase ^= 1;
@@ -687,8 +730,8 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView 
     }
     if (tid < nc) {
       const unsigned oi = o0 + c0 + tid;
-      const int cam = v.obs_cam[oi];
-      const int pl = v.obs_pt[oi] - p0;
+      const int cam = reload ? v.obs_cam[oi] : cam_pf;
+      const int pl = (reload ? v.obs_pt[oi] : pt_pf) - p0;
       const double z0 = sm.z[0][pl], z1 = sm.z[1][pl], z2 = sm.z[2][pl];
       if (z0 != 0.0 || z1 != 0.0 || z2 != 0.0) {
         const double2* wr = reinterpret_cast<const double2*>(sm.Wt + tid * kWDoubles);

@@ -101,6 +101,7 @@ struct b200sfm_ba_problem {
   // structure
   DevBuf<int> obs_cam, obs_pt, tile_pt_begin, camord_obs, pt_c, seg_cam, seg_begin, seg_end, cam_intr, intr_model;
   DevBuf<double2> obs_xy, xy_c;
+  DevBuf<int4> tile_desc;
   DevBuf<unsigned> pt_begin;
   DevBuf<unsigned char> cam_mask_base, cam_mask;
   // state + candidate + snapshot
@@ -123,7 +124,7 @@ struct b200sfm_ba_problem {
     BAView v;
     v.C = C; v.P = P; v.K = K; v.N = N; v.n_tiles = n_tiles; v.n_segs = n_segs; v.min_views = min_views;
     v.obs_cam = obs_cam.p; v.obs_pt = obs_pt.p; v.obs_xy = obs_xy.p; v.pt_begin = pt_begin.p;
-    v.tile_pt_begin = tile_pt_begin.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p; v.xy_c = xy_c.p;
+    v.tile_pt_begin = tile_pt_begin.p; v.tile_desc = tile_desc.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p; v.xy_c = xy_c.p;
     v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p;
     v.W = W.p; v.V = V.p; v.Vinv = Vinv.p; v.gp = gp.p; v.U = U(); v.gc = gc(); v.Sd = Sd.p; v.Minv = Minv.p;
     v.jscale_c = jscale_c.p; v.jscale_p = jscale_p.p; v.Dc = Dc.p;
@@ -168,6 +169,13 @@ struct b200sfm_ba_problem {
     obs_xy.upload(reinterpret_cast<const double2*>(h_obs_xy), N, s);
     pt_begin.upload(ptb.data(), (size_t)P + 1, s);
     tile_pt_begin.upload(tiles.data(), tiles.size(), s);
+    std::vector<int4> descs((size_t)n_tiles);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int a = tiles[t], b = tiles[t + 1];
+      descs[t] = make_int4(a, b - a, (int)ptb[a], (int)(ptb[b] - ptb[a]));
+    }
+    tile_desc.alloc(descs.size());
+    tile_desc.upload(descs.data(), descs.size(), s);
     cam_intr.upload(h_cam_intr, C, s);
     intr_model.upload(h_intr_model, K, s);
     if (h_cam_mask) cam_mask_base.upload(h_cam_mask, C, s);

@@ -315,19 +315,93 @@ __global__ void ra_update(int n, double* __restrict__ theta, const double* __res
   }
 }
 
-// |vec|^2 of a node vector -> out[0] (single CTA, deterministic)
-__global__ void ra_norm2(int n3, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+// |a|^2, |b|^2 of node vectors: per-CTA partials (deterministic two-stage sum)
+__global__ void __launch_bounds__(256) ra_norm2_partial(int n3, const double* __restrict__ a, const double* __restrict__ b,
+                                                        double* __restrict__ part_a, double* __restrict__ part_b) {
+  __shared__ double scratch[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s0 = 0, s1 = 0;
+  if (i < n3) {
+    s0 = a[i] * a[i];
+    s1 = b[i] * b[i];
+  }
+  s0 = block_sum(s0, scratch);
+  s1 = block_sum(s1, scratch);
+  if (threadIdx.x == 0) {
+    part_a[blockIdx.x] = s0;
+    part_b[blockIdx.x] = s1;
+  }
+}
+__global__ void ra_norm2_final(int nblk, const double* __restrict__ part_a, const double* __restrict__ part_b,
+                               double* __restrict__ out) {
   __shared__ double scratch[32];
   double s0 = 0, s1 = 0;
-  for (int i = threadIdx.x; i < n3; i += blockDim.x) {
-    s0 += a[i] * a[i];
-    if (b) s1 += b[i] * b[i];
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    s0 += part_a[i];
+    s1 += part_b[i];
   }
   s0 = block_sum(s0, scratch);
   s1 = block_sum(s1, scratch);
   if (threadIdx.x == 0) {
     out[0] = s0;
     out[1] = s1;
+  }
+}
+
+// Warm-started PCG initialisation: x is kept, Ax holds L x (all-reduced):
+//   r = b - Ax; z = Minv r; p = z; Ax <- 0; partial r.z, r.r, b.b
+__global__ void __launch_bounds__(128) ra_pcg_init_warm(int nb, const double* __restrict__ Minv,
+                                                        const double* __restrict__ b, double* __restrict__ Ax,
+                                                        double* __restrict__ r, double* __restrict__ z,
+                                                        double* __restrict__ p, double* __restrict__ part_bb,
+                                                        double* __restrict__ part_rz, double* __restrict__ part_rr) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0, rr = 0, bb = 0;
+  if (c < nb) {
+    const double minv = Minv[6 * (size_t)c];   // diagonal preconditioner
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const size_t i = 3 * (size_t)c + k;
+      const double bv = b[i];
+      const double rv = bv - Ax[i];
+      Ax[i] = 0.0;
+      const double zv = minv * rv;
+      r[i] = rv;
+      z[i] = zv;
+      p[i] = zv;
+      rz += rv * zv;
+      rr += rv * rv;
+      bb += bv * bv;
+    }
+  }
+  rz = block_sum(rz, scratch);
+  rr = block_sum(rr, scratch);
+  bb = block_sum(bb, scratch);
+  if (threadIdx.x == 0) {
+    part_rz[blockIdx.x] = rz;
+    part_rr[blockIdx.x] = rr;
+    part_bb[blockIdx.x] = bb;
+  }
+}
+__global__ void __launch_bounds__(128) ra_publish_warm(int nblk, const double* __restrict__ part_bb,
+                                                       const double* __restrict__ part_rz,
+                                                       const double* __restrict__ part_rr, double* __restrict__ dots0) {
+  __shared__ double scratch[32];
+  double a = 0, b = 0, c = 0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    a += part_bb[i];
+    b += part_rz[i];
+    c += part_rr[i];
+  }
+  a = block_sum(a, scratch);
+  b = block_sum(b, scratch);
+  c = block_sum(c, scratch);
+  if (threadIdx.x == 0) {
+    dots0[0] = 0.0;
+    dots0[1] = b;
+    dots0[2] = c;
+    dots0[3] = a;   // |b|^2: the convergence reference of a warm-started solve
   }
 }
 

@@ -81,7 +81,7 @@ struct b200sfm_ra_problem {
   }
 
   // x = L(w^p)^-1 rhs_vec by PCG (result in px); returns iterations
-  int pcg_solve(const b200sfm_ra_opts& o, int square, const double* rhs_vec, bool& finite) {
+  int pcg_solve(const b200sfm_ra_opts& o, int square, const double* rhs_vec, bool& finite, bool warm = false) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     RAView v = view();
@@ -91,15 +91,26 @@ struct b200sfm_ra_problem {
     if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
     double *part_pq = part.p, *part_rz = part.p + nblk, *part_rr = part.p + 2 * (size_t)nblk;
     const int egrid = cdiv(std::max<long long>(E, 1), 256);
-    B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
-    B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
+    if (warm) {
+      // r0 = b - L x_prev (ADMM x-updates change little between iterations)
+      yw.zero(s);
+      if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, px.p, yw.p);
+      ctx->allreduce_sum(yw.p, (size_t)n * 3);
+      B200_LAUNCH(ctx, ra_pcg_init_warm, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, yw.p, pr.p, pz.p, pp.p, part_pq, part_rz, part_rr);
+      B200_LAUNCH(ctx, ra_publish_warm, 1, kPcgThreads, 0, nblk, part_pq, part_rz, part_rr, dots.p);
+    } else {
+      B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
+      B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
+    }
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     const double rr0 = ctx->h_scal[2];
+    const double ref2 = warm ? ctx->h_scal[3] : rr0;
     int it = 0;
     finite = std::isfinite(rr0);
-    if (!(rr0 > 0.0) || !finite) return 0;
-    const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * rr0;
+    if (!(ref2 > 0.0) || !finite) return 0;
+    const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * ref2;
+    if (rr0 <= tol2) return 0;
     const int check_every = 4;   // convergence is polled every few iterations (host sync)
     for (it = 1; it <= max_it; ++it) {
       double* d_prev = dots.p + (size_t)(it - 1) * 4;
@@ -180,7 +191,7 @@ struct b200sfm_ra_problem {
         const double eps_dual_thr = std::sqrt(3.0 * n) * o.l1_absolute_tolerance;
         for (int k = 0; k < o.l1_max_admm_iterations; ++k) {
           bool finite = true;
-          local.pcg_iterations += pcg_solve(o, 1, rhs.p, finite);
+          local.pcg_iterations += pcg_solve(o, 1, rhs.p, finite, /*warm=*/k > 0);
           ++local.admm_iterations;
           if (!finite) { failed = true; break; }
           B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 9 * sizeof(double), s));
@@ -190,7 +201,12 @@ struct b200sfm_ra_problem {
                         rhs.p + (size_t)n * 6, scal.p);
           ctx->allreduce_sum(rhs.p, (size_t)n * 9);
           ctx->allreduce_sum(scal.p + 1, 3);
-          B200_LAUNCH(ctx, ra_norm2, 1, 256, 0, n * 3, rhs.p + (size_t)n * 3, rhs.p + (size_t)n * 6, scal.p + 4);
+          {
+            const int nb2 = cdiv((long long)n * 3, 256);
+            if (part.n < (size_t)nb2 * 2) part.alloc((size_t)nb2 * 2 + 3 * (size_t)cdiv(n, kPcgThreads));
+            B200_LAUNCH(ctx, ra_norm2_partial, nb2, 256, 0, n * 3, rhs.p + (size_t)n * 3, rhs.p + (size_t)n * 6, part.p, part.p + nb2);
+            B200_LAUNCH(ctx, ra_norm2_final, 1, 256, 0, nb2, part.p, part.p + nb2, scal.p + 4);
+          }
           B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
           B200_CUDA_OK(cudaStreamSynchronize(s));
           const double* h = ctx->h_scal;
