@@ -105,7 +105,15 @@ struct b200sfm_ba_problem {
   DevBuf<unsigned> pt_begin;
   DevBuf<unsigned char> cam_mask_base, cam_mask;
   // state + candidate + snapshot
-  DevBuf<double> quat[2], trans[2], points[2], intr, quat_saved, trans_saved, points_saved, intr_saved;
+  DevBuf<double> quat[2], trans[2], points[2], intr, intr_cand, quat_saved, trans_saved, points_saved, intr_saved;
+  // shared-intrinsics border (optimize_intrinsics)
+  int m_intr = 0;
+  std::vector<int> h_intr_model;
+  std::vector<b200::IntrVarRec> h_ivar;
+  std::vector<double> h_intr, h_intr_cand, h_ukk, h_js_k, h_Dk, h_gk, h_bk, h_CkInv, h_dk;
+  DevBuf<b200::IntrVarRec> ivar;
+  DevBuf<double> Buck, Bmat, spk, part_seg, intr_out, part_tile, tile_sum, CkInv, vvec, part_bt, tvec, dkv;
+  size_t smem_ki = 0;
   int cur = 0;
   DevBuf<double> cam_rec, intr_rec;
   // linear system
@@ -178,6 +186,7 @@ struct b200sfm_ba_problem {
     tile_desc.upload(descs.data(), descs.size(), s);
     cam_intr.upload(h_cam_intr, C, s);
     intr_model.upload(h_intr_model, K, s);
+    this->h_intr_model.assign(h_intr_model, h_intr_model + K);
     if (h_cam_mask) cam_mask_base.upload(h_cam_mask, C, s);
     else cam_mask_base.zero(s);
     if (st) st->h2d_bytes += N * 20 + ((long long)P + 1) * 4 + (long long)tiles.size() * 4 + (long long)C * 5 + K * 4;
@@ -223,6 +232,7 @@ struct b200sfm_ba_problem {
       quat[i].alloc((size_t)C * 4); trans[i].alloc((size_t)C * 3); points[i].alloc((size_t)P * 3);
     }
     intr.alloc((size_t)K * B200SFM_INTR_STRIDE);
+    intr_cand.alloc((size_t)K * B200SFM_INTR_STRIDE);
     cam_rec.alloc((size_t)C * kCamRec); intr_rec.alloc((size_t)K * kIntrRec);
     W.alloc((size_t)N * kWDoubles); V.alloc((size_t)P * 6); Vinv.alloc((size_t)P * 6); gp.alloc((size_t)P * 3);
     lin.alloc((size_t)C * 27 + 2); Sd.alloc((size_t)C * 21); Minv.alloc((size_t)C * 21);
@@ -242,6 +252,9 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    smem_ki = sizeof(KISmem) + 128;
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaStreamSynchronize(s));   // temporaries go out of scope
   }
 
@@ -289,7 +302,7 @@ struct b200sfm_ba_problem {
   void build_records(int which) {
     using namespace b200;
     B200_LAUNCH(ctx, ba_build_records, cdiv(std::max(C, K), 256), 256, 0, C, K, quat[which].p, trans[which].p,
-                cam_intr.p, cam_mask.p, intr.p, intr_model.p, cam_rec.p, intr_rec.p);
+                cam_intr.p, cam_mask.p, (which == cur ? intr.p : intr_cand.p), intr_model.p, cam_rec.p, intr_rec.p);
   }
 
   // robust cost of state `which` -> host (synchronises)
@@ -331,11 +344,38 @@ struct b200sfm_ba_problem {
     ctx->allreduce_max(scal.p + 1, 1);
     B200_LAUNCH(ctx, ba_finalize_cams, cdiv(C, 128), 128, 0, C, U(), gc(), cam_mask.p, jscale_c.p, first ? 1 : 0,
                 scal.p);
+    if (m_intr > 0) {
+      // U_ck into the (local) border, U_kk / g_k per block (camera order)
+      Buck.zero(s);
+      if (n_segs > 0) {
+        B200_LAUNCH(ctx, ba_intr_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p, ivar.p,
+                    points[cur].p, huber_a, m_intr, Buck.p, part_seg.p);
+        B200_LAUNCH(ctx, ba_intr_reduce_segs, K, 256, 0, n_segs, seg_cam.p, cam_intr.p, part_seg.p, intr_out.p);
+      } else {
+        intr_out.zero(s);
+      }
+      ctx->allreduce_sum(intr_out.p, (size_t)K * 20);
+      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, intr_out.p, (size_t)K * 20 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, cost_ptr(), sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 1, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     cost = ctx->h_scal[0];
     gmax = ctx->h_scal[1];
+    if (m_intr > 0) {
+      h_ukk.assign(ctx->h_scal + 64, ctx->h_scal + 64 + (size_t)K * 20);
+      h_gk.assign(m_intr, 0.0);
+      if (first) h_js_k.assign(m_intr, 1.0);
+      for (int k = 0; k < K; ++k) {
+        const b200::IntrVarRec& iv = h_ivar[k];
+        for (int a = 0; a < iv.mb; ++a) {
+          const double d = h_ukk[(size_t)k * 20 + (a * kMaxBlockDof - a * (a - 1) / 2)];   // packed (a,a) of a 5x5
+          if (first) h_js_k[iv.col0 + a] = 1.0 / (1.0 + std::sqrt(std::max(d, 0.0)));
+          h_gk[iv.col0 + a] = h_ukk[(size_t)k * 20 + 15 + a];
+          gmax = std::max(gmax, std::fabs(h_gk[iv.col0 + a]));
+        }
+      }
+    }
   }
 
   struct StepResult {
@@ -360,6 +400,77 @@ struct b200sfm_ba_problem {
       ctx->allreduce_sum(Sd.p, (size_t)C * 21);
     }
     B200_LAUNCH(ctx, ba_build_precond, cdiv(C, 128), 128, 0, C, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
+    const int m = m_intr;
+    const int npair = m * (m + 1) / 2, nacc = npair + m;
+    if (m > 0) {
+      // border B = U_ck - W_c Vinv W_k^T, Ck = U_kk + D_k - W_k Vinv W_k^T, b_k
+      B200_CUDA_OK(cudaMemcpyAsync(Bmat.p, Buck.p, Buck.bytes(), cudaMemcpyDeviceToDevice, s));
+      if (points_var) {
+        B200_LAUNCH(ctx, ba_intr_points, n_tiles, kTile, smem_ki, v, cam_rec.p, intr_rec.p, ivar.p, points[cur].p,
+                    o.thres_loss_function, m, spk.p, Bmat.p, part_tile.p);
+        B200_LAUNCH(ctx, ba_colsum, nacc, 256, 0, n_tiles, nacc, part_tile.p, tile_sum.p);
+      } else {
+        tile_sum.zero(s);
+        spk.zero(s);
+      }
+      ctx->allreduce_sum(Bmat.p, (size_t)C * 6 * m);
+      ctx->allreduce_sum(tile_sum.p, nacc);
+      B200_LAUNCH(ctx, ba_border_mask, cdiv(nC6, 256), 256, 0, C, m, jscale_c.p, Bmat.p);
+      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, tile_sum.p, nacc * sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      const double* ts = ctx->h_scal + 64;
+      std::vector<double> Ck((size_t)m * m, 0.0);
+      h_Dk.assign(m, 0.0);
+      h_bk.assign(m, 0.0);
+      for (int k = 0; k < K; ++k) {
+        const b200::IntrVarRec& iv = h_ivar[k];
+        for (int a = 0; a < iv.mb; ++a)
+          for (int c2 = a; c2 < iv.mb; ++c2) {
+            const double u = h_ukk[(size_t)k * 20 + (a * kMaxBlockDof - a * (a - 1) / 2) + (c2 - a)];
+            Ck[(size_t)(iv.col0 + a) * m + iv.col0 + c2] = u;
+            Ck[(size_t)(iv.col0 + c2) * m + iv.col0 + a] = u;
+          }
+      }
+      for (int a = 0; a < m; ++a) {
+        const double d = Ck[(size_t)a * m + a], js2 = h_js_k[a] * h_js_k[a];
+        h_Dk[a] = std::min(std::max(d * js2, 1e-6), 1e32) / (radius * js2);
+        for (int c2 = 0; c2 <= a; ++c2) {   // Schur part: pair (a, c2), c2 <= a
+          const double sv = ts[a * (a + 1) / 2 + c2];
+          Ck[(size_t)a * m + c2] -= sv;
+          if (c2 != a) Ck[(size_t)c2 * m + a] -= sv;
+        }
+        Ck[(size_t)a * m + a] += h_Dk[a];
+        h_bk[a] = -(h_gk[a] - ts[npair + a]);
+      }
+      // invert Ck (SPD, tiny) by Gauss-Jordan with partial pivoting
+      h_CkInv.assign((size_t)m * m, 0.0);
+      for (int a = 0; a < m; ++a) h_CkInv[(size_t)a * m + a] = 1.0;
+      for (int col = 0; col < m; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < m; ++r)
+          if (std::fabs(Ck[(size_t)r * m + col]) > std::fabs(Ck[(size_t)piv * m + col])) piv = r;
+        if (piv != col)
+          for (int c2 = 0; c2 < m; ++c2) {
+            std::swap(Ck[(size_t)piv * m + c2], Ck[(size_t)col * m + c2]);
+            std::swap(h_CkInv[(size_t)piv * m + c2], h_CkInv[(size_t)col * m + c2]);
+          }
+        const double d = Ck[(size_t)col * m + col];
+        const double inv = d != 0.0 ? 1.0 / d : 0.0;
+        for (int c2 = 0; c2 < m; ++c2) { Ck[(size_t)col * m + c2] *= inv; h_CkInv[(size_t)col * m + c2] *= inv; }
+        for (int r = 0; r < m; ++r) {
+          if (r == col) continue;
+          const double f = Ck[(size_t)r * m + col];
+          if (f == 0.0) continue;
+          for (int c2 = 0; c2 < m; ++c2) { Ck[(size_t)r * m + c2] -= f * Ck[(size_t)col * m + c2]; h_CkInv[(size_t)r * m + c2] -= f * h_CkInv[(size_t)col * m + c2]; }
+        }
+      }
+      std::vector<double> vv(m, 0.0);
+      for (int a = 0; a < m; ++a)
+        for (int c2 = 0; c2 < m; ++c2) vv[a] += h_CkInv[(size_t)a * m + c2] * h_bk[c2];
+      B200_CUDA_OK(cudaMemcpyAsync(CkInv.p, h_CkInv.data(), (size_t)m * m * sizeof(double), cudaMemcpyHostToDevice, s));
+      B200_CUDA_OK(cudaMemcpyAsync(vvec.p, vv.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // vv is a local
+    }
     // right-hand side b = -(gc - W Vinv gp)
     if (points_var) {
       yw.zero(s);
@@ -367,6 +478,7 @@ struct b200sfm_ba_problem {
       ctx->allreduce_sum(yw.p, nC6);
     }
     B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yw.p : nullptr, bvec.p);
+    if (m > 0) B200_LAUNCH(ctx, ba_border_rhs, cdiv(nC6, 256), 256, 0, C, m, Bmat.p, vvec.p, jscale_c.p, bvec.p);
     // ---- PCG ------------------------------------------------------------------
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(C, kPcgThreads);
@@ -399,6 +511,10 @@ struct b200sfm_ba_problem {
           ctx->allreduce_sum(yw.p, nC6);
         }
         B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, part_pq);
+        if (m > 0) {   // q -= B Ck^-1 B^T p
+          B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, pp.p, part_bt.p);
+          B200_LAUNCH(ctx, pcg_border_apply, nblk, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, pp.p, pq.p, part_pq, nullptr);
+        }
         B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq,
                     part_rz, part_rr, d_it);
         B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, C, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
@@ -414,9 +530,41 @@ struct b200sfm_ba_problem {
     // ---- back-substitution + candidate ------------------------------------------
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));
     const int nxt = cur ^ 1;
+    double gk_dot = 0, dk_D = 0, dk_norm2 = 0, xk_norm2 = 0;
+    if (m > 0) {
+      // dk = Ck^-1 (b_k - B^T dc); candidate intrinsics
+      B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, px.p, part_bt.p);
+      B200_LAUNCH(ctx, pcg_border_apply, 1, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, px.p, nullptr, nullptr, tvec.p);
+      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, tvec.p, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      h_dk.assign(m, 0.0);
+      for (int a = 0; a < m; ++a)
+        for (int c2 = 0; c2 < m; ++c2) h_dk[a] += h_CkInv[(size_t)a * m + c2] * (h_bk[c2] - ctx->h_scal[64 + c2]);
+      h_intr_cand = h_intr;
+      for (int k = 0; k < K; ++k) {
+        const b200::IntrVarRec& iv = h_ivar[k];
+        for (int a = 0; a < iv.mb; ++a) h_intr_cand[(size_t)k * B200SFM_INTR_STRIDE + iv.pidx[a]] += h_dk[iv.col0 + a];
+        if (iv.mb > 0) {
+          static const int npar[4] = {3, 4, 4, 5};
+          for (int j = 0; j < npar[h_intr_model[k]]; ++j) {
+            const double x0 = h_intr[(size_t)k * B200SFM_INTR_STRIDE + j];
+            xk_norm2 += x0 * x0;
+          }
+        }
+      }
+      for (int a = 0; a < m; ++a) {
+        gk_dot += h_gk[a] * h_dk[a];
+        dk_D += h_Dk[a] * h_dk[a] * h_dk[a];
+        dk_norm2 += h_dk[a] * h_dk[a];
+      }
+      B200_CUDA_OK(cudaMemcpyAsync(dkv.p, h_dk.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
+      B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, h_intr_cand.data(), h_intr_cand.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+      B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, intr.p, intr.bytes(), cudaMemcpyDeviceToDevice, s));
+    }
     if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
-                  scal.p + 2);
+                  scal.p + 2, spk.p, dkv.p, m);
     } else {
       B200_CUDA_OK(cudaMemcpyAsync(points[nxt].p, points[cur].p, points[cur].bytes(), cudaMemcpyDeviceToDevice, s));
     }
@@ -433,12 +581,12 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaStreamSynchronize(s));
     double* h = ctx->h_scal;
     for (int k = 8; k <= 12; ++k) h[k] /= (double)ctx->world;
-    const double g_dot_d = h[8] + h[2];
-    const double dDd = h[10] + h[3];
+    const double g_dot_d = h[8] + h[2] + gk_dot;
+    const double dDd = h[10] + h[3] + dk_D;
     res.model_cost_change = 0.5 * (-g_dot_d + h[9] + dDd);
     res.cand_cost = h[6];
-    res.step_norm = std::sqrt(h[11] + h[4]);
-    res.x_norm = std::sqrt(h[12] + h[5]);
+    res.step_norm = std::sqrt(h[11] + h[4] + dk_norm2);
+    res.x_norm = std::sqrt(h[12] + h[5] + xk_norm2);
     if (!std::isfinite(res.model_cost_change) || !std::isfinite(res.cand_cost)) res.finite = false;
     return res;
   }
@@ -448,7 +596,42 @@ struct b200sfm_ba_problem {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     if (o.optimize_rig_poses) { ctx->err = "optimize_rig_poses: non-trivial rigs are not supported"; return B200SFM_ERR_UNSUPPORTED; }
-    if (o.optimize_intrinsics) { ctx->err = "optimize_intrinsics=1 is not implemented on the device yet"; return B200SFM_ERR_UNSUPPORTED; }
+    m_intr = 0;
+    if (o.optimize_intrinsics) {
+      // variable parameters per block: all but the principal point unless optimize_principal_point
+      // (SubsetManifold, bundle_adjustment.cc:273-286); order = ascending parameter index
+      static const int nfoc[4][3] = {{0, -1, -1}, {0, 1, -1}, {0, 3, -1}, {0, 3, 4}};
+      static const int pp[4][2] = {{1, 2}, {2, 3}, {1, 2}, {1, 2}};
+      h_ivar.assign(K, b200::IntrVarRec{});
+      for (int k = 0; k < K; ++k) {
+        std::vector<int> idx;
+        for (int j = 0; j < 3; ++j)
+          if (nfoc[h_intr_model[k]][j] >= 0) idx.push_back(nfoc[h_intr_model[k]][j]);
+        if (o.optimize_principal_point) { idx.push_back(pp[h_intr_model[k]][0]); idx.push_back(pp[h_intr_model[k]][1]); }
+        std::sort(idx.begin(), idx.end());
+        h_ivar[k].col0 = m_intr;
+        h_ivar[k].mb = (int)idx.size();
+        for (size_t j = 0; j < idx.size(); ++j) h_ivar[k].pidx[j] = idx[j];
+        m_intr += (int)idx.size();
+      }
+      if (m_intr > kMaxIntrDof) {
+        ctx->err = "optimize_intrinsics: " + std::to_string(m_intr) + " variable intrinsics parameters exceed the dense-border limit (" +
+                   std::to_string(kMaxIntrDof) + "); per-image intrinsics are not supported yet";
+        m_intr = 0;
+        return B200SFM_ERR_UNSUPPORTED;
+      }
+      const int m = m_intr, nacc = m * (m + 1) / 2 + m;
+      ivar.alloc(K);
+      B200_CUDA_OK(cudaMemcpyAsync(ivar.p, h_ivar.data(), K * sizeof(b200::IntrVarRec), cudaMemcpyHostToDevice, s));
+      Buck.alloc((size_t)C * 6 * m); Bmat.alloc((size_t)C * 6 * m); spk.alloc((size_t)P * 3 * m);
+      part_seg.alloc((size_t)std::max(n_segs, 1) * 20); intr_out.alloc((size_t)K * 20);
+      part_tile.alloc((size_t)n_tiles * nacc); tile_sum.alloc(nacc); CkInv.alloc((size_t)m * m); vvec.alloc(m);
+      part_bt.alloc((size_t)cdiv(C, kPcgThreads) * m); tvec.alloc(m); dkv.alloc(m);
+      if ((size_t)K * 20 + 64 > (size_t)b200sfm_ctx::kHScal) { ctx->err = "too many intrinsics blocks"; return B200SFM_ERR_UNSUPPORTED; }
+      h_intr.resize((size_t)K * B200SFM_INTR_STRIDE);
+      B200_CUDA_OK(cudaMemcpyAsync(h_intr.data(), intr.p, h_intr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+    }
     const long long launches0 = ctx->launches;
     timer_lin.reset();
     timer_mv.reset();
@@ -493,6 +676,8 @@ struct b200sfm_ba_problem {
       const double rel = (cost - r.cand_cost) / r.model_cost_change;
       if (rel > 1e-3) {
         cur ^= 1;
+        std::swap(intr.p, intr_cand.p);   // the candidate intrinsics become current (buffers have equal size)
+        if (m_intr > 0) h_intr = h_intr_cand;
         ++local.num_successful_steps;
         linearize(o.thres_loss_function, points_var, false, profile, cost, gmax);
         radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));

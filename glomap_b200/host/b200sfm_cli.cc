@@ -242,7 +242,7 @@ static int RunFlat(int argc, char** argv, bool is_ba) {
   bool ok;
   if (is_ba) {
     BundleAdjusterOptions o;
-    o.optimize_intrinsics = false;
+    o.optimize_intrinsics = args.count("optimize_intrinsics") && args["optimize_intrinsics"] == "1";
     if (args.count("pcg_tol")) o.pcg_rel_tolerance = std::stod(args["pcg_tol"]);
     BundleAdjuster ba(o);
     if (args.count("fix_rotations") && args["fix_rotations"] == "1") {

@@ -116,7 +116,7 @@ typedef struct {
   int32_t optimize_rig_poses;        /* must be 0: non-trivial rigs unsupported (B200SFM_ERR_UNSUPPORTED) */
   int32_t optimize_rotations;        /* default 1 */
   int32_t optimize_translation;      /* default 1 */
-  int32_t optimize_intrinsics;       /* default 1 in the reference */
+  int32_t optimize_intrinsics;       /* default 1 in the reference; shared blocks, <= 12 variable parameters in total */
   int32_t optimize_principal_point;  /* default 0 */
   int32_t optimize_points;           /* default 1 */
   int32_t min_num_view_per_track;    /* default 3 */

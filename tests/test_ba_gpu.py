@@ -184,3 +184,65 @@ def test_medium_scene_against_c_oracle_and_properties():
     assert rot < 1e-4 and cen < 1e-6
     ok2, dev2, st2 = _device_solve(dev, mask, tol=1e-10)
     assert ok2 and st2.iterations <= 2 and abs(st2.final_cost - st.final_cost) <= 1e-5 * st.final_cost
+
+
+# ---------------------------------------------------------------------------
+# optimize_intrinsics (the reference default, bundle_adjustment.h:18-19, .cc:273-293)
+# ---------------------------------------------------------------------------
+def _device_solve_intr(init, mask, tol=1e-12, **kw):
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=True, **kw)
+    opts.solver_options.pcg_rel_tolerance = tol
+    opts.solver_options.pcg_max_iterations = 3000
+    ba = E.BundleAdjuster(opts)
+    dev = init.copy()
+    ok = ba.Solve(dev, mask)
+    return ok, dev, ba.summary
+
+
+@pytest.mark.parametrize("model,K,pp", [(S.SIMPLE_RADIAL, 1, False), (S.SIMPLE_PINHOLE, 2, False), (S.RADIAL, 1, False),
+                                        (S.PINHOLE, 2, True)])
+def test_intrinsics_refinement_matches_oracle(model, K, pp):
+    """Shared intrinsics blocks refined with the principal point held fixed
+    (SubsetManifold, bundle_adjustment.cc:273-286) or free."""
+    sc = S.make_scene(24, 700, mean_track_len=7, seed=41, pixel_sigma=0.3, model=model, num_intrinsics=K)
+    init = S.perturb_scene(sc, rot_deg=0.2, center_frac=0.004, point_frac=0.004)
+    init.intr_params = sc.intr_params.copy()
+    init.intr_params[:, 0] *= 1.01
+    if model in (S.SIMPLE_RADIAL, S.RADIAL):
+        init.intr_params[:, 3] = 0.0
+    mask = E.first_frame_mask(sc.C)
+    ok, dev, st = _device_solve_intr(init, mask, optimize_principal_point=pp)
+    x, summ = B.solve_ba(*_oracle_args(sc, init)[:8], init.intr_params,
+                         B.BAOptions(optimize_intrinsics=True, optimize_principal_point=pp), mask)
+    assert ok
+    assert st.iterations == summ.iterations, (st.iterations, summ.iterations)
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-7 * summ.final_cost
+    npar = S.MODEL_NUM_PARAMS[model]
+    assert np.abs(dev.intr_params[:, :npar] / x["intr"][:, :npar] - 1).max() < 1e-6
+    if not pp:   # principal point untouched
+        pp_idx = [2, 3] if model == S.PINHOLE else [1, 2]
+        assert np.array_equal(dev.intr_params[:, pp_idx], init.intr_params[:, pp_idx])
+    rot, cen = _compare(dev, x)
+    assert rot < 1e-4 and cen < 1e-5
+
+
+def test_intrinsics_recover_ground_truth_noise_free():
+    sc = S.make_scene(24, 700, mean_track_len=7, seed=42, model=S.SIMPLE_RADIAL)
+    init = S.perturb_scene(sc, rot_deg=0.2, center_frac=0.004, point_frac=0.004)
+    init.intr_params = sc.intr_params.copy()
+    init.intr_params[0, 0] *= 1.02
+    init.intr_params[0, 3] = 0.0
+    ok, dev, st = _device_solve_intr(init, E.first_frame_mask(sc.C), tol=1e-10)
+    assert ok and abs(dev.intr_params[0, 0] / sc.intr_params[0, 0] - 1) < 1e-6
+    assert abs(dev.intr_params[0, 3] - sc.intr_params[0, 3]) < 1e-6
+    rot, cen = _compare(dev, dict(quat=sc.quat, trans=sc.trans))
+    assert rot < 1e-2 and cen < 1e-4
+
+
+def test_too_many_intrinsics_blocks_is_reported():
+    sc = S.make_scene(10, 100, mean_track_len=5, seed=43, model=S.RADIAL, num_intrinsics=6)
+    init = S.perturb_scene(sc)
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=True)
+    with pytest.raises(E.B200Error):
+        E.BundleAdjuster(opts).Solve(init, E.first_frame_mask(sc.C))
