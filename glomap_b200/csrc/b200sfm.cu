@@ -426,6 +426,13 @@ void b200sfm_ra_default_opts(b200sfm_ra_opts* o) {
 int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int64_t n_edges,
                      const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
                      int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats) {
+  return b200sfm_ra_solve_gravity(ctx, opts, n_frames, n_edges, ei, ej, R_rel, edge_w, nullptr, fixed_frame, theta, stats);
+}
+
+int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int64_t n_edges,
+                             const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
+                             const uint8_t* frame_has_gravity, int32_t fixed_frame, double* theta,
+                             b200sfm_ra_stats* stats) {
   if (!ctx || !opts || !theta) return B200SFM_ERR_INVALID_ARG;
   if (n_frames <= 0) { ctx->err = "no frames"; return B200SFM_ERR_EMPTY; }
   if (n_edges < 0 || (n_edges > 0 && (!ei || !ej || !R_rel))) { ctx->err = "null edge array"; return B200SFM_ERR_INVALID_ARG; }
@@ -436,7 +443,7 @@ int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_fr
   int rc = guarded(ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(ctx->device));
     b200sfm_ra_problem p;
-    p.create(ctx, n_frames, n_edges, ei, ej, R_rel, edge_w, opts->use_weight, fixed_frame, theta);
+    p.create(ctx, n_frames, n_edges, ei, ej, R_rel, edge_w, opts->use_weight, fixed_frame, theta, frame_has_gravity);
     int r = p.solve(*opts, &st);
     if (r != B200SFM_OK) return r;
     p.theta.download(theta, (size_t)n_frames * 3, ctx->stream);

@@ -24,9 +24,27 @@ struct RAView {
   long long E;            // local edges including the gauge pseudo-edge (rank 0)
   const int* ei;
   const int* ej;
-  const double* Rrel;     // [E][9] row-major
+  const double* Rrel;     // [E][9] row-major (gravity-aligned when use_gravity, .cc:311-326)
   const double* w_edge;   // [E] weights_ (.cc:466-472)
+  // use_gravity (1-DoF frames, .cc:207-217): frames with gravity keep theta = (0, phi, 0) and
+  // only their y slot is an unknown; pairs of two gravity frames carry ONE row (.cc:387-394)
+  const unsigned char* node_grav;   // [n] or nullptr
+  const double* angle_rel;          // [E] y angle of R_rel (both-gravity pairs / gravity gauge), or nullptr
+  const double* xz_err;             // [E] x^2 + z^2 of log(R_rel) (.cc:330-337), or nullptr
 };
+
+// which rows / coefficients an edge has
+struct EdgeRows {
+  bool gi, gj, y_only;
+};
+__device__ __forceinline__ EdgeRows edge_rows(const RAView& v, int i, int j) {
+  EdgeRows r;
+  r.gi = v.node_grav && i >= 0 && v.node_grav[i];
+  r.gj = v.node_grav && v.node_grav[j];
+  r.y_only = (i >= 0) ? (r.gi && r.gj) : r.gj;   // gauge rows: 1 row if the fixed frame has gravity (.cc:449-453)
+  return r;
+}
+__device__ __forceinline__ double coef(bool grav, int k) { return (!grav || k == 1) ? 1.0 : 0.0; }
 
 // AngleAxisToRotation (math/rigid3d.cc:45-63): first-order fallback below EPS
 __device__ __forceinline__ void aa_to_R(const double v[3], double R[9]) {
@@ -112,6 +130,34 @@ __global__ void ra_residuals(RAView v, const double* __restrict__ theta, int mod
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= v.E) return;
   const int i = v.ei[e], j = v.ej[e];
+  const EdgeRows er = edge_rows(v, i, j);
+  if (er.y_only) {
+    // RelAngleError (.cc:19-36; the rand() jitter near +-pi is not reproduced) / gravity gauge row (.cc:746-749)
+    const double pi_ = 3.14159265358979323846;
+    double est = theta[3 * (size_t)j + 1] - (i >= 0 ? theta[3 * (size_t)i + 1] : 0.0) - v.angle_rel[e];
+    if (i >= 0) {
+      while (est >= pi_) est -= 2 * pi_;
+      while (est < -pi_) est += 2 * pi_;
+    }
+    res[3 * e] = 0.0;
+    res[3 * e + 1] = est;
+    res[3 * e + 2] = 0.0;
+    double wgt = v.w_edge[e];
+    if (i >= 0 && mode != 0) {
+      const double e2 = est * est + v.xz_err[e];
+      double wi;
+      if (mode == 1) {
+        const double tmp = e2 + sigma2;
+        wi = sigma2 / (tmp * tmp);
+      } else {
+        wi = pow(e2, (0.5 - 2.0) / 2.0);
+      }
+      if (isnan(wi)) atomicOr(flags, 1);
+      wgt *= wi;
+    }
+    w_out[e] = wgt;
+    return;
+  }
   double Rrel[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) Rrel[k] = v.Rrel[9 * e + k];
@@ -156,16 +202,20 @@ __global__ void ra_scatter(RAView v, const double* __restrict__ w, int square, c
   const int i = v.ei[e], j = v.ej[e];
   double we = w[e];
   if (square) we *= we;
-  const double a0 = we * vec[3 * e], a1 = we * vec[3 * e + 1], a2 = we * vec[3 * e + 2];
-  atomicAdd(&out[3 * (size_t)j], a0);
-  atomicAdd(&out[3 * (size_t)j + 1], a1);
-  atomicAdd(&out[3 * (size_t)j + 2], a2);
-  if (deg) atomicAdd(&deg[j], we);
-  if (i >= 0) {
-    atomicAdd(&out[3 * (size_t)i], -a0);
-    atomicAdd(&out[3 * (size_t)i + 1], -a1);
-    atomicAdd(&out[3 * (size_t)i + 2], -a2);
-    if (deg) atomicAdd(&deg[i], we);
+  const EdgeRows er = edge_rows(v, i, j);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (er.y_only && k != 1) continue;
+    const double a = we * vec[3 * e + k];
+    const double cj = coef(er.gj, k);
+    if (cj != 0.0) {
+      atomicAdd(&out[3 * (size_t)j + k], a);
+      if (deg) atomicAdd(&deg[3 * (size_t)j + k], we);
+    }
+    if (i >= 0 && coef(er.gi, k) != 0.0) {
+      atomicAdd(&out[3 * (size_t)i + k], -a);
+      if (deg) atomicAdd(&deg[3 * (size_t)i + k], we);
+    }
   }
 }
 
@@ -177,20 +227,16 @@ __global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square,
   const int i = v.ei[e], j = v.ej[e];
   double we = w[e];
   if (square) we *= we;
-  double t0 = x[3 * (size_t)j], t1 = x[3 * (size_t)j + 1], t2 = x[3 * (size_t)j + 2];
-  if (i >= 0) {
-    t0 -= x[3 * (size_t)i];
-    t1 -= x[3 * (size_t)i + 1];
-    t2 -= x[3 * (size_t)i + 2];
-  }
-  t0 *= we; t1 *= we; t2 *= we;
-  atomicAdd(&y[3 * (size_t)j], t0);
-  atomicAdd(&y[3 * (size_t)j + 1], t1);
-  atomicAdd(&y[3 * (size_t)j + 2], t2);
-  if (i >= 0) {
-    atomicAdd(&y[3 * (size_t)i], -t0);
-    atomicAdd(&y[3 * (size_t)i + 1], -t1);
-    atomicAdd(&y[3 * (size_t)i + 2], -t2);
+  const EdgeRows er = edge_rows(v, i, j);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (er.y_only && k != 1) continue;
+    const double cj = coef(er.gj, k), ci = (i >= 0) ? coef(er.gi, k) : 0.0;
+    double t = cj * x[3 * (size_t)j + k];
+    if (ci != 0.0) t -= x[3 * (size_t)i + k];
+    t *= we;
+    if (cj != 0.0) atomicAdd(&y[3 * (size_t)j + k], t);
+    if (ci != 0.0) atomicAdd(&y[3 * (size_t)i + k], -t);
   }
 }
 
@@ -198,10 +244,9 @@ __global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square,
 __global__ void ra_build_precond(int n, const double* __restrict__ deg, double* __restrict__ Minv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double d = deg[i];
-  const double inv = d > 0.0 ? 1.0 / d : 1.0;
+  const double d0 = deg[3 * (size_t)i], d1 = deg[3 * (size_t)i + 1], d2 = deg[3 * (size_t)i + 2];
   double* m = Minv + 6 * (size_t)i;
-  m[0] = inv; m[1] = 0; m[2] = 0; m[3] = inv; m[4] = 0; m[5] = inv;
+  m[0] = d0 > 0.0 ? 1.0 / d0 : 1.0; m[1] = 0; m[2] = 0; m[3] = d1 > 0.0 ? 1.0 / d1 : 1.0; m[4] = 0; m[5] = d2 > 0.0 ? 1.0 / d2 : 1.0;
 }
 
 // b = w * r  (row-weighted residual of the L1 stage); norms[0] += |b|^2
@@ -239,11 +284,13 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
     const int i = v.ei[e], j = v.ej[e];
     const double we = w[e];
     const double kappa = 1.0 / rho;
-    double r3[3], s3[3], u3[3];
+    const EdgeRows er = edge_rows(v, i, j);
+    double r3[3] = {0, 0, 0}, s3[3] = {0, 0, 0}, u3[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      double a = x[3 * (size_t)j + k];
-      if (i >= 0) a -= x[3 * (size_t)i + k];
+      if (er.y_only && k != 1) continue;   // this row does not exist
+      double a = coef(er.gj, k) * x[3 * (size_t)j + k];
+      if (i >= 0) a -= coef(er.gi, k) * x[3 * (size_t)i + k];
       a *= we;
       const double bo = b[3 * e + k], zo = z[3 * e + k], uo = u[3 * e + k];
       const double vv = a - bo + uo;
@@ -261,10 +308,13 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      atomicAdd(&rhs[3 * (size_t)j + k], r3[k]);
-      atomicAdd(&svec[3 * (size_t)j + k], s3[k]);
-      atomicAdd(&uvec[3 * (size_t)j + k], u3[k]);
-      if (i >= 0) {
+      if (er.y_only && k != 1) continue;
+      if (coef(er.gj, k) != 0.0) {
+        atomicAdd(&rhs[3 * (size_t)j + k], r3[k]);
+        atomicAdd(&svec[3 * (size_t)j + k], s3[k]);
+        atomicAdd(&uvec[3 * (size_t)j + k], u3[k]);
+      }
+      if (i >= 0 && coef(er.gi, k) != 0.0) {
         atomicAdd(&rhs[3 * (size_t)i + k], -r3[k]);
         atomicAdd(&svec[3 * (size_t)i + k], -s3[k]);
         atomicAdd(&uvec[3 * (size_t)i + k], -u3[k]);
@@ -284,7 +334,8 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
 // UpdateGlobalRotations (.cc:631-640): theta <- log(exp(theta) exp(-step));
 // sums[0] += |step_i| (ComputeAverageStepSize .cc:758-772), sums[1] += |step|^2,
 // sums[2] = NaN flag
-__global__ void ra_update(int n, double* __restrict__ theta, const double* __restrict__ step, double* __restrict__ sums) {
+__global__ void ra_update(int n, double* __restrict__ theta, const double* __restrict__ step, double* __restrict__ sums,
+                          const unsigned char* __restrict__ node_grav) {
   __shared__ double scratch[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double s1 = 0, s2 = 0, bad = 0;
@@ -293,10 +344,16 @@ __global__ void ra_update(int n, double* __restrict__ theta, const double* __res
     const double nd[3] = {-d[0], -d[1], -d[2]};
     const double t[3] = {theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2]};
     double R[9], Rd[9], M[9], out[3];
-    aa_to_R(t, R);
-    aa_to_R(nd, Rd);
-    mat3_mul(R, Rd, M);
-    R_to_aa(M, out);
+    if (node_grav && node_grav[i]) {       // 1-DoF frame: phi -= step (.cc:641-643)
+      out[0] = 0.0;
+      out[1] = t[1] - d[1];
+      out[2] = 0.0;
+    } else {
+      aa_to_R(t, R);
+      aa_to_R(nd, Rd);
+      mat3_mul(R, Rd, M);
+      R_to_aa(M, out);
+    }
     theta[3 * (size_t)i] = out[0];
     theta[3 * (size_t)i + 1] = out[1];
     theta[3 * (size_t)i + 2] = out[2];

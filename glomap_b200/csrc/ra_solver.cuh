@@ -17,17 +17,24 @@ struct b200sfm_ra_problem {
   long long E_total = 0;  // valid edges over all ranks
   int fixed = 0;
   DevBuf<int> ei, ej, flags;
+  DevBuf<unsigned char> node_grav;
+  DevBuf<double> angle_rel, xz_err;
+  bool has_grav = false;
+  long long rows_total = 0;
   DevBuf<double> Rrel, w_edge, theta, res, w, b, z, u;
   DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, dots, part, scal;
 
   b200::RAView view() {
     b200::RAView v;
     v.n = n; v.E = E; v.ei = ei.p; v.ej = ej.p; v.Rrel = Rrel.p; v.w_edge = w_edge.p;
+    v.node_grav = has_grav ? node_grav.p : nullptr;
+    v.angle_rel = has_grav ? angle_rel.p : nullptr;
+    v.xz_err = has_grav ? xz_err.p : nullptr;
     return v;
   }
 
   void create(b200sfm_ctx* c, int n_, long long E_, const int32_t* h_ei, const int32_t* h_ej, const double* h_Rrel,
-              const double* h_w, int use_weight, int fixed_, const double* h_theta) {
+              const double* h_w, int use_weight, int fixed_, const double* h_theta, const uint8_t* h_grav = nullptr) {
     using namespace b200;
     ctx = c; n = n_; E_real = E_; fixed = fixed_;
     cudaStream_t s = ctx->stream;
@@ -57,25 +64,68 @@ struct b200sfm_ra_problem {
       hr.insert(hr.end(), R, R + 9);
       hw.push_back(1.0);
     }
+    // use_gravity: y angle / xz error of the (gravity-aligned) relative rotations (.cc:328-337)
+    has_grav = h_grav != nullptr;
+    std::vector<double> h_ang((size_t)E, 0.0), h_xz((size_t)E, 0.0);
+    long long rows_local = 0;
+    for (long long e = 0; e < E; ++e) {
+      const int i = hi[e], j = hj[e];
+      const bool gi = has_grav && i >= 0 && h_grav[i], gj = has_grav && h_grav[j];
+      const bool y_only = (i >= 0) ? (gi && gj) : gj;
+      rows_local += y_only ? 1 : 3;
+      if (!y_only) continue;
+      if (i < 0) { h_ang[e] = h_theta[3 * (size_t)j + 1]; continue; }   // gauge: phi_fixed(initial)
+      const double* R = &hr[9 * (size_t)e];
+      // Eigen matrix -> quaternion -> angle-axis (math/rigid3d.cc:39-43)
+      double q[4];
+      const double t = R[0] + R[4] + R[8];
+      if (t > 0.0) {
+        double tt = std::sqrt(t + 1.0);
+        q[3] = 0.5 * tt; tt = 0.5 / tt;
+        q[0] = (R[7] - R[5]) * tt; q[1] = (R[2] - R[6]) * tt; q[2] = (R[3] - R[1]) * tt;
+      } else {
+        int a = 0;
+        if (R[4] > R[0]) a = 1;
+        if (R[8] > R[4 * a]) a = 2;
+        const int b2 = (a + 1) % 3, c2 = (a + 2) % 3;
+        double tt = std::sqrt(R[4 * a] - R[4 * b2] - R[4 * c2] + 1.0);
+        q[a] = 0.5 * tt; tt = 0.5 / tt;
+        q[3] = (R[3 * c2 + b2] - R[3 * b2 + c2]) * tt; q[b2] = (R[3 * b2 + a] + R[3 * a + b2]) * tt; q[c2] = (R[3 * c2 + a] + R[3 * a + c2]) * tt;
+      }
+      const double nv = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+      double aa[3] = {0, 0, 0};
+      if (nv > 0) {
+        const double ang = 2.0 * std::atan2(nv, std::fabs(q[3]));
+        const double f = (q[3] < 0 ? -ang : ang) / nv;
+        aa[0] = q[0] * f; aa[1] = q[1] * f; aa[2] = q[2] * f;
+      }
+      h_ang[e] = aa[1];
+      h_xz[e] = aa[0] * aa[0] + aa[2] * aa[2];
+    }
     const size_t Ea = (size_t)std::max<long long>(E, 1);
+    if (has_grav) {
+      node_grav.alloc(n); angle_rel.alloc(Ea); xz_err.alloc(Ea);
+      node_grav.upload(h_grav, n, s); angle_rel.upload(h_ang.data(), E, s); xz_err.upload(h_xz.data(), E, s);
+    }
     ei.alloc(Ea); ej.alloc(Ea); Rrel.alloc(Ea * 9); w_edge.alloc(Ea); flags.alloc(4);
     ei.upload(hi.data(), E, s); ej.upload(hj.data(), E, s); Rrel.upload(hr.data(), (size_t)E * 9, s); w_edge.upload(hw.data(), E, s);
     theta.alloc((size_t)n * 3);
     theta.upload(h_theta, (size_t)n * 3, s);
     res.alloc(Ea * 3); w.alloc(Ea); b.alloc(Ea * 3); z.alloc(Ea * 3); u.alloc(Ea * 3);
-    deg.alloc(n); Minv.alloc((size_t)n * 6); Azero.alloc((size_t)n * 6); Dzero.alloc((size_t)n * 3);
+    deg.alloc((size_t)n * 3); Minv.alloc((size_t)n * 6); Azero.alloc((size_t)n * 6); Dzero.alloc((size_t)n * 3);
     rhs.alloc((size_t)n * 9);   // rhs | svec | uvec contiguous for one all-reduce
     px.alloc((size_t)n * 3); pr.alloc((size_t)n * 3); pz.alloc((size_t)n * 3); pp.alloc((size_t)n * 3);
     pq.alloc((size_t)n * 3); yw.alloc((size_t)n * 3); scal.alloc(16);
     Azero.zero(s); Dzero.zero(s);
     {
-      const double cnt = (double)E_real;
-      B200_CUDA_OK(cudaMemcpyAsync(scal.p, &cnt, sizeof(double), cudaMemcpyHostToDevice, s));
-      ctx->allreduce_sum(scal.p, 1);
-      double tot = 0;
-      B200_CUDA_OK(cudaMemcpyAsync(&tot, scal.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+      const double cnt[2] = {(double)E_real, (double)rows_local};
+      B200_CUDA_OK(cudaMemcpyAsync(scal.p, cnt, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+      ctx->allreduce_sum(scal.p, 2);
+      double tot[2] = {0, 0};
+      B200_CUDA_OK(cudaMemcpyAsync(tot, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
       B200_CUDA_OK(cudaStreamSynchronize(s));
-      E_total = (long long)(tot + 0.5);
+      E_total = (long long)(tot[0] + 0.5);
+      rows_total = (long long)(tot[1] + 0.5);
     }
     B200_CUDA_OK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
@@ -141,7 +191,7 @@ struct b200sfm_ra_problem {
     B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 3 * sizeof(double), s));
     if (E > 0) B200_LAUNCH(ctx, ra_scatter, cdiv(E, 256), 256, 0, v, w.p, square, vec, rhs.p, deg.p);
     ctx->allreduce_sum(rhs.p, (size_t)n * 3);
-    ctx->allreduce_sum(deg.p, n);
+    ctx->allreduce_sum(deg.p, (size_t)n * 3);
     B200_LAUNCH(ctx, ra_build_precond, cdiv(n, 256), 256, 0, n, deg.p, Minv.p);
   }
 
@@ -150,7 +200,7 @@ struct b200sfm_ra_problem {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 8, 0, 4 * sizeof(double), s));
-    B200_LAUNCH(ctx, ra_update, cdiv(n, 256), 256, 0, n, theta.p, px.p, scal.p + 8);
+    B200_LAUNCH(ctx, ra_update, cdiv(n, 256), 256, 0, n, theta.p, px.p, scal.p + 8, has_grav ? node_grav.p : nullptr);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, scal.p + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     avg = ctx->h_scal[8] / n;
@@ -187,7 +237,7 @@ struct b200sfm_ra_problem {
         u.zero(s);
         prepare_system(1, res.p);   // rhs = A^T W^2 r = A_w^T b ; deg = sum w^2
         double b_norm2 = 0;
-        const double eps_pri_thr = std::sqrt(3.0 * (double)(E_total + 1)) * o.l1_absolute_tolerance;   // sqrt(rows)
+        const double eps_pri_thr = std::sqrt((double)rows_total) * o.l1_absolute_tolerance;   // sqrt(A.rows())
         const double eps_dual_thr = std::sqrt(3.0 * n) * o.l1_absolute_tolerance;
         for (int k = 0; k < o.l1_max_admm_iterations; ++k) {
           bool finite = true;

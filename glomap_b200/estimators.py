@@ -359,8 +359,7 @@ class GlobalPositioner:
 # ---------------------------------------------------------------------------
 @dataclasses.dataclass
 class RotationEstimatorOptions:
-    """global_rotation_averaging.h:39-75 (defaults identical).  use_gravity
-    (1-DoF frames) is not implemented on the device yet."""
+    """global_rotation_averaging.h:39-75 (defaults identical)."""
     GEMAN_MCCLURE = 0
     HALF_NORM = 1
     max_num_l1_iterations: int = 5
@@ -422,28 +421,72 @@ class RotationEstimator:
         self.ctx = ctx
         self.summary: _lib.RAStats | None = None
 
-    def EstimateRotations(self, vg, R_init: np.ndarray | None = None, fixed: int = 0):
+    def EstimateRotations(self, vg, R_init: np.ndarray | None = None, fixed: int = 0, gravity: np.ndarray | None = None):
         """Returns (ok, R [n,3,3] cam_from_world rotations).  False on a NaN
-        step/weight (.cc:508-512,590-593) or when gravity is requested."""
+        step/weight (.cc:508-512,590-593).  ``gravity`` [n,3] (NaN rows = no
+        gravity prior) is used when options.use_gravity: those frames become
+        1-DoF (.cc:207-217) and the initialisation is skipped (.cc:61-63)."""
         from . import geometry as geo
         o = self.options_
-        if o.use_gravity:
-            raise NotImplementedError("gravity-aligned (1-DoF) rotation averaging is not implemented on the device")
         n = vg.n_images
-        if not o.skip_initialization:
+        use_grav = o.use_gravity and gravity is not None
+        if not o.skip_initialization and not o.use_gravity:
             R0 = initialize_from_maximum_spanning_tree(vg, R_init)
         else:
-            R0 = np.tile(np.eye(3), (n, 1, 1)) if R_init is None else np.asarray(R_init)
-        theta = _c(geo.so3_log(R0), np.float64)
+            R0 = np.tile(np.eye(3), (n, 1, 1)) if R_init is None else np.asarray(R_init, dtype=np.float64)
         ctx = self.ctx or default_context()
         co = o.to_c()
         st = _lib.RAStats()
         ei, ej = _c(vg.ei, np.int32), _c(vg.ej, np.int32)
-        Rr, w = _c(vg.R_rel.reshape(-1, 9), np.float64), _c(vg.weight, np.float64)
-        rc = ctx.lib.b200sfm_ra_solve(ctx.handle, ct.byref(co), n, vg.E, _ptr(ei), _ptr(ej), _ptr(Rr), _ptr(w), fixed,
-                                      _ptr(theta), ct.byref(st))
+        w = _c(vg.weight, np.float64)
+        if not use_grav:
+            theta = _c(geo.so3_log(R0), np.float64)
+            Rr = _c(vg.R_rel.reshape(-1, 9), np.float64)
+            rc = ctx.lib.b200sfm_ra_solve(ctx.handle, ct.byref(co), n, vg.E, _ptr(ei), _ptr(ej), _ptr(Rr), _ptr(w), fixed,
+                                          _ptr(theta), ct.byref(st))
+            self.summary = st
+            if rc == 4:
+                return False, None
+            _lib.check(ctx.handle, rc)
+            return bool(st.usable), geo.so3_exp(theta)
+        # ---- gravity-aligned frames (host prep: SetupLinearSystem .cc:207-217,311-326) ----
+        g = np.asarray(gravity, dtype=np.float64)
+        hg = ~np.isnan(g).any(axis=1)
+        R_align = np.tile(np.eye(3), (n, 1, 1))
+        for i in np.nonzero(hg)[0]:
+            R_align[i] = get_align_rot(g[i])
+        theta = geo.so3_log(R0)
+        for i in np.nonzero(hg)[0]:
+            theta[i] = [0.0, geo.so3_log((R_align[i].T @ R0[i])[None])[0, 1], 0.0]     # RotUpToAngle
+        Rr = np.array(vg.R_rel, dtype=np.float64, copy=True)
+        gi, gj = hg[vg.ei], hg[vg.ej]
+        Rr[gi] = Rr[gi] @ R_align[vg.ei[gi]]
+        Rr[gj] = np.swapaxes(R_align[vg.ej[gj]], -1, -2) @ Rr[gj]
+        fixed = int(np.nonzero(hg)[0][0]) if hg.any() else fixed                          # .cc:213-217
+        theta = _c(theta, np.float64)
+        Rr = _c(Rr.reshape(-1, 9), np.float64)
+        hg8 = _c(hg, np.uint8)
+        rc = ctx.lib.b200sfm_ra_solve_gravity(ctx.handle, ct.byref(co), n, vg.E, _ptr(ei), _ptr(ej), _ptr(Rr), _ptr(w),
+                                              _ptr(hg8), fixed, _ptr(theta), ct.byref(st))
         self.summary = st
         if rc == 4:
             return False, None
         _lib.check(ctx.handle, rc)
-        return bool(st.usable), geo.so3_exp(theta)
+        R = geo.so3_exp(theta)
+        R[hg] = R_align[hg] @ R[hg]                                                       # ConvertResults .cc:787-793
+        return bool(st.usable), R
+
+
+def get_align_rot(gravity) -> np.ndarray:
+    """GetAlignRot (math/gravity.cc:11-24): rotation whose second column is the
+    gravity direction (any orthonormal completion; the 1-DoF angle absorbs the choice)."""
+    v = np.asarray(gravity, dtype=np.float64)
+    v = v / np.linalg.norm(v)
+    a = np.array([1.0, 0, 0]) if abs(v[0]) < 0.9 else np.array([0, 0, 1.0])
+    x = np.cross(v, a)
+    x /= np.linalg.norm(x)
+    z = np.cross(x, v)
+    R = np.stack([x, v, z], axis=1)
+    if np.linalg.det(R) < 0:
+        R[:, 2] = -R[:, 2]
+    return R

@@ -289,6 +289,17 @@ int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_fr
                      const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
                      int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats);
 
+/* use_gravity variant (global_rotation_averaging.cc:207-217,311-340,386-421): frames flagged in
+ * frame_has_gravity carry ONE unknown, the angle about the gravity axis, passed as theta = (0, phi, 0)
+ * with phi = RotUpToAngle(R_align^T R) (.cc:208-210); R_rel must already be gravity-aligned by the host
+ * (R_align2^T R_rel R_align1, .cc:311-326); fixed_frame must be the first frame with gravity if any
+ * (.cc:213-217).  Pairs of two gravity frames contribute one row; the rand() jitter of RelAngleError
+ * near +-pi (.cc:28-33) is not reproduced.  frame_has_gravity == NULL is b200sfm_ra_solve. */
+int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int64_t n_edges,
+                             const int32_t* ei, const int32_t* ej, const double* R_rel, const double* edge_w,
+                             const uint8_t* frame_has_gravity, int32_t fixed_frame, double* theta,
+                             b200sfm_ra_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -240,3 +240,161 @@ def max_pairwise_rotation_error_deg(theta, R_gt):
         c = np.clip((np.trace(M, axis1=-2, axis2=-1) - 1) / 2, -1, 1)
         worst = max(worst, float(np.degrees(np.arccos(c)).max()))
     return worst
+
+
+# ---------------------------------------------------------------------------
+# Gravity-aligned (1-DoF) frames -- options_.use_gravity
+# ---------------------------------------------------------------------------
+def get_align_rot(gravity):
+    """GetAlignRot (math/gravity.cc:11-24): a rotation whose second column is
+    the (normalised) gravity direction.  The other two columns are any
+    orthonormal completion (the reference takes them from a Householder QR;
+    a different completion only shifts the 1-DoF angle by a constant)."""
+    v = np.asarray(gravity, dtype=np.float64)
+    v = v / np.linalg.norm(v)
+    a = np.array([1.0, 0, 0]) if abs(v[0]) < 0.9 else np.array([0, 0, 1.0])
+    x = np.cross(v, a); x /= np.linalg.norm(x)
+    z = np.cross(x, v)
+    R = np.stack([x, v, z], axis=1)
+    if np.linalg.det(R) < 0:
+        R[:, 2] = -R[:, 2]
+    return R
+
+
+def rel_angle_error(angle_12, angle_1, angle_2):
+    """RelAngleError (global_rotation_averaging.cc:19-36) without the rand()
+    jitter near +-pi (which is not reproducible in the reference either)."""
+    est = (angle_2 - angle_1) - angle_12
+    return (est + np.pi) % (2 * np.pi) - np.pi
+
+
+def estimate_rotations_gravity(n, ei, ej, R_rel, R0, has_gravity, R_align, opts: RAOptions | None = None, verbose=False):
+    """use_gravity path (trivial rigs): frames with gravity carry ONE unknown
+    (the angle about the gravity axis, .cc:207-217), the others three.
+    R0 [n,3,3] initial rotations, R_align [n,3,3] (identity where no gravity).
+    Rows follow SetupLinearSystem (.cc:386-421), residuals ComputeResiduals
+    (.cc:709-743), weights SolveIRLS (.cc:574-580), update (.cc:634-643).
+    Returns (R [n,3,3], info)."""
+    o = opts or RAOptions()
+    ei = np.asarray(ei, dtype=np.int64); ej = np.asarray(ej, dtype=np.int64)
+    hg = np.asarray(has_gravity, dtype=bool)
+    E = len(ei)
+    # unknown layout
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(np.where(hg, 1, 3))
+    ndof = int(off[-1])
+    est = np.zeros(ndof)
+    for i in range(n):
+        if hg[i]:
+            est[off[i]] = R_to_aa((R_align[i].T @ R0[i])[None])[0, 1]        # RotUpToAngle (.cc:208-210)
+        else:
+            est[off[i]:off[i] + 3] = R_to_aa(R0[i][None])[0]
+    # gravity-aligned relative rotations (.cc:311-340)
+    Rr = np.array(R_rel, dtype=np.float64, copy=True)
+    for e in range(E):
+        if hg[ei[e]]:
+            Rr[e] = Rr[e] @ R_align[ei[e]]
+        if hg[ej[e]]:
+            Rr[e] = R_align[ej[e]].T @ Rr[e]
+    both = hg[ei] & hg[ej]
+    aa = R_to_aa(Rr)
+    xz_error = np.where(both, aa[:, 0] ** 2 + aa[:, 2] ** 2, 0.0)
+    angle_rel = aa[:, 1]
+    # fixed camera: first frame with gravity, else first frame (.cc:213-217,248-256)
+    fixed = int(np.nonzero(hg)[0][0]) if hg.any() else 0
+    fixed0 = est[off[fixed]:off[fixed + 1]].copy()
+    rows, cols, vals = [], [], []
+    row_of = np.zeros(E, dtype=np.int64)
+    pos = 0
+    for e in range(E):
+        i, j = ei[e], ej[e]
+        row_of[e] = pos
+        if both[e]:
+            rows += [pos, pos]; cols += [off[i], off[j]]; vals += [-1, 1]; pos += 1
+        else:
+            if not hg[i]:
+                rows += [pos, pos + 1, pos + 2]; cols += [off[i], off[i] + 1, off[i] + 2]; vals += [-1, -1, -1]
+            else:
+                rows.append(pos + 1); cols.append(off[i]); vals.append(-1)
+            if not hg[j]:
+                rows += [pos, pos + 1, pos + 2]; cols += [off[j], off[j] + 1, off[j] + 2]; vals += [1, 1, 1]
+            else:
+                rows.append(pos + 1); cols.append(off[j]); vals.append(1)
+            pos += 3
+    gauge_row = pos
+    if hg[fixed]:
+        rows.append(pos); cols.append(off[fixed]); vals.append(1); pos += 1
+    else:
+        rows += [pos, pos + 1, pos + 2]; cols += [off[fixed], off[fixed] + 1, off[fixed] + 2]; vals += [1, 1, 1]; pos += 3
+    m = pos
+    A = sp.csc_matrix((vals, (rows, cols)), shape=(m, ndof))
+
+    def node_R(i):
+        return aa_to_R(np.array([[0, est[off[i]], 0]]))[0] if hg[i] else aa_to_R(est[off[i]:off[i] + 3][None])[0]
+
+    def residuals():
+        r = np.zeros(m)
+        for e in range(E):
+            i, j = ei[e], ej[e]
+            if both[e]:
+                r[row_of[e]] = rel_angle_error(angle_rel[e], est[off[i]], est[off[j]])
+            else:
+                r[row_of[e]:row_of[e] + 3] = -R_to_aa((node_R(j).T @ Rr[e] @ node_R(i))[None])[0]
+        if hg[fixed]:
+            r[gauge_row] = est[off[fixed]] - fixed0[0]
+        else:
+            r[gauge_row:gauge_row + 3] = R_to_aa((aa_to_R(fixed0[None])[0].T @ node_R(fixed))[None])[0]
+        return r
+
+    def update(step):
+        for i in range(n):
+            if hg[i]:
+                est[off[i]] -= step[off[i]]
+            else:
+                Rn = aa_to_R(est[off[i]:off[i] + 3][None])[0] @ aa_to_R(-step[off[i]:off[i] + 3][None])[0]
+                est[off[i]:off[i] + 3] = R_to_aa(Rn[None])[0]
+
+    def avg_step(step):
+        return sum(abs(step[off[i]]) if hg[i] else np.linalg.norm(step[off[i]:off[i] + 3]) for i in range(n)) / n
+
+    info = dict(l1_iterations=0, irls_iterations=0, admm_iterations=0)
+    res = residuals()
+    if o.max_num_l1_iterations > 0:
+        last_norm = curr_norm = 0.0
+        for it in range(o.max_num_l1_iterations):
+            last_norm = curr_norm
+            step, n_admm = l1_admm(A, res, max_iter=10)
+            info["admm_iterations"] += n_admm
+            curr_norm = np.linalg.norm(step)
+            update(step)
+            res = residuals()
+            info["l1_iterations"] += 1
+            if avg_step(step) < o.l1_step_convergence_threshold or abs(last_norm - curr_norm) < EPS:
+                break
+    if o.max_num_irls_iterations > 0:
+        sigma = np.radians(o.irls_loss_parameter_sigma)
+        for it in range(o.max_num_irls_iterations):
+            w_rows = np.ones(m)
+            for e in range(E):
+                if both[e]:
+                    err2 = res[row_of[e]] ** 2 + xz_error[e]
+                    nrow = 1
+                else:
+                    err2 = (res[row_of[e]:row_of[e] + 3] ** 2).sum()
+                    nrow = 3
+                if o.weight_type == "GEMAN_MCCLURE":
+                    tmp = err2 + sigma * sigma
+                    w = sigma * sigma / (tmp * tmp)
+                else:
+                    w = err2 ** ((0.5 - 2) / 2)
+                w_rows[row_of[e]:row_of[e] + nrow] = w
+            AtW = A.T @ sp.diags(w_rows)
+            step = spla.splu((AtW @ A).tocsc()).solve(AtW @ res)
+            update(step)
+            res = residuals()
+            info["irls_iterations"] += 1
+            if avg_step(step) < o.irls_step_convergence_threshold:
+                break
+    R = np.stack([R_align[i] @ node_R(i) if hg[i] else node_R(i) for i in range(n)])   # ConvertResults (.cc:787-799)
+    info["fixed"] = fixed
+    return R, info

@@ -87,3 +87,31 @@ def test_text_formats_roundtrip(tmp_path):
     # names are numbered in order of first appearance (pose_io.cc:46-59): map back before comparing
     idx = np.array([int(nm[3:]) for nm in names])
     assert RA.max_pairwise_rotation_error_deg(G.so3_log(R), vg.R_gt[idx]) < 3.0
+
+
+def _gravity_setup(vg, frac, seed):
+    rng = np.random.default_rng(seed)
+    hg = rng.uniform(size=vg.n_images) < frac
+    g = np.full((vg.n_images, 3), np.nan)
+    g[hg] = vg.R_gt[hg][:, :, 1]          # gravity = second column of R (docs/rotation_averager.md:51-60)
+    return hg, g
+
+
+@pytest.mark.parametrize("frac", [1.0, 0.6])
+def test_gravity_aligned_frames_match_oracle(frac):
+    """use_gravity: 1-DoF frames, mixed 1-DoF/3-DoF pairs (global_rotation_averaging.cc:207-217,386-421)."""
+    vg = S.make_random_view_graph(80, 8, seed=13, noise_deg=1.0, outlier_ratio=0.05)
+    hg, g = _gravity_setup(vg, frac, 2)
+    est = E.RotationEstimator(E.RotationEstimatorOptions(use_gravity=True, pcg_rel_tolerance=1e-12))
+    ok, R = est.EstimateRotations(vg, gravity=g)
+    st = est.summary
+    R_align = np.tile(np.eye(3), (vg.n_images, 1, 1))
+    for i in np.nonzero(hg)[0]:
+        R_align[i] = E.get_align_rot(g[i])
+    Ro, info = RA.estimate_rotations_gravity(vg.n_images, vg.ei, vg.ej, vg.R_rel, np.tile(np.eye(3), (vg.n_images, 1, 1)), hg, R_align)
+    assert ok
+    assert (st.l1_iterations, st.irls_iterations, st.admm_iterations) == (info["l1_iterations"], info["irls_iterations"], info["admm_iterations"])
+    assert np.abs(R - Ro).max() < 1e-8
+    assert _pairwise_err(R, vg.R_gt) < 2.0                  # rotation_averager_test.cc:359-362
+    # gravity is honoured exactly: second column of every gravity frame's rotation
+    assert np.abs(R[hg][:, :, 1] - g[hg]).max() < 1e-12
