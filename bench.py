@@ -236,6 +236,16 @@ def run_b200(args):
                "achieved": li_bytes / (ms_li / max(n_li, 1) * 1e-3) / 1e9 if n_li else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_li, "avg_ms": ms_li / max(n_li, 1),
                "bytes_model": "168*N + 96*P + 64*C per launch"}
+    # DRAM traffic per launch from the committed `ncu --set full` capture (same workload, 1 GPU)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tr.get("workload") == args.workload and world == 1:
+            roof_mv["traffic"] = tr["dram_bytes_per_launch"]["ba_schur_pass<0>"]
+            roof_li["traffic"] = tr["dram_bytes_per_launch"]["ba_linearize_points"]
+            roof_mv["traffic_source"] = roof_li["traffic_source"] = tr["source"]
+    except Exception:
+        pass
+    roof_mv["algorithmic_bytes"], roof_li["algorithmic_bytes"] = mv_bytes, li_bytes
     for r in (roof_mv, roof_li):
         r["frac"] = r["achieved"] / peak if r["achieved"] else None
     final_cost, init_cost = stats[-1]["final_cost"], stats[-1]["initial_cost"]
