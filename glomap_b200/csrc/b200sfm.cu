@@ -215,6 +215,39 @@ int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, 
   });
 }
 
+int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_reprojection_error, uint8_t* keep,
+                                           int64_t* num_tracks_changed) {
+  if (!p || !keep) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    const long long n = p->run_filter(0, max_reprojection_error, nullptr, nullptr, keep);
+    if (num_tracks_changed) *num_tracks_changed = n;
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings, const uint8_t* cam_calibrated,
+                                    double max_angle_error_deg, uint8_t* keep, int64_t* num_tracks_changed) {
+  if (!p || !keep || !bearings) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    const long long n = p->run_filter(1, max_angle_error_deg, bearings, cam_calibrated, keep);
+    if (num_tracks_changed) *num_tracks_changed = n;
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double min_angle_deg, uint8_t* keep_track,
+                                                  int64_t* num_tracks_removed) {
+  if (!p || !keep_track) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    const long long n = p->run_filter(2, min_angle_deg, nullptr, nullptr, keep_track);
+    if (num_tracks_removed) *num_tracks_removed = n;
+    return (int)B200SFM_OK;
+  });
+}
+
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "filter_kernels.cuh"
 #include "context.cuh"
 #include "pcg.cuh"
 
@@ -376,6 +377,51 @@ struct b200sfm_ba_problem {
         }
       }
     }
+  }
+
+  // ---- track filters on the resident arrays (glomap/processors/track_filter.cc) -----------------
+  // mode 0: reprojection (pixels), 1: angle (needs bearings), 2: triangulation angle (per track)
+  long long run_filter(int mode, double thr, const double* h_bearings, const uint8_t* h_calibrated, uint8_t* h_keep) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    B200_LAUNCH(ctx, k_eff_mask, cdiv(C, 256), 256, 0, C, cam_mask_base.p, 0, 0, cam_mask.p);
+    build_records(cur);
+    BAView v = view();
+    const double kPi = 3.14159265358979323846;
+    DevBuf<int> changed, counter;
+    DevBuf<unsigned char> keep;
+    counter.alloc(1);
+    counter.zero(s);
+    long long result = 0;
+    if (mode == 2) {
+      keep.alloc(P);
+      B200_LAUNCH(ctx, filter_triangulation_angle, cdiv((long long)P * 32, 256), 256, 0, v, cam_rec.p, points[cur].p,
+                  std::cos(thr * kPi / 180.0), keep.p, counter.p);
+      keep.download(h_keep, P, s);
+    } else {
+      keep.alloc(N);
+      changed.alloc(P);
+      changed.zero(s);
+      if (mode == 0) {
+        B200_LAUNCH(ctx, filter_reprojection, cdiv(N, 256), 256, 0, v, cam_rec.p, intr_rec.p, points[cur].p, thr, keep.p, changed.p);
+      } else {
+        DevBuf<double> bear;
+        DevBuf<unsigned char> cal;
+        bear.alloc((size_t)N * 3);
+        bear.upload(h_bearings, (size_t)N * 3, s);
+        if (h_calibrated) { cal.alloc(C); cal.upload(h_calibrated, C, s); }
+        B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, h_calibrated ? cal.p : nullptr,
+                    std::cos(thr * kPi / 180.0), std::cos(2.0 * thr * kPi / 180.0), keep.p, changed.p);
+        B200_CUDA_OK(cudaStreamSynchronize(s));   // bear / cal go out of scope
+      }
+      B200_LAUNCH(ctx, count_flags, cdiv(P, 256), 256, 0, P, changed.p, counter.p);
+      keep.download(h_keep, N, s);
+    }
+    int h_cnt = 0;
+    B200_CUDA_OK(cudaMemcpyAsync(&h_cnt, counter.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    result = h_cnt;
+    return result;
   }
 
   struct StepResult {

@@ -178,6 +178,30 @@ class BAProblem:
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_cost(self.handle, ct.byref(o), ct.byref(c)))
         return c.value
 
+    # -- track filters on the resident state (glomap/processors/track_filter.cc) --
+    def filter_reprojection(self, max_reprojection_error: float):
+        """TrackFilter::FilterTracksByReprojection (pixel space): (keep [N] bool, #tracks changed)."""
+        keep = np.empty(self.N, np.uint8)
+        cnt = ct.c_int64()
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_reprojection(self.handle, max_reprojection_error, _ptr(keep), ct.byref(cnt)))
+        return keep.astype(bool), cnt.value
+
+    def filter_angle(self, bearings, max_angle_error_deg: float, cam_calibrated=None):
+        """TrackFilter::FilterTracksByAngle."""
+        keep = np.empty(self.N, np.uint8)
+        cnt = ct.c_int64()
+        b = _c(bearings, np.float64)
+        cal = None if cam_calibrated is None else _c(cam_calibrated, np.uint8)
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_angle(self.handle, _ptr(b), _ptr(cal), max_angle_error_deg, _ptr(keep), ct.byref(cnt)))
+        return keep.astype(bool), cnt.value
+
+    def filter_triangulation_angle(self, min_angle_deg: float):
+        """TrackFilter::FilterTrackTriangulationAngle: (keep_track [P] bool, #tracks removed)."""
+        keep = np.empty(self.P, np.uint8)
+        cnt = ct.c_int64()
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_triangulation_angle(self.handle, min_angle_deg, _ptr(keep), ct.byref(cnt)))
+        return keep.astype(bool), cnt.value
+
     def free(self):
         if self.handle:
             self.lib.b200sfm_ba_problem_free(self.handle)

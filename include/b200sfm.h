@@ -181,6 +181,19 @@ int b200sfm_ba_problem_restore_state(b200sfm_ba_problem* p);
 int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, b200sfm_lm_stats* stats);
 /* robust cost 1/2 sum rho(|r|^2) of the current state (all ranks) */
 int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, double* cost);
+/* Track filters on the resident problem: the mapper runs them between the
+ * BA solves (controllers/global_mapper.cc:164-186,243-276,309-337) on the arrays the problem already
+ * holds.  Reference: glomap/processors/track_filter.cc:7-52 (pixel reprojection), :54-90 (angle),
+ * :92-127 (triangulation angle).  They evaluate the CURRENT state and return a keep-mask (1 = keep)
+ * per observation / per track plus the reference's return value (number of tracks changed / removed);
+ * the caller compacts Track::observations. */
+int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_reprojection_error, uint8_t* keep /*[N]*/,
+                                           int64_t* num_tracks_changed);
+int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings /*[N][3] features_undist*/,
+                                    const uint8_t* cam_calibrated /*[C] or NULL*/, double max_angle_error_deg,
+                                    uint8_t* keep /*[N]*/, int64_t* num_tracks_changed);
+int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double min_angle_deg, uint8_t* keep_track /*[P]*/,
+                                                  int64_t* num_tracks_removed);
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p);
 
 /* ---- (ii) global positioning (BATA) ----------------------------------------- */
