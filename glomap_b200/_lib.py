@@ -38,7 +38,7 @@ class BAOpts(ct.Structure):
         ("parameter_tolerance", c_double),
         ("pcg_max_iterations", c_int32), ("pcg_min_iterations", c_int32), ("pcg_rel_tolerance", c_double),
         ("preconditioner", c_int32), ("profile_kernels", c_int32), ("fixed_num_iterations", c_int32),
-        ("reserved0", c_int32),
+        ("design", c_int32),
     ]
 
 

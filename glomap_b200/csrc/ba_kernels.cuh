@@ -26,6 +26,8 @@ constexpr int kIntrRec = 8;   // fx fy cx cy k1 k2 model pad
 constexpr double kZEps = 1e-12;
 constexpr int kSeg = 256;     // observations per camera-order segment (one warp)
 constexpr int kIntrSmem = 16; // intrinsics blocks cached in shared memory by the point-order kernels
+constexpr int kJpDoubles = 10; // v2 point-order row: J(6) RX(3) pad -> 80 B
+constexpr int kJcDoubles = 10; // v2 camera-order row: J(6) RX(3) pad -> 80 B
 
 struct BAView {
   int C, P, K;
@@ -108,6 +110,8 @@ __device__ __forceinline__ void project_only(const double* __restrict__ ir, doub
 struct ObsLin {
   double Jr[6], Jt[6], Jp[6], r[2], rho0;
   double u, v, w;   // normalised image coordinates and sqrt(rho') (for the intrinsics Jacobian)
+  double J[6];      // sqrt(rho') * d(px,py)/d(Xc), unmasked (the compact row of the v2 layout)
+  double a[3];      // R X (rotated point, without the translation)
   bool valid;
 };
 
@@ -132,6 +136,9 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
     o.r[0] = o.r[1] = 0.0;
     o.rho0 = 0.0;
     o.u = o.v = o.w = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.J[k] = 0.0;
+    o.a[0] = rx; o.a[1] = ry; o.a[2] = rz;
     return;
   }
   double px, py, J[6];
@@ -146,7 +153,11 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
   o.r[0] = w * r0;
   o.r[1] = w * r1;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) J[k] *= w;
+  for (int k = 0; k < 6; ++k) {
+    J[k] *= w;
+    o.J[k] = J[k];
+  }
+  o.a[0] = rx; o.a[1] = ry; o.a[2] = rz;
   // translation block
   const bool tvar = !(mask & 2), rvar = !(mask & 1);
 #pragma unroll
@@ -215,6 +226,9 @@ struct K1Smem {
   double scratch[32];
 };
 
+// V2 = false: writes W[N][18] (6x3 blocks).  V2 = true: writes the compact rows Jp[N][10] = {J (2x3), R X, 0}
+// of the matrix-free layout (ba_kernels_v2.cuh) into v.W instead.
+template <bool V2>
 __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(BAView v, const double* __restrict__ cam_rec,
                                                              const double* __restrict__ intr_rec,
                                                              const double* __restrict__ points, double huber_a,
@@ -285,15 +299,31 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
       o.r[0] = o.r[1] = 0.0;
     }
     if (points_var) {
-      // W = [Jr^T; Jt^T] Jp  (6x3), rows of 3 -> smem tile (stride 144 B: conflict-free STS.128)
-      double* wrow = sm.Wt + tid * kWDoubles;
+      if (V2) {
+        // compact row {J, R X, 0}: 80 B (16-B multiple so that every tile is a legal TMA bulk copy)
+        double* jrow = sm.Wt + tid * kJpDoubles;
+        if (!use) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          wrow[3 * a + b] = o.Jr[a] * o.Jp[b] + o.Jr[3 + a] * o.Jp[3 + b];
-          wrow[9 + 3 * a + b] = o.Jt[a] * o.Jp[b] + o.Jt[3 + a] * o.Jp[3 + b];
+          for (int k = 0; k < 6; ++k) o.J[k] = 0.0;
+          o.a[0] = o.a[1] = o.a[2] = 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) jrow[k] = o.J[k];
+        jrow[6] = o.a[0];
+        jrow[7] = o.a[1];
+        jrow[8] = o.a[2];
+        jrow[9] = 0.0;
+      } else {
+        // W = [Jr^T; Jt^T] Jp  (6x3), rows of 3 -> smem tile (stride 144 B: conflict-free STS.128)
+        double* wrow = sm.Wt + tid * kWDoubles;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            wrow[3 * a + b] = o.Jr[a] * o.Jp[b] + o.Jr[3 + a] * o.Jp[3 + b];
+            wrow[9 + 3 * a + b] = o.Jt[a] * o.Jp[b] + o.Jt[3 + a] * o.Jp[3 + b];
+          }
+      }
       // V_o (packed sym) and g_o
       sm.red[0][tid] = o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3];
       sm.red[1][tid] = o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4];
@@ -307,7 +337,8 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
       fence_proxy_async_smem();
       __syncthreads();
       if (tid == 0) {
-        tma_store_1d(v.W + (size_t)(o0 + c0) * kWDoubles, sm.Wt, (uint32_t)nc * kWBytes);
+        if (V2) tma_store_1d(v.W + (size_t)(o0 + c0) * kJpDoubles, sm.Wt, (uint32_t)nc * kJpDoubles * 8);
+        else tma_store_1d(v.W + (size_t)(o0 + c0) * kWDoubles, sm.Wt, (uint32_t)nc * kWBytes);
         tma_store_commit();
       }
       // per-point sums: thread -> (point j, component k), 9 threads per point

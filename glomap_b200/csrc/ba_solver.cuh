@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "ba_kernels_v2.cuh"
 #include "filter_kernels.cuh"
 #include "context.cuh"
 #include "pcg.cuh"
@@ -115,6 +116,15 @@ struct b200sfm_ba_problem {
   DevBuf<b200::IntrVarRec> ivar;
   DevBuf<double> Buck, Bmat, spk, part_seg, intr_out, part_tile, tile_sum, CkInv, vvec, part_bt, tvec, dkv;
   size_t smem_ki = 0;
+  // design v2 (compact rows, camera-order second pass)
+  bool use_v2 = false;
+  DevBuf<double> Jc, z4, xq;
+  size_t smem_k3v2 = 0;
+  b200::BAViewV2 view2() {
+    b200::BAViewV2 w;
+    w.Jp = W.p; w.Jc = Jc.p; w.z4 = z4.p;
+    return w;
+  }
   int cur = 0;
   DevBuf<double> cam_rec, intr_rec;
   // linear system
@@ -243,16 +253,24 @@ struct b200sfm_ba_problem {
     scal.alloc(16);
     smem_k1 = sizeof(K1Smem) + 128;
     smem_k3 = sizeof(K3Smem) + 128;
-    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k1));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     // several 50-KB CTAs per SM: ask for the full shared-memory carve-out
     const int carve = getenv("B200SFM_CARVEOUT") ? atoi(getenv("B200SFM_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;
-    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    smem_k3v2 = sizeof(K3v2Smem) + 128;
+    B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3v2));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3v2));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    Jc.alloc((size_t)std::max(Nv, 1) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXq);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -333,12 +351,21 @@ struct b200sfm_ba_problem {
       e1 = timer_lin.next();
       B200_CUDA_OK(cudaEventRecord(e0, s));
     }
-    B200_LAUNCH(ctx, ba_linearize_points, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
-                points_var ? 1 : 0, scal.p);
+    if (use_v2)
+      B200_LAUNCH(ctx, ba_linearize_points<true>, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
+                  points_var ? 1 : 0, scal.p);
+    else
+      B200_LAUNCH(ctx, ba_linearize_points<false>, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
+                  points_var ? 1 : 0, scal.p);
     if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
-    if (n_segs > 0)
-      B200_LAUNCH(ctx, ba_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p,
-                  points[cur].p, huber_a);
+    if (n_segs > 0) {
+      if (use_v2)
+        B200_LAUNCH(ctx, ba2_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, intr_rec.p,
+                    points[cur].p, huber_a);
+      else
+        B200_LAUNCH(ctx, ba_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p,
+                    points[cur].p, huber_a);
+    }
     // cost travels with U|gc through one all-reduce
     B200_CUDA_OK(cudaMemcpyAsync(cost_ptr(), scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
     ctx->allreduce_sum(lin.p, (size_t)C * 27 + 1);
@@ -442,7 +469,10 @@ struct b200sfm_ba_problem {
     const bool schur_jacobi = points_var && o.preconditioner == 1;
     if (schur_jacobi) {
       Sd.zero(s);
-      if (n_segs > 0) B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
+      if (n_segs > 0) {
+        if (use_v2) B200_LAUNCH(ctx, ba2_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p);
+        else B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
+      }
       ctx->allreduce_sum(Sd.p, (size_t)C * 21);
     }
     B200_LAUNCH(ctx, ba_build_precond, cdiv(C, 128), 128, 0, C, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
@@ -520,7 +550,12 @@ struct b200sfm_ba_problem {
     // right-hand side b = -(gc - W Vinv gp)
     if (points_var) {
       yw.zero(s);
-      B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yw.p, nullptr, nullptr, radius, nullptr);
+      if (use_v2) {
+        B200_LAUNCH(ctx, ba2_point_rhs_z, cdiv(P, 256), 256, 0, v, view2());
+        if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
+      } else {
+        B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yw.p, nullptr, nullptr, radius, nullptr);
+      }
       ctx->allreduce_sum(yw.p, nC6);
     }
     B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yw.p : nullptr, bvec.p);
@@ -552,7 +587,13 @@ struct b200sfm_ba_problem {
             e1 = timer_mv.next();
             B200_CUDA_OK(cudaEventRecord(e0, s));
           }
-          B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr);
+          if (use_v2) {
+            B200_LAUNCH(ctx, ba2_pack_xq, cdiv(C, 256), 256, 0, C, pp.p, cam_rec.p, xq.p);
+            B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, nullptr, nullptr, radius, nullptr);
+            if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
+          } else {
+            B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr);
+          }
           if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
           ctx->allreduce_sum(yw.p, nC6);
         }
@@ -608,7 +649,10 @@ struct b200sfm_ba_problem {
     } else {
       B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, intr.p, intr.bytes(), cudaMemcpyDeviceToDevice, s));
     }
-    if (points_var) {
+    if (points_var && use_v2) {
+      B200_LAUNCH(ctx, ba2_pack_xq, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
+      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, scal.p + 2);
+    } else if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
                   scal.p + 2, spk.p, dkv.p, m);
     } else {
@@ -678,6 +722,7 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaMemcpyAsync(h_intr.data(), intr.p, h_intr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
       B200_CUDA_OK(cudaStreamSynchronize(s));
     }
+    use_v2 = (m_intr == 0) && (o.design != 1);   // v2 (compact rows) unless the intrinsics border needs W
     const long long launches0 = ctx->launches;
     timer_lin.reset();
     timer_mv.reset();

@@ -109,6 +109,7 @@ class BundleAdjusterOptions:
     # implementation extras
     profile_kernels: bool = False
     fixed_num_iterations: int = 0
+    design: int = 0          # 0 auto, 1 = v1 (W blocks + atomics), 2 = v2 (compact rows, two passes)
 
     def to_c(self) -> BAOpts:
         o = BAOpts()
@@ -119,6 +120,7 @@ class BundleAdjusterOptions:
         o.min_num_view_per_track = self.min_num_view_per_track
         o.thres_loss_function = self.thres_loss_function
         o.fixed_num_iterations = self.fixed_num_iterations
+        o.design = self.design
         so = self.solver_options
         for f in ("max_num_iterations", "function_tolerance", "gradient_tolerance", "parameter_tolerance",
                   "pcg_max_iterations", "pcg_min_iterations", "pcg_rel_tolerance", "preconditioner"):

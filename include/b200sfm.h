@@ -133,7 +133,9 @@ typedef struct {
   int32_t preconditioner;            /* 0 = block-Jacobi on U, 1 = Schur-Jacobi (default) */
   int32_t profile_kernels;           /* 1: time linearize / mat-vec kernels with CUDA events */
   int32_t fixed_num_iterations;      /* >0: run exactly this many LM iterations (bench), ignore tolerances */
-  int32_t reserved0;
+  int32_t design;                    /* data layout of the Schur passes: 0 = auto, 1 = v1 (stored 6x3 W blocks, atomics per
+                                        observation), 2 = v2 (compact J rows in both orders, camera-order second pass).
+                                        Identical arithmetic; auto picks v2 unless intrinsics are optimised. */
 } b200sfm_ba_opts;
 
 void b200sfm_ba_default_opts(b200sfm_ba_opts* opts);
