@@ -26,8 +26,8 @@ constexpr int kIntrRec = 8;   // fx fy cx cy k1 k2 model pad
 constexpr double kZEps = 1e-12;
 constexpr int kSeg = 256;     // observations per camera-order segment (one warp)
 constexpr int kIntrSmem = 16; // intrinsics blocks cached in shared memory by the point-order kernels
-constexpr int kJpDoubles = 10; // v2 point-order row: J(6) RX(3) pad -> 80 B
-constexpr int kJcDoubles = 10; // v2 camera-order row: J(6) RX(3) pad -> 80 B
+constexpr int kJpDoubles = 6;  // v2 point-order row: A_o = J_pt^T J_pt (packed symmetric 3x3) -> 48 B
+constexpr int kJcDoubles = 10; // v2 camera-order row: A_o (6), X_p (3), pad -> 80 B
 
 struct BAView {
   int C, P, K;
@@ -226,8 +226,8 @@ struct K1Smem {
   double scratch[32];
 };
 
-// V2 = false: writes W[N][18] (6x3 blocks).  V2 = true: writes the compact rows Jp[N][10] = {J (2x3), R X, 0}
-// of the matrix-free layout (ba_kernels_v2.cuh) into v.W instead.
+// V2 = false: writes W[N][18] (6x3 blocks).  V2 = true: writes the compact rows Ap[N][6] = J_pt^T J_pt
+// of the world-frame layout (ba_kernels_v2.cuh) into v.W instead.
 template <bool V2>
 __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(BAView v, const double* __restrict__ cam_rec,
                                                              const double* __restrict__ intr_rec,
@@ -300,19 +300,14 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
     }
     if (points_var) {
       if (V2) {
-        // compact row {J, R X, 0}: 80 B (16-B multiple so that every tile is a legal TMA bulk copy)
-        double* jrow = sm.Wt + tid * kJpDoubles;
-        if (!use) {
-#pragma unroll
-          for (int k = 0; k < 6; ++k) o.J[k] = 0.0;
-          o.a[0] = o.a[1] = o.a[2] = 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) jrow[k] = o.J[k];
-        jrow[6] = o.a[0];
-        jrow[7] = o.a[1];
-        jrow[8] = o.a[2];
-        jrow[9] = 0.0;
+        // compact row A_o = J_pt^T J_pt (packed symmetric 3x3, 48 B: every tile is a legal TMA bulk copy)
+        double* arow = sm.Wt + tid * kJpDoubles;
+        arow[0] = o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3];
+        arow[1] = o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4];
+        arow[2] = o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5];
+        arow[3] = o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4];
+        arow[4] = o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5];
+        arow[5] = o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5];
       } else {
         // W = [Jr^T; Jt^T] Jp  (6x3), rows of 3 -> smem tile (stride 144 B: conflict-free STS.128)
         double* wrow = sm.Wt + tid * kWDoubles;

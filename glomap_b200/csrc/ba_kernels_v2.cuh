@@ -2,49 +2,52 @@
 //
 // v1 stores the 6x3 block W_o = J_cam^T J_pt (144 B/observation) and scatters
 // W_o z_p into y[cam] with 6 FP64 atomics per observation; ncu shows that
-// mat-vec bound by L2 operations (profiles/r1_matvec_ncu.md).  v2 stores what
-// W is made of instead -- per observation the robustified projective Jacobian
-// J = sqrt(rho') d(pi)/d(X_c) (2x3) and a = R X (3) -- in BOTH traversal orders
-//     Jp[N][10]  point order  {J, a, pad}        80 B, tiles moved by TMA
-//     Jc[Nv][10] camera order {J, a, pad}        80 B
-// and applies W = J_c^T J_p on the fly, J_c = [-2 J [a]x | J] (masked),
-// J_p = J R(q_cam).  The implicit-Schur mat-vec becomes two streaming passes
-//     pass A (point order):  s_p = sum_o R^T J^T (J v_o),  z_p = Vinv s_p -> z[P][4]
-//                            v_o = m_t x_t - 2 m_r (a x x_r)
-//     pass B (camera order): y_c -= sum_o J_c^T (J (R z_p))   one warp per <= 256-observation
-//                            segment of ONE camera: register accumulation, shuffle
-//                            reduction, 6 atomics per segment instead of per observation.
-// All arithmetic stays FP64; only the traffic changes:
-//     bytes/mat-vec = 84 N + 80 P (pass A) + 84 N + 32 P (pass B)  vs  152 N + 6 FP64 RED per observation.
+// mat-vec bound by L2 operations (profiles/r1_matvec_ncu.md).  v2 exploits
+//     J_cam = J_pt G,   G = [ -2 [X]x R^T | R^T ]   (3 x 6;  X = the world point, R = R(q_cam))
+// (left-perturbed rotation, translation), so that with the symmetric 3x3
+//     A_o = J_pt^T J_pt        (what the observation adds to V_p)
+// W_o = G^T A_o,  W_o^T x = A_o v  with  v = R^T x_t - 2 X x (R^T x_r),
+// W_o z = [ 2 R (X x w) ; R w ],  w = A_o z.   Only A_o (48 B) is stored per
+// observation, in BOTH traversal orders:
+//     Ap[N][6]   point order  (tiles moved by TMA)
+//     Ac[Nv][10] camera order {A_o, X_p, pad}  (80 B, written by the camera-order linearisation)
+// and the implicit-Schur mat-vec is two streaming passes
+//     pass A (point order):  s_p = sum_o A_o v_o,  z_p = Vinv s_p -> z4[P]      gathers R^T x (48 B)
+//     pass B (camera order): y_c -= R-rotated sum_o [2 X x (A_o z_p) ; A_o z_p]  gathers z_p (32 B)
+//                            one warp per <= 256-observation segment of ONE camera: register
+//                            accumulation, shuffle reduction, 6 atomics per segment.
+// All arithmetic stays FP64.  Algorithmic bytes per mat-vec: 52 N + 80 P (A) + 84 N + 32 P (B).
 #pragma once
 #include "ba_kernels.cuh"
 
 namespace b200 {
 
-constexpr int kXq = 12;   // per-camera gather record of pass A: x(6) q(4) mask pad -> 96 B
-
 struct BAViewV2 {
-  const double* Jp;   // [N][10]   (aliases BAView::W)
-  double* Jc;         // [Nv][10]
+  const double* Ap;   // [N][6]   (aliases BAView::W)
+  double* Ac;         // [Nv][10]
   double* z4;         // [P][4]
 };
 
-// xq[c] = {x_c (6), q_c (4), mask, 0}
-__global__ void ba2_pack_xq(int C, const double* __restrict__ x, const double* __restrict__ cam_rec,
-                            double* __restrict__ xq) {
+// xp[c] = { R^T x_r , R^T x_t }   (masked dofs of x are zero already: PCG keeps them at 0)
+__global__ void ba2_pack_x(int C, const double* __restrict__ x, const double* __restrict__ cam_rec,
+                           double* __restrict__ xp) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double* o = xq + (size_t)c * kXq;
   const double* r = cam_rec + (size_t)c * kCamRec;
+  const double q[4] = {r[0], r[1], r[2], r[3]};
+  double R[9];
+  quat_to_R(q, R);
+  const double* xc = x + (size_t)c * 6;
+  double* o = xp + (size_t)c * 6;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) o[k] = x[(size_t)c * 6 + k];
-  o[6] = r[0]; o[7] = r[1]; o[8] = r[2]; o[9] = r[3];
-  o[10] = (double)(__double_as_longlong(r[7]) & 0xff);
-  o[11] = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    o[k] = R[k] * xc[0] + R[3 + k] * xc[1] + R[6 + k] * xc[2];
+    o[3 + k] = R[k] * xc[3] + R[3 + k] * xc[4] + R[6 + k] * xc[5];
+  }
 }
 
 // ---------------------------------------------------------------------------
-// camera-order linearisation: U_c, g_c AND the camera-order rows Jc
+// camera-order linearisation: U_c, g_c AND the camera-order rows Ac = {A_o, X_p}
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                          const double* __restrict__ intr_rec,
@@ -68,12 +71,12 @@ __global__ void __launch_bounds__(128) ba2_linearize_cams(BAView v, BAViewV2 v2,
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
     ObsLin o;
     linearize_obs(q4c, t4c, irc, X0, X1, X2, xy, huber_a, o);
-    double2* row = reinterpret_cast<double2*>(v2.Jc + (size_t)i * kJcDoubles);
-    row[0] = make_double2(o.J[0], o.J[1]);
-    row[1] = make_double2(o.J[2], o.J[3]);
-    row[2] = make_double2(o.J[4], o.J[5]);
-    row[3] = make_double2(o.a[0], o.a[1]);
-    row[4] = make_double2(o.a[2], 0.0);
+    double2* row = reinterpret_cast<double2*>(v2.Ac + (size_t)i * kJcDoubles);
+    row[0] = make_double2(o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3], o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4]);
+    row[1] = make_double2(o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5], o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4]);
+    row[2] = make_double2(o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5], o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5]);
+    row[3] = make_double2(X0, X1);
+    row[4] = make_double2(X2, 0.0);
     double Jc[2][6];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -102,24 +105,10 @@ __global__ void __launch_bounds__(128) ba2_linearize_cams(BAView v, BAViewV2 v2,
   }
 }
 
-// J_c = [-2 J [a]x (masked) | J (masked)] from a compact row
-__device__ __forceinline__ void jc_from_row(const double J[6], const double a[3], int mask, double Jc[2][6]) {
-  const bool rvar = !(mask & 1), tvar = !(mask & 2);
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const double j0 = J[3 * r], j1 = J[3 * r + 1], j2 = J[3 * r + 2];
-    Jc[r][0] = rvar ? -2.0 * (j1 * a[2] - j2 * a[1]) : 0.0;
-    Jc[r][1] = rvar ? -2.0 * (j2 * a[0] - j0 * a[2]) : 0.0;
-    Jc[r][2] = rvar ? -2.0 * (j0 * a[1] - j1 * a[0]) : 0.0;
-    Jc[r][3] = tvar ? j0 : 0.0;
-    Jc[r][4] = tvar ? j1 : 0.0;
-    Jc[r][5] = tvar ? j2 : 0.0;
-  }
-}
-
 // ---------------------------------------------------------------------------
-// Schur-Jacobi diagonal from the camera-order rows:
-//   Sd_c = sum_o J_c^T (J R Vinv_p R^T J^T) J_c
+// Schur-Jacobi diagonal from the camera-order rows, accumulated in the world
+// frame:  Sd_c = Rb ( sum_o Gh^T N Gh ) Rb^T,  N = A_o Vinv_p A_o,
+//         Gh = [ -2 [X]x | I ],  Rb = blockdiag(R, R)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -127,73 +116,115 @@ __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, con
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
-  const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
-  double R[9];
-  quat_to_R(q, R);
-  double S[21];
-#pragma unroll
-  for (int k = 0; k < 21; ++k) S[k] = 0.0;
+  // world-frame accumulators: RR (sym 6), RT (full 9), TT (sym 6)
+  double RR[6] = {0, 0, 0, 0, 0, 0}, RT[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, TT[6] = {0, 0, 0, 0, 0, 0};
   for (int i = b + lane; i < e; i += 32) {
-    const double2* row = reinterpret_cast<const double2*>(v2.Jc + (size_t)i * kJcDoubles);
+    const double2* row = reinterpret_cast<const double2*>(v2.Ac + (size_t)i * kJcDoubles);
     const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];
-    const double J[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-    const double a[3] = {r3.x, r3.y, r4.x};
+    const double A[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
+    const double X[3] = {r3.x, r3.y, r4.x};
     const int pt = v.pt_c[i];
     const double2* vp = reinterpret_cast<const double2*>(v.Vinv + (size_t)pt * 6);
     const double2 v0 = vp[0], v1 = vp[1], v2_ = vp[2];
     const double vi[6] = {v0.x, v0.y, v1.x, v1.y, v2_.x, v2_.y};
-    // Jp = J R (2x3);  T = Jp Vinv (2x3);  M2 = T Jp^T (2x2 sym)
-    double Jp[2][3], T[2][3];
+    // T = Vinv A (columns), N = A T (symmetric 3x3)
+    const double Ac0[3] = {A[0], A[1], A[2]}, Ac1[3] = {A[1], A[3], A[4]}, Ac2[3] = {A[2], A[4], A[5]};
+    double T0[3], T1[3], T2[3];
+    sym3_mul(vi, Ac0, T0);
+    sym3_mul(vi, Ac1, T1);
+    sym3_mul(vi, Ac2, T2);
+    double N[3][3];
+    {
+      double c0[3], c1[3], c2[3];
+      sym3_mul(A, T0, c0);
+      sym3_mul(A, T1, c1);
+      sym3_mul(A, T2, c2);
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) Jp[r][c] = J[3 * r] * R[c] + J[3 * r + 1] * R[3 + c] + J[3 * r + 2] * R[6 + c];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) sym3_mul(vi, Jp[r], T[r]);
-    const double m00 = T[0][0] * Jp[0][0] + T[0][1] * Jp[0][1] + T[0][2] * Jp[0][2];
-    const double m01 = T[0][0] * Jp[1][0] + T[0][1] * Jp[1][1] + T[0][2] * Jp[1][2];
-    const double m11 = T[1][0] * Jp[1][0] + T[1][1] * Jp[1][1] + T[1][2] * Jp[1][2];
-    double Jc[2][6];
-    jc_from_row(J, a, mask, Jc);
-    // S += Jc^T M2 Jc
-    double A0[6], A1[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      A0[k] = m00 * Jc[0][k] + m01 * Jc[1][k];
-      A1[k] = m01 * Jc[0][k] + m11 * Jc[1][k];
+      for (int r = 0; r < 3; ++r) { N[r][0] = c0[r]; N[r][1] = c1[r]; N[r][2] = c2[r]; }
     }
-    int idx = 0;
+    // P = 2 [X]x N  (rows: 2 X x N_col);  rr = -2 P [X]x;  rt = P;  tt = N
+    double P[3][3];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double n0 = N[0][c], n1 = N[1][c], n2 = N[2][c];
+      P[0][c] = 2.0 * (X[1] * n2 - X[2] * n1);
+      P[1][c] = 2.0 * (X[2] * n0 - X[0] * n2);
+      P[2][c] = 2.0 * (X[0] * n1 - X[1] * n0);
+    }
+    // (P [X]x)[r][c] = sum_k P[r][k] K[k][c],  K = [X]x = [[0,-X2,X1],[X2,0,-X0],[-X1,X0,0]]
+    double PK[3][3];
 #pragma unroll
-      for (int c = r; c < 6; ++c) S[idx++] += Jc[0][r] * A0[c] + Jc[1][r] * A1[c];
+    for (int r = 0; r < 3; ++r) {
+      PK[r][0] = P[r][1] * X[2] - P[r][2] * X[1];
+      PK[r][1] = -P[r][0] * X[2] + P[r][2] * X[0];
+      PK[r][2] = P[r][0] * X[1] - P[r][1] * X[0];
+    }
+    RR[0] += -2.0 * PK[0][0]; RR[1] += -2.0 * PK[0][1]; RR[2] += -2.0 * PK[0][2];
+    RR[3] += -2.0 * PK[1][1]; RR[4] += -2.0 * PK[1][2]; RR[5] += -2.0 * PK[2][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) RT[3 * r + c] += P[r][c];
+    TT[0] += N[0][0]; TT[1] += N[0][1]; TT[2] += N[0][2]; TT[3] += N[1][1]; TT[4] += N[1][2]; TT[5] += N[2][2];
   }
 #pragma unroll
-  for (int k = 0; k < 21; ++k) {
-    const double s = warp_sum(S[k]);
-    if (lane == k && s != 0.0) atomicAdd(&v.Sd[(size_t)cam * 21 + k], s);
+  for (int k = 0; k < 6; ++k) RR[k] = warp_sum(RR[k]);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) RT[k] = warp_sum(RT[k]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) TT[k] = warp_sum(TT[k]);
+  if (lane == 0) {
+    const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+    const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+    const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
+    const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
+    double R[9];
+    quat_to_R(q, R);
+    // full 6x6 in the world frame, then S = Rb M Rb^T
+    double M[6][6];
+    const double rr[3][3] = {{RR[0], RR[1], RR[2]}, {RR[1], RR[3], RR[4]}, {RR[2], RR[4], RR[5]}};
+    const double tt[3][3] = {{TT[0], TT[1], TT[2]}, {TT[1], TT[3], TT[4]}, {TT[2], TT[4], TT[5]}};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        M[r][c] = rr[r][c];
+        M[3 + r][3 + c] = tt[r][c];
+        M[r][3 + c] = RT[3 * r + c];
+        M[3 + c][r] = RT[3 * r + c];
+      }
+    double T[6][6];
+    for (int blk = 0; blk < 2; ++blk)       // T = Rb M
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 6; ++c)
+          T[3 * blk + r][c] = R[3 * r] * M[3 * blk][c] + R[3 * r + 1] * M[3 * blk + 1][c] + R[3 * r + 2] * M[3 * blk + 2][c];
+    int idx = 0;
+    for (int r = 0; r < 6; ++r)
+      for (int c = r; c < 6; ++c, ++idx) {
+        const int cb = c / 3, cc = c % 3;     // S[r][c] = sum_k T[r][3cb+k] R[cc][k]
+        double s = T[r][3 * cb] * R[3 * cc] + T[r][3 * cb + 1] * R[3 * cc + 1] + T[r][3 * cb + 2] * R[3 * cc + 2];
+        const bool rfix = (r < 3) ? (mask & 1) : (mask & 2), cfix = (c < 3) ? (mask & 1) : (mask & 2);
+        if (rfix || cfix) s = 0.0;
+        if (s != 0.0) atomicAdd(&v.Sd[(size_t)cam * 21 + idx], s);
+      }
   }
 }
 
 // ---------------------------------------------------------------------------
-// pass A (point order):  s_p = [g_p] + sum_o J_p^T (J_c x_c);  z_p = Vinv s_p
+// pass A (point order):  s_p = [g_p] + sum_o A_o v_o,  v_o = x'_t - 2 X_p x x'_r ;  z_p = Vinv s_p
 //   MODE 0: z -> z4[P][4]                      (mat-vec)
 //   MODE 2: back-substitution epilogue (points_new, step scalars), as ba_schur_pass<2>
 // ---------------------------------------------------------------------------
 struct K3v2Smem {
-  alignas(128) double Jt[kTile * kJpDoubles];
+  alignas(128) double At[kTile * kJpDoubles];
   double t[3][kTile + 1];
   double z[3][kTilePts + 1];
+  double X[3][kTilePts + 1];
   unsigned pb[kTilePts + 1];
   double scratch[32];
   alignas(8) uint64_t mbar;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xq,
+__global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
                                                                      const double* __restrict__ points,
                                                                      double* __restrict__ points_new, double radius,
                                                                      double* __restrict__ bscal) {
@@ -212,19 +243,23 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
     if (n > 0) {
       const int nc0 = min(kTile, n);
       mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc0 * kRowBytes);
-      tma_load_1d(sm.Jt, v2.Jp + (size_t)o0 * kJpDoubles, (uint32_t)nc0 * kRowBytes, &sm.mbar);
+      tma_load_1d(sm.At, v2.Ap + (size_t)o0 * kJpDoubles, (uint32_t)nc0 * kRowBytes, &sm.mbar);
     }
   }
-  // prefetch the camera record of the first chunk
-  double2 g0 = make_double2(0, 0), g1 = g0, g2 = g0, g3 = g0, g4 = g0, g5 = g0;
+  // prefetch the first chunk: camera index -> R^T x record, local point index
+  double2 g0 = make_double2(0, 0), g1 = g0, g2 = g0;
+  int pl_pf = 0;
   if (tid < n) {
     const int cam = v.obs_cam[o0 + tid];
-    const double2* gp_ = reinterpret_cast<const double2*>(xq + (size_t)cam * kXq);
-    g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2]; g3 = gp_[3]; g4 = gp_[4]; g5 = gp_[5];
+    pl_pf = v.obs_pt[o0 + tid] - p0;
+    const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
+    g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
   }
   if (tid < npts) {
     sm.pb[tid] = v.pt_begin[p0 + tid];
     if (tid == npts - 1) sm.pb[npts] = o1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sm.X[k][tid] = points[3 * (size_t)(p0 + tid) + k];
     sm.z[0][tid] = sm.z[1][tid] = sm.z[2][tid] = 0.0;
   }
   __syncthreads();
@@ -234,38 +269,28 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
     const int nc = min(kTile, n - c0);
     if (tid == 0 && ch > 0) {
       mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kRowBytes);
-      tma_load_1d(sm.Jt, v2.Jp + (size_t)(o0 + c0) * kJpDoubles, (uint32_t)nc * kRowBytes, &sm.mbar);
+      tma_load_1d(sm.At, v2.Ap + (size_t)(o0 + c0) * kJpDoubles, (uint32_t)nc * kRowBytes, &sm.mbar);
     }
     const bool active = tid < nc;
     if (active && ch > 0) {
       const int cam = v.obs_cam[o0 + c0 + tid];
-      const double2* gp_ = reinterpret_cast<const double2*>(xq + (size_t)cam * kXq);
-      g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2]; g3 = gp_[3]; g4 = gp_[4]; g5 = gp_[5];
+      pl_pf = v.obs_pt[o0 + c0 + tid] - p0;
+      const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
+      g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
     }
     mbar_wait(&sm.mbar, phase);
     phase ^= 1;
     double t0 = 0, t1 = 0, t2 = 0;
     if (active) {
-      const double2* jr = reinterpret_cast<const double2*>(sm.Jt + tid * kJpDoubles);
-      const double2 r0 = jr[0], r1 = jr[1], r2 = jr[2], r3 = jr[3], r4 = jr[4];
-      const double J[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-      const double a[3] = {r3.x, r3.y, r4.x};
+      const double2* ar = reinterpret_cast<const double2*>(sm.At + tid * kJpDoubles);
+      const double2 a0 = ar[0], a1 = ar[1], a2 = ar[2];
+      const double X[3] = {sm.X[0][pl_pf], sm.X[1][pl_pf], sm.X[2][pl_pf]};
       const double xr[3] = {g0.x, g0.y, g1.x}, xt[3] = {g1.y, g2.x, g2.y};
-      const double q[4] = {g3.x, g3.y, g4.x, g4.y};
-      const int mask = (int)g5.x;
-      const double mr = (mask & 1) ? 0.0 : 1.0, mt = (mask & 2) ? 0.0 : 1.0;
-      // v = m_t x_t - 2 m_r (a x x_r)
-      const double vv[3] = {mt * xt[0] - 2.0 * mr * (a[1] * xr[2] - a[2] * xr[1]),
-                            mt * xt[1] - 2.0 * mr * (a[2] * xr[0] - a[0] * xr[2]),
-                            mt * xt[2] - 2.0 * mr * (a[0] * xr[1] - a[1] * xr[0])};
-      const double u0 = J[0] * vv[0] + J[1] * vv[1] + J[2] * vv[2];
-      const double u1 = J[3] * vv[0] + J[4] * vv[1] + J[5] * vv[2];
-      const double h[3] = {J[0] * u0 + J[3] * u1, J[1] * u0 + J[4] * u1, J[2] * u0 + J[5] * u1};
-      double R[9];
-      quat_to_R(q, R);
-      t0 = R[0] * h[0] + R[3] * h[1] + R[6] * h[2];   // R^T h
-      t1 = R[1] * h[0] + R[4] * h[1] + R[7] * h[2];
-      t2 = R[2] * h[0] + R[5] * h[1] + R[8] * h[2];
+      const double vv[3] = {xt[0] - 2.0 * (X[1] * xr[2] - X[2] * xr[1]), xt[1] - 2.0 * (X[2] * xr[0] - X[0] * xr[2]),
+                            xt[2] - 2.0 * (X[0] * xr[1] - X[1] * xr[0])};
+      t0 = a0.x * vv[0] + a0.y * vv[1] + a1.x * vv[2];
+      t1 = a0.y * vv[0] + a1.y * vv[1] + a2.x * vv[2];
+      t2 = a1.x * vv[0] + a2.x * vv[1] + a2.y * vv[2];
     }
     sm.t[0][tid] = t0;
     sm.t[1][tid] = t1;
@@ -306,7 +331,7 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const double dp = -z[k];
-          const double xo = points[3 * p + k];
+          const double xo = sm.X[k][tid];
           points_new[3 * p + k] = xo + dp;
           b0 += g[k] * dp;
           b1 += Dp[k] * dp * dp;
@@ -316,7 +341,7 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
       }
     } else if (MODE == 2) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) points_new[3 * p + k] = points[3 * p + k];
+      for (int k = 0; k < 3; ++k) points_new[3 * p + k] = sm.X[k][tid];
     }
     if (MODE == 0) *reinterpret_cast<double4*>(v2.z4 + 4 * p) = make_double4(z[0], z[1], z[2], 0.0);
   }
@@ -349,7 +374,7 @@ __global__ void ba2_point_rhs_z(BAView v, BAViewV2 v2) {
 }
 
 // ---------------------------------------------------------------------------
-// pass B (camera order): y_c -= sum_{o in segment} J_c^T ( J ( R z_p ) )
+// pass B (camera order): y_c -= [ 2 R sum (X x w) ; R sum w ],  w = A_o z_p
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                  double* __restrict__ y) {
@@ -358,38 +383,36 @@ __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const d
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
-  const double mr = (mask & 1) ? 0.0 : 1.0, mt = (mask & 2) ? 0.0 : 1.0;
-  const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
-  double R[9];
-  quat_to_R(q, R);
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int i = b + lane; i < e; i += 32) {
     const int pt = v.pt_c[i];
     const double4 z = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt);
-    const double2* row = reinterpret_cast<const double2*>(v2.Jc + (size_t)i * kJcDoubles);
+    const double2* row = reinterpret_cast<const double2*>(v2.Ac + (size_t)i * kJcDoubles);
     const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];
-    const double J[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-    const double a[3] = {r3.x, r3.y, r4.x};
-    const double bz[3] = {R[0] * z.x + R[1] * z.y + R[2] * z.z, R[3] * z.x + R[4] * z.y + R[5] * z.z,
-                          R[6] * z.x + R[7] * z.y + R[8] * z.z};
-    const double u0 = J[0] * bz[0] + J[1] * bz[1] + J[2] * bz[2];
-    const double u1 = J[3] * bz[0] + J[4] * bz[1] + J[5] * bz[2];
-    const double h[3] = {J[0] * u0 + J[3] * u1, J[1] * u0 + J[4] * u1, J[2] * u0 + J[5] * u1};
-    // J_r^T u = 2 a x h ; J_t^T u = h
-    acc[0] += 2.0 * (a[1] * h[2] - a[2] * h[1]);
-    acc[1] += 2.0 * (a[2] * h[0] - a[0] * h[2]);
-    acc[2] += 2.0 * (a[0] * h[1] - a[1] * h[0]);
-    acc[3] += h[0];
-    acc[4] += h[1];
-    acc[5] += h[2];
+    const double w0 = r0.x * z.x + r0.y * z.y + r1.x * z.z;
+    const double w1 = r0.y * z.x + r1.y * z.y + r2.x * z.z;
+    const double w2 = r1.x * z.x + r2.x * z.y + r2.y * z.z;
+    const double X0 = r3.x, X1 = r3.y, X2 = r4.x;
+    acc[0] += 2.0 * (X1 * w2 - X2 * w1);
+    acc[1] += 2.0 * (X2 * w0 - X0 * w2);
+    acc[2] += 2.0 * (X0 * w1 - X1 * w0);
+    acc[3] += w0;
+    acc[4] += w1;
+    acc[5] += w2;
   }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double s = warp_sum(acc[k]) * (k < 3 ? mr : mt);
-    if (lane == k && s != 0.0) atomicAdd(&y[(size_t)cam * 6 + k], -s);
+  for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane < 6) {
+    const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+    const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+    const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
+    const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
+    double R[9];
+    quat_to_R(q, R);
+    const int blk = lane / 3, r = lane % 3;
+    const bool fixed = blk == 0 ? (mask & 1) : (mask & 2);
+    const double s = R[3 * r] * acc[3 * blk] + R[3 * r + 1] * acc[3 * blk + 1] + R[3 * r + 2] * acc[3 * blk + 2];
+    if (!fixed && s != 0.0) atomicAdd(&y[(size_t)cam * 6 + lane], -s);
   }
 }
 

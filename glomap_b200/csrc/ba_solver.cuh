@@ -122,7 +122,7 @@ struct b200sfm_ba_problem {
   size_t smem_k3v2 = 0;
   b200::BAViewV2 view2() {
     b200::BAViewV2 w;
-    w.Jp = W.p; w.Jc = Jc.p; w.z4 = z4.p;
+    w.Ap = W.p; w.Ac = Jc.p; w.z4 = z4.p;
     return w;
   }
   int cur = 0;
@@ -270,7 +270,7 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3v2));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    Jc.alloc((size_t)std::max(Nv, 1) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXq);
+    Jc.alloc((size_t)std::max(Nv, 1) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * 6);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -588,7 +588,7 @@ struct b200sfm_ba_problem {
             B200_CUDA_OK(cudaEventRecord(e0, s));
           }
           if (use_v2) {
-            B200_LAUNCH(ctx, ba2_pack_xq, cdiv(C, 256), 256, 0, C, pp.p, cam_rec.p, xq.p);
+            B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, pp.p, cam_rec.p, xq.p);
             B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, nullptr, nullptr, radius, nullptr);
             if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
           } else {
@@ -650,7 +650,7 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, intr.p, intr.bytes(), cudaMemcpyDeviceToDevice, s));
     }
     if (points_var && use_v2) {
-      B200_LAUNCH(ctx, ba2_pack_xq, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
+      B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
       B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, scal.p + 2);
     } else if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
