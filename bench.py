@@ -177,7 +177,7 @@ def run_b200(args):
     n_global, p_global, nraw_global = (int(x) for x in tot.tolist())
     mask = E.first_frame_mask(C)
 
-    opts = E.BundleAdjusterOptions(optimize_intrinsics=False, profile_kernels=True)
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=False, profile_kernels=True, design=args.design)
     opts.solver_options.max_num_iterations = args.lm_iters
     opts.solver_options.pcg_rel_tolerance = args.pcg_tol
     opts.solver_options.pcg_max_iterations = args.pcg_max
@@ -226,20 +226,29 @@ def run_b200(args):
     peak, peak_src = peaks()
     n_mv = sum(s["n_matvec"] for s in stats); ms_mv = sum(s["ms_matvec"] for s in stats)
     n_li = sum(s["n_linearize"] for s in stats); ms_li = sum(s["ms_linearize"] for s in stats)
-    mv_bytes = 152 * sc.N + 56 * sc.P + 96 * C
-    li_bytes = 168 * sc.N + 96 * sc.P + 64 * C
-    roof_mv = {"kernel": "ba_schur_pass<0> (implicit-Schur mat-vec)", "bound": "hbm",
+    if args.design == 1:
+        mv_bytes = 152 * sc.N + 56 * sc.P + 96 * C
+        li_bytes = 168 * sc.N + 96 * sc.P + 64 * C
+        mv_name, mv_model = "ba_schur_pass<0> (implicit-Schur mat-vec, design v1)", "152*N + 56*P + 96*C per launch"
+        li_model = "168*N + 96*P + 64*C per launch"
+    else:
+        # design v2: pass A streams A_o rows in point order (48 B + 4 B index), pass B in camera order (80 B + 4 B)
+        mv_bytes = 136 * sc.N + 136 * sc.P + 144 * C
+        li_bytes = 72 * sc.N + 96 * sc.P + 64 * C
+        mv_name = "ba2_pack_x + ba2_pass_a<0> + ba2_pass_b (implicit-Schur mat-vec, design v2: two streaming passes)"
+        mv_model, li_model = "136*N + 136*P + 144*C per mat-vec", "72*N + 96*P + 64*C per launch"
+    roof_mv = {"kernel": mv_name, "bound": "hbm",
                "achieved": mv_bytes / (ms_mv / max(n_mv, 1) * 1e-3) / 1e9 if n_mv else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_mv, "avg_ms": ms_mv / max(n_mv, 1),
-               "bytes_model": "152*N + 56*P + 96*C per launch"}
+               "bytes_model": mv_model}
     roof_li = {"kernel": "ba_linearize_points (Jacobian + point Schur blocks)", "bound": "hbm",
                "achieved": li_bytes / (ms_li / max(n_li, 1) * 1e-3) / 1e9 if n_li else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_li, "avg_ms": ms_li / max(n_li, 1),
-               "bytes_model": "168*N + 96*P + 64*C per launch"}
+               "bytes_model": li_model}
     # DRAM traffic per launch from the committed `ncu --set full` capture (same workload, 1 GPU)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if tr.get("workload") == args.workload and world == 1:
+        if tr.get("workload") == args.workload and world == 1 and args.design == 1:
             roof_mv["traffic"] = tr["dram_bytes_per_launch"]["ba_schur_pass<0>"]
             roof_li["traffic"] = tr["dram_bytes_per_launch"]["ba_linearize_points"]
             roof_mv["traffic_source"] = roof_li["traffic_source"] = tr["source"]
@@ -263,7 +272,7 @@ def run_b200(args):
     for f in ("quat", "trans", "points", "intr_params"):
         arr, t = pinned(getattr(init, f)); keep.append(t); setattr(host, f, arr)
         state0[f] = np.array(arr, copy=True)
-    opts_e = E.BundleAdjusterOptions(optimize_intrinsics=False)
+    opts_e = E.BundleAdjusterOptions(optimize_intrinsics=False, design=args.design)
     opts_e.solver_options.max_num_iterations = args.lm_iters
     opts_e.solver_options.pcg_rel_tolerance = args.pcg_tol
     opts_e.solver_options.pcg_max_iterations = args.pcg_max
@@ -307,7 +316,7 @@ def run_b200(args):
                                    f"0.5 px noise, start = GT perturbed 0.5 deg / 1% / 1%",
                        "parallelism": f"points sharded over {world} GPU(s), cameras replicated, NCCL all-reduce per PCG mat-vec",
                        "lm_iterations_per_step": lm_its / args.steps, "pcg_iterations_per_lm_iteration": pcg_its / max(lm_its, 1),
-                       "pcg_rel_tolerance": args.pcg_tol, "preconditioner": "schur-jacobi",
+                       "pcg_rel_tolerance": args.pcg_tol, "preconditioner": "schur-jacobi", "design": "v1 (W blocks, atomics)" if args.design == 1 else "v2 (A_o rows, two passes)",
                        "l2_policy": "inputs_exceed_L2 (W alone is 144 B x N >> 126 MB)",
                        "cost": [init_cost, final_cost], "wall_ms_per_step": 1e3 * wall / args.steps,
                        "scene_generation_s": gen_s},
@@ -335,6 +344,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-lm-iters", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--design", type=int, default=0, help="BA data layout: 0 auto (v2), 1 = v1 (W blocks + atomics), 2 = v2")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -384,21 +384,42 @@ __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const d
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = b + lane; i < e; i += 32) {
-    const int pt = v.pt_c[i];
-    const double4 z = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt);
-    const double2* row = reinterpret_cast<const double2*>(v2.Ac + (size_t)i * kJcDoubles);
-    const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];
-    const double w0 = r0.x * z.x + r0.y * z.y + r1.x * z.z;
-    const double w1 = r0.y * z.x + r1.y * z.y + r2.x * z.z;
-    const double w2 = r1.x * z.x + r2.x * z.y + r2.y * z.z;
-    const double X0 = r3.x, X1 = r3.y, X2 = r4.x;
-    acc[0] += 2.0 * (X1 * w2 - X2 * w1);
-    acc[1] += 2.0 * (X2 * w0 - X0 * w2);
-    acc[2] += 2.0 * (X0 * w1 - X1 * w0);
-    acc[3] += w0;
-    acc[4] += w1;
-    acc[5] += w2;
+  // two observations per lane and iteration: both index loads, then both gathers, are in flight together
+  for (int i0 = b + lane; i0 < e; i0 += 64) {
+    const int i1 = i0 + 32;
+    const bool ok1 = i1 < e;
+    const int pt0 = v.pt_c[i0];
+    const int pt1 = ok1 ? v.pt_c[i1] : pt0;
+    const double2* row0 = reinterpret_cast<const double2*>(v2.Ac + (size_t)i0 * kJcDoubles);
+    const double2* row1 = reinterpret_cast<const double2*>(v2.Ac + (size_t)(ok1 ? i1 : i0) * kJcDoubles);
+    const double2 a0 = row0[0], a1 = row0[1], a2 = row0[2], a3 = row0[3], a4 = row0[4];
+    const double2 c0 = row1[0], c1 = row1[1], c2 = row1[2], c3 = row1[3], c4 = row1[4];
+    const double4 z0 = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt0);
+    const double4 z1 = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt1);
+    {
+      const double w0 = a0.x * z0.x + a0.y * z0.y + a1.x * z0.z;
+      const double w1 = a0.y * z0.x + a1.y * z0.y + a2.x * z0.z;
+      const double w2 = a1.x * z0.x + a2.x * z0.y + a2.y * z0.z;
+      const double X0 = a3.x, X1 = a3.y, X2 = a4.x;
+      acc[0] += 2.0 * (X1 * w2 - X2 * w1);
+      acc[1] += 2.0 * (X2 * w0 - X0 * w2);
+      acc[2] += 2.0 * (X0 * w1 - X1 * w0);
+      acc[3] += w0;
+      acc[4] += w1;
+      acc[5] += w2;
+    }
+    if (ok1) {
+      const double w0 = c0.x * z1.x + c0.y * z1.y + c1.x * z1.z;
+      const double w1 = c0.y * z1.x + c1.y * z1.y + c2.x * z1.z;
+      const double w2 = c1.x * z1.x + c2.x * z1.y + c2.y * z1.z;
+      const double X0 = c3.x, X1 = c3.y, X2 = c4.x;
+      acc[0] += 2.0 * (X1 * w2 - X2 * w1);
+      acc[1] += 2.0 * (X2 * w0 - X0 * w2);
+      acc[2] += 2.0 * (X0 * w1 - X1 * w0);
+      acc[3] += w0;
+      acc[4] += w1;
+      acc[5] += w2;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);

@@ -589,7 +589,7 @@ struct b200sfm_ba_problem {
           }
           if (use_v2) {
             B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, pp.p, cam_rec.p, xq.p);
-            B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, nullptr, nullptr, radius, nullptr);
+            B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr);
             if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
           } else {
             B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr);
