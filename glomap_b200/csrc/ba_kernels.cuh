@@ -110,8 +110,6 @@ __device__ __forceinline__ void project_only(const double* __restrict__ ir, doub
 struct ObsLin {
   double Jr[6], Jt[6], Jp[6], r[2], rho0;
   double u, v, w;   // normalised image coordinates and sqrt(rho') (for the intrinsics Jacobian)
-  double J[6];      // sqrt(rho') * d(px,py)/d(Xc), unmasked (the compact row of the v2 layout)
-  double a[3];      // R X (rotated point, without the translation)
   bool valid;
 };
 
@@ -136,9 +134,6 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
     o.r[0] = o.r[1] = 0.0;
     o.rho0 = 0.0;
     o.u = o.v = o.w = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o.J[k] = 0.0;
-    o.a[0] = rx; o.a[1] = ry; o.a[2] = rz;
     return;
   }
   double px, py, J[6];
@@ -153,11 +148,7 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
   o.r[0] = w * r0;
   o.r[1] = w * r1;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    J[k] *= w;
-    o.J[k] = J[k];
-  }
-  o.a[0] = rx; o.a[1] = ry; o.a[2] = rz;
+  for (int k = 0; k < 6; ++k) J[k] *= w;
   // translation block
   const bool tvar = !(mask & 2), rvar = !(mask & 1);
 #pragma unroll
