@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--pcg-tol", type=float, default=0.1, help="PCG forcing tolerance (Ceres eta default 0.1)")
     ap.add_argument("--pcg-max", type=int, default=200)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-lm-iters", type=int, default=2)
+    ap.add_argument("--cpu-lm-iters", type=int, default=1, help="LM iterations of the CPU port per step / sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--design", type=int, default=0, help="BA data layout: 0 auto (v2), 1 = v1 (W blocks + atomics), 2 = v2")
     args = ap.parse_args()

@@ -1,0 +1,93 @@
+"""Run under torchrun on >= 2 GPUs (not collected by pytest): sharded GP
+(points) and RA (edges) must reproduce the single-GPU solves.
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tests/multigpu_gp_ra_check.py
+"""
+import ctypes as ct
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from glomap_b200 import _lib, dist as D, estimators as E, geometry as G, synthetic as S  # noqa: E402
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+def gp_solve(ctx, sc, t_obs, c0, X0, a, b):
+    """b200sfm_gp_solve on the point range [a, b) of the scene."""
+    o0, o1 = int(sc.pt_obs_begin[a]), int(sc.pt_obs_begin[b])
+    ptb = np.ascontiguousarray(sc.pt_obs_begin[a:b + 1] - o0, np.int64)
+    cam = np.ascontiguousarray(sc.obs_cam[o0:o1], np.int32)
+    dirs = np.ascontiguousarray(t_obs[o0:o1], np.float64)
+    cen, pts, scl = c0.copy(), np.ascontiguousarray(X0[a:b]), np.ones(o1 - o0)
+    opts = E.GlobalPositionerOptions()
+    opts.solver_options.pcg_rel_tolerance = 1e-10
+    opts.solver_options.pcg_max_iterations = 3000
+    opts.solver_options.function_tolerance = 1e-12
+    opts.solver_options.max_num_iterations = 200
+    co = opts.to_c()
+    st = _lib.LMStats()
+    rc = ctx.lib.b200sfm_gp_solve(ctx.handle, ct.byref(co), sc.C, b - a, o1 - o0, _p(ptb), _p(cam), _p(dirs), None, None,
+                                  _p(cen), _p(pts), _p(scl), ct.byref(st))
+    assert rc == 0, ctx.lib.b200sfm_last_error(ctx.handle)
+    return cen, st
+
+
+def ra_solve(ctx, vg, theta0, lo, hi):
+    opts = E.RotationEstimatorOptions(pcg_rel_tolerance=1e-12)
+    co = opts.to_c()
+    st = _lib.RAStats()
+    ei = np.ascontiguousarray(vg.ei[lo:hi], np.int32); ej = np.ascontiguousarray(vg.ej[lo:hi], np.int32)
+    Rr = np.ascontiguousarray(vg.R_rel[lo:hi].reshape(-1, 9), np.float64)
+    w = np.ascontiguousarray(vg.weight[lo:hi], np.float64)
+    th = np.ascontiguousarray(theta0, np.float64).copy()
+    rc = ctx.lib.b200sfm_ra_solve(ctx.handle, ct.byref(co), vg.n_images, hi - lo, _p(ei), _p(ej), _p(Rr), _p(w), 0, _p(th), ct.byref(st))
+    assert rc == 0, ctx.lib.b200sfm_last_error(ctx.handle)
+    return th, st
+
+
+def main():
+    rank, world, local = D.env_rank_world()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = E.Context(local, rank, world, D.broadcast_nccl_id(E.Context.nccl_unique_id, rank, world))
+    ok = True
+    # ---- GP -----------------------------------------------------------------------------------
+    sc = S.make_scene(40, 3000, 6, seed=7, pixel_sigma=0.5, chunk=500)
+    t_obs = E.world_bearings(sc.quat, S.bearings_from_scene(sc), sc.obs_cam)
+    rng = np.random.default_rng(1)
+    c0 = 100 * rng.uniform(-1, 1, size=(sc.C, 3)); X0 = 100 * rng.uniform(-1, 1, size=(sc.P, 3))
+    a, b = D.shard_range(sc.P, 500, rank, world)
+    cen, st = gp_solve(ctx, sc, t_obs, c0, X0, a, b)
+    # ---- RA -----------------------------------------------------------------------------------
+    vg = S.make_random_view_graph(400, 14, seed=9, noise_deg=1.0, outlier_ratio=0.05)
+    lo, hi = D.shard_range(vg.E, 64, rank, world)
+    th, rst = ra_solve(ctx, vg, np.zeros((vg.n_images, 3)), lo, hi)
+    if rank == 0:
+        one = E.Context(local)
+        cen1, st1 = gp_solve(one, sc, t_obs, c0, X0, 0, sc.P)
+        s_, R_, t_ = G.umeyama_sim3(cen, cen1)
+        gerr = np.linalg.norm((s_ * (R_ @ cen.T)).T + t_ - cen1, axis=1).max() / np.abs(cen1).max()
+        th1, rst1 = ra_solve(one, vg, np.zeros((vg.n_images, 3)), 0, vg.E)
+        rerr = np.abs(G.so3_exp(th) - G.so3_exp(th1)).max()
+        print(f"GP multi({world})/single: its {st.iterations}/{st1.iterations} cost {st.final_cost:.10e}/{st1.final_cost:.10e} centre rel err {gerr:.2e}")
+        print(f"RA multi({world})/single: L1 {rst.l1_iterations}/{rst1.l1_iterations} IRLS {rst.irls_iterations}/{rst1.irls_iterations} max |dR| {rerr:.2e}")
+        ok = (abs(st.final_cost - st1.final_cost) <= 1e-6 * max(st1.final_cost, 1e-12) + 1e-9 and gerr < 1e-5 and
+              (rst.l1_iterations, rst.irls_iterations) == (rst1.l1_iterations, rst1.irls_iterations) and rerr < 1e-7)
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ctx.close()
+    dist.destroy_process_group()
+    if flag.item() < 1:
+        raise SystemExit("multi-GPU GP/RA parity FAILED")
+    if rank == 0:
+        print("multi-GPU GP/RA parity OK")
+
+
+if __name__ == "__main__":
+    main()
