@@ -48,3 +48,26 @@ def test_no_cpu_fallback_without_device():
     h = ct.c_void_p()
     assert lib.b200sfm_create(0, ct.byref(h)) != 0
     assert not h.value
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile a tiny C program against include/b200sfm.h and compare sizeof /
+    offsetof of every struct with the ctypes mirrors (ABI drift guard)."""
+    import subprocess
+    structs = {"b200sfm_lm_stats": _lib.LMStats, "b200sfm_ba_opts": _lib.BAOpts, "b200sfm_gp_opts": _lib.GPOpts,
+               "b200sfm_ra_opts": _lib.RAOpts, "b200sfm_ra_stats": _lib.RAStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "b200sfm.h")}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ct.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
