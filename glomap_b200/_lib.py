@@ -91,6 +91,7 @@ PROTOTYPES = {
     "b200sfm_ba_default_opts": (None, [P(BAOpts)]),
     "b200sfm_ba_solve": (c_int32, [c_void_p, P(BAOpts), c_int32, c_int32, c_int64, c_int32] + [c_void_p] * 10 + [P(LMStats)]),
     "b200sfm_ba_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32] + [c_void_p] * 6 + [c_int32, P(c_void_p)]),
+    "b200sfm_ba_problem_create_rig": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32] + [c_void_p] * 9 + [c_int32, P(c_void_p)]),
     "b200sfm_ba_problem_set_state": (c_int32, [c_void_p] * 5),
     "b200sfm_ba_problem_get_state": (c_int32, [c_void_p] * 5),
     "b200sfm_ba_problem_save_state": (c_int32, [c_void_p]),
@@ -104,6 +105,7 @@ PROTOTYPES = {
     "b200sfm_gp_default_opts": (None, [P(GPOpts)]),
     "b200sfm_gp_solve": (c_int32, [c_void_p, P(GPOpts), c_int32, c_int32, c_int64] + [c_void_p] * 8 + [P(LMStats)]),
     "b200sfm_gp_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 5 + [c_int32, P(c_void_p)]),
+    "b200sfm_gp_problem_set_rig_terms": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "b200sfm_gp_problem_set_state": (c_int32, [c_void_p] * 4),
     "b200sfm_gp_problem_get_state": (c_int32, [c_void_p] * 4),
     "b200sfm_gp_problem_save_state": (c_int32, [c_void_p]),

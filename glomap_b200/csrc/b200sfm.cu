@@ -151,6 +151,42 @@ int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
   });
 }
 
+int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_t N, int32_t K, int32_t S,
+                                  const int64_t* pt_obs_begin, const int32_t* obs_frame, const uint16_t* obs_sensor,
+                                  const double* obs_xy, const double* sensor_quat_xyzw, const double* sensor_trans,
+                                  const int32_t* sensor_intr, const int32_t* intr_model, const uint8_t* frame_const_mask,
+                                  int32_t min_num_view_per_track, b200sfm_ba_problem** out) {
+  if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (F <= 0 || P <= 0 || N <= 0 || K <= 0 || S <= 0) { ctx->err = "empty problem (no frames / tracks / observations / sensors)"; return B200SFM_ERR_EMPTY; }
+  if (!pt_obs_begin || !obs_frame || !obs_sensor || !obs_xy || !sensor_quat_xyzw || !sensor_trans || !sensor_intr || !intr_model) {
+    ctx->err = "null input array";
+    return B200SFM_ERR_INVALID_ARG;
+  }
+  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+  if (S > 65535 || (long long)F * S >= (1ll << 31) - 1) { ctx->err = "too many sensors (S <= 65535, F * S < 2^31)"; return B200SFM_ERR_INVALID_ARG; }
+  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+  for (int k = 0; k < K; ++k)
+    if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
+  for (int i = 0; i < S; ++i)
+    if (sensor_intr[i] < 0 || sensor_intr[i] >= K) { ctx->err = "sensor_intr out of range"; return B200SFM_ERR_INVALID_ARG; }
+  for (int64_t o = 0; o < N; ++o)
+    if (obs_sensor[o] >= S || obs_frame[o] < 0 || obs_frame[o] >= F) { ctx->err = "obs_frame / obs_sensor out of range"; return B200SFM_ERR_INVALID_ARG; }
+  return guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    auto* p = new b200sfm_ba_problem();
+    try {
+      p->create(ctx, F, P, N, K, pt_obs_begin, obs_frame, obs_xy, nullptr, intr_model, frame_const_mask,
+                min_num_view_per_track, nullptr, S, obs_sensor, sensor_quat_xyzw, sensor_trans, sensor_intr);
+    } catch (...) {
+      delete p;
+      throw;
+    }
+    *out = p;
+    return (int)B200SFM_OK;
+  });
+}
+
 int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
                                  const double* trans, const double* points) {
   if (!p || !intr_params || !quat_xyzw || !trans || !points) return B200SFM_ERR_INVALID_ARG;
@@ -346,6 +382,15 @@ int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
       throw;
     }
     *out = p;
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* obs_offset, const uint8_t* obs_calibrated) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->set_rig_terms(obs_offset, obs_calibrated);
     return (int)B200SFM_OK;
   });
 }

@@ -27,7 +27,8 @@ constexpr double kZEps = 1e-12;
 constexpr int kSeg = 256;     // observations per camera-order segment (one warp)
 constexpr int kIntrSmem = 16; // intrinsics blocks cached in shared memory by the point-order kernels
 constexpr int kJpDoubles = 6;  // v2 point-order row: A_o = J_pt^T J_pt (packed symmetric 3x3) -> 48 B
-constexpr int kJcDoubles = 10; // v2 camera-order row: A_o (6), X_p (3), pad -> 80 B
+constexpr int kJcDoubles = 9;  // v2 camera-order row: A_o (6), X_p (3) -> 72 B, stored SoA in groups of 32 rows
+constexpr int kSensorRec = 16; // known rigs: R_cam_from_rig (9, row-major), t_cam_from_rig (3), intrinsics idx, pad
 
 struct BAView {
   int C, P, K;
@@ -48,6 +49,16 @@ struct BAView {
   const int* seg_cam;           // [n_segs]
   const int* seg_begin;         // [n_segs+1] (only within one camera: seg_end = seg_begin2[s])
   const int* seg_end;
+  const int* seg_row0;          // [n_segs] first (32-aligned) padded row of the segment in the v2 camera-order rows
+  // known (constant) rigs -- bundle_adjustment.cc:147-161.  S == 0: every frame is trivial, obs_cam is the
+  // image and the intrinsics index rides in the camera record.  S > 0: obs_cam is the FRAME (rig_from_world),
+  // obs_sensor picks the constant cam_from_rig + intrinsics of the observing image; camera-order segments
+  // are homogeneous in (frame, sensor).
+  int S;
+  const unsigned short* obs_sensor;   // [N]
+  const int* seg_sensor;              // [n_segs]
+  const int* seg_intr;                // [n_segs] intrinsics block of the segment (always filled)
+  const double* sensor_rec;           // [S][kSensorRec]
   // linear system
   double* W;
   double* V;
@@ -115,8 +126,27 @@ struct ObsLin {
 
 __device__ __forceinline__ int cam_rec_intr(const double4& t4) { return (int)(__double_as_longlong(t4.w) >> 8); }
 
-// q4/t4 = the camera record (already loaded), ir = the intrinsics record of that camera
+// camera-frame point of a known-rig image: X_c = R_cr X_f + t_cr
+__device__ __forceinline__ void sensor_apply(const double* __restrict__ sr, double& x, double& y, double& z) {
+  const double a = sr[0] * x + sr[1] * y + sr[2] * z + sr[9];
+  const double b = sr[3] * x + sr[4] * y + sr[5] * z + sr[10];
+  const double c = sr[6] * x + sr[7] * y + sr[8] * z + sr[11];
+  x = a; y = b; z = c;
+}
+__device__ __forceinline__ int obs_intr_idx(const double4& t4, const double* __restrict__ sr) {
+  return sr ? (int)sr[12] : cam_rec_intr(t4);
+}
+__device__ __forceinline__ const double* sensor_of_obs(const BAView& v, long long o) {
+  return v.S > 0 ? v.sensor_rec + (size_t)v.obs_sensor[o] * kSensorRec : nullptr;
+}
+__device__ __forceinline__ const double* sensor_of_seg(const BAView& v, int seg) {
+  return v.S > 0 ? v.sensor_rec + (size_t)v.seg_sensor[seg] * kSensorRec : nullptr;
+}
+
+// q4/t4 = the camera (frame) record (already loaded), ir = the intrinsics record of the observing image,
+// sr = its sensor record (nullptr: trivial frame, cam_from_rig = identity)
 __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& t4, const double* __restrict__ ir,
+                                              const double* __restrict__ sr,
                                               double X0, double X1, double X2, double2 xy, double huber_a, ObsLin& o) {
   const long long packed = __double_as_longlong(t4.w);
   const int mask = (int)(packed & 0xff);
@@ -126,7 +156,8 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
   const double rx = R[0] * X0 + R[1] * X1 + R[2] * X2;
   const double ry = R[3] * X0 + R[4] * X1 + R[5] * X2;
   const double rz = R[6] * X0 + R[7] * X1 + R[8] * X2;
-  const double xc = rx + t4.x, yc = ry + t4.y, zc = rz + t4.z;
+  double xc = rx + t4.x, yc = ry + t4.y, zc = rz + t4.z;
+  if (sr) sensor_apply(sr, xc, yc, zc);
   o.valid = zc > kZEps;
   if (!o.valid) {
 #pragma unroll
@@ -138,6 +169,15 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
   }
   double px, py, J[6];
   project_jac(ir, xc, yc, zc, px, py, J);
+  if (sr) {   // chain through the constant cam_from_rig rotation: J <- J R_cr
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const double j0 = J[3 * a], j1 = J[3 * a + 1], j2 = J[3 * a + 2];
+      J[3 * a] = j0 * sr[0] + j1 * sr[3] + j2 * sr[6];
+      J[3 * a + 1] = j0 * sr[1] + j1 * sr[4] + j2 * sr[7];
+      J[3 * a + 2] = j0 * sr[2] + j1 * sr[5] + j2 * sr[8];
+    }
+  }
   o.u = xc / zc;
   o.v = yc / zc;
   const double r0 = px - xy.x, r1 = py - xy.y;
@@ -236,12 +276,14 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
   int cam_pf = 0, pt_pf = 0;
   double2 xy_pf = make_double2(0.0, 0.0);
   double4 q4_pf = make_double4(0, 0, 0, 1), t4_pf = make_double4(0, 0, 0, 0);
+  const double* sr_pf = nullptr;
   if (tid < n) {
     cam_pf = v.obs_cam[o0 + tid];
     xy_pf = v.obs_xy[o0 + tid];
     pt_pf = v.obs_pt[o0 + tid];
     q4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec);
     t4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec + 4);
+    sr_pf = sensor_of_obs(v, o0 + tid);
   }
   for (int i = tid; i < min(v.K, kIntrSmem) * kIntrRec; i += kTile) (&sm.intr[0][0])[i] = intr_rec[i];
   // per-point accumulators live in shared memory (thread j <-> point p0 + j)
@@ -273,14 +315,15 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
         pt_pf = v.obs_pt[oi];
         q4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec);
         t4_pf = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam_pf * kCamRec + 4);
+        sr_pf = sensor_of_obs(v, oi);
       }
       const int pl = pt_pf - p0;     // point index within the tile: X and validity come from smem
       use = (int)(sm.pb[pl + 1] - sm.pb[pl]) >= v.min_views;
       if (use) {
         const double X0 = sm.X[0][pl], X1 = sm.X[1][pl], X2 = sm.X[2][pl];
-        const int intr = cam_rec_intr(t4_pf);
+        const int intr = obs_intr_idx(t4_pf, sr_pf);
         const double* ir = intr < kIntrSmem ? sm.intr[intr] : intr_rec + (size_t)intr * kIntrRec;
-        linearize_obs(q4_pf, t4_pf, ir, X0, X1, X2, xy_pf, huber_a, o);
+        linearize_obs(q4_pf, t4_pf, ir, sr_pf, X0, X1, X2, xy_pf, huber_a, o);
         cost += 0.5 * o.rho0;
       }
     }
@@ -378,7 +421,8 @@ __global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double*
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
   const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const double* irc = intr_rec + (size_t)cam_rec_intr(t4c) * kIntrRec;
+  const double* irc = intr_rec + (size_t)v.seg_intr[warp] * kIntrRec;
+  const double* src = sensor_of_seg(v, warp);
   double U[21], g[6];
 #pragma unroll
   for (int k = 0; k < 21; ++k) U[k] = 0.0;
@@ -389,7 +433,7 @@ __global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double*
     const double2 xy = v.xy_c[i];
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
     ObsLin o;
-    linearize_obs(q4c, t4c, irc, X0, X1, X2, xy, huber_a, o);
+    linearize_obs(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
     double Jc[2][6];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -793,14 +837,16 @@ __global__ void __launch_bounds__(256) ba_cost(BAView v, const double* __restric
     const double2 xy = v.obs_xy[o];
     const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
     const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-    const int intr = (int)(__double_as_longlong(t4.w) >> 8);
+    const double* sr = sensor_of_obs(v, o);
+    const int intr = obs_intr_idx(t4, sr);
     const double q[4] = {q4.x, q4.y, q4.z, q4.w};
     double R[9];
     quat_to_R(q, R);
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
-    const double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
-    const double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
-    const double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+    double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
+    double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
+    double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+    if (sr) sensor_apply(sr, xc, yc, zc);
     if (zc > kZEps) {
       double px, py;
       project_only(intr_rec + (size_t)intr * kIntrRec, xc, yc, zc, px, py);
@@ -943,8 +989,9 @@ __global__ void __launch_bounds__(128) ba_intr_cams(BAView v, const double* __re
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
   const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const int blk = cam_rec_intr(t4c);
+  const int blk = v.seg_intr[warp];
   const double* irc = intr_rec + (size_t)blk * kIntrRec;
+  const double* src = sensor_of_seg(v, warp);
   const IntrVarRec iv = ivar[blk];
   double Uck[6][kMaxBlockDof], Ukk[15], gk[kMaxBlockDof];
 #pragma unroll
@@ -961,7 +1008,7 @@ __global__ void __launch_bounds__(128) ba_intr_cams(BAView v, const double* __re
       const double2 xy = v.xy_c[i];
       const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
       ObsLin o;
-      linearize_obs(q4c, t4c, irc, X0, X1, X2, xy, huber_a, o);
+      linearize_obs(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
       if (!o.valid) continue;
       double Jk[2][kMaxBlockDof];
 #pragma unroll
@@ -1002,9 +1049,8 @@ __global__ void __launch_bounds__(128) ba_intr_cams(BAView v, const double* __re
   }
 }
 
-// out[blk][20] = sum over the segments whose camera uses block blk (one CTA per block, deterministic)
-__global__ void __launch_bounds__(256) ba_intr_reduce_segs(int n_segs, const int* __restrict__ seg_cam,
-                                                          const int* __restrict__ cam_intr,
+// out[blk][20] = sum over the segments whose image uses block blk (one CTA per block, deterministic)
+__global__ void __launch_bounds__(256) ba_intr_reduce_segs(int n_segs, const int* __restrict__ seg_intr,
                                                           const double* __restrict__ part, double* __restrict__ out) {
   __shared__ double scratch[32];
   const int blk = blockIdx.x;
@@ -1012,7 +1058,7 @@ __global__ void __launch_bounds__(256) ba_intr_reduce_segs(int n_segs, const int
 #pragma unroll
   for (int k = 0; k < 20; ++k) acc[k] = 0.0;
   for (int sgm = threadIdx.x; sgm < n_segs; sgm += blockDim.x) {
-    if (cam_intr[seg_cam[sgm]] != blk) continue;
+    if (seg_intr[sgm] != blk) continue;
 #pragma unroll
     for (int k = 0; k < 20; ++k) acc[k] += part[(size_t)sgm * 20 + k];
   }
@@ -1090,12 +1136,13 @@ __global__ void __launch_bounds__(kTile) ba_intr_points(BAView v, const double* 
         const int cam = v.obs_cam[oi];
         const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
         const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-        const int blk = cam_rec_intr(t4);
+        const double* sr = sensor_of_obs(v, oi);
+        const int blk = obs_intr_idx(t4, sr);
         const double* ir = intr_rec + (size_t)blk * kIntrRec;
         const IntrVarRec iv = ivar[blk];
         if (iv.mb > 0) {
           ObsLin o;
-          linearize_obs(q4, t4, ir, sm.X[0][pl], sm.X[1][pl], sm.X[2][pl], v.obs_xy[oi], huber_a, o);
+          linearize_obs(q4, t4, ir, sr, sm.X[0][pl], sm.X[1][pl], sm.X[2][pl], v.obs_xy[oi], huber_a, o);
           if (o.valid) {
             for (int j = 0; j < iv.mb; ++j) {
               double jx, jy;

@@ -10,13 +10,16 @@
 // W_o z = [ 2 R (X x w) ; R w ],  w = A_o z.   Only A_o (48 B) is stored per
 // observation, in BOTH traversal orders:
 //     Ap[N][6]   point order  (tiles moved by TMA)
-//     Ac[Nv][10] camera order {A_o, X_p, pad}  (80 B, written by the camera-order linearisation)
+//     Ac         camera order {A_o, X_p} (72 B, written by the camera-order linearisation), SoA in
+//                groups of 32 rows: element k of padded row r at ((r >> 5) * 9 + k) * 32 + (r & 31); every
+//                segment starts on a group boundary (seg_row0), so lane l of the segment's warp owns
+//                rows l, l + 32, ... and every load/store of the warp is one contiguous 256-B line pair
 // and the implicit-Schur mat-vec is two streaming passes
 //     pass A (point order):  s_p = sum_o A_o v_o,  z_p = Vinv s_p -> z4[P]      gathers R^T x (48 B)
 //     pass B (camera order): y_c -= R-rotated sum_o [2 X x (A_o z_p) ; A_o z_p]  gathers z_p (32 B)
 //                            one warp per <= 256-observation segment of ONE camera: register
 //                            accumulation, shuffle reduction, 6 atomics per segment.
-// All arithmetic stays FP64.  Algorithmic bytes per mat-vec: 52 N + 80 P (A) + 84 N + 32 P (B).
+// All arithmetic stays FP64.  Algorithmic bytes per mat-vec: 52 N + 80 P (A) + 76 N + 32 P (B).
 #pragma once
 #include "ba_kernels.cuh"
 
@@ -24,7 +27,7 @@ namespace b200 {
 
 struct BAViewV2 {
   const double* Ap;   // [N][6]   (aliases BAView::W)
-  double* Ac;         // [Nv][10]
+  double* Ac;         // camera-order rows, SoA-32 (see above)
   double* z4;         // [P][4]
 };
 
@@ -49,7 +52,7 @@ __global__ void ba2_pack_x(int C, const double* __restrict__ x, const double* __
 // ---------------------------------------------------------------------------
 // camera-order linearisation: U_c, g_c AND the camera-order rows Ac = {A_o, X_p}
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
+__global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                          const double* __restrict__ intr_rec,
                                                          const double* __restrict__ points, double huber_a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -59,24 +62,29 @@ __global__ void __launch_bounds__(128) ba2_linearize_cams(BAView v, BAViewV2 v2,
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
   const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const double* irc = intr_rec + (size_t)cam_rec_intr(t4c) * kIntrRec;
+  const double* irc = intr_rec + (size_t)v.seg_intr[warp] * kIntrRec;
+  const double* src = sensor_of_seg(v, warp);
   double U[21], g[6];
 #pragma unroll
   for (int k = 0; k < 21; ++k) U[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) g[k] = 0.0;
-  for (int i = b + lane; i < e; i += 32) {
-    const int pt = v.pt_c[i];
-    const double2 xy = v.xy_c[i];
+  double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
+  for (int i = b + lane; i < e; i += 32, row += kJcDoubles * 32) {
+    const int pt = ld_stream(v.pt_c + i);
+    const double2 xy = ld_stream(v.xy_c + i);
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
     ObsLin o;
-    linearize_obs(q4c, t4c, irc, X0, X1, X2, xy, huber_a, o);
-    double2* row = reinterpret_cast<double2*>(v2.Ac + (size_t)i * kJcDoubles);
-    row[0] = make_double2(o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3], o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4]);
-    row[1] = make_double2(o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5], o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4]);
-    row[2] = make_double2(o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5], o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5]);
-    row[3] = make_double2(X0, X1);
-    row[4] = make_double2(X2, 0.0);
+    linearize_obs(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
+    st_stream(row, o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3]);
+    st_stream(row + 32, o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4]);
+    st_stream(row + 64, o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5]);
+    st_stream(row + 96, o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4]);
+    st_stream(row + 128, o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5]);
+    st_stream(row + 160, o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5]);
+    st_stream(row + 192, X0);
+    st_stream(row + 224, X1);
+    st_stream(row + 256, X2);
     double Jc[2][6];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -118,12 +126,12 @@ __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, con
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   // world-frame accumulators: RR (sym 6), RT (full 9), TT (sym 6)
   double RR[6] = {0, 0, 0, 0, 0, 0}, RT[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, TT[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = b + lane; i < e; i += 32) {
-    const double2* row = reinterpret_cast<const double2*>(v2.Ac + (size_t)i * kJcDoubles);
-    const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];
-    const double A[6] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
-    const double X[3] = {r3.x, r3.y, r4.x};
-    const int pt = v.pt_c[i];
+  const double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
+  for (int i = b + lane; i < e; i += 32, row += kJcDoubles * 32) {
+    const double A[6] = {ld_stream(row), ld_stream(row + 32), ld_stream(row + 64), ld_stream(row + 96), ld_stream(row + 128),
+                         ld_stream(row + 160)};
+    const double X[3] = {ld_stream(row + 192), ld_stream(row + 224), ld_stream(row + 256)};
+    const int pt = ld_stream(v.pt_c + i);
     const double2* vp = reinterpret_cast<const double2*>(v.Vinv + (size_t)pt * 6);
     const double2 v0 = vp[0], v1 = vp[1], v2_ = vp[2];
     const double vi[6] = {v0.x, v0.y, v1.x, v1.y, v2_.x, v2_.y};
@@ -224,7 +232,7 @@ struct K3v2Smem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
+__global__ void __launch_bounds__(kTile, B200_PA_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
                                                                      const double* __restrict__ points,
                                                                      double* __restrict__ points_new, double radius,
                                                                      double* __restrict__ bscal) {
@@ -243,15 +251,15 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
     if (n > 0) {
       const int nc0 = min(kTile, n);
       mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc0 * kRowBytes);
-      tma_load_1d(sm.At, v2.Ap + (size_t)o0 * kJpDoubles, (uint32_t)nc0 * kRowBytes, &sm.mbar);
+      tma_load_1d_stream(sm.At, v2.Ap + (size_t)o0 * kJpDoubles, (uint32_t)nc0 * kRowBytes, &sm.mbar);
     }
   }
   // prefetch the first chunk: camera index -> R^T x record, local point index
   double2 g0 = make_double2(0, 0), g1 = g0, g2 = g0;
   int pl_pf = 0;
   if (tid < n) {
-    const int cam = v.obs_cam[o0 + tid];
-    pl_pf = v.obs_pt[o0 + tid] - p0;
+    const int cam = ld_stream(v.obs_cam + o0 + tid);
+    pl_pf = ld_stream(v.obs_pt + o0 + tid) - p0;
     const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
     g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
   }
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
     sm.pb[tid] = v.pt_begin[p0 + tid];
     if (tid == npts - 1) sm.pb[npts] = o1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sm.X[k][tid] = points[3 * (size_t)(p0 + tid) + k];
+    for (int k = 0; k < 3; ++k) sm.X[k][tid] = ld_stream(points + 3 * (size_t)(p0 + tid) + k);
     sm.z[0][tid] = sm.z[1][tid] = sm.z[2][tid] = 0.0;
   }
   __syncthreads();
@@ -269,12 +277,12 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
     const int nc = min(kTile, n - c0);
     if (tid == 0 && ch > 0) {
       mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kRowBytes);
-      tma_load_1d(sm.At, v2.Ap + (size_t)(o0 + c0) * kJpDoubles, (uint32_t)nc * kRowBytes, &sm.mbar);
+      tma_load_1d_stream(sm.At, v2.Ap + (size_t)(o0 + c0) * kJpDoubles, (uint32_t)nc * kRowBytes, &sm.mbar);
     }
     const bool active = tid < nc;
     if (active && ch > 0) {
-      const int cam = v.obs_cam[o0 + c0 + tid];
-      pl_pf = v.obs_pt[o0 + c0 + tid] - p0;
+      const int cam = ld_stream(v.obs_cam + o0 + c0 + tid);
+      pl_pf = ld_stream(v.obs_pt + o0 + c0 + tid) - p0;
       const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
       g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
     }
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
       }
       double vi[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) vi[k] = v.Vinv[6 * p + k];
+      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(v.Vinv + 6 * p + k);
       sym3_mul(vi, s, z);
       if (MODE == 2) {
         double v6[6], js[3], Dp[3];
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba2_pass_a(BAView v, 
 #pragma unroll
       for (int k = 0; k < 3; ++k) points_new[3 * p + k] = sm.X[k][tid];
     }
-    if (MODE == 0) *reinterpret_cast<double4*>(v2.z4 + 4 * p) = make_double4(z[0], z[1], z[2], 0.0);
+    if (MODE == 0) st_keep4(v2.z4 + 4 * p, make_double4(z[0], z[1], z[2], 0.0), l2_policy_evict_last());
   }
   if (MODE == 2) {
     b0 = block_sum(b0, sm.scratch);
@@ -385,22 +393,26 @@ __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const d
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   double acc[6] = {0, 0, 0, 0, 0, 0};
   // two observations per lane and iteration: both index loads, then both gathers, are in flight together
-  for (int i0 = b + lane; i0 < e; i0 += 64) {
+  const double* row0 = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
+  const uint64_t keep = l2_policy_evict_last();
+  for (int i0 = b + lane; i0 < e; i0 += 64, row0 += 2 * kJcDoubles * 32) {
     const int i1 = i0 + 32;
     const bool ok1 = i1 < e;
-    const int pt0 = v.pt_c[i0];
-    const int pt1 = ok1 ? v.pt_c[i1] : pt0;
-    const double2* row0 = reinterpret_cast<const double2*>(v2.Ac + (size_t)i0 * kJcDoubles);
-    const double2* row1 = reinterpret_cast<const double2*>(v2.Ac + (size_t)(ok1 ? i1 : i0) * kJcDoubles);
-    const double2 a0 = row0[0], a1 = row0[1], a2 = row0[2], a3 = row0[3], a4 = row0[4];
-    const double2 c0 = row1[0], c1 = row1[1], c2 = row1[2], c3 = row1[3], c4 = row1[4];
-    const double4 z0 = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt0);
-    const double4 z1 = *reinterpret_cast<const double4*>(v2.z4 + 4 * (size_t)pt1);
+    const int pt0 = ld_stream(v.pt_c + i0);
+    const int pt1 = ok1 ? ld_stream(v.pt_c + i1) : pt0;
+    const double* row1 = ok1 ? row0 + kJcDoubles * 32 : row0;
+    double a[kJcDoubles], c[kJcDoubles];
+#pragma unroll
+    for (int k = 0; k < kJcDoubles; ++k) a[k] = ld_stream(row0 + 32 * k);
+#pragma unroll
+    for (int k = 0; k < kJcDoubles; ++k) c[k] = ld_stream(row1 + 32 * k);
+    const double4 z0 = ld_keep4(v2.z4 + 4 * (size_t)pt0, keep);
+    const double4 z1 = ld_keep4(v2.z4 + 4 * (size_t)pt1, keep);
     {
-      const double w0 = a0.x * z0.x + a0.y * z0.y + a1.x * z0.z;
-      const double w1 = a0.y * z0.x + a1.y * z0.y + a2.x * z0.z;
-      const double w2 = a1.x * z0.x + a2.x * z0.y + a2.y * z0.z;
-      const double X0 = a3.x, X1 = a3.y, X2 = a4.x;
+      const double w0 = a[0] * z0.x + a[1] * z0.y + a[2] * z0.z;
+      const double w1 = a[1] * z0.x + a[3] * z0.y + a[4] * z0.z;
+      const double w2 = a[2] * z0.x + a[4] * z0.y + a[5] * z0.z;
+      const double X0 = a[6], X1 = a[7], X2 = a[8];
       acc[0] += 2.0 * (X1 * w2 - X2 * w1);
       acc[1] += 2.0 * (X2 * w0 - X0 * w2);
       acc[2] += 2.0 * (X0 * w1 - X1 * w0);
@@ -409,10 +421,10 @@ __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const d
       acc[5] += w2;
     }
     if (ok1) {
-      const double w0 = c0.x * z1.x + c0.y * z1.y + c1.x * z1.z;
-      const double w1 = c0.y * z1.x + c1.y * z1.y + c2.x * z1.z;
-      const double w2 = c1.x * z1.x + c2.x * z1.y + c2.y * z1.z;
-      const double X0 = c3.x, X1 = c3.y, X2 = c4.x;
+      const double w0 = c[0] * z1.x + c[1] * z1.y + c[2] * z1.z;
+      const double w1 = c[1] * z1.x + c[3] * z1.y + c[4] * z1.z;
+      const double w2 = c[2] * z1.x + c[4] * z1.y + c[5] * z1.z;
+      const double X0 = c[6], X1 = c[7], X2 = c[8];
       acc[0] += 2.0 * (X1 * w2 - X2 * w1);
       acc[1] += 2.0 * (X2 * w0 - X0 * w2);
       acc[2] += 2.0 * (X0 * w1 - X1 * w0);

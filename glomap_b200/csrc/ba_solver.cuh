@@ -25,14 +25,17 @@ __global__ void k_expand_obs_pt(int P, const unsigned* __restrict__ pt_begin, in
   if (p >= P) return;
   for (unsigned o = pt_begin[p]; o < pt_begin[p + 1]; ++o) obs_pt[o] = p;
 }
-__global__ void k_cam_keys(long long N, int C, int min_views, const int* __restrict__ obs_cam,
+// sort key = "virtual camera" (frame, sensor): vc = frame * smul + sensor  (smul = 1, sensor = 0 without rigs)
+__global__ void k_cam_keys(long long N, int VC, int smul, int min_views, const int* __restrict__ obs_cam,
+                           const unsigned short* __restrict__ obs_sensor,
                            const int* __restrict__ obs_pt, const unsigned* __restrict__ pt_begin,
                            int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ cam_count) {
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= N) return;
   const int pt = obs_pt[o];
   const bool valid = (int)(pt_begin[pt + 1] - pt_begin[pt]) >= min_views;
-  const int cam = obs_cam[o];
+  const int cam = obs_cam[o] * smul + (obs_sensor ? (int)obs_sensor[o] : 0);
+  const int C = VC;
   keys[o] = valid ? cam : C;
   vals[o] = (int)o;
   if (valid) atomicAdd(&cam_count[cam], 1);
@@ -41,17 +44,30 @@ __global__ void k_seg_counts(int C, const int* __restrict__ cam_count, int* __re
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) seg_count[c] = (cam_count[c] + kSeg - 1) / kSeg;
 }
-__global__ void k_fill_segs(int C, const int* __restrict__ cam_begin, const int* __restrict__ seg_off,
-                            int* __restrict__ seg_cam, int* __restrict__ seg_begin, int* __restrict__ seg_end) {
+__global__ void k_fill_segs(int VC, int smul, const int* __restrict__ cam_begin, const int* __restrict__ seg_off,
+                            const int* __restrict__ cam_intr, const int* __restrict__ sensor_intr,
+                            int* __restrict__ seg_cam, int* __restrict__ seg_sensor, int* __restrict__ seg_intr,
+                            int* __restrict__ seg_begin, int* __restrict__ seg_end) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (c >= VC) return;
   const int b = cam_begin[c], e = cam_begin[c + 1];
+  const int frame = c / smul, sensor = c - frame * smul;
+  const int blk = sensor_intr ? sensor_intr[sensor] : (cam_intr ? cam_intr[frame] : 0);
   int s = seg_off[c];
   for (int i = b; i < e; i += kSeg, ++s) {
-    seg_cam[s] = c;
+    seg_cam[s] = frame;
+    if (seg_sensor) seg_sensor[s] = sensor;
+    if (seg_intr) seg_intr[s] = blk;
     seg_begin[s] = i;
     seg_end[s] = min(i + kSeg, e);
   }
+}
+// padded length (multiple of 32 rows) of every segment -> scanned into seg_row0
+__global__ void k_seg_padded_len(int n_segs, const int* __restrict__ seg_begin, const int* __restrict__ seg_end,
+                                 int* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_segs) out[s] = (seg_end[s] - seg_begin[s] + 31) & ~31;
+  if (s == n_segs) out[s] = 0;
 }
 __global__ void k_gather_camorder(int Nv, const int* __restrict__ camord_obs, const int* __restrict__ obs_pt,
                                   const double2* __restrict__ obs_xy, int* __restrict__ pt_c,
@@ -102,6 +118,12 @@ struct b200sfm_ba_problem {
 
   // structure
   DevBuf<int> obs_cam, obs_pt, tile_pt_begin, camord_obs, pt_c, seg_cam, seg_begin, seg_end, cam_intr, intr_model;
+  // known rigs (S > 0): see BAView
+  int S = 0;
+  DevBuf<unsigned short> obs_sensor;
+  DevBuf<int> seg_sensor, seg_intr, sensor_intr, seg_row0;
+  long long n_rows_padded = 0;   // v2 camera-order rows incl. the per-segment padding to 32
+  DevBuf<double> sensor_rec;
   DevBuf<double2> obs_xy, xy_c;
   DevBuf<int4> tile_desc;
   DevBuf<unsigned> pt_begin;
@@ -144,7 +166,8 @@ struct b200sfm_ba_problem {
     v.C = C; v.P = P; v.K = K; v.N = N; v.n_tiles = n_tiles; v.n_segs = n_segs; v.min_views = min_views;
     v.obs_cam = obs_cam.p; v.obs_pt = obs_pt.p; v.obs_xy = obs_xy.p; v.pt_begin = pt_begin.p;
     v.tile_pt_begin = tile_pt_begin.p; v.tile_desc = tile_desc.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p; v.xy_c = xy_c.p;
-    v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p;
+    v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p; v.seg_row0 = seg_row0.p;
+    v.S = S; v.obs_sensor = obs_sensor.p; v.seg_sensor = seg_sensor.p; v.seg_intr = seg_intr.p; v.sensor_rec = sensor_rec.p;
     v.W = W.p; v.V = V.p; v.Vinv = Vinv.p; v.gp = gp.p; v.U = U(); v.gc = gc(); v.Sd = Sd.p; v.Minv = Minv.p;
     v.jscale_c = jscale_c.p; v.jscale_p = jscale_p.p; v.Dc = Dc.p;
     return v;
@@ -153,9 +176,13 @@ struct b200sfm_ba_problem {
   // -------------------------------------------------------------------------
   void create(b200sfm_ctx* c, int C_, int P_, long long N_, int K_, const int64_t* h_pt_begin, const int32_t* h_obs_cam,
               const double* h_obs_xy, const int32_t* h_cam_intr, const int32_t* h_intr_model,
-              const uint8_t* h_cam_mask, int min_views_, b200sfm_lm_stats* st) {
+              const uint8_t* h_cam_mask, int min_views_, b200sfm_lm_stats* st, int S_ = 0,
+              const uint16_t* h_obs_sensor = nullptr, const double* h_sensor_q = nullptr,
+              const double* h_sensor_t = nullptr, const int32_t* h_sensor_intr = nullptr) {
     using namespace b200;
-    ctx = c; C = C_; P = P_; N = N_; K = K_; min_views = min_views_;
+    ctx = c; C = C_; P = P_; N = N_; K = K_; min_views = min_views_; S = S_;
+    const int smul = std::max(S, 1);
+    const int VC = C * smul;
     cudaStream_t s = ctx->stream;
     // host: CSR offsets -> uint32, greedy tiling of whole points into <= kTile observations
     std::vector<unsigned> ptb((size_t)P + 1);
@@ -195,7 +222,34 @@ struct b200sfm_ba_problem {
     }
     tile_desc.alloc(descs.size());
     tile_desc.upload(descs.data(), descs.size(), s);
-    cam_intr.upload(h_cam_intr, C, s);
+    if (S > 0) {
+      // constant sensor records: R_cam_from_rig row-major, t_cam_from_rig, intrinsics block
+      std::vector<double> rec((size_t)S * kSensorRec, 0.0);
+      for (int i = 0; i < S; ++i) {
+        const double* q = h_sensor_q + 4 * (size_t)i;
+        const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+        double* r = rec.data() + (size_t)i * kSensorRec;
+        r[0] = 1 - 2 * (y * y + z * z); r[1] = 2 * (x * y - z * w); r[2] = 2 * (x * z + y * w);
+        r[3] = 2 * (x * y + z * w); r[4] = 1 - 2 * (x * x + z * z); r[5] = 2 * (y * z - x * w);
+        r[6] = 2 * (x * z - y * w); r[7] = 2 * (y * z + x * w); r[8] = 1 - 2 * (x * x + y * y);
+        r[9] = h_sensor_t[3 * (size_t)i]; r[10] = h_sensor_t[3 * (size_t)i + 1]; r[11] = h_sensor_t[3 * (size_t)i + 2];
+        r[12] = (double)h_sensor_intr[i];
+      }
+      sensor_rec.alloc(rec.size());
+      sensor_rec.upload(rec.data(), rec.size(), s);
+      sensor_intr.alloc(S);
+      sensor_intr.upload(h_sensor_intr, S, s);
+      obs_sensor.alloc(N);
+      obs_sensor.upload(h_obs_sensor, N, s);
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // rec is a local
+      // cam_intr is unused with rigs (the intrinsics block belongs to the sensor); keep it defined
+      std::vector<int> zeros(C, 0);
+      cam_intr.upload(zeros.data(), C, s);
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+    } else {
+      cam_intr.upload(h_cam_intr, C, s);
+    }
     intr_model.upload(h_intr_model, K, s);
     this->h_intr_model.assign(h_intr_model, h_intr_model + K);
     if (h_cam_mask) cam_mask_base.upload(h_cam_mask, C, s);
@@ -206,38 +260,58 @@ struct b200sfm_ba_problem {
     // camera order
     DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off;
     keys.alloc(N); vals.alloc(N); keys_out.alloc(N); camord_obs.alloc(N);
-    cam_count.alloc((size_t)C + 1); seg_count.alloc((size_t)C + 1); cam_begin.alloc((size_t)C + 1); seg_off.alloc((size_t)C + 1);
+    cam_count.alloc((size_t)VC + 1); seg_count.alloc((size_t)VC + 1); cam_begin.alloc((size_t)VC + 1); seg_off.alloc((size_t)VC + 1);
     cam_count.zero(s); seg_count.zero(s);
-    B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, C, min_views, obs_cam.p, obs_pt.p, pt_begin.p, keys.p, vals.p,
-                cam_count.p);
+    B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, VC, smul, min_views, obs_cam.p, S > 0 ? obs_sensor.p : nullptr,
+                obs_pt.p, pt_begin.p, keys.p, vals.p, cam_count.p);
     int end_bit = 1;
-    while ((1ll << end_bit) <= C) ++end_bit;
+    while ((1ll << end_bit) <= VC) ++end_bit;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_out.p, vals.p, camord_obs.p, (int)N, 0, end_bit, s);
     size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cam_count.p, cam_begin.p, C + 1, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cam_count.p, cam_begin.p, VC + 1, s);
     DevBuf<unsigned char> tmp;
     tmp.alloc(std::max(tmp_bytes, scan_bytes) + 16);
     size_t tb = tmp.bytes();
     cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_out.p, vals.p, camord_obs.p, (int)N, 0, end_bit, s);
     ctx->launches += 8;
     tb = tmp.bytes();
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, cam_count.p, cam_begin.p, C + 1, s);
-    B200_LAUNCH(ctx, k_seg_counts, cdiv(C, 256), 256, 0, C, cam_count.p, seg_count.p);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, cam_count.p, cam_begin.p, VC + 1, s);
+    B200_LAUNCH(ctx, k_seg_counts, cdiv(VC, 256), 256, 0, VC, cam_count.p, seg_count.p);
     tb = tmp.bytes();
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, seg_count.p, seg_off.p, C + 1, s);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, seg_count.p, seg_off.p, VC + 1, s);
     ctx->launches += 4;
     int h_tot[2];
-    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[0], cam_begin.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[1], seg_off.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[0], cam_begin.p + VC, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[1], seg_off.p + VC, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     Nv = h_tot[0];
     n_segs = h_tot[1];
     seg_cam.alloc(std::max(n_segs, 1)); seg_begin.alloc(std::max(n_segs, 1)); seg_end.alloc(std::max(n_segs, 1));
+    seg_sensor.alloc(std::max(n_segs, 1)); seg_intr.alloc(std::max(n_segs, 1));
     pt_c.alloc(std::max(Nv, 1)); xy_c.alloc(std::max(Nv, 1));
-    B200_LAUNCH(ctx, k_fill_segs, cdiv(C, 256), 256, 0, C, cam_begin.p, seg_off.p, seg_cam.p, seg_begin.p, seg_end.p);
+    B200_LAUNCH(ctx, k_fill_segs, cdiv(VC, 256), 256, 0, VC, smul, cam_begin.p, seg_off.p, cam_intr.p,
+                S > 0 ? sensor_intr.p : nullptr, seg_cam.p, seg_sensor.p, seg_intr.p, seg_begin.p, seg_end.p);
     if (Nv > 0)
       B200_LAUNCH(ctx, k_gather_camorder, cdiv(Nv, 256), 256, 0, Nv, camord_obs.p, obs_pt.p, obs_xy.p, pt_c.p, xy_c.p);
+    // v2 camera-order rows: every segment starts on a 32-row group boundary
+    {
+      DevBuf<int> padded;
+      padded.alloc((size_t)n_segs + 1);
+      seg_row0.alloc((size_t)n_segs + 1);
+      B200_LAUNCH(ctx, k_seg_padded_len, cdiv(n_segs + 1, 256), 256, 0, n_segs, seg_begin.p, seg_end.p, padded.p);
+      size_t need = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, padded.p, seg_row0.p, n_segs + 1, s);
+      DevBuf<unsigned char> tmp2;
+      tmp2.alloc(need + 16);
+      size_t tb2 = tmp2.bytes();
+      cub::DeviceScan::ExclusiveSum(tmp2.p, tb2, padded.p, seg_row0.p, n_segs + 1, s);
+      ctx->launches += 1;
+      int h_rows = 0;
+      B200_CUDA_OK(cudaMemcpyAsync(&h_rows, seg_row0.p + n_segs, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      n_rows_padded = h_rows;
+    }
 
     for (int i = 0; i < 2; ++i) {
       quat[i].alloc((size_t)C * 4); trans[i].alloc((size_t)C * 3); points[i].alloc((size_t)P * 3);
@@ -259,7 +333,9 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3));
     // several 50-KB CTAs per SM: ask for the full shared-memory carve-out
-    const int carve = getenv("B200SFM_CARVEOUT") ? atoi(getenv("B200SFM_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;
+    // shared-memory carve-out of the tiled kernels: 75 % leaves ~60 KB of L1 for the camera-record / R^T x gathers
+    // (sweep: profiles/r1_v2_sweep.md; 100 % = max shared is 10 % slower, 25 % halves the resident CTAs)
+    const int carve = getenv("B200SFM_CARVEOUT") ? atoi(getenv("B200SFM_CARVEOUT")) : 75;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_linearize_points<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_schur_pass<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -270,7 +346,7 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3v2));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    Jc.alloc((size_t)std::max(Nv, 1) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * 6);
+    Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * 6);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -378,7 +454,7 @@ struct b200sfm_ba_problem {
       if (n_segs > 0) {
         B200_LAUNCH(ctx, ba_intr_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p, ivar.p,
                     points[cur].p, huber_a, m_intr, Buck.p, part_seg.p);
-        B200_LAUNCH(ctx, ba_intr_reduce_segs, K, 256, 0, n_segs, seg_cam.p, cam_intr.p, part_seg.p, intr_out.p);
+        B200_LAUNCH(ctx, ba_intr_reduce_segs, K, 256, 0, n_segs, seg_intr.p, part_seg.p, intr_out.p);
       } else {
         intr_out.zero(s);
       }
@@ -436,7 +512,8 @@ struct b200sfm_ba_problem {
         DevBuf<unsigned char> cal;
         bear.alloc((size_t)N * 3);
         bear.upload(h_bearings, (size_t)N * 3, s);
-        if (h_calibrated) { cal.alloc(C); cal.upload(h_calibrated, C, s); }
+        const int ncal = S > 0 ? S : C;
+        if (h_calibrated) { cal.alloc(ncal); cal.upload(h_calibrated, ncal, s); }
         B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, h_calibrated ? cal.p : nullptr,
                     std::cos(thr * kPi / 180.0), std::cos(2.0 * thr * kPi / 180.0), keep.p, changed.p);
         B200_CUDA_OK(cudaStreamSynchronize(s));   // bear / cal go out of scope
@@ -685,7 +762,10 @@ struct b200sfm_ba_problem {
   int solve(const b200sfm_ba_opts& o, b200sfm_lm_stats* st) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
-    if (o.optimize_rig_poses) { ctx->err = "optimize_rig_poses: non-trivial rigs are not supported"; return B200SFM_ERR_UNSUPPORTED; }
+    if (o.optimize_rig_poses) {
+      ctx->err = "optimize_rig_poses: unknown cam_from_rig blocks are not supported (known rigs: b200sfm_ba_problem_create_rig)";
+      return B200SFM_ERR_UNSUPPORTED;
+    }
     m_intr = 0;
     if (o.optimize_intrinsics) {
       // variable parameters per block: all but the principal point unless optimize_principal_point

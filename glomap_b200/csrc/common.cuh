@@ -18,6 +18,15 @@ namespace b200 {
 #ifndef B200_K3_MIN_CTAS
 #define B200_K3_MIN_CTAS 8
 #endif
+#ifndef B200_PA_MIN_CTAS   // v2 pass A: 12 CTAs x 128 threads (40 registers, no spills) -- sweep in profiles/r1_v2_sweep.md
+#define B200_PA_MIN_CTAS 12
+#endif
+#ifndef B200_LC_MIN_CTAS   // v2 camera-order linearisation: 128 registers (a few spills) -> 4 CTAs of 4 warps; sweep: profiles/r1_v2_sweep.md
+#define B200_LC_MIN_CTAS 4
+#endif
+#ifndef B200_STREAM_HINTS  // evict-first loads/stores on the once-per-pass streams so the gathered arrays stay in L2
+#define B200_STREAM_HINTS 1
+#endif
 constexpr int kTile = B200_TILE; // observations per point-order tile == threads per CTA
 constexpr int kTilePts = 64;     // max points per tile (bounds the per-point shared-memory arrays)
 constexpr int kWDoubles = 18;    // W block of one observation: 6x3 doubles, row-major
@@ -72,6 +81,68 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// same, with an L2 evict-first policy: a once-per-pass stream must not push the gathered arrays out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+#if B200_STREAM_HINTS
+  const uint64_t pol = l2_policy_evict_first();
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+#else
+  tma_load_1d(smem_dst, gsrc, bytes, bar);
+#endif
+}
+// streaming (evict-first) scalar accesses
+template <class T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+#if B200_STREAM_HINTS
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+template <class T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+#if B200_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+// gathered-array accesses that should stay L2-resident between the passes (evict-last policy)
+#ifndef B200_KEEP_HINTS
+#define B200_KEEP_HINTS 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double4 ld_keep4(const double* p, uint64_t pol) {
+#if B200_KEEP_HINTS
+  double4 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.z), "=d"(v.w) : "l"(p + 2), "l"(pol));
+  return v;
+#else
+  return *reinterpret_cast<const double4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_keep4(double* p, double4 v, uint64_t pol) {
+#if B200_KEEP_HINTS
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p + 2), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+#else
+  *reinterpret_cast<double4*>(p) = v;
+#endif
 }
 // shared -> global (bulk async group)
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {

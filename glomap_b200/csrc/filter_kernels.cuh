@@ -29,13 +29,15 @@ __global__ void filter_reprojection(BAView v, const double* __restrict__ cam_rec
   double R[9];
   quat_to_R(q, R);
   const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
-  const double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
-  const double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
-  const double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+  double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
+  double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
+  double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+  const double* sr = sensor_of_obs(v, o);
+  if (sr) sensor_apply(sr, xc, yc, zc);   // cam_from_world = cam_from_rig * rig_from_world
   bool k = false;
   if (!(zc < kFilterEps)) {
     double px, py;
-    project_only(intr_rec + (size_t)cam_rec_intr(t4) * kIntrRec, xc, yc, zc, px, py);
+    project_only(intr_rec + (size_t)obs_intr_idx(t4, sr) * kIntrRec, xc, yc, zc, px, py);
     const double dx = px - xy.x, dy = py - xy.y;
     k = sqrt(dx * dx + dy * dy) < max_err;
   }
@@ -58,14 +60,18 @@ __global__ void filter_angle(BAView v, const double* __restrict__ cam_rec, const
   double R[9];
   quat_to_R(q, R);
   const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
-  const double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
-  const double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
-  const double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+  double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
+  double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
+  double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+  const double* sr = sensor_of_obs(v, o);
+  if (sr) sensor_apply(sr, xc, yc, zc);
   bool k = false;
   if (!(zc < kFilterEps)) {
     const double inv = 1.0 / sqrt(xc * xc + yc * yc + zc * zc);
     const double d = (xc * bearings[3 * o] + yc * bearings[3 * o + 1] + zc * bearings[3 * o + 2]) * inv;
-    const double th = (calibrated == nullptr || calibrated[cam]) ? thres : thres_uncalib;
+    // the prior-focal flag belongs to the camera: per image without rigs, per sensor with rigs
+    const int ci = v.S > 0 ? (int)v.obs_sensor[o] : cam;
+    const double th = (calibrated == nullptr || calibrated[ci]) ? thres : thres_uncalib;
     k = d > th;
   }
   keep[o] = k ? 1 : 0;
@@ -95,16 +101,25 @@ __global__ void filter_triangulation_angle(BAView v, const double* __restrict__ 
     double ray[2][3];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int cam = v.obs_cam[b + (s == 0 ? i : j)];
+      const unsigned oo = b + (s == 0 ? i : j);
+      const int cam = v.obs_cam[oo];
       const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
       const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
       const double q[4] = {q4.x, q4.y, q4.z, q4.w};
       double R[9];
       quat_to_R(q, R);
-      // centre c = -R^T t ; ray = normalized(X - c)
-      const double c0 = -(R[0] * t4.x + R[3] * t4.y + R[6] * t4.z);
-      const double c1 = -(R[1] * t4.x + R[4] * t4.y + R[7] * t4.z);
-      const double c2 = -(R[2] * t4.x + R[5] * t4.y + R[8] * t4.z);
+      // centre c = -R^T t ; ray = normalized(X - c).  Known rig: the image centre in the rig frame is
+      // -R_cr^T t_cr, so t_f is replaced by t_f + R_cr^T t_cr.
+      double tx = t4.x, ty = t4.y, tz = t4.z;
+      const double* sr = sensor_of_obs(v, oo);
+      if (sr) {
+        tx += sr[0] * sr[9] + sr[3] * sr[10] + sr[6] * sr[11];
+        ty += sr[1] * sr[9] + sr[4] * sr[10] + sr[7] * sr[11];
+        tz += sr[2] * sr[9] + sr[5] * sr[10] + sr[8] * sr[11];
+      }
+      const double c0 = -(R[0] * tx + R[3] * ty + R[6] * tz);
+      const double c1 = -(R[1] * tx + R[4] * ty + R[7] * tz);
+      const double c2 = -(R[2] * tx + R[5] * ty + R[8] * tz);
       const double d0 = X0 - c0, d1 = X1 - c1, d2 = X2 - c2;
       const double inv = 1.0 / sqrt(d0 * d0 + d1 * d1 + d2 * d2);
       ray[s][0] = d0 * inv; ray[s][1] = d1 * inv; ray[s][2] = d2 * inv;

@@ -34,6 +34,8 @@ struct GPView {
   const int* obs_cam;
   const int* obs_pt;
   const double* obs_dir;          // [N][3] world-rotated unit bearings
+  const double* obs_off;          // [N][3] or nullptr: known-rig offset R_cw^T t_cam_from_rig (RigBATA, rig scale = 1)
+  const unsigned char* obs_cal;   // [N] or nullptr: prior-focal flag of the observing CAMERA (overrides the per-frame flag)
   const unsigned* pt_begin;
   const int* tile_pt_begin;
   const int* camord_obs;
@@ -163,8 +165,11 @@ __global__ void __launch_bounds__(kTile) gp_linearize_points(GPView v, const dou
         const double s = scales[oi];
         const double2 ca = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam);
         const double2 cb = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam + 2);
-        const double c4[4] = {ca.x, ca.y, cb.x, cb.y};
-        const double X[3] = {sm.X[0][pl], sm.X[1][pl], sm.X[2][pl]};
+        const double c4[4] = {ca.x, ca.y, cb.x, v.obs_cal ? (v.obs_cal[oi] ? 1.0 : 0.5) : cb.y};
+        double X[3] = {sm.X[0][pl], sm.X[1][pl], sm.X[2][pl]};
+        if (v.obs_off) {   // d = X - c_frame + t_rig: fold the constant offset into the point
+          X[0] += v.obs_off[3 * oi]; X[1] += v.obs_off[3 * oi + 1]; X[2] += v.obs_off[3 * oi + 2];
+        }
         const bool svar = v.scales_var && (long long)oi != v.const_obs;
         double js = set_js ? 0.0 : v.jscale_s[oi];
         gp_obs(t, s, c4, X, huber_a, svar, js, set_js != 0, radius, js, o);
@@ -480,9 +485,12 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
           const double s = scales[oi];
           const double2 ca = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam);
           const double2 cb = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam + 2);
-          const double c4[4] = {ca.x, ca.y, cb.x, cb.y};
+          const double c4[4] = {ca.x, ca.y, cb.x, v.obs_cal ? (v.obs_cal[oi] ? 1.0 : 0.5) : cb.y};
           const size_t p = (size_t)(p0 + pl);
-          const double X[3] = {points[3 * p], points[3 * p + 1], points[3 * p + 2]};
+          double X[3] = {points[3 * p], points[3 * p + 1], points[3 * p + 2]};
+          if (v.obs_off) {
+            X[0] += v.obs_off[3 * oi]; X[1] += v.obs_off[3 * oi + 1]; X[2] += v.obs_off[3 * oi + 2];
+          }
           const bool svar = v.scales_var && (long long)oi != v.const_obs;
           GPObs o;
           double js = v.jscale_s[oi];
@@ -608,12 +616,14 @@ __global__ void __launch_bounds__(256) gp_cost(GPView v, const double* __restric
     const double s = scales[o];
     const double2 ca = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam);
     const double2 cb = *reinterpret_cast<const double2*>(cen4 + 4 * (size_t)cam + 2);
-    const double r0 = v.obs_dir[3 * o] - s * (points[3 * (size_t)pt] - ca.x);
-    const double r1 = v.obs_dir[3 * o + 1] - s * (points[3 * (size_t)pt + 1] - ca.y);
-    const double r2 = v.obs_dir[3 * o + 2] - s * (points[3 * (size_t)pt + 2] - cb.x);
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    if (v.obs_off) { f0 = v.obs_off[3 * o]; f1 = v.obs_off[3 * o + 1]; f2 = v.obs_off[3 * o + 2]; }
+    const double r0 = v.obs_dir[3 * o] - s * (points[3 * (size_t)pt] + f0 - ca.x);
+    const double r1 = v.obs_dir[3 * o + 1] - s * (points[3 * (size_t)pt + 1] + f1 - ca.y);
+    const double r2 = v.obs_dir[3 * o + 2] - s * (points[3 * (size_t)pt + 2] + f2 - cb.x);
     double rho0, rho1;
     huber(r0 * r0 + r1 * r1 + r2 * r2, huber_a, rho0, rho1);
-    cost += 0.5 * cb.y * rho0;
+    cost += 0.5 * (v.obs_cal ? (v.obs_cal[o] ? 1.0 : 0.5) : cb.y) * rho0;
   }
   cost = block_sum(cost, scratch);
   if (threadIdx.x == 0 && cost != 0.0) atomicAdd(&scal[0], cost);

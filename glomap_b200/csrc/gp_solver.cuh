@@ -18,7 +18,8 @@ struct b200sfm_gp_problem {
   int Nv = 0, n_tiles = 0, n_segs = 0, min_views = 3;
   DevBuf<int> obs_cam, obs_pt, tile_pt_begin, camord_obs, pt_c, seg_cam, seg_begin, seg_end;
   DevBuf<unsigned> pt_begin;
-  DevBuf<double> obs_dir;
+  DevBuf<double> obs_dir, obs_off;
+  DevBuf<unsigned char> obs_cal;
   DevBuf<unsigned char> calibrated, cam_const_base, cam_const;
   bool has_calibrated = false;
   // state / candidate / snapshot
@@ -37,10 +38,21 @@ struct b200sfm_gp_problem {
     v.const_obs = (ctx->rank == 0) ? first_valid_obs : -1;
     v.scales_var = scales_var ? 1 : 0;
     v.obs_cam = obs_cam.p; v.obs_pt = obs_pt.p; v.obs_dir = obs_dir.p; v.pt_begin = pt_begin.p;
+    v.obs_off = obs_off.p; v.obs_cal = obs_cal.p;
     v.tile_pt_begin = tile_pt_begin.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p;
     v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p;
     v.M = M.p; v.bw = bw.p; v.jscale_s = jscale_s.p; v.Vinv = Vinv.p; v.gX = gX.p; v.Dp = Dp.p; v.jscale_p = jscale_p.p;
     return v;
+  }
+
+  // known rigs: constant per-observation offset (and the camera's prior-focal flag); nullptr clears
+  void set_rig_terms(const double* h_off, const uint8_t* h_cal) {
+    cudaStream_t s = ctx->stream;
+    if (h_off) { obs_off.alloc((size_t)N * 3); obs_off.upload(h_off, (size_t)N * 3, s); }
+    else obs_off.release();
+    if (h_cal) { obs_cal.alloc(N); obs_cal.upload(h_cal, N, s); }
+    else obs_cal.release();
+    B200_CUDA_OK(cudaStreamSynchronize(s));
   }
 
   void create(b200sfm_ctx* c, int C_, int P_, long long N_, const int64_t* h_pt_begin, const int32_t* h_obs_cam,
@@ -89,7 +101,7 @@ struct b200sfm_gp_problem {
     keys.alloc(N); vals.alloc(N); keys_out.alloc(N); camord_obs.alloc(N);
     cam_count.alloc((size_t)C + 1); seg_count.alloc((size_t)C + 1); cam_begin.alloc((size_t)C + 1); seg_off.alloc((size_t)C + 1);
     cam_count.zero(s); seg_count.zero(s);
-    B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, C, min_views, obs_cam.p, obs_pt.p, pt_begin.p, keys.p, vals.p,
+    B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, C, 1, min_views, obs_cam.p, nullptr, obs_pt.p, pt_begin.p, keys.p, vals.p,
                 cam_count.p);
     int end_bit = 1;
     while ((1ll << end_bit) <= C) ++end_bit;
@@ -114,7 +126,8 @@ struct b200sfm_gp_problem {
     n_segs = h_tot[1];
     seg_cam.alloc(std::max(n_segs, 1)); seg_begin.alloc(std::max(n_segs, 1)); seg_end.alloc(std::max(n_segs, 1));
     pt_c.alloc(std::max(Nv, 1));
-    B200_LAUNCH(ctx, k_fill_segs, cdiv(C, 256), 256, 0, C, cam_begin.p, seg_off.p, seg_cam.p, seg_begin.p, seg_end.p);
+    B200_LAUNCH(ctx, k_fill_segs, cdiv(C, 256), 256, 0, C, 1, cam_begin.p, seg_off.p, nullptr, nullptr, seg_cam.p, nullptr, nullptr,
+                seg_begin.p, seg_end.p);
     if (Nv > 0) B200_LAUNCH(ctx, k_gather_int, cdiv(Nv, 256), 256, 0, Nv, camord_obs.p, obs_pt.p, pt_c.p);
     for (int i = 0; i < 2; ++i) {
       centers[i].alloc((size_t)C * 3); points[i].alloc((size_t)P * 3); scales[i].alloc(N);

@@ -143,10 +143,21 @@ class BAProblem:
     def __init__(self, ctx: Context, scene, min_num_view_per_track: int = 3, cam_const_mask: np.ndarray | None = None):
         self.ctx, self.lib = ctx, ctx.lib
         self.C, self.P, self.N, self.K = scene.C, scene.P, scene.N, len(scene.intr_model)
-        self._keep = [_c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64),
-                      _c(scene.cam_intr, np.int32), _c(scene.intr_model, np.int32)]
         mask = first_frame_mask(self.C) if cam_const_mask is None else _c(cam_const_mask, np.uint8)
         h = ct.c_void_p()
+        if hasattr(scene, "obs_sensor"):
+            # known rigs (synthetic.RigScene): the pose blocks are frames, the images carry a constant cam_from_rig
+            self._keep = [_c(scene.pt_obs_begin, np.int64), _c(scene.obs_frame, np.int32), _c(scene.obs_sensor, np.uint16),
+                          _c(scene.obs_xy, np.float64), _c(scene.sensor_quat, np.float64), _c(scene.sensor_trans, np.float64),
+                          _c(scene.sensor_intr, np.int32), _c(scene.intr_model, np.int32)]
+            rc = self.lib.b200sfm_ba_problem_create_rig(ctx.handle, self.C, self.P, self.N, self.K, scene.S,
+                                                        *[_ptr(a) for a in self._keep], _ptr(mask), min_num_view_per_track,
+                                                        ct.byref(h))
+            _lib.check(ctx.handle, rc)
+            self.handle = h
+            return
+        self._keep = [_c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64),
+                      _c(scene.cam_intr, np.int32), _c(scene.intr_model, np.int32)]
         rc = self.lib.b200sfm_ba_problem_create(ctx.handle, self.C, self.P, self.N, self.K, *[_ptr(a) for a in self._keep],
                                                 _ptr(mask), min_num_view_per_track, ct.byref(h))
         _lib.check(ctx.handle, rc)
@@ -237,6 +248,16 @@ class BundleAdjuster:
             return False
         ctx = self.ctx or default_context()
         lib = ctx.lib
+        if hasattr(scene, "obs_sensor"):
+            # known rigs (bundle_adjustment.cc:147-161): resident-problem path, pose blocks = frames
+            prob = BAProblem(ctx, scene, self.options_.min_num_view_per_track, cam_const_mask)
+            try:
+                prob.set_state(scene.intr_params, scene.quat, scene.trans, scene.points)
+                self.summary = prob.solve(self.options_)
+                scene.intr_params, scene.quat, scene.trans, scene.points = prob.get_state()
+            finally:
+                prob.free()
+            return bool(self.summary.usable)
         o = self.options_.to_c()
         st = LMStats()
         ptb, cam, xy = _c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64)
@@ -310,6 +331,11 @@ class PositioningProblem:
     points: np.ndarray | None = None           # [P,3]
     scales: np.ndarray | None = None           # [N]
     trans: np.ndarray | None = None            # [C,3] cam_from_world translations, written by Solve
+    # known rigs (global_positioning.cc:325-346): quat/obs_cam/centers then refer to FRAMES (rig_from_world)
+    obs_sensor: np.ndarray | None = None       # [N] sensor of the observing image
+    sensor_quat: np.ndarray | None = None      # [S,4] cam_from_rig rotations
+    sensor_trans: np.ndarray | None = None     # [S,3] cam_from_rig translations (rig scale 1)
+    sensor_calibrated: np.ndarray | None = None  # [S] has_prior_focal_length of the sensor's camera
 
     @property
     def C(self):
@@ -329,6 +355,18 @@ def world_bearings(quat, bearings_cam, obs_cam):
     from . import geometry as geo
     R = geo.quat_xyzw_to_rotmat(np.asarray(quat, dtype=np.float64))[np.asarray(obs_cam)]
     return np.einsum("nji,nj->ni", R, bearings_cam)
+
+
+def rig_world_terms(quat_frames, sensor_quat, sensor_trans, bearings_cam, obs_frame, obs_sensor):
+    """Known rigs: (t_obs, t_rig) per observation with R_cw = R_cam_from_rig R_rig_from_world --
+    t_obs = R_cw^T bearing (.cc:294-296), t_rig = R_cw^T t_cam_from_rig (.cc:339-345)."""
+    from . import geometry as geo
+    Rf = geo.quat_xyzw_to_rotmat(np.asarray(quat_frames, dtype=np.float64))[np.asarray(obs_frame)]
+    Rs = geo.quat_xyzw_to_rotmat(np.asarray(sensor_quat, dtype=np.float64))[np.asarray(obs_sensor)]
+    Rcw = np.einsum("nij,njk->nik", Rs, Rf)
+    t_obs = np.einsum("nji,nj->ni", Rcw, bearings_cam)
+    t_rig = np.einsum("nji,nj->ni", Rcw, np.asarray(sensor_trans, dtype=np.float64)[np.asarray(obs_sensor)])
+    return t_obs, t_rig
 
 
 class GlobalPositioner:
@@ -361,12 +399,37 @@ class GlobalPositioner:
             prob.points = 100.0 * self.rng.uniform(-1, 1, size=(prob.P, 3))
         if o.generate_scales or prob.scales is None:
             prob.scales = np.ones(prob.N)                               # .cc:298
-        t_obs = _c(world_bearings(prob.quat, prob.bearings, prob.obs_cam), np.float64)
         ptb, cam = _c(prob.pt_obs_begin, np.int64), _c(prob.obs_cam, np.int32)
         cal = None if prob.cam_calibrated is None else _c(prob.cam_calibrated, np.uint8)
         cen, pts, sc = _c(prob.centers, np.float64), _c(prob.points, np.float64), _c(prob.scales, np.float64)
         co = o.to_c()
         st = LMStats()
+        if prob.obs_sensor is not None:
+            # RigBATA with constant rig scale: resident-problem path + per-observation rig terms
+            t_obs, t_rig = rig_world_terms(prob.quat, prob.sensor_quat, prob.sensor_trans, prob.bearings, prob.obs_cam,
+                                           prob.obs_sensor)
+            t_obs, t_rig = _c(t_obs, np.float64), _c(t_rig, np.float64)
+            ocal = None if prob.sensor_calibrated is None else _c(
+                np.asarray(prob.sensor_calibrated)[np.asarray(prob.obs_sensor)], np.uint8)
+            h = ct.c_void_p()
+            rc = lib.b200sfm_gp_problem_create(ctx.handle, prob.C, prob.P, prob.N, _ptr(ptb), _ptr(cam), _ptr(t_obs), None,
+                                               None, o.min_num_view_per_track, ct.byref(h))
+            if rc == 4:
+                return False
+            _lib.check(ctx.handle, rc)
+            try:
+                _lib.check(ctx.handle, lib.b200sfm_gp_problem_set_rig_terms(h, _ptr(t_rig), _ptr(ocal)))
+                _lib.check(ctx.handle, lib.b200sfm_gp_problem_set_state(h, _ptr(cen), _ptr(pts), _ptr(sc)))
+                _lib.check(ctx.handle, lib.b200sfm_gp_problem_solve(h, ct.byref(co), ct.byref(st)))
+                _lib.check(ctx.handle, lib.b200sfm_gp_problem_get_state(h, _ptr(cen), _ptr(pts), _ptr(sc)))
+            finally:
+                lib.b200sfm_gp_problem_free(h)
+            self.summary = st
+            prob.centers, prob.points, prob.scales = cen, pts, sc
+            from . import geometry as geo
+            prob.trans = -np.einsum("nij,nj->ni", geo.quat_xyzw_to_rotmat(prob.quat), cen)   # ConvertResults .cc:566-570
+            return bool(st.usable)
+        t_obs = _c(world_bearings(prob.quat, prob.bearings, prob.obs_cam), np.float64)
         rc = lib.b200sfm_gp_solve(ctx.handle, ct.byref(co), prob.C, prob.P, prob.N, _ptr(ptb), _ptr(cam), _ptr(t_obs),
                                   _ptr(cal), None, _ptr(cen), _ptr(pts), _ptr(sc), ct.byref(st))
         self.summary = st
@@ -437,6 +500,26 @@ def initialize_from_maximum_spanning_tree(vg, R_init: np.ndarray | None = None) 
         else:                                # R_curr = R_rel R_parent                          (.cc:130-134)
             R[node] = vg.R_rel[lut[(par, int(node))]] @ R[par]
     return R
+
+
+def rig_view_graph(vg, img_frame, img_sensor, sensor_quat, R_gt_frames=None):
+    """Known rigs in rotation averaging (global_rotation_averaging.cc:274-309): the unknowns are the
+    FRAME rotations, an image pair (i, j) contributes
+        R_rel(frames) = R_cam2_from_rig2^T * R_cam2_from_cam1 * R_cam1_from_rig1
+    and pairs inside one frame are skipped (self loops).  Returns a ViewGraph over the frames."""
+    from . import geometry as geo
+    from .synthetic import ViewGraph
+    img_frame, img_sensor = np.asarray(img_frame), np.asarray(img_sensor)
+    Rs = geo.quat_xyzw_to_rotmat(np.asarray(sensor_quat, dtype=np.float64))
+    fi, fj = img_frame[vg.ei], img_frame[vg.ej]
+    keep = fi != fj
+    R1 = Rs[img_sensor[vg.ei[keep]]]
+    R2 = Rs[img_sensor[vg.ej[keep]]]
+    R_rel = np.einsum("nji,njk,nkl->nil", R2, vg.R_rel[keep], R1)
+    n_frames = int(img_frame.max()) + 1
+    R_gt = np.tile(np.eye(3), (n_frames, 1, 1)) if R_gt_frames is None else np.asarray(R_gt_frames)
+    return ViewGraph(n_frames, fi[keep].astype(np.int32), fj[keep].astype(np.int32), R_rel,
+                     np.asarray(vg.weight)[keep].copy(), R_gt)
 
 
 class RotationEstimator:

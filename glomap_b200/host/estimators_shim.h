@@ -6,8 +6,10 @@
 //   glomap::BundleAdjuster      glomap/estimators/bundle_adjustment.h:12-51
 // Each Solve flattens the unordered_map world into SoA in SORTED-ID order
 // (deterministic, unlike the reference's hash-map order), calls the GPU solver
-// and scatters the results back in place.  Trivial rigs only (one image per
-// frame); anything else returns false with a message on stderr.
+// and scatters the results back in place.  Known (constant) camera rigs are
+// supported in BundleAdjuster and GlobalPositioner (frames = pose blocks, every
+// image carries its sensor's cam_from_rig); unknown cam_from_rig / optimize_rig_poses
+// return false with a message on stderr.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -81,7 +83,6 @@ class BundleAdjuster {
   bool Solve(std::unordered_map<rig_t, Rig>& rigs, std::unordered_map<camera_t, Camera>& cameras,
              std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images,
              std::unordered_map<track_t, Track>& tracks) {
-    (void)rigs;
     if (images.empty()) { std::fprintf(stderr, "Number of images = 0\n"); return false; }     // .cc:17-20
     if (tracks.empty()) { std::fprintf(stderr, "Number of tracks = 0\n"); return false; }     // .cc:21-24
     b200sfm_ctx* ctx = DefaultContext();
@@ -110,15 +111,40 @@ class BundleAdjuster {
       intr_model[k] = c->model_id;
       for (size_t j = 0; j < c->params.size() && j < B200SFM_INTR_STRIDE; ++j) intr[(size_t)k * B200SFM_INTR_STRIDE + j] = c->params[j];
     }
-    for (auto& [id, im] : images) {
-      if (!im.HasTrivialFrame()) { std::fprintf(stderr, "b200sfm: non-trivial rigs are not supported\n"); return false; }
-      cam_intr[fidx[im.frame_id]] = cidx[im.camera_id];
+    // sensors = (rig, camera) pairs in sorted order; trivial frames use the identity cam_from_rig
+    bool any_rig = false;
+    for (auto& [id, im] : images) any_rig = any_rig || !im.HasTrivialFrame();
+    if (any_rig && options_.optimize_rig_poses) {
+      std::fprintf(stderr, "b200sfm: optimize_rig_poses (unknown cam_from_rig) is not supported\n");
+      return false;
+    }
+    std::map<std::pair<rig_t, camera_t>, int> sidx;
+    std::vector<double> sensor_q, sensor_t;
+    std::vector<int32_t> sensor_intr;
+    if (any_rig) {
+      for (auto& [id, im] : images) sidx[{frames[im.frame_id].RigId(), im.camera_id}] = 0;
+      int n = 0;
+      for (auto& [key, idx] : sidx) {
+        idx = n++;
+        Rigid3d cfr;   // identity
+        bool trivial = true;
+        for (auto& [iid, im] : images)
+          if (frames[im.frame_id].RigId() == key.first && im.camera_id == key.second) { trivial = im.HasTrivialFrame(); break; }
+        if (!trivial) cfr = b200host_adapt::CamFromRig(rigs[key.first], key.second);
+        for (int k = 0; k < 4; ++k) sensor_q.push_back(cfr.rotation.coeffs_data()[k]);
+        for (int k = 0; k < 3; ++k) sensor_t.push_back(cfr.translation[k]);
+        sensor_intr.push_back(cidx[key.second]);
+      }
+      if (n > 65535) { std::fprintf(stderr, "b200sfm: too many rig sensors\n"); return false; }
+    } else {
+      for (auto& [id, im] : images) cam_intr[fidx[im.frame_id]] = cidx[im.camera_id];
     }
     std::map<track_t, Track*> tsorted;
     for (auto& [id, t] : tracks) tsorted[id] = &t;
     const int P = (int)tsorted.size();
     std::vector<int64_t> ptb(1, 0);
     std::vector<int32_t> obs_cam;
+    std::vector<uint16_t> obs_sensor;
     std::vector<double> obs_xy, points(3 * (size_t)P);
     int p = 0;
     for (auto& [id, t] : tsorted) {
@@ -126,6 +152,7 @@ class BundleAdjuster {
         auto it = images.find(ob.first);
         if (it == images.end()) continue;                                                     // .cc:125
         obs_cam.push_back(fidx[it->second.frame_id]);
+        if (any_rig) obs_sensor.push_back((uint16_t)sidx[{frames[it->second.frame_id].RigId(), it->second.camera_id}]);
         obs_xy.push_back(it->second.features[ob.second][0]);
         obs_xy.push_back(it->second.features[ob.second][1]);
       }
@@ -145,9 +172,21 @@ class BundleAdjuster {
     o.gradient_tolerance = options_.solver_options.gradient_tolerance;
     o.parameter_tolerance = options_.solver_options.parameter_tolerance;
     o.pcg_rel_tolerance = options_.pcg_rel_tolerance; o.pcg_max_iterations = options_.pcg_max_iterations;
-    const int rc = b200sfm_ba_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), K, ptb.data(), obs_cam.data(), obs_xy.data(),
-                                    cam_intr.data(), intr_model.data(), intr.data(), quat.data(), trans.data(), mask.data(),
-                                    points.data(), &summary);
+    int rc;
+    if (any_rig) {   // known rigs: resident-problem path (bundle_adjustment.cc:147-161)
+      b200sfm_ba_problem* prob = nullptr;
+      rc = b200sfm_ba_problem_create_rig(ctx, C, P, (int64_t)obs_cam.size(), K, (int32_t)sensor_intr.size(), ptb.data(),
+                                         obs_cam.data(), obs_sensor.data(), obs_xy.data(), sensor_q.data(), sensor_t.data(),
+                                         sensor_intr.data(), intr_model.data(), mask.data(), o.min_num_view_per_track, &prob);
+      if (rc == B200SFM_OK) rc = b200sfm_ba_problem_set_state(prob, intr.data(), quat.data(), trans.data(), points.data());
+      if (rc == B200SFM_OK) rc = b200sfm_ba_problem_solve(prob, &o, &summary);
+      if (rc == B200SFM_OK) rc = b200sfm_ba_problem_get_state(prob, intr.data(), quat.data(), trans.data(), points.data());
+      b200sfm_ba_problem_free(prob);
+    } else {
+      rc = b200sfm_ba_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), K, ptb.data(), obs_cam.data(), obs_xy.data(),
+                            cam_intr.data(), intr_model.data(), intr.data(), quat.data(), trans.data(), mask.data(),
+                            points.data(), &summary);
+    }
     if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ba_solve: %s\n", b200sfm_last_error(ctx)); return false; }
     for (auto& [id, f] : fsorted) {                                                           // results in place (.cc:140-146)
       const int i = fidx[id];
@@ -192,7 +231,7 @@ class GlobalPositioner {
   bool Solve(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
              std::unordered_map<camera_t, Camera>& cameras, std::unordered_map<frame_t, Frame>& frames,
              std::unordered_map<image_t, Image>& images, std::unordered_map<track_t, Track>& tracks) {
-    (void)view_graph; (void)rigs;
+    (void)view_graph;
     if (images.empty()) { std::fprintf(stderr, "Number of images = 0\n"); return false; }     // .cc:37-40
     if (tracks.empty()) { std::fprintf(stderr, "Number of tracks = 0\n"); return false; }     // .cc:46-50
     if (options_.constraint_type != GlobalPositionerOptions::ONLY_POINTS) {
@@ -222,7 +261,13 @@ class GlobalPositioner {
         }
       }
     }
-    for (auto& [id, im] : images) calibrated[fidx[im.frame_id]] = cameras[im.camera_id].has_prior_focal_length ? 1 : 0;
+    bool any_rig = false;
+    for (auto& [id, im] : images) {
+      calibrated[fidx[im.frame_id]] = cameras[im.camera_id].has_prior_focal_length ? 1 : 0;
+      any_rig = any_rig || !im.HasTrivialFrame();
+    }
+    std::vector<double> obs_off;      // known rigs: R_cw^T t_cam_from_rig per observation (.cc:339-345)
+    std::vector<uint8_t> obs_cal;     // the loss is chosen per CAMERA (.cc:313-316)
     std::map<track_t, Track*> tsorted;
     for (auto& [id, t] : tracks) tsorted[id] = &t;
     const int P = (int)tsorted.size();
@@ -238,7 +283,29 @@ class GlobalPositioner {
         if (std::isnan(b[0]) || std::isnan(b[1]) || std::isnan(b[2])) continue;               // .cc:286-292
         const int ci = fidx[it->second.frame_id];
         const double* R = &Rm[9 * (size_t)ci];
-        for (int k = 0; k < 3; ++k) obs_dir.push_back(R[k] * b[0] + R[3 + k] * b[1] + R[6 + k] * b[2]);   // R^T b (.cc:294-296)
+        if (any_rig) {
+          // cam_from_world = cam_from_rig * rig_from_world;  t_obs = R_cw^T b,  t_rig = R_cw^T t_cam_from_rig
+          Rigid3d cfr;
+          if (!it->second.HasTrivialFrame())
+            cfr = b200host_adapt::CamFromRig(rigs[frames[it->second.frame_id].RigId()], it->second.camera_id);
+          if (std::isnan(cfr.translation[0]) || std::isnan(cfr.translation[1]) || std::isnan(cfr.translation[2])) {
+            std::fprintf(stderr, "b200sfm: unknown cam_from_rig (RigUnknownBATA) is not supported\n");
+            return false;
+          }
+          double Rs[9], bb[3], tt[3];
+          QuatToR(cfr.rotation.coeffs_data(), Rs);
+          for (int k = 0; k < 3; ++k) {   // R_cr^T b, R_cr^T t_cr
+            bb[k] = Rs[k] * b[0] + Rs[3 + k] * b[1] + Rs[6 + k] * b[2];
+            tt[k] = Rs[k] * cfr.translation[0] + Rs[3 + k] * cfr.translation[1] + Rs[6 + k] * cfr.translation[2];
+          }
+          for (int k = 0; k < 3; ++k) {
+            obs_dir.push_back(R[k] * bb[0] + R[3 + k] * bb[1] + R[6 + k] * bb[2]);
+            obs_off.push_back(R[k] * tt[0] + R[3 + k] * tt[1] + R[6 + k] * tt[2]);
+          }
+          obs_cal.push_back(cameras[it->second.camera_id].has_prior_focal_length ? 1 : 0);
+        } else {
+          for (int k = 0; k < 3; ++k) obs_dir.push_back(R[k] * b[0] + R[3 + k] * b[1] + R[6 + k] * b[2]);   // R^T b (.cc:294-296)
+        }
         obs_cam.push_back(ci);
       }
       ptb.push_back((int64_t)obs_cam.size());
@@ -257,8 +324,20 @@ class GlobalPositioner {
     o.thres_loss_function = options_.thres_loss_function;
     o.function_tolerance = options_.solver_options.function_tolerance;
     o.pcg_rel_tolerance = options_.pcg_rel_tolerance; o.pcg_max_iterations = options_.pcg_max_iterations;
-    const int rc = b200sfm_gp_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),
-                                    calibrated.data(), nullptr, centers.data(), points.data(), scales.data(), &summary);
+    int rc;
+    if (any_rig) {   // RigBATA with the rig scales held constant (.cc:325-346,493-497)
+      b200sfm_gp_problem* prob = nullptr;
+      rc = b200sfm_gp_problem_create(ctx, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),
+                                     calibrated.data(), nullptr, o.min_num_view_per_track, &prob);
+      if (rc == B200SFM_OK) rc = b200sfm_gp_problem_set_rig_terms(prob, obs_off.data(), obs_cal.data());
+      if (rc == B200SFM_OK) rc = b200sfm_gp_problem_set_state(prob, centers.data(), points.data(), scales.data());
+      if (rc == B200SFM_OK) rc = b200sfm_gp_problem_solve(prob, &o, &summary);
+      if (rc == B200SFM_OK) rc = b200sfm_gp_problem_get_state(prob, centers.data(), points.data(), scales.data());
+      b200sfm_gp_problem_free(prob);
+    } else {
+      rc = b200sfm_gp_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),
+                            calibrated.data(), nullptr, centers.data(), points.data(), scales.data(), &summary);
+    }
     if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_gp_solve: %s\n", b200sfm_last_error(ctx)); return false; }
     for (auto& [id, f] : fsorted) {                                                           // ConvertResults: t = -R c (.cc:566-568)
       const int i = fidx[id];

@@ -9,7 +9,14 @@
 #ifdef B200SFM_WITH_GLOMAP
 #include "glomap/scene/types_sfm.h"
 namespace b200host = glomap;
+namespace b200host_adapt {
+// cam_from_rig of a camera of a rig (colmap::Rig::SensorFromRig)
+inline glomap::Rigid3d CamFromRig(glomap::Rig& rig, glomap::camera_t camera_id) {
+  return rig.SensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id));
+}
+}  // namespace b200host_adapt
 #else
+#include <map>
 #include <array>
 #include <cstdint>
 #include <string>
@@ -42,10 +49,18 @@ struct Camera {
   std::vector<double> params;
   bool has_prior_focal_length = true;
 };
-struct Rig {};
+struct Rig {   // colmap::Rig: one reference sensor (identity) + sensors with a cam_from_rig
+  rig_t rig_id = 0;
+  std::map<camera_t, Rigid3d> cam_from_rig;
+  Rigid3d SensorFromRig(camera_t camera_id) const {
+    auto it = cam_from_rig.find(camera_id);
+    return it == cam_from_rig.end() ? Rigid3d{} : it->second;
+  }
+};
 struct Frame {
   frame_t frame_id = 0;
   rig_t rig_id = 0;
+  rig_t RigId() const { return rig_id; }
   bool is_registered = true;
   Rigid3d rig_from_world;
   Rigid3d& RigFromWorld() { return rig_from_world; }
@@ -60,8 +75,9 @@ struct Image {
   Frame* frame_ptr = nullptr;
   std::vector<std::array<double, 2>> features;          // distorted pixels (scene/image.h:29)
   std::vector<std::array<double, 3>> features_undist;   // unit bearings (scene/image.h:31)
+  bool trivial_frame = true;                            // false: the frame holds several images of a rig
   bool IsRegistered() const { return frame_ptr && frame_ptr->is_registered; }
-  bool HasTrivialFrame() const { return true; }
+  bool HasTrivialFrame() const { return trivial_frame; }
 };
 struct Track {
   track_t track_id = 0;
@@ -84,4 +100,7 @@ inline image_pair_t ImagePairToPairId(image_t a, image_t b) {   // colmap::Image
 }
 
 }  // namespace b200host
+namespace b200host_adapt {
+inline b200host::Rigid3d CamFromRig(b200host::Rig& rig, b200host::camera_t camera_id) { return rig.SensorFromRig(camera_id); }
+}  // namespace b200host_adapt
 #endif

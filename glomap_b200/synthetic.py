@@ -230,6 +230,136 @@ def perturb_scene(scene: Scene, rot_deg: float = 0.5, center_frac: float = 0.01,
     return out
 
 
+@dataclasses.dataclass
+class RigScene:
+    """Flat BA/GP problem with KNOWN camera rigs (b200sfm_ba_problem_create_rig): the pose unknowns are
+    the F frames (rig_from_world); image (f, s) = frame f seen through sensor s, whose cam_from_rig and
+    intrinsics block are constants of the sensor (glomap/scene/frame.h, colmap::Rig)."""
+    quat: np.ndarray          # [F,4] xyzw rig_from_world
+    trans: np.ndarray         # [F,3]
+    points: np.ndarray        # [P,3]
+    pt_obs_begin: np.ndarray  # [P+1] int64
+    obs_frame: np.ndarray     # [N] int32
+    obs_sensor: np.ndarray    # [N] uint16
+    obs_xy: np.ndarray        # [N,2] pixels
+    sensor_quat: np.ndarray   # [S,4] xyzw cam_from_rig
+    sensor_trans: np.ndarray  # [S,3]
+    sensor_intr: np.ndarray   # [S] int32 -> intrinsics block
+    intr_model: np.ndarray    # [K] int32
+    intr_params: np.ndarray   # [K, INTR_STRIDE]
+
+    @property
+    def C(self):
+        return len(self.quat)
+
+    @property
+    def F(self):
+        return len(self.quat)
+
+    @property
+    def S(self):
+        return len(self.sensor_quat)
+
+    @property
+    def P(self):
+        return len(self.points)
+
+    @property
+    def N(self):
+        return len(self.obs_frame)
+
+    def copy(self):
+        return RigScene(*[np.array(getattr(self, f.name), copy=True) for f in dataclasses.fields(self)])
+
+    def image_poses(self):
+        """cam_from_world of all F*S images, image id = f * S + s."""
+        Rf = geo.quat_xyzw_to_rotmat(self.quat)
+        Rs = geo.quat_xyzw_to_rotmat(self.sensor_quat)
+        R = np.einsum("sij,fjk->fsik", Rs, Rf).reshape(-1, 3, 3)
+        t = (np.einsum("sij,fj->fsi", Rs, self.trans) + self.sensor_trans[None]).reshape(-1, 3)
+        return R, t
+
+    def images_scene(self) -> Scene:
+        """The same observations as a trivial-frame Scene over the F*S images (poses composed)."""
+        R, t = self.image_poses()
+        obs_cam = (self.obs_frame.astype(np.int64) * self.S + self.obs_sensor).astype(np.int32)
+        cam_intr = np.tile(self.sensor_intr, self.F).astype(np.int32)
+        return Scene(geo.rotmat_to_quat_xyzw_fast(R), t, self.points.copy(), self.pt_obs_begin.copy(), obs_cam,
+                     self.obs_xy.copy(), cam_intr, self.intr_model.copy(), self.intr_params.copy())
+
+    def rig_dict(self):
+        """The ``rig`` argument of oracle.ba_oracle (per-image arrays, image id = f * S + s)."""
+        return dict(obs_img=self.obs_frame.astype(np.int64) * self.S + self.obs_sensor,
+                    img_q=np.tile(self.sensor_quat, (self.F, 1)), img_t=np.tile(self.sensor_trans, (self.F, 1)),
+                    img_intr=np.tile(self.sensor_intr, self.F))
+
+
+def make_rig_scene(F: int, S: int, P: int, mean_track_len: float = 8.0, seed: int = 1, pixel_sigma: float = 0.0,
+                   model: int = SIMPLE_PINHOLE, focal: float = 1000.0, image_size: int = 1000,
+                   shared_intrinsics: bool = False, sensor_rot_deg: float = 20.0, sensor_offset: float = 0.4) -> RigScene:
+    """F rigs of S cameras looking at a ball of points.  Sensor 0 is the reference sensor (identity
+    cam_from_rig); the others are rotated by up to ``sensor_rot_deg`` and shifted by ``sensor_offset``.
+    Every sensor has its own intrinsics block unless ``shared_intrinsics``.  Small sizes only (tests)."""
+    rng = np.random.default_rng([seed, 77])
+    Rf, tf = make_cameras(F, seed=seed, jitter_deg=5.0)
+    w = rng.normal(size=(S, 3))
+    w = w / np.linalg.norm(w, axis=1, keepdims=True) * np.radians(sensor_rot_deg) * rng.uniform(0.3, 1.0, size=(S, 1))
+    w[0] = 0.0
+    Rs = geo.so3_exp(w)
+    ts = rng.normal(size=(S, 3))
+    ts = ts / np.linalg.norm(ts, axis=1, keepdims=True) * sensor_offset
+    ts[0] = 0.0
+    K = 1 if shared_intrinsics else S
+    _, intr_model, intr_params = make_intrinsics(S, model, focal, image_size, K)
+    sensor_intr = (np.arange(S) % K).astype(np.int32)
+    scene = RigScene(geo.rotmat_to_quat_xyzw_fast(Rf), tf, np.zeros((P, 3)), np.zeros(P + 1, np.int64),
+                     np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros((0, 2)), geo.rotmat_to_quat_xyzw_fast(Rs), ts,
+                     sensor_intr, intr_model, intr_params)
+    Ri, ti = scene.image_poses()
+    d = rng.normal(size=(P, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    points = d * 3.0 * rng.uniform(0, 1, size=(P, 1)) ** (1 / 3)
+    lens = 3 + rng.poisson(max(mean_track_len - 3, 0.0), size=P)
+    fr, se, xy, begin = [], [], [], [0]
+    lim = 0.5 * image_size / focal * 1.2
+    for p in range(P):
+        Xc = np.einsum("nij,j->ni", Ri, points[p]) + ti
+        u, v = Xc[:, 0] / Xc[:, 2], Xc[:, 1] / Xc[:, 2]
+        ok = np.nonzero((Xc[:, 2] > 0.5) & (np.abs(u) < lim) & (np.abs(v) < lim))[0]
+        pick = rng.permutation(ok)[: lens[p]]
+        pick.sort()
+        for img in pick:
+            f, sidx = divmod(int(img), S)
+            k = sensor_intr[sidx]
+            px = project(int(intr_model[k]), intr_params[k], Xc[img])
+            fr.append(f); se.append(sidx); xy.append(px)
+        begin.append(len(fr))
+    scene.points = points
+    scene.pt_obs_begin = np.asarray(begin, np.int64)
+    scene.obs_frame = np.asarray(fr, np.int32)
+    scene.obs_sensor = np.asarray(se, np.uint16)
+    scene.obs_xy = np.asarray(xy, np.float64).reshape(-1, 2)
+    if pixel_sigma > 0:
+        scene.obs_xy = scene.obs_xy + rng.normal(size=scene.obs_xy.shape) * pixel_sigma
+    return scene
+
+
+def perturb_rig_scene(scene: RigScene, rot_deg: float = 0.5, center_frac: float = 0.01, point_frac: float = 0.01,
+                      seed: int = 2, extent: float = 10.0) -> RigScene:
+    """BA initial state for a rig scene: frame poses and points perturbed like ``perturb_scene``."""
+    rng = np.random.default_rng([seed, 5])
+    out = scene.copy()
+    R = geo.quat_xyzw_to_rotmat(scene.quat)
+    c = geo.centers_from_pose(R, scene.trans)
+    w = rng.normal(size=(scene.F, 3)) * np.radians(rot_deg) / np.sqrt(3)
+    Rn = geo.so3_exp(w) @ R
+    cn = c + rng.normal(size=c.shape) * center_frac * extent / np.sqrt(3)
+    out.quat = geo.rotmat_to_quat_xyzw_fast(Rn)
+    out.trans = -np.einsum("nij,nj->ni", Rn, cn)
+    out.points = scene.points + rng.normal(size=scene.points.shape) * point_frac * 3.0 / np.sqrt(3)
+    return out
+
+
 def bearings_from_scene(scene: Scene) -> np.ndarray:
     """Unit bearing of each observation in the camera frame -- what the
     reference keeps in ``Image::features_undist`` (glomap/scene/image.h:31,

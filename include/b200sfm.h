@@ -173,6 +173,21 @@ int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
                               const int64_t* pt_obs_begin, const int32_t* obs_cam, const double* obs_xy,
                               const int32_t* cam_intr, const int32_t* intr_model, const uint8_t* cam_const_mask,
                               int32_t min_num_view_per_track, b200sfm_ba_problem** out);
+/* Known (constant) camera rigs -- the `!optimize_rig_poses` branch of
+ * BundleAdjuster::AddPointToCameraConstraints (glomap/estimators/bundle_adjustment.cc:147-161,
+ * colmap::RigReprojErrorConstantRigCostFunctor): the unknown pose blocks are the F FRAMES
+ * (rig_from_world); every observation is made by an image = (frame, sensor) whose cam_from_rig is a
+ * constant and whose intrinsics block belongs to the sensor:
+ *     r = ImgFromCam(intr[sensor_intr[s]], R_cr[s] (R_f X + t_f) + t_cr[s]) - xy.
+ * obs_frame[N] indexes the frames (state arrays quat/trans are [F]), obs_sensor[N] the S sensors
+ * (S <= 65535; reference sensors carry the identity transform).  Everything else -- masks, state
+ * calls, solve, filters -- is b200sfm_ba_problem_*; the angle filter's `cam_calibrated` is then [S]. */
+int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_t N, int32_t K, int32_t S,
+                                  const int64_t* pt_obs_begin, const int32_t* obs_frame, const uint16_t* obs_sensor,
+                                  const double* obs_xy, const double* sensor_quat_xyzw /*[S][4] cam_from_rig*/,
+                                  const double* sensor_trans /*[S][3]*/, const int32_t* sensor_intr /*[S]*/,
+                                  const int32_t* intr_model, const uint8_t* frame_const_mask,
+                                  int32_t min_num_view_per_track, b200sfm_ba_problem** out);
 int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
                                  const double* trans, const double* points);
 int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr_params, double* quat_xyzw, double* trans,
@@ -246,6 +261,14 @@ typedef struct b200sfm_gp_problem b200sfm_gp_problem;
 int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, const int64_t* pt_obs_begin,
                               const int32_t* obs_cam, const double* obs_dir, const uint8_t* cam_calibrated,
                               const uint8_t* cam_const_mask, int32_t min_num_view_per_track, b200sfm_gp_problem** out);
+/* Known rigs in global positioning -- RigBATAPairwiseDirectionError with the rig scale held at 1
+ * (glomap/estimators/cost_function.h:49-82, global_positioning.cc:325-346,493-497):
+ *     r = t_obs - s (X - c_frame + obs_offset),   obs_offset = R_cam_from_world^T t_cam_from_rig.
+ * obs_cam then indexes FRAMES (c = rig centre).  obs_calibrated[N] (optional) is the prior-focal flag
+ * of the observing camera and replaces the per-frame cam_calibrated (the loss is chosen per camera,
+ * .cc:313-316).  NULL/NULL restores the trivial-frame behaviour. */
+int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* obs_offset /*[N][3]*/,
+                                     const uint8_t* obs_calibrated /*[N] or NULL*/);
 int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* centers, const double* points, const double* scales);
 int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* centers, double* points, double* scales);
 int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p);

@@ -147,7 +147,11 @@ class BAProblem:
     """Flat BA problem (the arrays of include/b200sfm.h: b200sfm_ba_solve)."""
 
     def __init__(self, quat, trans, points, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, intr_params,
-                 opts: BAOptions, cam_const_mask=None):
+                 opts: BAOptions, cam_const_mask=None, rig=None):
+        """``rig`` (known, constant camera rigs; bundle_adjustment.cc:147-161,
+        RigReprojErrorConstantRigCostFunctor): dict(obs_img [N], img_q [I,4], img_t [I,3], img_intr [I]) --
+        then quat/trans/obs_cam refer to FRAMES (rig_from_world) and every observation's image carries a
+        constant cam_from_rig transform and its own intrinsics block."""
         self.opts = opts
         self.C, self.P = len(quat), len(points)
         lens = np.diff(pt_obs_begin)
@@ -159,6 +163,12 @@ class BAProblem:
         self.obs_xy = np.asarray(obs_xy, dtype=np.float64)[keep]
         self.N = len(self.obs_pt)
         self.cam_intr = np.asarray(cam_intr).astype(np.int64)
+        self.rig = None
+        if rig is not None:
+            oi = np.asarray(rig["obs_img"])[keep].astype(np.int64)
+            self.rig = dict(obs_img=oi, R_cr=quat_rotmat(np.asarray(rig["img_q"], dtype=np.float64))[oi],
+                            t_cr=np.asarray(rig["img_t"], dtype=np.float64)[oi],
+                            obs_intr=np.asarray(rig["img_intr"]).astype(np.int64)[oi])
         self.intr_model = np.asarray(intr_model).astype(np.int64)
         self.K = len(self.intr_model)
         self.x0 = dict(quat=np.array(quat, dtype=np.float64), trans=np.array(trans, dtype=np.float64),
@@ -180,7 +190,7 @@ class BAProblem:
                 self.trn_col[c] = col; col += 3
         self.intr_cols = []  # per intrinsics block: list of (param idx, col)
         used_intr = np.zeros(self.K, dtype=bool)
-        used_intr[self.cam_intr[self.obs_cam]] = True
+        used_intr[self.rig["obs_intr"] if self.rig is not None else self.cam_intr[self.obs_cam]] = True
         for k in range(self.K):
             ent = []
             if opts.optimize_intrinsics and used_intr[k]:
@@ -236,12 +246,14 @@ class BAProblem:
         X = x["points"][self.obs_pt]
         RX = np.einsum("nij,nj->ni", R, X)
         Xc = RX + x["trans"][self.obs_cam]
+        if self.rig is not None:      # X_c = R_cr (R_f X + t_f) + t_cr
+            Xc = np.einsum("nij,nj->ni", self.rig["R_cr"], Xc) + self.rig["t_cr"]
         valid = Xc[:, 2] > Z_EPS
         Xs = np.where(valid[:, None], Xc, np.array([0.0, 0.0, 1.0]))
         res = np.zeros((self.N, 2))
         Jp = np.zeros((self.N, 2, 3)) if want_jac else None
         Jk_all = {}
-        ci = self.cam_intr[self.obs_cam]
+        ci = self.rig["obs_intr"] if self.rig is not None else self.cam_intr[self.obs_cam]
         for k in range(self.K):
             mk = ci == k
             if not mk.any():
@@ -258,6 +270,8 @@ class BAProblem:
         if not want_jac:
             return res, None
         Jp[~valid] = 0.0
+        if self.rig is not None:      # chain through the constant cam_from_rig rotation
+            Jp = np.einsum("nij,njk->nik", Jp, self.rig["R_cr"])
         # d Xc / d delta (quaternion manifold, left perturbation angle 2|d|): -2 [R X]x
         Jrot = np.einsum("nij,njk->nik", Jp, -2.0 * skew(RX))
         Jtrn = Jp
@@ -310,14 +324,14 @@ class BAProblem:
 
 
 def solve_ba(quat, trans, points, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, intr_params,
-             opts: BAOptions | None = None, cam_const_mask=None, verbose=False):
+             opts: BAOptions | None = None, cam_const_mask=None, verbose=False, rig=None):
     """Oracle counterpart of BundleAdjuster::Solve (bundle_adjustment.cc:11-106).
     ``cam_const_mask`` [C] uint8: bit0 rotation constant, bit1 translation
     constant (the caller marks the first frame with 3, .cc:261-266).
     Returns (state dict, LMSummary)."""
     opts = opts or BAOptions()
     prob = BAProblem(quat, trans, points, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, intr_params, opts,
-                     cam_const_mask)
+                     cam_const_mask, rig)
     lm = LMOptions(max_num_iterations=opts.max_num_iterations, function_tolerance=opts.function_tolerance,
                    verbose=verbose)
     if prob.N == 0 or prob.ncols == 0:

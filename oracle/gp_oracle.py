@@ -48,7 +48,11 @@ class GPOptions:
 
 
 class GPProblem:
-    def __init__(self, centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts: GPOptions, scales=None):
+    def __init__(self, centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts: GPOptions, scales=None,
+                 obs_offset=None):
+        """``obs_offset`` [N,3]: known-rig term of RigBATAPairwiseDirectionError (cost_function.h:49-82) with the rig
+        scale held at 1 (global_positioning.cc:493-497): r = t_obs - s (X - c_frame + t_rig), t_rig = R_cw^T t_cam_from_rig
+        (.cc:339-345)."""
         self.opts = opts
         self.C, self.P = len(centers), len(points)
         lens = np.diff(pt_obs_begin)
@@ -58,6 +62,7 @@ class GPProblem:
         self.obs_pt = pt_of_obs[self.keep]
         self.obs_cam = np.asarray(obs_cam)[self.keep].astype(np.int64)
         self.obs_dir = np.asarray(obs_dir, dtype=np.float64)[self.keep]
+        self.obs_off = None if obs_offset is None else np.asarray(obs_offset, dtype=np.float64)[self.keep]
         self.N = len(self.obs_pt)
         cal = np.ones(self.C, bool) if cam_calibrated is None else np.asarray(cam_calibrated).astype(bool)
         self.loss_scale = np.where(cal[self.obs_cam], 1.0, 0.5)
@@ -107,6 +112,8 @@ class GPProblem:
 
     def evaluate(self, x, want_jac):
         d = x["points"][self.obs_pt] - x["centers"][self.obs_cam]
+        if self.obs_off is not None:
+            d = d + self.obs_off
         s = x["scales"]
         res = self.obs_dir - s[:, None] * d
         sq = (res * res).sum(1)
@@ -135,12 +142,12 @@ class GPProblem:
 
 
 def solve_gp(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated=None, opts: GPOptions | None = None,
-             scales=None, verbose=False):
+             scales=None, verbose=False, obs_offset=None):
     """Oracle counterpart of the ceres::Solve inside GlobalPositioner::Solve
     (global_positioning.cc:83) on already-initialised centres/points.
     Returns (state dict with centers, points, scales (valid observations only), LMSummary)."""
     opts = opts or GPOptions()
-    prob = GPProblem(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts, scales)
+    prob = GPProblem(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts, scales, obs_offset)
     if prob.N == 0 or prob.ncols == 0:
         return prob.x0, LMSummary(termination="empty problem")
     lm = LMOptions(max_num_iterations=opts.max_num_iterations, function_tolerance=opts.function_tolerance, verbose=verbose)

@@ -1,0 +1,161 @@
+"""GPU parity tests for KNOWN camera rigs (non-trivial frames with constant cam_from_rig):
+BundleAdjuster (bundle_adjustment.cc:147-161, RigReprojErrorConstantRigCostFunctor),
+GlobalPositioner (RigBATAPairwiseDirectionError with constant rig scale,
+global_positioning.cc:325-346,493-497), RotationEstimator over frames
+(global_rotation_averaging.cc:274-309) and the track filters -- through the C ABI against the
+CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from glomap_b200 import estimators as E, geometry as G, synthetic as S
+from oracle import ba_oracle as B, filter_oracle as FO, gp_oracle as GPO, ra_oracle as RO
+
+pytestmark = pytest.mark.gpu
+
+
+def _rig_oracle(rs, init, opts, mask):
+    return B.solve_ba(init.quat, init.trans, init.points, rs.pt_obs_begin, rs.obs_frame, rs.obs_xy,
+                      np.zeros(rs.F, np.int32), rs.intr_model, init.intr_params, opts, mask, rig=rs.rig_dict())
+
+
+def _device(init, mask, design=0, tol=1e-12, **kw):
+    opts = E.BundleAdjusterOptions(**kw)
+    opts.design = design
+    opts.solver_options.pcg_rel_tolerance = tol
+    opts.solver_options.pcg_max_iterations = 3000
+    ba = E.BundleAdjuster(opts)
+    dev = init.copy()
+    ok = ba.Solve(dev, mask)
+    return ok, dev, ba.summary
+
+
+@pytest.mark.parametrize("design", [1, 2])
+def test_rig_ba_tracks_oracle(design):
+    rs = S.make_rig_scene(12, 3, 500, seed=5, pixel_sigma=0.5)
+    init = S.perturb_rig_scene(rs)
+    mask = E.first_frame_mask(rs.F)
+    ok, dev, st = _device(init, mask, design=design, optimize_intrinsics=False)
+    x, summ = _rig_oracle(rs, init, B.BAOptions(), mask)
+    assert ok and st.usable
+    assert st.iterations == summ.iterations
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-8 * summ.final_cost
+    assert np.abs(dev.quat - x["quat"]).max() < 1e-6
+    assert np.abs(dev.trans - x["trans"]).max() < 1e-6
+    assert np.abs(dev.points - x["points"]).max() < 1e-6
+
+
+def test_rig_ba_noise_free_recovers_ground_truth():
+    rs = S.make_rig_scene(10, 4, 500, seed=6, model=S.SIMPLE_RADIAL)
+    init = S.perturb_rig_scene(rs)
+    ok, dev, st = _device(init, None, tol=1e-10, optimize_intrinsics=False)
+    assert ok and st.final_cost < 1e-8 * st.initial_cost
+    rot, cen = G.compare_reconstructions(G.quat_xyzw_to_rotmat(dev.quat), dev.trans, G.quat_xyzw_to_rotmat(rs.quat),
+                                         rs.trans)[:2]
+    assert rot < 1e-2 and cen < 1e-4, (rot, cen)
+
+
+@pytest.mark.parametrize("model", [S.SIMPLE_PINHOLE, S.SIMPLE_RADIAL])
+def test_rig_ba_with_intrinsics_matches_oracle(model):
+    """optimize_intrinsics (the reference default): one intrinsics block per SENSOR, shared by the
+    images of that sensor in all frames -- the dense border of the reduced system."""
+    rs = S.make_rig_scene(12, 3, 600, seed=8, pixel_sigma=0.3, model=model)
+    init = S.perturb_rig_scene(rs)
+    init.intr_params = init.intr_params.copy()
+    init.intr_params[:, 0] *= 1.01
+    mask = E.first_frame_mask(rs.F)
+    ok, dev, st = _device(init, mask, optimize_intrinsics=True)
+    x, summ = _rig_oracle(rs, init, B.BAOptions(optimize_intrinsics=True), mask)
+    assert ok
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-6 * summ.final_cost
+    npar = S.MODEL_NUM_PARAMS[model]
+    assert np.abs(dev.intr_params[:, :npar] - x["intr"][:, :npar]).max() < 1e-4 * 1000
+    assert np.abs(dev.quat - x["quat"]).max() < 1e-5
+
+
+def test_rig_cost_and_filters_equal_the_equivalent_image_problem():
+    """A rig problem and the same observations posed over the F*S images with composed poses are the
+    same functions of the state: cost and all three track filters must agree."""
+    rs = S.make_rig_scene(10, 3, 400, seed=9, pixel_sigma=1.0)
+    st_ = S.perturb_rig_scene(rs, rot_deg=0.3)
+    im = st_.images_scene()
+    ctx = E.default_context()
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=False)
+    pr = E.BAProblem(ctx, st_, 3)
+    pi = E.BAProblem(ctx, im, 3)
+    pr.set_state(st_.intr_params, st_.quat, st_.trans, st_.points)
+    pi.set_state(im.intr_params, im.quat, im.trans, im.points)
+    c_r, c_i = pr.cost(opts), pi.cost(opts)
+    assert abs(c_r - c_i) <= 1e-11 * c_i
+    k_r, n_r = pr.filter_reprojection(20.0)
+    k_i, n_i = pi.filter_reprojection(20.0)
+    k_o, n_o = FO.filter_reprojection(im, 20.0, S.project)
+    assert np.array_equal(k_r, k_i) and n_r == n_i and np.array_equal(k_r, k_o) and n_r == n_o
+    assert 0 < n_r < rs.P
+    bear = S.bearings_from_scene(im)
+    k_r, n_r = pr.filter_angle(bear, 1.0)
+    k_i, n_i = pi.filter_angle(bear, 1.0)
+    assert np.array_equal(k_r, k_i) and n_r == n_i and 0 < n_r < rs.P
+    t_r, m_r = pr.filter_triangulation_angle(100.0)
+    t_i, m_i = pi.filter_triangulation_angle(100.0)
+    t_o, m_o = FO.filter_triangulation_angle(im, 100.0)
+    assert np.array_equal(t_r, t_i) and m_r == m_i and np.array_equal(t_r, t_o) and m_r > 0
+    pr.free(); pi.free()
+
+
+def test_rig_global_positioning_matches_oracle():
+    rs = S.make_rig_scene(14, 3, 500, seed=10, pixel_sigma=0.3)
+    im = rs.images_scene()
+    bear = S.bearings_from_scene(im)
+    rng = np.random.default_rng(3)
+    cen0 = G.centers_from_pose(G.quat_xyzw_to_rotmat(rs.quat), rs.trans) + rng.normal(size=(rs.F, 3)) * 0.5
+    pts0 = rs.points + rng.normal(size=rs.points.shape) * 0.5
+    opts = E.GlobalPositionerOptions(generate_random_positions=False, generate_random_points=False, generate_scales=True)
+    opts.solver_options.pcg_rel_tolerance = 1e-12
+    opts.solver_options.pcg_max_iterations = 3000
+    prob = E.PositioningProblem(rs.quat, rs.pt_obs_begin, rs.obs_frame, bear, centers=cen0.copy(), points=pts0.copy(),
+                                obs_sensor=rs.obs_sensor, sensor_quat=rs.sensor_quat, sensor_trans=rs.sensor_trans,
+                                sensor_calibrated=np.array([1, 0, 1], np.uint8))
+    gp = E.GlobalPositioner(opts)
+    assert gp.Solve(prob)
+    t_obs, t_rig = E.rig_world_terms(rs.quat, rs.sensor_quat, rs.sensor_trans, bear, rs.obs_frame, rs.obs_sensor)
+    # the oracle takes the loss scale per "camera": pose the calibrated flag per image (F*S pseudo cameras)
+    ocal = np.array([1, 0, 1], bool)[rs.obs_sensor]
+    po = GPO.GPProblem(cen0, pts0, rs.pt_obs_begin, rs.obs_frame, t_obs, None, GPO.GPOptions(), None, obs_offset=t_rig)
+    po.loss_scale = np.where(ocal[po.keep], 1.0, 0.5)
+    from oracle.ceres_lm import LMOptions, solve_lm
+    x, summ = solve_lm(po.x0, po.evaluate, po.plus, LMOptions(max_num_iterations=100, function_tolerance=1e-5),
+                       project=po.project, x_norm_fn=po.x_norm)
+    st = gp.summary
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-6 * max(summ.final_cost, 1e-12)
+    assert np.abs(prob.centers - x["centers"]).max() < 1e-5
+    assert np.abs(prob.points - x["points"]).max() < 1e-5
+
+
+def test_rig_rotation_averaging_over_frames():
+    """Image-pair rotations folded onto frames (R_c2r2^T R_21 R_c1r1), same-frame pairs skipped."""
+    rs = S.make_rig_scene(16, 3, 10, seed=11)
+    Ri, _ = rs.image_poses()
+    rng = np.random.default_rng(5)
+    n_img = rs.F * rs.S
+    ei, ej = np.triu_indices(n_img, 1)
+    sel = rng.uniform(size=len(ei)) < 0.25
+    ei, ej = ei[sel].astype(np.int32), ej[sel].astype(np.int32)
+    noise = G.so3_exp(rng.normal(size=(len(ei), 3)) * np.radians(0.5))
+    R_rel = noise @ Ri[ej] @ np.swapaxes(Ri[ei], -1, -2)
+    vg_img = S.ViewGraph(n_img, ei, ej, R_rel, np.ones(len(ei)), Ri)
+    img_frame = np.repeat(np.arange(rs.F), rs.S)
+    img_sensor = np.tile(np.arange(rs.S), rs.F)
+    Rf = G.quat_xyzw_to_rotmat(rs.quat)
+    vg = E.rig_view_graph(vg_img, img_frame, img_sensor, rs.sensor_quat, Rf)
+    assert vg.E < vg_img.E and (vg.ei != vg.ej).all()
+    est = E.RotationEstimator(E.RotationEstimatorOptions())
+    ok, R = est.EstimateRotations(vg)
+    assert ok
+    R0 = E.initialize_from_maximum_spanning_tree(vg, None)
+    th, info = RO.estimate_rotations(vg.n_images, vg.ei, vg.ej, vg.R_rel, G.so3_log(R0))
+    assert np.abs(R - G.so3_exp(th)).max() < 1e-7
+    err = G.rotation_angle_deg(R @ np.swapaxes(R[:1], -1, -2), Rf @ np.swapaxes(Rf[:1], -1, -2))
+    assert err.max() < 1.0
