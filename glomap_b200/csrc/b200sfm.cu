@@ -12,6 +12,7 @@ namespace {
 
 template <class F>
 int guarded(b200sfm_ctx* ctx, F&& f) {
+  b200::AllocScope alloc_scope(ctx ? ctx->stream : nullptr);
   try {
     return f();
   } catch (const b200::CudaError& e) {
@@ -40,6 +41,14 @@ int create_common(int device, b200sfm_ctx** out) {
       cudaMallocHost(&c->h_scal, b200sfm_ctx::kHScal * sizeof(double)) != cudaSuccess) {
     delete c;
     return B200SFM_ERR_CUDA;
+  }
+  if (b200::async_alloc_enabled()) {   // keep freed device memory in the pool between solves (best effort)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
   }
   *out = c;
   return B200SFM_OK;
@@ -88,7 +97,15 @@ void b200sfm_destroy(b200sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  if (b200::async_alloc_enabled()) {   // give the cached device memory back
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+  }
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   delete ctx;
 }
@@ -288,6 +305,7 @@ void b200sfm_ba_problem_free(b200sfm_ba_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
+  b200::AllocScope alloc_scope(p->ctx->stream);   // buffers go back to the stream-ordered pool
   delete p;
 }
 
@@ -451,6 +469,7 @@ void b200sfm_gp_problem_free(b200sfm_gp_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
+  b200::AllocScope alloc_scope(p->ctx->stream);   // buffers go back to the stream-ordered pool
   delete p;
 }
 

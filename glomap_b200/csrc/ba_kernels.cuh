@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(kTile, B200_K1_MIN_CTAS) ba_linearize_points(B
                                                              const double* __restrict__ intr_rec,
                                                              const double* __restrict__ points, double huber_a,
                                                              int points_var, double* __restrict__ scal) {
-  extern __shared__ unsigned char smem_raw[];
-  K1Smem& sm = *reinterpret_cast<K1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   // one 16-B descriptor per tile: the dependent-load chain is descriptor -> {observations, points} -> camera record
@@ -633,8 +633,8 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView 
                                                           double* __restrict__ points_new, double radius,
                                                           double* __restrict__ bscal, const double* __restrict__ spk = nullptr,
                                                           const double* __restrict__ dk = nullptr, int m_intr = 0) {
-  extern __shared__ unsigned char smem_raw[];
-  K3Smem& sm = *reinterpret_cast<K3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  K3Smem& sm = *reinterpret_cast<K3Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   const int4 td = v.tile_desc[tile];
@@ -1099,8 +1099,8 @@ __global__ void __launch_bounds__(kTile) ba_intr_points(BAView v, const double* 
                                                         const double* __restrict__ points, double huber_a, int m,
                                                         double* __restrict__ spk, double* __restrict__ B,
                                                         double* __restrict__ part) {
-  extern __shared__ unsigned char smem_raw[];
-  KISmem& sm = *reinterpret_cast<KISmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  KISmem& sm = *reinterpret_cast<KISmem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   const int4 td = v.tile_desc[tile];

@@ -31,7 +31,9 @@ struct BAViewV2 {
   double* z4;         // [P][4]
 };
 
-// xp[c] = { R^T x_r , R^T x_t }   (masked dofs of x are zero already: PCG keeps them at 0)
+// xp[c] = { R^T x_r , R^T x_t, pad, pad }: 64-B rows, so pass A gathers a camera with one 256-bit and one
+// 128-bit load out of a single line  (masked dofs of x are zero already: PCG keeps them at 0)
+constexpr int kXqStride = 8;
 __global__ void ba2_pack_x(int C, const double* __restrict__ x, const double* __restrict__ cam_rec,
                            double* __restrict__ xp) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,7 +43,7 @@ __global__ void ba2_pack_x(int C, const double* __restrict__ x, const double* __
   double R[9];
   quat_to_R(q, R);
   const double* xc = x + (size_t)c * 6;
-  double* o = xp + (size_t)c * 6;
+  double* o = xp + (size_t)c * kXqStride;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     o[k] = R[k] * xc[0] + R[3 + k] * xc[1] + R[6 + k] * xc[2];
@@ -232,12 +234,12 @@ struct K3v2Smem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTile, B200_PA_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
+__global__ void __launch_bounds__(kTile, MODE == 0 ? B200_PA_MIN_CTAS : B200_K3_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
                                                                      const double* __restrict__ points,
                                                                      double* __restrict__ points_new, double radius,
                                                                      double* __restrict__ bscal) {
-  extern __shared__ unsigned char smem_raw[];
-  K3v2Smem& sm = *reinterpret_cast<K3v2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  K3v2Smem& sm = *reinterpret_cast<K3v2Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
   const int4 td = v.tile_desc[tile];
@@ -255,13 +257,14 @@ __global__ void __launch_bounds__(kTile, B200_PA_MIN_CTAS) ba2_pass_a(BAView v, 
     }
   }
   // prefetch the first chunk: camera index -> R^T x record, local point index
-  double2 g0 = make_double2(0, 0), g1 = g0, g2 = g0;
+  double xr0 = 0, xr1 = 0, xr2 = 0, xt0 = 0;
+  double2 xt12 = make_double2(0, 0);
   int pl_pf = 0;
   if (tid < n) {
     const int cam = ld_stream(v.obs_cam + o0 + tid);
     pl_pf = ld_stream(v.obs_pt + o0 + tid) - p0;
-    const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
-    g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
+    ld_nc_256(xp + (size_t)cam * kXqStride, xr0, xr1, xr2, xt0);
+    xt12 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)cam * kXqStride + 4));
   }
   if (tid < npts) {
     sm.pb[tid] = v.pt_begin[p0 + tid];
@@ -283,8 +286,8 @@ __global__ void __launch_bounds__(kTile, B200_PA_MIN_CTAS) ba2_pass_a(BAView v, 
     if (active && ch > 0) {
       const int cam = ld_stream(v.obs_cam + o0 + c0 + tid);
       pl_pf = ld_stream(v.obs_pt + o0 + c0 + tid) - p0;
-      const double2* gp_ = reinterpret_cast<const double2*>(xp + (size_t)cam * 6);
-      g0 = gp_[0]; g1 = gp_[1]; g2 = gp_[2];
+      ld_nc_256(xp + (size_t)cam * kXqStride, xr0, xr1, xr2, xt0);
+      xt12 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)cam * kXqStride + 4));
     }
     mbar_wait(&sm.mbar, phase);
     phase ^= 1;
@@ -293,13 +296,15 @@ __global__ void __launch_bounds__(kTile, B200_PA_MIN_CTAS) ba2_pass_a(BAView v, 
       const double2* ar = reinterpret_cast<const double2*>(sm.At + tid * kJpDoubles);
       const double2 a0 = ar[0], a1 = ar[1], a2 = ar[2];
       const double X[3] = {sm.X[0][pl_pf], sm.X[1][pl_pf], sm.X[2][pl_pf]};
-      const double xr[3] = {g0.x, g0.y, g1.x}, xt[3] = {g1.y, g2.x, g2.y};
+      const double xr[3] = {xr0, xr1, xr2}, xt[3] = {xt0, xt12.x, xt12.y};
       const double vv[3] = {xt[0] - 2.0 * (X[1] * xr[2] - X[2] * xr[1]), xt[1] - 2.0 * (X[2] * xr[0] - X[0] * xr[2]),
                             xt[2] - 2.0 * (X[0] * xr[1] - X[1] * xr[0])};
       t0 = a0.x * vv[0] + a0.y * vv[1] + a1.x * vv[2];
       t1 = a0.y * vv[0] + a1.y * vv[1] + a2.x * vv[2];
       t2 = a1.x * vv[0] + a2.x * vv[1] + a2.y * vv[2];
     }
+    // per-point sums through shared memory: thread -> (point j, component k).  (A warp-shuffle segmented
+    // reduction was measured slower: SHFL shares the LSU data pipe that bounds this kernel, profiles/r1_v2_sweep.md.)
     sm.t[0][tid] = t0;
     sm.t[1][tid] = t1;
     sm.t[2][tid] = t2;
@@ -384,7 +389,7 @@ __global__ void ba2_point_rhs_z(BAView v, BAViewV2 v2) {
 // ---------------------------------------------------------------------------
 // pass B (camera order): y_c -= [ 2 R sum (X x w) ; R sum w ],  w = A_o z_p
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
+__global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                  double* __restrict__ y) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -395,20 +400,41 @@ __global__ void __launch_bounds__(128) ba2_pass_b(BAView v, BAViewV2 v2, const d
   // two observations per lane and iteration: both index loads, then both gathers, are in flight together
   const double* row0 = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
   const uint64_t keep = l2_policy_evict_last();
-  for (int i0 = b + lane; i0 < e; i0 += 64, row0 += 2 * kJcDoubles * 32) {
-    const int i1 = i0 + 32;
-    const bool ok1 = i1 < e;
-    const int pt0 = ld_stream(v.pt_c + i0);
-    const int pt1 = ok1 ? ld_stream(v.pt_c + i1) : pt0;
-    const double* row1 = ok1 ? row0 + kJcDoubles * 32 : row0;
-    double a[kJcDoubles], c[kJcDoubles];
+  // all point indices of the segment first (<= kSeg / 32 per lane): the z gathers then depend on nothing but
+  // these registers, so every iteration costs one memory latency instead of two (index, then gather)
+  int ptr[kSeg / 32];
+#if B200_PB_PREFETCH
 #pragma unroll
-    for (int k = 0; k < kJcDoubles; ++k) a[k] = ld_stream(row0 + 32 * k);
+  for (int j = 0; j < kSeg / 32; ++j) {
+    const int i = b + lane + 32 * j;
+    ptr[j] = i < e ? ld_stream(v.pt_c + i) : -1;
+  }
+#endif
 #pragma unroll
-    for (int k = 0; k < kJcDoubles; ++k) c[k] = ld_stream(row1 + 32 * k);
-    const double4 z0 = ld_keep4(v2.z4 + 4 * (size_t)pt0, keep);
-    const double4 z1 = ld_keep4(v2.z4 + 4 * (size_t)pt1, keep);
+  for (int j = 0; j < kSeg / 32; j += 2) {
+    if (b + 32 * j >= e) break;
+#if !B200_PB_PREFETCH
     {
+      const int i = b + lane + 32 * j;
+      ptr[j] = i < e ? ld_stream(v.pt_c + i) : -1;
+      ptr[j + 1] = i + 32 < e ? ld_stream(v.pt_c + i + 32) : -1;
+    }
+#endif
+    const int pt0 = ptr[j], pt1 = ptr[j + 1];
+    const bool ok0 = pt0 >= 0, ok1 = pt1 >= 0;
+    const double* r0p = row0 + (size_t)j * (kJcDoubles * 32);
+    const double* r1p = ok1 ? r0p + kJcDoubles * 32 : r0p;
+    double a[kJcDoubles], c[kJcDoubles];
+    double4 z0 = make_double4(0, 0, 0, 0), z1 = z0;
+    if (ok0) {
+#pragma unroll
+      for (int k = 0; k < kJcDoubles; ++k) a[k] = ld_stream(r0p + 32 * k);
+#pragma unroll
+      for (int k = 0; k < kJcDoubles; ++k) c[k] = ld_stream(r1p + 32 * k);
+      z0 = ld_keep4(v2.z4 + 4 * (size_t)pt0, keep);
+      z1 = ld_keep4(v2.z4 + 4 * (size_t)(ok1 ? pt1 : pt0), keep);
+    }
+    if (ok0) {
       const double w0 = a[0] * z0.x + a[1] * z0.y + a[2] * z0.z;
       const double w1 = a[1] * z0.x + a[3] * z0.y + a[4] * z0.z;
       const double w2 = a[2] * z0.x + a[4] * z0.y + a[5] * z0.z;

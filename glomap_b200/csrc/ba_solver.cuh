@@ -346,7 +346,7 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k3v2));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * 6);
+    Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXqStride);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -803,6 +803,9 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaStreamSynchronize(s));
     }
     use_v2 = (m_intr == 0) && (o.design != 1);   // v2 (compact rows) unless the intrinsics border needs W
+    // v2: keep z4 (written by pass A, gathered by pass B) in the persisting part of L2
+    const bool l2_persist = use_v2 && !(getenv("B200SFM_L2_PERSIST") && atoi(getenv("B200SFM_L2_PERSIST")) == 0);
+    if (l2_persist) l2_persist_window(s, ctx->device, z4.p, z4.bytes());
     const long long launches0 = ctx->launches;
     timer_lin.reset();
     timer_mv.reset();
@@ -861,6 +864,7 @@ struct b200sfm_ba_problem {
     }
     B200_CUDA_OK(cudaEventRecord(ev1, s));
     B200_CUDA_OK(cudaEventSynchronize(ev1));
+    if (l2_persist) l2_persist_clear(s);
     float ms = 0;
     B200_CUDA_OK(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0);

@@ -24,6 +24,12 @@ namespace b200 {
 #ifndef B200_LC_MIN_CTAS   // v2 camera-order linearisation: 128 registers (a few spills) -> 4 CTAs of 4 warps; sweep: profiles/r1_v2_sweep.md
 #define B200_LC_MIN_CTAS 4
 #endif
+#ifndef B200_PB_PREFETCH   // v2 pass B: load all point indices of a segment before the gathers (one latency per iteration)
+#define B200_PB_PREFETCH 1
+#endif
+#ifndef B200_PB_MIN_CTAS
+#define B200_PB_MIN_CTAS 9
+#endif
 #ifndef B200_STREAM_HINTS  // evict-first loads/stores on the once-per-pass streams so the gathered arrays stay in L2
 #define B200_STREAM_HINTS 1
 #endif
@@ -99,6 +105,10 @@ __device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* g
 #else
   tma_load_1d(smem_dst, gsrc, bytes, bar);
 #endif
+}
+// 256-bit read-only gather (LDG.E.256, sm_100): p must be 32-B aligned
+__device__ __forceinline__ void ld_nc_256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 // streaming (evict-first) scalar accesses
 template <class T>

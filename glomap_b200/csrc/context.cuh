@@ -74,6 +74,25 @@ struct b200sfm_ctx {
 
 namespace b200 {
 
+// Device buffers come from the stream-ordered allocator (cudaMallocAsync on the context's stream, default
+// memory pool with an unbounded release threshold): a one-shot solve allocates a few GB in ~20 buffers, and
+// with the pool a repeated call re-uses them instead of paying cudaMalloc/cudaFree every time.  Every ABI
+// entry point installs its context's stream for the calling thread (AllocScope); without one -- or with
+// B200SFM_ASYNC_ALLOC=0 -- plain cudaMalloc/cudaFree are used.
+inline cudaStream_t& alloc_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+struct AllocScope {
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t s) : prev(alloc_stream()) { alloc_stream() = s; }
+  ~AllocScope() { alloc_stream() = prev; }
+};
+inline bool async_alloc_enabled() {
+  static const bool on = !(getenv("B200SFM_ASYNC_ALLOC") && atoi(getenv("B200SFM_ASYNC_ALLOC")) == 0);
+  return on;
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -85,10 +104,16 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) B200_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+    if (!count) return;
+    if (alloc_stream() && async_alloc_enabled()) B200_CUDA_OK(cudaMallocAsync(&p, count * sizeof(T), alloc_stream()));
+    else B200_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      // stream-ordered free when a context stream is installed (cudaFree is valid for both kinds otherwise)
+      if (alloc_stream() && async_alloc_enabled()) cudaFreeAsync(p, alloc_stream());
+      else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
@@ -103,6 +128,32 @@ struct DevBuf {
     if (count) B200_CUDA_OK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
 };
+
+// Persisting-L2 window over an array that one pass writes and the next gathers (design v2: z4).  The
+// set-aside is bounded by the device limits; every call is best-effort (a refusal only costs bandwidth).
+inline void l2_persist_window(cudaStream_t s, int device, void* base, size_t bytes) {
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+  if (max_persist <= 0 || max_window <= 0 || bytes == 0) { cudaGetLastError(); return; }
+  const size_t setaside = std::min((size_t)max_persist, bytes);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);
+  cudaStreamAttrValue a{};
+  a.accessPolicyWindow.base_ptr = base;
+  a.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+  a.accessPolicyWindow.hitRatio = std::min(1.0f, (float)setaside / (float)a.accessPolicyWindow.num_bytes);
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a);
+  cudaGetLastError();
+}
+inline void l2_persist_clear(cudaStream_t s) {
+  cudaStreamAttrValue a{};
+  a.accessPolicyWindow.num_bytes = 0;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a);
+  cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+}
 
 struct EventTimer {
   // pool of event pairs timing selected kernels; summed after a final sync

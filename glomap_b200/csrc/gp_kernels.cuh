@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kTile) gp_linearize_points(GPView v, const dou
                                                              const double* __restrict__ scales, double huber_a,
                                                              double radius, int set_js, int points_var,
                                                              double* __restrict__ scal) {
-  extern __shared__ unsigned char smem_raw[];
-  G1Smem& sm = *reinterpret_cast<G1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  G1Smem& sm = *reinterpret_cast<G1Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
   const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
                                                        const double* __restrict__ scales, double huber_a, double radius,
                                                        double* __restrict__ dX, double* __restrict__ ds,
                                                        double* __restrict__ bscal) {
-  extern __shared__ unsigned char smem_raw[];
-  G3Smem& sm = *reinterpret_cast<G3Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  G3Smem& sm = *reinterpret_cast<G3Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];
   const unsigned o0 = v.pt_begin[p0], o1 = v.pt_begin[p1];
