@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kTile, MODE == 0 ? B200_PA_MIN_CTAS : B200_K3_
     sm.pb[tid] = v.pt_begin[p0 + tid];
     if (tid == npts - 1) sm.pb[npts] = o1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sm.X[k][tid] = ld_stream(points + 3 * (size_t)(p0 + tid) + k);
+    for (int k = 0; k < 3; ++k) sm.X[k][tid] = points[3 * (size_t)(p0 + tid) + k];
     sm.z[0][tid] = sm.z[1][tid] = sm.z[2][tid] = 0.0;
   }
   __syncthreads();
@@ -330,9 +330,10 @@ __global__ void __launch_bounds__(kTile, MODE == 0 ? B200_PA_MIN_CTAS : B200_K3_
         g[0] = v.gp[3 * p]; g[1] = v.gp[3 * p + 1]; g[2] = v.gp[3 * p + 2];
         s[0] += g[0]; s[1] += g[1]; s[2] += g[2];
       }
-      double vi[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(v.Vinv + 6 * p + k);
+      // 48-B rows are 16-B aligned: three 128-bit loads (8-B streaming loads would re-fetch the sector six times)
+      const double2* vp = reinterpret_cast<const double2*>(v.Vinv + 6 * p);
+      const double2 va = vp[0], vb = vp[1], vc = vp[2];
+      const double vi[6] = {va.x, va.y, vb.x, vb.y, vc.x, vc.y};
       sym3_mul(vi, s, z);
       if (MODE == 2) {
         double v6[6], js[3], Dp[3];
@@ -359,16 +360,45 @@ __global__ void __launch_bounds__(kTile, MODE == 0 ? B200_PA_MIN_CTAS : B200_K3_
     if (MODE == 0) st_keep4(v2.z4 + 4 * p, make_double4(z[0], z[1], z[2], 0.0), l2_policy_evict_last());
   }
   if (MODE == 2) {
-    b0 = block_sum(b0, sm.scratch);
-    b1 = block_sum(b1, sm.scratch);
-    b2 = block_sum(b2, sm.scratch);
-    b3 = block_sum(b3, sm.scratch);
-    if (tid == 0) {
-      atomicAdd(&bscal[0], b0);
-      atomicAdd(&bscal[1], b1);
-      atomicAdd(&bscal[2], b2);
-      atomicAdd(&bscal[3], b3);
+    // step scalars: one partial row per tile (bscal = part[n_tiles][4]), column-summed by ba_colsum afterwards --
+    // deterministic, and no 4 x n_tiles same-address atomics
+    b0 = warp_sum(b0);
+    b1 = warp_sum(b1);
+    b2 = warp_sum(b2);
+    b3 = warp_sum(b3);
+    if ((tid & 31) == 0) {
+      sm.scratch[(tid >> 5)] = b0;
+      sm.scratch[4 + (tid >> 5)] = b1;
+      sm.scratch[8 + (tid >> 5)] = b2;
+      sm.scratch[12 + (tid >> 5)] = b3;
     }
+    __syncthreads();
+    if (tid < 4) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < kTile / 32; ++w) a += sm.scratch[4 * tid + w];
+      bscal[(size_t)tile * 4 + tid] = a;
+    }
+  }
+}
+
+// Column sums of the per-tile step scalars part[rows][4], stage 1: 4 partial sums per CTA (grid-stride over the
+// rows, one 32-B load per row); stage 2 is ba_colsum over the gridDim.x partial rows.  Deterministic.
+__global__ void __launch_bounds__(256) ba2_sum4_stage1(int rows, const double* __restrict__ part, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const double2* row = reinterpret_cast<const double2*>(part + 4 * r);
+    const double2 u = row[0], w = row[1];
+    a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+  }
+  a0 = block_sum(a0, scratch);
+  a1 = block_sum(a1, scratch);
+  a2 = block_sum(a2, scratch);
+  a3 = block_sum(a3, scratch);
+  if (threadIdx.x == 0) {
+    double* o = out + 4 * (size_t)blockIdx.x;
+    o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
   }
 }
 

@@ -140,7 +140,7 @@ struct b200sfm_ba_problem {
   size_t smem_ki = 0;
   // design v2 (compact rows, camera-order second pass)
   bool use_v2 = false;
-  DevBuf<double> Jc, z4, xq;
+  DevBuf<double> Jc, z4, xq, bpart, bpart2;
   size_t smem_k3v2 = 0;
   b200::BAViewV2 view2() {
     b200::BAViewV2 w;
@@ -347,6 +347,8 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXqStride);
+    bpart.alloc((size_t)std::max(n_tiles, 1) * 4);
+    bpart2.alloc(296 * 4);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
@@ -728,7 +730,10 @@ struct b200sfm_ba_problem {
     }
     if (points_var && use_v2) {
       B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
-      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, scal.p + 2);
+      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p);
+      const int nb = std::min(cdiv(n_tiles, 256), 296);
+      B200_LAUNCH(ctx, ba2_sum4_stage1, nb, 256, 0, n_tiles, bpart.p, bpart2.p);
+      B200_LAUNCH(ctx, ba_colsum, 4, 256, 0, nb, 4, bpart2.p, scal.p + 2);
     } else if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
                   scal.p + 2, spk.p, dkv.p, m);
