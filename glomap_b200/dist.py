@@ -28,9 +28,13 @@ def shard_range(n_items: int, chunk: int, rank: int, world: int) -> tuple[int, i
 def shard_scene(scene, rank: int, world: int, chunk: int = 1):
     """Slice a full flat scene into the shard of ``rank`` (points
     [a, b) and their observations); cameras/intrinsics are shared."""
-    from .synthetic import Scene
+    from .synthetic import RigScene, Scene
     a, b = shard_range(scene.P, chunk, rank, world)
     o0, o1 = int(scene.pt_obs_begin[a]), int(scene.pt_obs_begin[b])
+    if isinstance(scene, RigScene):   # known rigs: frames, sensors and intrinsics are replicated
+        return RigScene(scene.quat, scene.trans, scene.points[a:b], (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64),
+                        scene.obs_frame[o0:o1], scene.obs_sensor[o0:o1], scene.obs_xy[o0:o1], scene.sensor_quat,
+                        scene.sensor_trans, scene.sensor_intr, scene.intr_model, scene.intr_params), (a, b)
     return Scene(scene.quat, scene.trans, scene.points[a:b], (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64),
                  scene.obs_cam[o0:o1], scene.obs_xy[o0:o1], scene.cam_intr, scene.intr_model, scene.intr_params), (a, b)
 

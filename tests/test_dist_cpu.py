@@ -66,3 +66,24 @@ def test_shard_scene_partitions_points_and_observations():
         assert sh.pt_obs_begin[0] == 0 and sh.pt_obs_begin[-1] == sh.N
         assert np.array_equal(sh.points, sc.points[a:b])
         assert np.array_equal(np.diff(sh.pt_obs_begin), np.diff(sc.pt_obs_begin[a:b + 1]))
+
+
+def test_shard_rig_scene_keeps_frames_and_sensors_replicated():
+    """Known rigs shard like plain scenes: tracks (with their frame / sensor indices) are split, the frame
+    poses and the sensor table are replicated; the shard costs add up to the full cost (oracle)."""
+    from oracle import ba_oracle as B
+    rs = S.make_rig_scene(8, 3, 300, seed=3, pixel_sigma=0.5)
+    parts = [D.shard_scene(rs, r, 2, chunk=32) for r in range(2)]
+    assert sum(p[0].P for p in parts) == rs.P and sum(p[0].N for p in parts) == rs.N
+    total = 0.0
+    for sh, (a, b) in parts:
+        assert sh.F == rs.F and sh.S == rs.S and np.array_equal(sh.sensor_quat, rs.sensor_quat)
+        o0 = int(rs.pt_obs_begin[a])
+        assert np.array_equal(sh.obs_sensor, rs.obs_sensor[o0:o0 + sh.N])
+        assert np.array_equal(sh.obs_frame, rs.obs_frame[o0:o0 + sh.N])
+        p = B.BAProblem(sh.quat, sh.trans, sh.points, sh.pt_obs_begin, sh.obs_frame, sh.obs_xy, np.zeros(sh.F, np.int32),
+                        sh.intr_model, sh.intr_params, B.BAOptions(), rig=sh.rig_dict())
+        total += p.evaluate(p.x0, False)[0]
+    full = B.BAProblem(rs.quat, rs.trans, rs.points, rs.pt_obs_begin, rs.obs_frame, rs.obs_xy, np.zeros(rs.F, np.int32),
+                       rs.intr_model, rs.intr_params, B.BAOptions(), rig=rs.rig_dict())
+    assert abs(total - full.evaluate(full.x0, False)[0]) <= 1e-12 * total
