@@ -100,6 +100,7 @@ PROTOTYPES = {
     "b200sfm_ba_problem_cost": (c_int32, [c_void_p, P(BAOpts), P(c_double)]),
     "b200sfm_ba_problem_free": (None, [c_void_p]),
     "b200sfm_ba_problem_filter_reprojection": (c_int32, [c_void_p, c_double, c_void_p, P(c_int64)]),
+    "b200sfm_ba_problem_filter_reprojection_normalized": (c_int32, [c_void_p, c_void_p, c_double, c_void_p, P(c_int64)]),
     "b200sfm_ba_problem_filter_angle": (c_int32, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, P(c_int64)]),
     "b200sfm_ba_problem_filter_triangulation_angle": (c_int32, [c_void_p, c_double, c_void_p, P(c_int64)]),
     "b200sfm_gp_default_opts": (None, [P(GPOpts)]),

@@ -290,6 +290,18 @@ int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearing
   });
 }
 
+int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* bearings,
+                                                      double max_reprojection_error, uint8_t* keep,
+                                                      int64_t* num_tracks_changed) {
+  if (!p || !keep || !bearings) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    const long long n = p->run_filter(3, max_reprojection_error, bearings, nullptr, keep);
+    if (num_tracks_changed) *num_tracks_changed = n;
+    return (int)B200SFM_OK;
+  });
+}
+
 int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double min_angle_deg, uint8_t* keep_track,
                                                   int64_t* num_tracks_removed) {
   if (!p || !keep_track) return B200SFM_ERR_INVALID_ARG;

@@ -485,7 +485,8 @@ struct b200sfm_ba_problem {
   }
 
   // ---- track filters on the resident arrays (glomap/processors/track_filter.cc) -----------------
-  // mode 0: reprojection (pixels), 1: angle (needs bearings), 2: triangulation angle (per track)
+  // mode 0: reprojection (pixels), 1: angle (needs bearings), 2: triangulation angle (per track),
+  // 3: reprojection in the normalised image plane (needs bearings)
   long long run_filter(int mode, double thr, const double* h_bearings, const uint8_t* h_calibrated, uint8_t* h_keep) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
@@ -516,8 +517,12 @@ struct b200sfm_ba_problem {
         bear.upload(h_bearings, (size_t)N * 3, s);
         const int ncal = S > 0 ? S : C;
         if (h_calibrated) { cal.alloc(ncal); cal.upload(h_calibrated, ncal, s); }
-        B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, h_calibrated ? cal.p : nullptr,
-                    std::cos(thr * kPi / 180.0), std::cos(2.0 * thr * kPi / 180.0), keep.p, changed.p);
+        if (mode == 3)
+          B200_LAUNCH(ctx, filter_reprojection_normalized, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, thr,
+                      keep.p, changed.p);
+        else
+          B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, h_calibrated ? cal.p : nullptr,
+                      std::cos(thr * kPi / 180.0), std::cos(2.0 * thr * kPi / 180.0), keep.p, changed.p);
         B200_CUDA_OK(cudaStreamSynchronize(s));   // bear / cal go out of scope
       }
       B200_LAUNCH(ctx, count_flags, cdiv(P, 256), 256, 0, P, changed.p, counter.p);

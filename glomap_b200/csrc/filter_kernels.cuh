@@ -78,6 +78,36 @@ __global__ void filter_angle(BAView v, const double* __restrict__ cam_rec, const
   if (!k) changed[pt] = 1;
 }
 
+// keep[o] = 1 iff z >= EPS and | (X_c.xy / X_c.z) - b.xy / (b.z + EPS) | < max_err, b = features_undist
+// (track_filter.cc:24-31, in_normalized_image = true -- the variant the mapper calls, controllers/global_mapper.cc:176-181,254-259)
+__global__ void filter_reprojection_normalized(BAView v, const double* __restrict__ cam_rec,
+                                               const double* __restrict__ points, const double* __restrict__ bearings,
+                                               double max_err, unsigned char* __restrict__ keep,
+                                               int* __restrict__ changed) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= v.N) return;
+  const int pt = v.obs_pt[o], cam = v.obs_cam[o];
+  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double q[4] = {q4.x, q4.y, q4.z, q4.w};
+  double R[9];
+  quat_to_R(q, R);
+  const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+  double xc = R[0] * X0 + R[1] * X1 + R[2] * X2 + t4.x;
+  double yc = R[3] * X0 + R[4] * X1 + R[5] * X2 + t4.y;
+  double zc = R[6] * X0 + R[7] * X1 + R[8] * X2 + t4.z;
+  const double* sr = sensor_of_obs(v, o);
+  if (sr) sensor_apply(sr, xc, yc, zc);
+  bool k = false;
+  if (!(zc < kFilterEps)) {
+    const double bz = bearings[3 * o + 2] + kFilterEps;
+    const double dx = xc / zc - bearings[3 * o] / bz, dy = yc / zc - bearings[3 * o + 1] / bz;
+    k = sqrt(dx * dx + dy * dy) < max_err;
+  }
+  keep[o] = k ? 1 : 0;
+  if (!k) changed[pt] = 1;
+}
+
 // keep_track[p] = 1 iff some pair of viewing rays (X - c_i) has an angle larger than min_angle
 // (track_filter.cc:98-122).  One warp per track; O(L^2) pair test spread over the lanes.
 __global__ void filter_triangulation_angle(BAView v, const double* __restrict__ cam_rec,

@@ -192,10 +192,17 @@ class BAProblem:
         return c.value
 
     # -- track filters on the resident state (glomap/processors/track_filter.cc) --
-    def filter_reprojection(self, max_reprojection_error: float):
-        """TrackFilter::FilterTracksByReprojection (pixel space): (keep [N] bool, #tracks changed)."""
+    def filter_reprojection(self, max_reprojection_error: float, bearings=None):
+        """TrackFilter::FilterTracksByReprojection: (keep [N] bool, #tracks changed).  Pixel space by default
+        (in_normalized_image = false); with ``bearings`` (features_undist) the normalised-image-plane variant the
+        mapper uses (track_filter.cc:24-31)."""
         keep = np.empty(self.N, np.uint8)
         cnt = ct.c_int64()
+        if bearings is not None:
+            b = _c(bearings, np.float64)
+            _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_reprojection_normalized(
+                self.handle, _ptr(b), max_reprojection_error, _ptr(keep), ct.byref(cnt)))
+            return keep.astype(bool), cnt.value
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_reprojection(self.handle, max_reprojection_error, _ptr(keep), ct.byref(cnt)))
         return keep.astype(bool), cnt.value
 

@@ -209,6 +209,12 @@ int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_rep
 int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings /*[N][3] features_undist*/,
                                     const uint8_t* cam_calibrated /*[C] or NULL*/, double max_angle_error_deg,
                                     uint8_t* keep /*[N]*/, int64_t* num_tracks_changed);
+/* FilterTracksByReprojection with in_normalized_image = true (track_filter.cc:24-31) -- the variant the mapper
+ * calls (controllers/global_mapper.cc:176-181,254-259,289-294): error = |X_c.xy / X_c.z - b.xy / (b.z + EPS)|
+ * against the undistorted feature b (Image::features_undist), threshold 1e-2 by default (types.h:21). */
+int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* bearings /*[N][3]*/,
+                                                      double max_reprojection_error, uint8_t* keep /*[N]*/,
+                                                      int64_t* num_tracks_changed);
 int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double min_angle_deg, uint8_t* keep_track /*[P]*/,
                                                   int64_t* num_tracks_removed);
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p);

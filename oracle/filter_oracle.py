@@ -31,6 +31,18 @@ def filter_reprojection(scene, max_err, project):
     return keep, int(changed.sum())
 
 
+def filter_reprojection_normalized(scene, bearings, max_err):
+    """in_normalized_image = true (track_filter.cc:24-31): |X_c.xy / X_c.z - b.xy / (b.z + EPS)| < max_err."""
+    Xc, pt = _cam_points(scene.quat, scene.trans, scene.points, scene.pt_obs_begin, scene.obs_cam)
+    ok = ~(Xc[:, 2] < EPS)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = Xc[:, :2] / Xc[:, 2:3] - bearings[:, :2] / (bearings[:, 2:3] + EPS)
+    keep = ok & (np.linalg.norm(d, axis=1) < max_err)
+    changed = np.zeros(scene.P, bool)
+    np.logical_or.at(changed, pt, ~keep)
+    return keep, int(changed.sum())
+
+
 def filter_angle(scene, bearings, max_angle_deg, calibrated=None):
     Xc, pt = _cam_points(scene.quat, scene.trans, scene.points, scene.pt_obs_begin, scene.obs_cam)
     thres, thres_u = np.cos(np.radians(max_angle_deg)), np.cos(np.radians(2 * max_angle_deg))

@@ -1,0 +1,45 @@
+"""End-to-end run of the host mapper driver (stages 3, 5, 6 of controllers/global_mapper.cc) on the GPU solvers, with
+the reference's own end-to-end thresholds (global_mapper_test.cc:84-86: rotation < 1e-2 deg / centre < 1e-4 noise-free)
+relaxed for the noisy case (:213-215).
+
+Written after the GPU budget of round 1 was exhausted: it has NOT run on a GPU yet, so it is opt-in
+(B200SFM_UNVERIFIED_TESTS=1) until it has been validated; every solver and filter it composes is covered by the other
+GPU tests."""
+import os
+
+import numpy as np
+import pytest
+
+from glomap_b200 import geometry as G, mapper as M, synthetic as S
+from oracle import filter_oracle as FO
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200SFM_UNVERIFIED_TESTS") != "1", reason="not yet validated on a GPU")]
+
+
+def test_normalized_reprojection_filter_matches_oracle():
+    from glomap_b200 import estimators as E
+    sc = S.make_scene(12, 400, mean_track_len=5, seed=3, pixel_sigma=2.0)
+    st = S.perturb_scene(sc, rot_deg=0.2)
+    bear = S.bearings_from_scene(st)
+    prob = E.BAProblem(E.default_context(), st, 3)
+    prob.set_state(st.intr_params, st.quat, st.trans, st.points)
+    for thr in (1e-3, 1e-2, 1e-1):
+        keep, n = prob.filter_reprojection(thr, bear)
+        k0, n0 = FO.filter_reprojection_normalized(st, bear, thr)
+        assert np.array_equal(keep, k0) and n == n0
+    prob.free()
+
+
+def test_mapper_recovers_the_scene():
+    sc = S.make_scene(30, 2000, mean_track_len=6, seed=21, pixel_sigma=0.5)
+    vg = S.view_graph_from_scene(sc, min_shared=15, noise_deg=0.5)
+    start = sc.copy()
+    start.quat[:] = [0, 0, 0, 1]; start.trans[:] = 0; start.points[:] = 0     # nothing but tracks and relative rotations
+    opts = M.GlobalMapperOptions()
+    opts.opt_ba.optimize_intrinsics = False
+    mapper = M.GlobalMapper(opts)
+    ok, out = mapper.Solve(vg, start)
+    assert ok, mapper.log
+    rot, cen = G.compare_reconstructions(G.quat_xyzw_to_rotmat(out.quat), out.trans, G.quat_xyzw_to_rotmat(sc.quat), sc.trans)[:2]
+    assert rot < 1e-1 and cen < 1e-1, (rot, cen, mapper.log)
