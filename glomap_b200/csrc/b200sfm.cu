@@ -12,7 +12,9 @@ namespace {
 
 template <class F>
 int guarded(b200sfm_ctx* ctx, F&& f) {
-  b200::AllocScope alloc_scope(ctx ? ctx->stream : nullptr);
+  // stream-ordered allocation only for single-process contexts: with NCCL the buffers stay plain cudaMalloc
+  // memory (the pool + NCCL combination has not been exercised on this code path)
+  b200::AllocScope alloc_scope(ctx && ctx->world == 1 ? ctx->stream : nullptr);
   try {
     return f();
   } catch (const b200::CudaError& e) {
@@ -317,7 +319,7 @@ void b200sfm_ba_problem_free(b200sfm_ba_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
-  b200::AllocScope alloc_scope(p->ctx->stream);   // buffers go back to the stream-ordered pool
+  b200::AllocScope alloc_scope(p->ctx->world == 1 ? p->ctx->stream : nullptr);   // back to the stream-ordered pool
   delete p;
 }
 
@@ -481,7 +483,7 @@ void b200sfm_gp_problem_free(b200sfm_gp_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
-  b200::AllocScope alloc_scope(p->ctx->stream);   // buffers go back to the stream-ordered pool
+  b200::AllocScope alloc_scope(p->ctx->world == 1 ? p->ctx->stream : nullptr);   // back to the stream-ordered pool
   delete p;
 }
 
