@@ -71,3 +71,41 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(out[cname]) == ct.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (no C++-isms outside the extern "C" guards)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200sfm.h"\nint main(void) { b200sfm_ba_opts o; b200sfm_lm_stats s; (void)o; (void)s; return 0; }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I" + os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_null_arguments_are_rejected_without_touching_the_device():
+    """Every entry point validates its handles before any CUDA call: callable on a box without a GPU."""
+    lib = _lib.load()
+    INVALID = 1   # B200SFM_ERR_INVALID_ARG
+    st, ra_st = _lib.LMStats(), _lib.RAStats()
+    o_ba, o_gp, o_ra = _lib.BAOpts(), _lib.GPOpts(), _lib.RAOpts()
+    h = ct.c_void_p()
+    assert lib.b200sfm_create(0, None) == INVALID
+    assert lib.b200sfm_ba_problem_create(None, 1, 1, 1, 1, None, None, None, None, None, None, 3, ct.byref(h)) == INVALID
+    assert lib.b200sfm_ba_problem_create_rig(None, 1, 1, 1, 1, 1, None, None, None, None, None, None, None, None, None, 3,
+                                             ct.byref(h)) == INVALID
+    assert lib.b200sfm_ba_problem_solve(None, ct.byref(o_ba), ct.byref(st)) == INVALID
+    assert lib.b200sfm_ba_problem_set_state(None, None, None, None, None) == INVALID
+    assert lib.b200sfm_ba_problem_filter_reprojection(None, 1.0, None, None) == INVALID
+    assert lib.b200sfm_ba_problem_filter_reprojection_normalized(None, None, 1.0, None, None) == INVALID
+    assert lib.b200sfm_ba_problem_filter_angle(None, None, None, 1.0, None, None) == INVALID
+    assert lib.b200sfm_ba_problem_filter_triangulation_angle(None, 1.0, None, None) == INVALID
+    assert lib.b200sfm_gp_problem_create(None, 1, 1, 1, None, None, None, None, None, 3, ct.byref(h)) == INVALID
+    assert lib.b200sfm_gp_problem_set_rig_terms(None, None, None) == INVALID
+    assert lib.b200sfm_gp_problem_solve(None, ct.byref(o_gp), ct.byref(st)) == INVALID
+    assert lib.b200sfm_ba_solve(None, ct.byref(o_ba), 1, 1, 1, 1, *([None] * 10), ct.byref(st)) == INVALID
+    assert lib.b200sfm_gp_solve(None, ct.byref(o_gp), 1, 1, 1, *([None] * 8), ct.byref(st)) == INVALID
+    assert lib.b200sfm_ra_solve(None, ct.byref(o_ra), 1, 1, None, None, None, None, 0, None, ct.byref(ra_st)) == INVALID
+    assert lib.b200sfm_last_error(None) == b"null context" or lib.b200sfm_last_error(None) is not None
+    lib.b200sfm_ba_problem_free(None); lib.b200sfm_gp_problem_free(None); lib.b200sfm_destroy(None)   # no-ops
+    assert lib.b200sfm_rank(None) == -1 and lib.b200sfm_world_size(None) == -1 and lib.b200sfm_kernel_launches(None) == 0
