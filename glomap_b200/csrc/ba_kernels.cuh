@@ -7,15 +7,17 @@
 //
 // Data layout in HBM (FP64, DESIGN.md "BA layout"):
 //   observations in POINT order (CSR by point): obs_cam[N], obs_pt[N], obs_xy[N]
-//   W[N][18]   6x3 block J_cam^T J_pt of every observation, AoS (144-B rows) so
-//              that a tile of 256 consecutive observations is one contiguous
-//              36,864-B chunk moved by a single TMA bulk copy
+//   W[N][18]   (design v1) 6x3 block J_cam^T J_pt of every observation, AoS (144-B rows) so
+//              that a tile of kTile = 128 consecutive observations is one contiguous
+//              18,432-B chunk moved by a single TMA bulk copy; design v2 (ba_kernels_v2.cuh,
+//              the default with constant intrinsics) stores 48-B A_o rows in the same buffer
 //   V[P][6], Vinv[P][6], gp[P][3]         per point (packed symmetric)
 //   U[C][21], gc[C][6], Sd[C][21], Minv[C][21]   per camera (packed symmetric)
-//   camera-order copies pt_c[Nv], xy_c[Nv], camord_obs[Nv] + segments
-// Point-order kernels run one CTA (256 threads) per tile of whole points with
-// <= 256 observations; one thread per observation, per-point reductions
-// through shared memory.
+//   camera-order copies pt_c[Nv], xy_c[Nv], camord_obs[Nv] + segments (<= kSeg = 256 observations of ONE
+//   camera -- or of one (frame, sensor) with known rigs -- handled by one warp)
+// Point-order kernels run one CTA (kTile = 128 threads) per tile of whole points with
+// <= 128 observations (longer tracks: several chunks); one thread per observation, per-point
+// reductions through shared memory.
 #pragma once
 #include "common.cuh"
 
