@@ -65,3 +65,16 @@ def test_points_behind_cameras_are_dropped():
     k0, c0 = FO.filter_reprojection(sc, 1e9, S.project)
     assert np.array_equal(keep, k0) and cnt == c0 and not keep.all()
     prob.free()
+
+
+def test_normalized_reprojection_filter_matches_oracle():
+    sc = S.make_scene(12, 400, mean_track_len=5, seed=3, pixel_sigma=2.0)
+    st = S.perturb_scene(sc, rot_deg=0.2)
+    bear = S.bearings_from_scene(st)
+    prob = E.BAProblem(E.default_context(), st, 3)
+    prob.set_state(st.intr_params, st.quat, st.trans, st.points)
+    for thr in (1e-3, 1e-2, 1e-1):
+        keep, n = prob.filter_reprojection(thr, bear)
+        k0, n0 = FO.filter_reprojection_normalized(st, bear, thr)
+        assert np.array_equal(keep, k0) and n == n0
+    prob.free()

@@ -4,31 +4,16 @@ relaxed for the noisy case (:213-215).
 
 Written after the GPU budget of round 1 was exhausted: it has NOT run on a GPU yet, so it is opt-in
 (B200SFM_UNVERIFIED_TESTS=1) until it has been validated; every solver and filter it composes is covered by the other
-GPU tests."""
+GPU tests (the normalised-plane reprojection filter in tests/test_filters_gpu.py)."""
 import os
 
 import numpy as np
 import pytest
 
 from glomap_b200 import geometry as G, mapper as M, synthetic as S
-from oracle import filter_oracle as FO
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B200SFM_UNVERIFIED_TESTS") != "1", reason="not yet validated on a GPU")]
-
-
-def test_normalized_reprojection_filter_matches_oracle():
-    from glomap_b200 import estimators as E
-    sc = S.make_scene(12, 400, mean_track_len=5, seed=3, pixel_sigma=2.0)
-    st = S.perturb_scene(sc, rot_deg=0.2)
-    bear = S.bearings_from_scene(st)
-    prob = E.BAProblem(E.default_context(), st, 3)
-    prob.set_state(st.intr_params, st.quat, st.trans, st.points)
-    for thr in (1e-3, 1e-2, 1e-1):
-        keep, n = prob.filter_reprojection(thr, bear)
-        k0, n0 = FO.filter_reprojection_normalized(st, bear, thr)
-        assert np.array_equal(keep, k0) and n == n0
-    prob.free()
 
 
 def test_mapper_recovers_the_scene():
