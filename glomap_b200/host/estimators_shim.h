@@ -374,12 +374,11 @@ class RotationEstimator {
   explicit RotationEstimator(const RotationEstimatorOptions& options) : options_(options) {}
   b200sfm_ra_stats summary{};
 
-  // global_rotation_averaging.cc:40-85 (3-DoF frames, trivial rigs).  The
-  // spanning-tree initialisation is expected from the caller when
-  // skip_initialization is false (host-side, math/tree.cc).
+  // global_rotation_averaging.cc:40-85 (3-DoF frames; trivial frames and known rigs -- unknown
+  // cam_from_rig rotations are not estimated).  The spanning-tree initialisation is expected from the
+  // caller when skip_initialization is false (host-side, math/tree.cc).
   bool EstimateRotations(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
                          std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images) {
-    (void)rigs;
     if (options_.use_gravity) { std::fprintf(stderr, "b200sfm: gravity-aligned rotation averaging is not implemented\n"); return false; }
     b200sfm_ctx* ctx = DefaultContext();
     if (!ctx) return false;
@@ -402,10 +401,30 @@ class RotationEstimator {
       if (i1 == images.end() || i2 == images.end()) continue;
       const auto f1 = fidx.find(i1->second.frame_id), f2 = fidx.find(i2->second.frame_id);
       if (f1 == fidx.end() || f2 == fidx.end()) continue;                                     // .cc:365-368
+      double R[9];
+      QuatToR(pr->cam2_from_cam1.rotation.coeffs_data(), R);
+      // known rigs: the unknowns are the frame rotations, R_rel = R_c2r2^T R_21 R_c1r1 (.cc:274-309); an image
+      // pair inside one frame is a self loop and is skipped (.cc:300-303)
+      const bool rig1 = !i1->second.HasTrivialFrame(), rig2 = !i2->second.HasTrivialFrame();
+      if (rig1 && rig2 && f1->second == f2->second) continue;
+      if (rig1) {
+        const Rigid3d c = b200host_adapt::CamFromRig(rigs[frames[i1->second.frame_id].RigId()], i1->second.camera_id);
+        double Rc[9], T[9];
+        QuatToR(c.rotation.coeffs_data(), Rc);
+        for (int r = 0; r < 3; ++r)
+          for (int k = 0; k < 3; ++k) T[3 * r + k] = R[3 * r] * Rc[k] + R[3 * r + 1] * Rc[3 + k] + R[3 * r + 2] * Rc[6 + k];
+        std::copy(T, T + 9, R);
+      }
+      if (rig2) {
+        const Rigid3d c = b200host_adapt::CamFromRig(rigs[frames[i2->second.frame_id].RigId()], i2->second.camera_id);
+        double Rc[9], T[9];
+        QuatToR(c.rotation.coeffs_data(), Rc);
+        for (int r = 0; r < 3; ++r)   // Rc^T R
+          for (int k = 0; k < 3; ++k) T[3 * r + k] = Rc[r] * R[k] + Rc[3 + r] * R[3 + k] + Rc[6 + r] * R[6 + k];
+        std::copy(T, T + 9, R);
+      }
       ei.push_back(f1->second);
       ej.push_back(f2->second);
-      double R[9];
-      QuatToR(pr->cam2_from_cam1.rotation.coeffs_data(), R);                                  // .cc:306-309 (trivial rigs)
       Rrel.insert(Rrel.end(), R, R + 9);
       w.push_back(pr->weight);
     }
