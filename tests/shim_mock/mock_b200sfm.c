@@ -1,0 +1,136 @@
+/* TEST DOUBLE (tests only, never shipped): records what the C++ estimator shim passes across the C ABI so that
+ * the shim's host-side flattening (sorted-id order, rig sensor tables, per-observation rig terms, frame folding of
+ * the view graph) can be checked on a box without a GPU.  Every call appends "name n v0 v1 ..." lines to $MOCK_DUMP
+ * and leaves the state untouched (stats.usable = 1). */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200sfm.h"
+
+struct b200sfm_ctx { int dummy; };
+struct b200sfm_ba_problem { b200sfm_ctx* ctx; };
+struct b200sfm_gp_problem { b200sfm_ctx* ctx; };
+static struct b200sfm_ctx g_ctx;
+static long long g_gp_n = 0;
+
+static FILE* out(void) {
+  const char* p = getenv("MOCK_DUMP");
+  return fopen(p ? p : "/dev/null", "a");
+}
+static void dump_d(const char* name, const double* v, long long n) {
+  FILE* f = out();
+  fprintf(f, "%s %lld", name, v ? n : 0);
+  for (long long i = 0; v && i < n; ++i) fprintf(f, " %.17g", v[i]);
+  fprintf(f, "\n");
+  fclose(f);
+}
+#define DUMP_INT(NAME, PTR, N)                                              \
+  do {                                                                      \
+    FILE* f_ = out();                                                       \
+    fprintf(f_, "%s %lld", NAME, (PTR) ? (long long)(N) : 0ll);             \
+    for (long long i_ = 0; (PTR) && i_ < (long long)(N); ++i_) fprintf(f_, " %lld", (long long)(PTR)[i_]); \
+    fprintf(f_, "\n");                                                      \
+    fclose(f_);                                                             \
+  } while (0)
+static void dump_call(const char* name) {
+  FILE* f = out();
+  fprintf(f, "call %s\n", name);
+  fclose(f);
+}
+
+int b200sfm_version(void) { return B200SFM_VERSION; }
+int b200sfm_create(int device, b200sfm_ctx** o) { (void)device; *o = &g_ctx; return B200SFM_OK; }
+void b200sfm_destroy(b200sfm_ctx* c) { (void)c; }
+const char* b200sfm_last_error(const b200sfm_ctx* c) { (void)c; return "mock"; }
+
+void b200sfm_ba_default_opts(b200sfm_ba_opts* o) { memset(o, 0, sizeof(*o)); o->min_num_view_per_track = 3; }
+void b200sfm_gp_default_opts(b200sfm_gp_opts* o) { memset(o, 0, sizeof(*o)); o->min_num_view_per_track = 3; }
+void b200sfm_ra_default_opts(b200sfm_ra_opts* o) { memset(o, 0, sizeof(*o)); }
+
+int b200sfm_ba_solve(b200sfm_ctx* ctx, const b200sfm_ba_opts* o, int32_t C, int32_t P, int64_t N, int32_t K,
+                     const int64_t* ptb, const int32_t* obs_cam, const double* obs_xy, const int32_t* cam_intr,
+                     const int32_t* intr_model, double* intr, double* quat, double* trans, const uint8_t* mask, double* points,
+                     b200sfm_lm_stats* st) {
+  (void)ctx;
+  dump_call("ba_solve");
+  int32_t dims[4] = {C, P, (int32_t)N, K};
+  DUMP_INT("dims", dims, 4);
+  int32_t flags[3] = {o->optimize_rotations, o->optimize_intrinsics, o->optimize_rig_poses};
+  DUMP_INT("flags", flags, 3);
+  DUMP_INT("pt_obs_begin", ptb, P + 1); DUMP_INT("obs_cam", obs_cam, N); dump_d("obs_xy", obs_xy, 2 * N);
+  DUMP_INT("cam_intr", cam_intr, C); DUMP_INT("intr_model", intr_model, K); dump_d("intr", intr, (long long)K * B200SFM_INTR_STRIDE);
+  dump_d("quat", quat, 4ll * C); dump_d("trans", trans, 3ll * C); DUMP_INT("mask", mask, C); dump_d("points", points, 3ll * P);
+  memset(st, 0, sizeof(*st)); st->usable = 1;
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_t N, int32_t K, int32_t S, const int64_t* ptb,
+                                  const int32_t* obs_frame, const uint16_t* obs_sensor, const double* obs_xy,
+                                  const double* sq, const double* stv, const int32_t* sintr, const int32_t* intr_model,
+                                  const uint8_t* mask, int32_t minv, b200sfm_ba_problem** o) {
+  dump_call("ba_problem_create_rig");
+  int32_t dims[6] = {F, P, (int32_t)N, K, S, minv};
+  DUMP_INT("dims", dims, 6);
+  DUMP_INT("pt_obs_begin", ptb, P + 1); DUMP_INT("obs_frame", obs_frame, N); DUMP_INT("obs_sensor", obs_sensor, N);
+  dump_d("obs_xy", obs_xy, 2 * N); dump_d("sensor_quat", sq, 4ll * S); dump_d("sensor_trans", stv, 3ll * S);
+  DUMP_INT("sensor_intr", sintr, S); DUMP_INT("intr_model", intr_model, K); DUMP_INT("mask", mask, F);
+  static struct b200sfm_ba_problem p; p.ctx = ctx; *o = &p;
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr, const double* q, const double* t, const double* pts) {
+  (void)p; (void)intr; (void)q; (void)t; (void)pts;
+  dump_call("ba_problem_set_state");
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr, double* q, double* t, double* pts) {
+  (void)p; (void)intr; (void)q; (void)t; (void)pts;
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* o, b200sfm_lm_stats* st) {
+  (void)p; (void)o; dump_call("ba_problem_solve"); memset(st, 0, sizeof(*st)); st->usable = 1; return B200SFM_OK;
+}
+void b200sfm_ba_problem_free(b200sfm_ba_problem* p) { (void)p; }
+
+int b200sfm_gp_solve(b200sfm_ctx* ctx, const b200sfm_gp_opts* o, int32_t C, int32_t P, int64_t N, const int64_t* ptb,
+                     const int32_t* obs_cam, const double* obs_dir, const uint8_t* cal, const uint8_t* mask, double* cen,
+                     double* pts, double* sc, b200sfm_lm_stats* st) {
+  (void)ctx; (void)o; (void)mask; (void)cen; (void)pts; (void)sc;
+  dump_call("gp_solve");
+  DUMP_INT("pt_obs_begin", ptb, P + 1); DUMP_INT("obs_cam", obs_cam, N); dump_d("obs_dir", obs_dir, 3 * N); DUMP_INT("calibrated", cal, C);
+  memset(st, 0, sizeof(*st)); st->usable = 1;
+  return B200SFM_OK;
+}
+int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, const int64_t* ptb, const int32_t* obs_cam,
+                              const double* obs_dir, const uint8_t* cal, const uint8_t* mask, int32_t minv, b200sfm_gp_problem** o) {
+  (void)mask; (void)minv;
+  dump_call("gp_problem_create");
+  int32_t dims[3] = {C, P, (int32_t)N};
+  DUMP_INT("dims", dims, 3);
+  DUMP_INT("pt_obs_begin", ptb, P + 1); DUMP_INT("obs_cam", obs_cam, N); dump_d("obs_dir", obs_dir, 3 * N); DUMP_INT("calibrated", cal, C);
+  static struct b200sfm_gp_problem p; p.ctx = ctx; *o = &p;
+  g_gp_n = N;
+  return B200SFM_OK;
+}
+int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* off, const uint8_t* cal) {
+  (void)p;
+  dump_call("gp_problem_set_rig_terms");
+  dump_d("obs_offset", off, 3 * g_gp_n); DUMP_INT("obs_calibrated", cal, g_gp_n);
+  return B200SFM_OK;
+}
+int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* c, const double* x, const double* s) { (void)p; (void)c; (void)x; (void)s; return B200SFM_OK; }
+int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* c, double* x, double* s) { (void)p; (void)c; (void)x; (void)s; return B200SFM_OK; }
+int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* o, b200sfm_lm_stats* st) {
+  (void)p; (void)o; dump_call("gp_problem_solve"); memset(st, 0, sizeof(*st)); st->usable = 1; return B200SFM_OK;
+}
+void b200sfm_gp_problem_free(b200sfm_gp_problem* p) { (void)p; }
+
+int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t n, int64_t E, const int32_t* ei, const int32_t* ej,
+                     const double* R, const double* w, int32_t fixed, double* theta, b200sfm_ra_stats* st) {
+  (void)ctx; (void)o; (void)fixed;
+  dump_call("ra_solve");
+  int32_t dims[2] = {n, (int32_t)E};
+  DUMP_INT("dims", dims, 2);
+  DUMP_INT("ei", ei, E); DUMP_INT("ej", ej, E); dump_d("R_rel", R, 9 * E); dump_d("weight", w, E); dump_d("theta", theta, 3ll * n);
+  memset(st, 0, sizeof(*st)); st->usable = 1;
+  return B200SFM_OK;
+}

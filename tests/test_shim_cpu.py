@@ -1,0 +1,100 @@
+"""Host-side logic of the C++ estimator shim (glomap_b200/host/estimators_shim.h) on a box without a GPU: the shim is
+linked against a recording test double of the C ABI (tests/shim_mock/mock_b200sfm.c) and driven over a small world with
+a two-camera rig in three frames plus a trivial frame (tests/shim_mock/shim_driver.cc).  Checked: sorted-id flattening,
+the (rig, camera) sensor table and per-observation frame / sensor indices of the known-rig BA path
+(bundle_adjustment.cc:147-161), the RigBATA terms of global positioning (global_positioning.cc:294-296,339-345,
+313-316) and the folding of image pairs onto frames for rotation averaging (global_rotation_averaging.cc:274-309)."""
+import os
+import subprocess
+
+import numpy as np
+
+from glomap_b200 import geometry as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _quat(ax, ay, az, ang):
+    a = np.array([ax, ay, az], float)
+    return np.concatenate([a / np.linalg.norm(a) * np.sin(ang / 2), [np.cos(ang / 2)]])
+
+
+def _run(tmp_path):
+    lib, exe, dump = tmp_path / "libb200sfm_mock.so", tmp_path / "shim_driver", tmp_path / "dump.txt"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-O1", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-o", str(lib),
+                    os.path.join(ROOT, "tests", "shim_mock", "mock_b200sfm.c")], check=True, capture_output=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "glomap_b200", "host"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "shim_mock", "shim_driver.cc"), str(lib), "-Wl,-rpath," + str(tmp_path)],
+                   check=True, capture_output=True)
+    r = subprocess.run([str(exe)], env=dict(os.environ, MOCK_DUMP=str(dump)), capture_output=True, text=True)
+    assert r.returncode == 0 and "shim driver ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+    calls, cur = [], None
+    for line in dump.read_text().splitlines():
+        f = line.split()
+        if f[0] == "call":
+            cur = {"_name": f[1]}
+            calls.append(cur)
+        else:
+            cur[f[0]] = np.array([float(x) for x in f[2:]])
+            assert len(cur[f[0]]) == int(f[1])
+    return calls
+
+
+def test_shim_flattening_of_a_rig_world(tmp_path):
+    calls = _run(tmp_path)
+    assert [c["_name"] for c in calls] == ["ba_problem_create_rig", "ba_problem_set_state", "ba_problem_solve",
+                                           "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
+                                           "ba_solve"]
+    # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
+    img_ids = [101, 102, 201, 202, 301, 302, 401]
+    kimg = {i: k for k, i in enumerate(img_ids)}
+    frame_of = {101: 0, 102: 0, 201: 1, 202: 1, 301: 2, 302: 2, 401: 3}
+    sensor_of = {101: 0, 102: 1, 201: 0, 202: 1, 301: 0, 302: 1, 401: 2}       # sorted (rig, camera): (1,1) (1,2) (2,3)
+    q_c2r, t_c2r = _quat(0.2, 1.0, -0.3, 0.35), np.array([0.4, -0.1, 0.05])
+    q_f = np.array([_quat(0.1 * k, 1.0, 0.2, 0.3 + 0.4 * k) for k in range(4)])
+    tracks = {7: [(101, 0), (202, 1), (301, 2), (401, 3)], 3: [(102, 1), (201, 2), (302, 3), (401, 0)],
+              5: [(101, 2), (102, 3), (201, 0), (301, 1)]}
+    order = sorted(tracks)                                                        # tracks in sorted-id order
+    obs = [o for t in order for o in tracks[t]]
+    # ---- BA: known-rig entry -----------------------------------------------------------------------------------
+    ba = calls[0]
+    assert ba["dims"].tolist() == [4, 3, 12, 3, 3, 3]                            # F P N K S min_views
+    assert ba["pt_obs_begin"].tolist() == [0, 4, 8, 12]
+    assert ba["obs_frame"].tolist() == [frame_of[i] for i, _ in obs]
+    assert ba["obs_sensor"].tolist() == [sensor_of[i] for i, _ in obs]
+    want_xy = np.array([[10.0 * kimg[i] + f, 20.0 * kimg[i] + 2.0 * f] for i, f in obs])
+    assert np.array_equal(ba["obs_xy"].reshape(-1, 2), want_xy)
+    sq = ba["sensor_quat"].reshape(3, 4)
+    assert np.abs(sq[0] - [0, 0, 0, 1]).max() == 0 and np.abs(sq[2] - [0, 0, 0, 1]).max() == 0   # reference / trivial: identity
+    assert np.abs(sq[1] - q_c2r).max() < 1e-15 and np.abs(ba["sensor_trans"].reshape(3, 3)[1] - t_c2r).max() == 0
+    assert ba["sensor_intr"].tolist() == [0, 1, 2] and ba["intr_model"].tolist() == [0, 0, 0]
+    assert ba["mask"].tolist() == [3, 0, 0, 0]                                    # first frame constant (.cc:261-266)
+    # ---- GP: RigBATA terms -------------------------------------------------------------------------------------
+    gp, terms = calls[3], calls[4]
+    assert gp["dims"].tolist() == [4, 3, 12] and gp["obs_cam"].tolist() == ba["obs_frame"].tolist()
+    Rf = G.quat_xyzw_to_rotmat(q_f)
+    Rs = G.quat_xyzw_to_rotmat(np.array([[0, 0, 0, 1.0], q_c2r, [0, 0, 0, 1.0]]))
+    ts = np.array([[0, 0, 0], t_c2r, [0, 0, 0]])
+    want_dir, want_off, want_cal = [], [], []
+    for i, f in obs:
+        k = kimg[i]
+        b = np.array([0.01 * k - 0.02 * f, 0.03 * f - 0.01 * k, 1.0]); b /= np.linalg.norm(b)
+        Rcw = Rs[sensor_of[i]] @ Rf[frame_of[i]]
+        want_dir.append(Rcw.T @ b); want_off.append(Rcw.T @ ts[sensor_of[i]])
+        want_cal.append(0 if sensor_of[i] == 1 else 1)                           # camera 2 has no prior focal length
+    assert np.abs(gp["obs_dir"].reshape(-1, 3) - np.array(want_dir)).max() < 1e-14
+    assert np.abs(terms["obs_offset"].reshape(-1, 3) - np.array(want_off)).max() < 1e-14
+    assert terms["obs_calibrated"].tolist() == want_cal
+    # ---- RA: pairs folded onto frames, the same-frame pair (101,102) dropped -------------------------------------
+    ra = calls[6]
+    assert ra["dims"].tolist() == [4, 4]
+    assert ra["ei"].tolist() == [0, 0, 1, 2] and ra["ej"].tolist() == [1, 2, 2, 3]
+    assert ra["weight"].tolist() == [2.0, 3.0, 4.0, 5.0]
+    R21 = G.quat_xyzw_to_rotmat(np.array([_quat(1.0, 0.1 * k, -0.2, 0.2 + 0.1 * k) for k in range(5)]))
+    want_R = [R21[1], R21[2] @ Rs[1], Rs[1].T @ R21[3] @ Rs[1], R21[4]]
+    assert np.abs(ra["R_rel"].reshape(-1, 3, 3) - np.array(want_R)).max() < 1e-14
+    assert np.abs(G.so3_exp(ra["theta"].reshape(-1, 3)) - Rf).max() < 1e-13       # initial angle-axis of the frames
+    # ---- trivial frames still take the one-shot entry -------------------------------------------------------------
+    one = calls[7]
+    assert one["dims"].tolist() == [1, 1, 3, 1] and one["obs_cam"].tolist() == [0, 0, 0] and one["cam_intr"].tolist() == [0]
+    assert one["flags"].tolist() == [1, 1, 0]
