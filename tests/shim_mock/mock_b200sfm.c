@@ -10,6 +10,33 @@
 
 struct b200sfm_ctx { int dummy; };
 struct b200sfm_ba_problem { b200sfm_ctx* ctx; };
+/* structure of the last BA problem (for the filter stubs) */
+static long long g_ba_n = 0, g_ba_p = 0;
+static long long* g_ba_ptb = NULL;
+static void remember_ba(int32_t P, int64_t N, const int64_t* ptb) {
+  g_ba_n = N; g_ba_p = P;
+  free(g_ba_ptb);
+  g_ba_ptb = (long long*)malloc(sizeof(long long) * (size_t)(P + 1));
+  for (int32_t i = 0; i <= P; ++i) g_ba_ptb[i] = ptb[i];
+}
+/* filter stub: keeps everything, or drops every m-th observation when $MOCK_DROP_EVERY = m > 0 */
+static long long stub_filter(const char* name, double thr, uint8_t* keep) {
+  FILE* f = fopen(getenv("MOCK_DUMP") ? getenv("MOCK_DUMP") : "/dev/null", "a");
+  fprintf(f, "call %s\nthreshold 1 %.17g\nnobs 1 %lld\n", name, thr, g_ba_n);
+  fclose(f);
+  const char* e = getenv("MOCK_DROP_EVERY");
+  const long long m = e ? atoll(e) : 0;
+  long long changed = 0;
+  for (long long p = 0; p < g_ba_p; ++p) {
+    int any = 0;
+    for (long long o = g_ba_ptb[p]; o < g_ba_ptb[p + 1]; ++o) {
+      keep[o] = (m > 0 && o % m == 0) ? 0 : 1;
+      any |= !keep[o];
+    }
+    changed += any;
+  }
+  return changed;
+}
 struct b200sfm_gp_problem { b200sfm_ctx* ctx; };
 static struct b200sfm_ctx g_ctx;
 static long long g_gp_n = 0;
@@ -74,6 +101,7 @@ int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_
   DUMP_INT("pt_obs_begin", ptb, P + 1); DUMP_INT("obs_frame", obs_frame, N); DUMP_INT("obs_sensor", obs_sensor, N);
   dump_d("obs_xy", obs_xy, 2 * N); dump_d("sensor_quat", sq, 4ll * S); dump_d("sensor_trans", stv, 3ll * S);
   DUMP_INT("sensor_intr", sintr, S); DUMP_INT("intr_model", intr_model, K); DUMP_INT("mask", mask, F);
+  remember_ba(P, N, ptb);
   static struct b200sfm_ba_problem p; p.ctx = ctx; *o = &p;
   return B200SFM_OK;
 }
@@ -131,6 +159,56 @@ int b200sfm_ra_solve(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t n, int6
   int32_t dims[2] = {n, (int32_t)E};
   DUMP_INT("dims", dims, 2);
   DUMP_INT("ei", ei, E); DUMP_INT("ej", ej, E); dump_d("R_rel", R, 9 * E); dump_d("weight", w, E); dump_d("theta", theta, 3ll * n);
+  memset(st, 0, sizeof(*st)); st->usable = 1;
+  return B200SFM_OK;
+}
+
+/* ---- the rest of the ABI (stubs so that the Python host classes can be exercised without a GPU) ---- */
+int b200sfm_create_dist(int device, int rank, int world, const void* id, b200sfm_ctx** o) { (void)device; (void)rank; (void)world; (void)id; *o = &g_ctx; return B200SFM_OK; }
+int b200sfm_nccl_unique_id(void* id) { memset(id, 0, B200SFM_NCCL_ID_BYTES); return B200SFM_OK; }
+int b200sfm_rank(const b200sfm_ctx* c) { (void)c; return 0; }
+int b200sfm_world_size(const b200sfm_ctx* c) { (void)c; return 1; }
+void* b200sfm_cuda_stream(const b200sfm_ctx* c) { (void)c; return NULL; }
+int64_t b200sfm_kernel_launches(const b200sfm_ctx* c) { (void)c; return 0; }
+int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N, int32_t K, const int64_t* ptb,
+                              const int32_t* obs_cam, const double* obs_xy, const int32_t* cam_intr, const int32_t* intr_model,
+                              const uint8_t* mask, int32_t minv, b200sfm_ba_problem** o) {
+  (void)obs_cam; (void)obs_xy; (void)cam_intr; (void)intr_model; (void)mask;
+  dump_call("ba_problem_create");
+  int32_t dims[5] = {C, P, (int32_t)N, K, minv};
+  DUMP_INT("dims", dims, 5);
+  remember_ba(P, N, ptb);
+  static struct b200sfm_ba_problem p; p.ctx = ctx; *o = &p;
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_save_state(b200sfm_ba_problem* p) { (void)p; return B200SFM_OK; }
+int b200sfm_ba_problem_restore_state(b200sfm_ba_problem* p) { (void)p; return B200SFM_OK; }
+int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* o, double* c) { (void)p; (void)o; *c = 0.0; return B200SFM_OK; }
+int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double thr, uint8_t* keep, int64_t* n) {
+  (void)p; const long long c = stub_filter("filter_reprojection", thr, keep); if (n) *n = c; return B200SFM_OK;
+}
+int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* b, double thr, uint8_t* keep, int64_t* n) {
+  (void)p; (void)b; const long long c = stub_filter("filter_reprojection_normalized", thr, keep); if (n) *n = c; return B200SFM_OK;
+}
+int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* b, const uint8_t* cal, double thr, uint8_t* keep, int64_t* n) {
+  (void)p; (void)b; (void)cal; const long long c = stub_filter("filter_angle", thr, keep); if (n) *n = c; return B200SFM_OK;
+}
+int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double thr, uint8_t* keep_track, int64_t* n) {
+  (void)p;
+  FILE* f = out(); fprintf(f, "call filter_triangulation_angle\nthreshold 1 %.17g\n", thr); fclose(f);
+  for (long long i = 0; i < g_ba_p; ++i) keep_track[i] = 1;
+  if (n) *n = 0;
+  return B200SFM_OK;
+}
+int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p) { (void)p; return B200SFM_OK; }
+int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p) { (void)p; return B200SFM_OK; }
+int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t n, int64_t E, const int32_t* ei, const int32_t* ej,
+                             const double* R, const double* w, const uint8_t* hg, int32_t fixed, double* theta, b200sfm_ra_stats* st) {
+  (void)ctx; (void)o; (void)w;
+  dump_call("ra_solve_gravity");
+  int32_t dims[3] = {n, (int32_t)E, fixed};
+  DUMP_INT("dims", dims, 3);
+  DUMP_INT("ei", ei, E); DUMP_INT("ej", ej, E); dump_d("R_rel", R, 9 * E); DUMP_INT("has_gravity", hg, n); dump_d("theta", theta, 3ll * n);
   memset(st, 0, sizeof(*st)); st->usable = 1;
   return B200SFM_OK;
 }
