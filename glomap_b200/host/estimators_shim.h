@@ -374,12 +374,11 @@ class RotationEstimator {
   explicit RotationEstimator(const RotationEstimatorOptions& options) : options_(options) {}
   b200sfm_ra_stats summary{};
 
-  // global_rotation_averaging.cc:40-85 (3-DoF frames; trivial frames and known rigs -- unknown
-  // cam_from_rig rotations are not estimated).  The spanning-tree initialisation is expected from the
+  // global_rotation_averaging.cc:40-85 (3-DoF frames and, with use_gravity, 1-DoF frames that carry a gravity
+  // prior; trivial frames and known rigs -- unknown cam_from_rig rotations are not estimated).  The spanning-tree initialisation is expected from the
   // caller when skip_initialization is false (host-side, math/tree.cc).
   bool EstimateRotations(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
                          std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images) {
-    if (options_.use_gravity) { std::fprintf(stderr, "b200sfm: gravity-aligned rotation averaging is not implemented\n"); return false; }
     b200sfm_ctx* ctx = DefaultContext();
     if (!ctx) return false;
     std::map<frame_t, Frame*> fsorted;
@@ -391,6 +390,30 @@ class RotationEstimator {
     if (n == 0) return false;
     std::vector<double> theta(3 * (size_t)n);
     for (auto& [id, f] : fsorted) QuatToAngleAxis(f->RigFromWorld().rotation.coeffs_data(), &theta[3 * (size_t)fidx[id]]);   // .cc:223-224
+    // use_gravity (.cc:207-217): a frame with a gravity prior keeps theta = (0, phi, 0), phi = RotUpToAngle(R_align^T R);
+    // the first such frame (sorted-id order) is the fixed one
+    std::vector<uint8_t> has_gravity(n, 0);
+    std::vector<double> R_align(9 * (size_t)n, 0.0);
+    int fixed_frame = 0;
+    bool any_gravity = false;
+    if (options_.use_gravity) {
+      for (auto& [id, f] : fsorted) {
+        if (!f->HasGravity()) continue;
+        const int i = fidx[id];
+        double* Ra = &R_align[9 * (size_t)i];
+        b200host_adapt::RAlignRowMajor(*f, Ra);
+        double R0[9], M[9], q[4], aa[3];
+        QuatToR(f->RigFromWorld().rotation.coeffs_data(), R0);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) M[3 * r + c] = Ra[r] * R0[c] + Ra[3 + r] * R0[3 + c] + Ra[6 + r] * R0[6 + c];   // R_align^T R
+        RToQuat(M, q);
+        QuatToAngleAxis(q, aa);
+        theta[3 * (size_t)i] = 0.0; theta[3 * (size_t)i + 1] = aa[1]; theta[3 * (size_t)i + 2] = 0.0;
+        has_gravity[i] = 1;
+        if (!any_gravity) fixed_frame = i;
+        any_gravity = true;
+      }
+    }
     std::map<image_pair_t, const ImagePair*> psorted;
     for (const auto& [id, pr] : view_graph.image_pairs)
       if (pr.is_valid) psorted[id] = &pr;
@@ -423,6 +446,21 @@ class RotationEstimator {
           for (int k = 0; k < 3; ++k) T[3 * r + k] = Rc[r] * R[k] + Rc[3 + r] * R[3 + k] + Rc[6 + r] * R[6 + k];
         std::copy(T, T + 9, R);
       }
+      if (any_gravity) {   // align the relative rotation with the gravity frames (.cc:311-326)
+        double T[9];
+        if (has_gravity[f1->second]) {
+          const double* Ra = &R_align[9 * (size_t)f1->second];
+          for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) T[3 * r + k] = R[3 * r] * Ra[k] + R[3 * r + 1] * Ra[3 + k] + R[3 * r + 2] * Ra[6 + k];
+          std::copy(T, T + 9, R);
+        }
+        if (has_gravity[f2->second]) {
+          const double* Ra = &R_align[9 * (size_t)f2->second];
+          for (int r = 0; r < 3; ++r)   // R_align^T R
+            for (int k = 0; k < 3; ++k) T[3 * r + k] = Ra[r] * R[k] + Ra[3 + r] * R[3 + k] + Ra[6 + r] * R[6 + k];
+          std::copy(T, T + 9, R);
+        }
+      }
       ei.push_back(f1->second);
       ej.push_back(f2->second);
       Rrel.insert(Rrel.end(), R, R + 9);
@@ -436,14 +474,49 @@ class RotationEstimator {
     o.irls_loss_parameter_sigma = options_.irls_loss_parameter_sigma;
     o.weight_type = options_.weight_type == RotationEstimatorOptions::HALF_NORM ? 1 : 0;
     o.use_weight = options_.use_weight; o.pcg_rel_tolerance = options_.pcg_rel_tolerance;
-    const int rc = b200sfm_ra_solve(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), 0, theta.data(), &summary);
+    const int rc = any_gravity
+                       ? b200sfm_ra_solve_gravity(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(),
+                                                  has_gravity.data(), fixed_frame, theta.data(), &summary)
+                       : b200sfm_ra_solve(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), 0,
+                                          theta.data(), &summary);
     if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ra_solve: %s\n", b200sfm_last_error(ctx)); return false; }
     if (!summary.usable) return false;                                                        // NaN (.cc:508-512,590-593)
-    for (auto& [id, f] : fsorted) {                                                           // ConvertResults (.cc:795-798)
-      AngleAxisToQuat(&theta[3 * (size_t)fidx[id]], f->RigFromWorld().rotation.coeffs_data());
+    for (auto& [id, f] : fsorted) {                                                           // ConvertResults (.cc:787-798)
+      const int i = fidx[id];
+      double* qout = f->RigFromWorld().rotation.coeffs_data();
+      if (has_gravity[i]) {   // R = R_align * AngleToRotUp(phi)
+        double qa[4], Ry[9], M[9];
+        AngleAxisToQuat(&theta[3 * (size_t)i], qa);
+        QuatToR(qa, Ry);
+        const double* Ra = &R_align[9 * (size_t)i];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) M[3 * r + c] = Ra[3 * r] * Ry[c] + Ra[3 * r + 1] * Ry[3 + c] + Ra[3 * r + 2] * Ry[6 + c];
+        RToQuat(M, qout);
+      } else {
+        AngleAxisToQuat(&theta[3 * (size_t)i], qout);
+      }
       f->RigFromWorld().translation = {{0, 0, 0}};
     }
     return true;
+  }
+
+  // rotation matrix (row-major) -> unit quaternion xyzw, w >= 0 (Shepperd's branches, as Eigen's conversion)
+  static void RToQuat(const double* R, double* q) {
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+      const double s = std::sqrt(tr + 1.0) * 2;
+      q[3] = 0.25 * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+      const double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+      q[3] = (R[7] - R[5]) / s; q[0] = 0.25 * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s;
+    } else if (R[4] > R[8]) {
+      const double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+      q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25 * s; q[2] = (R[5] + R[7]) / s;
+    } else {
+      const double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+      q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25 * s;
+    }
+    if (q[3] < 0) for (int k = 0; k < 4; ++k) q[k] = -q[k];
   }
 
   static void QuatToAngleAxis(const double* q, double* v) {

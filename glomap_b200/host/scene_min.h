@@ -14,10 +14,17 @@ namespace b200host_adapt {
 inline glomap::Rigid3d CamFromRig(glomap::Rig& rig, glomap::camera_t camera_id) {
   return rig.SensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id));
 }
+// GravityInfo::GetRAlign() (scene/frame.h:16) as row-major doubles
+inline void RAlignRowMajor(const glomap::Frame& f, double out[9]) {
+  const Eigen::Matrix3d& R = f.gravity_info.GetRAlign();
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out[3 * r + c] = R(r, c);
+}
 }  // namespace b200host_adapt
 #else
 #include <map>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <unordered_map>
@@ -57,8 +64,29 @@ struct Rig {   // colmap::Rig: one reference sensor (identity) + sensors with a 
     return it == cam_from_rig.end() ? Rigid3d{} : it->second;
   }
 };
+struct GravityInfo {   // scene/frame.h:11-27
+  bool has_gravity = false;
+  double R_align[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major; second COLUMN = gravity direction
+  std::array<double, 3> gravity_in_rig{{0, 0, 0}};
+  // GetAlignRot (math/gravity.cc:11-24): any right-handed orthonormal completion of the gravity direction (the
+  // reference takes the Householder one; the 1-DoF angle about gravity absorbs the choice)
+  void SetGravity(const std::array<double, 3>& g) {
+    gravity_in_rig = g;
+    const double n = std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    const double v[3] = {g[0] / n, g[1] / n, g[2] / n};
+    const double a[3] = {std::fabs(v[0]) < 0.9 ? 1.0 : 0.0, 0.0, std::fabs(v[0]) < 0.9 ? 0.0 : 1.0};
+    double x[3] = {v[1] * a[2] - v[2] * a[1], v[2] * a[0] - v[0] * a[2], v[0] * a[1] - v[1] * a[0]};
+    const double xn = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    for (double& e : x) e /= xn;
+    const double z[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
+    for (int r = 0; r < 3; ++r) { R_align[3 * r] = x[r]; R_align[3 * r + 1] = v[r]; R_align[3 * r + 2] = z[r]; }
+    has_gravity = true;
+  }
+};
 struct Frame {
   frame_t frame_id = 0;
+  GravityInfo gravity_info;
+  bool HasGravity() const { return gravity_info.has_gravity; }
   rig_t rig_id = 0;
   rig_t RigId() const { return rig_id; }
   bool is_registered = true;
@@ -102,5 +130,8 @@ inline image_pair_t ImagePairToPairId(image_t a, image_t b) {   // colmap::Image
 }  // namespace b200host
 namespace b200host_adapt {
 inline b200host::Rigid3d CamFromRig(b200host::Rig& rig, b200host::camera_t camera_id) { return rig.SensorFromRig(camera_id); }
+inline void RAlignRowMajor(const b200host::Frame& f, double out[9]) {
+  for (int k = 0; k < 9; ++k) out[k] = f.gravity_info.R_align[k];
+}
 }  // namespace b200host_adapt
 #endif

@@ -77,6 +77,15 @@ int main() {
   RotationEstimatorOptions ro;
   RotationEstimator ra(ro);
   if (!ra.EstimateRotations(vg, rigs, frames, images)) return 3;
+  // gravity-aligned rotation averaging: frames 20 and 40 carry a gravity prior
+  frames[20].gravity_info.SetGravity({{0.1, 1.0, 0.05}});
+  frames[40].gravity_info.SetGravity({{0.0, 1.0, 0.0}});
+  RotationEstimatorOptions rg;
+  rg.use_gravity = true;
+  RotationEstimator rag(rg);
+  if (!rag.EstimateRotations(vg, rigs, frames, images)) return 5;
+  std::printf("q20 %.17g %.17g %.17g %.17g\n", frames[20].rig_from_world.rotation.c[0], frames[20].rig_from_world.rotation.c[1],
+              frames[20].rig_from_world.rotation.c[2], frames[20].rig_from_world.rotation.c[3]);
   // trivial-frame world through the one-shot entry: only frame 40 / image 401 / camera 3
   std::unordered_map<frame_t, Frame> f2; f2[40] = frames[40];
   std::unordered_map<image_t, Image> i2; i2[401] = images[401]; i2[401].frame_ptr = &f2[40];

@@ -28,7 +28,7 @@ def _run(tmp_path):
                    check=True, capture_output=True)
     r = subprocess.run([str(exe)], env=dict(os.environ, MOCK_DUMP=str(dump)), capture_output=True, text=True)
     assert r.returncode == 0 and "shim driver ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
-    calls, cur = [], None
+    calls, cur = [{"_name": "_stdout", "lines": r.stdout.splitlines()}], None
     for line in dump.read_text().splitlines():
         f = line.split()
         if f[0] == "call":
@@ -40,11 +40,21 @@ def _run(tmp_path):
     return calls
 
 
+def stdout_line(calls, key):
+    (line,) = [l for l in calls_stdout[0] if l.startswith(key + " ")]
+    return line.split()[1:]
+
+
+calls_stdout = [None]
+
+
 def test_shim_flattening_of_a_rig_world(tmp_path):
     calls = _run(tmp_path)
+    calls_stdout[0] = calls[0]["lines"]
+    calls = calls[1:]
     assert [c["_name"] for c in calls] == ["ba_problem_create_rig", "ba_problem_set_state", "ba_problem_solve",
                                            "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
-                                           "ba_solve"]
+                                           "ra_solve_gravity", "ba_solve"]
     # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
     img_ids = [101, 102, 201, 202, 301, 302, 401]
     kimg = {i: k for k, i in enumerate(img_ids)}
@@ -94,7 +104,33 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     want_R = [R21[1], R21[2] @ Rs[1], Rs[1].T @ R21[3] @ Rs[1], R21[4]]
     assert np.abs(ra["R_rel"].reshape(-1, 3, 3) - np.array(want_R)).max() < 1e-14
     assert np.abs(G.so3_exp(ra["theta"].reshape(-1, 3)) - Rf).max() < 1e-13       # initial angle-axis of the frames
+    # ---- use_gravity: frames 20 and 40 (indices 1, 3) are 1-DoF; host preparation of .cc:207-217,311-326 ------------
+    from glomap_b200 import estimators as E
+    rg = calls[7]
+    assert rg["dims"].tolist() == [4, 4, 1]                                       # fixed frame = first gravity frame
+    assert rg["has_gravity"].tolist() == [0, 1, 0, 1]
+    Ra = {1: E.get_align_rot([0.1, 1.0, 0.05]), 3: E.get_align_rot([0.0, 1.0, 0.0])}
+    # (the first RA call zeroed nothing: the mock leaves theta alone and the shim wrote the same rotations back)
+    th = rg["theta"].reshape(-1, 3)
+    for i in (1, 3):
+        phi = G.so3_log((Ra[i].T @ Rf[i])[None])[0, 1]
+        assert np.abs(th[i] - [0.0, phi, 0.0]).max() < 1e-12
+    for i in (0, 2):
+        assert np.abs(G.so3_exp(th[i][None])[0] - Rf[i]).max() < 1e-12
+    want_g = []
+    for (a, b), R in zip([(0, 1), (0, 2), (1, 2), (2, 3)], want_R):
+        if a in Ra:
+            R = R @ Ra[a]
+        if b in Ra:
+            R = Ra[b].T @ R
+        want_g.append(R)
+    assert np.abs(rg["R_rel"].reshape(-1, 3, 3) - np.array(want_g)).max() < 1e-13
+    # ConvertResults for a gravity frame: R = R_align * RotY(phi) -- only the rotation about gravity survives
+    q20 = np.array([float(x) for x in stdout_line(calls, "q20")])
+    phi = th[1][1]
+    want20 = Ra[1] @ G.so3_exp(np.array([[0.0, phi, 0.0]]))[0]
+    assert np.abs(G.quat_xyzw_to_rotmat(q20[None])[0] - want20).max() < 1e-12
     # ---- trivial frames still take the one-shot entry -------------------------------------------------------------
-    one = calls[7]
+    one = calls[8]
     assert one["dims"].tolist() == [1, 1, 3, 1] and one["obs_cam"].tolist() == [0, 0, 0] and one["cam_intr"].tolist() == [0]
     assert one["flags"].tolist() == [1, 1, 0]
