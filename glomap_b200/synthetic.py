@@ -289,9 +289,12 @@ class RigScene:
 
     def rig_dict(self):
         """The ``rig`` argument of oracle.ba_oracle (per-image arrays, image id = f * S + s)."""
+        # img_sensor / sensor_q / sensor_t are read only with optimize_rig_poses (sensor 0 = reference sensor: constant)
+        img_sensor = np.tile(np.where(np.arange(self.S) == 0, -1, np.arange(self.S)), self.F)
         return dict(obs_img=self.obs_frame.astype(np.int64) * self.S + self.obs_sensor,
                     img_q=np.tile(self.sensor_quat, (self.F, 1)), img_t=np.tile(self.sensor_trans, (self.F, 1)),
-                    img_intr=np.tile(self.sensor_intr, self.F))
+                    img_intr=np.tile(self.sensor_intr, self.F), img_sensor=img_sensor,
+                    sensor_q=self.sensor_quat.copy(), sensor_t=self.sensor_trans.copy())
 
 
 def make_rig_scene(F: int, S: int, P: int, mean_track_len: float = 8.0, seed: int = 1, pixel_sigma: float = 0.0,

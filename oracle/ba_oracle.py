@@ -50,6 +50,7 @@ class BAOptions:
     optimize_intrinsics: bool = False
     optimize_principal_point: bool = False
     optimize_points: bool = True
+    optimize_rig_poses: bool = False
     thres_loss_function: float = 1.0
     min_num_view_per_track: int = 3
     max_num_iterations: int = 200
@@ -151,7 +152,11 @@ class BAProblem:
         """``rig`` (known, constant camera rigs; bundle_adjustment.cc:147-161,
         RigReprojErrorConstantRigCostFunctor): dict(obs_img [N], img_q [I,4], img_t [I,3], img_intr [I]) --
         then quat/trans/obs_cam refer to FRAMES (rig_from_world) and every observation's image carries a
-        constant cam_from_rig transform and its own intrinsics block."""
+        constant cam_from_rig transform and its own intrinsics block.
+        With ``opts.optimize_rig_poses`` (bundle_adjustment.cc:162-180,297-308, RigReprojErrorCostFunctor) the rig dict also
+        carries img_sensor [I] (sensor of each image, -1 = reference sensor / constant) and sensor_q [S,4], sensor_t [S,3]:
+        the cam_from_rig of every non-reference sensor is then an unknown (quaternion manifold + translation) shared by
+        all images of that sensor."""
         self.opts = opts
         self.C, self.P = len(quat), len(points)
         lens = np.diff(pt_obs_begin)
@@ -168,11 +173,18 @@ class BAProblem:
             oi = np.asarray(rig["obs_img"])[keep].astype(np.int64)
             self.rig = dict(obs_img=oi, R_cr=quat_rotmat(np.asarray(rig["img_q"], dtype=np.float64))[oi],
                             t_cr=np.asarray(rig["img_t"], dtype=np.float64)[oi],
-                            obs_intr=np.asarray(rig["img_intr"]).astype(np.int64)[oi])
+                            obs_intr=np.asarray(rig["img_intr"]).astype(np.int64)[oi], obs_sensor=None)
+            if opts.optimize_rig_poses and "img_sensor" in rig:
+                self.rig["obs_sensor"] = np.asarray(rig["img_sensor"]).astype(np.int64)[oi]
         self.intr_model = np.asarray(intr_model).astype(np.int64)
         self.K = len(self.intr_model)
         self.x0 = dict(quat=np.array(quat, dtype=np.float64), trans=np.array(trans, dtype=np.float64),
                        points=np.array(points, dtype=np.float64), intr=np.array(intr_params, dtype=np.float64))
+        self.S = 0
+        if self.rig is not None and self.rig["obs_sensor"] is not None:
+            self.x0["sq"] = np.array(rig["sensor_q"], dtype=np.float64)
+            self.x0["st"] = np.array(rig["sensor_t"], dtype=np.float64)
+            self.S = len(self.x0["sq"])
         # ---- variable layout (tangent space) --------------------------------
         # cam_const_mask bit0: rotation constant, bit1: translation constant.
         mask = np.zeros(self.C, dtype=np.int64) if cam_const_mask is None else np.asarray(cam_const_mask).astype(np.int64)
@@ -188,6 +200,16 @@ class BAProblem:
                 self.rot_col[c] = col; col += 3
             if trn_var[c]:
                 self.trn_col[c] = col; col += 3
+        # unknown cam_from_rig blocks (group 1 as well, bundle_adjustment.cc:222-236)
+        self.sq_col = np.full(self.S, -1)
+        self.st_col = np.full(self.S, -1)
+        if self.S:
+            s_used = np.zeros(self.S, dtype=bool)
+            s_used[self.rig["obs_sensor"][self.rig["obs_sensor"] >= 0]] = True
+            for si in range(self.S):
+                if s_used[si]:
+                    self.sq_col[si] = col; col += 3
+                    self.st_col[si] = col; col += 3
         self.intr_cols = []  # per intrinsics block: list of (param idx, col)
         used_intr = np.zeros(self.K, dtype=bool)
         used_intr[self.rig["obs_intr"] if self.rig is not None else self.cam_intr[self.obs_cam]] = True
@@ -224,13 +246,20 @@ class BAProblem:
         for k, ent in enumerate(self.intr_cols):
             for i, c in ent:
                 out["intr"][k, i] += delta[c]
+        sv = self.sq_col >= 0
+        if sv.any():
+            out["sq"][sv] = quat_plus(x["sq"][sv], delta[self.sq_col[sv][:, None] + np.arange(3)])
+            out["st"][sv] += delta[self.st_col[sv][:, None] + np.arange(3)]
         return out
 
     def x_norm(self, x, y=None):
         """Ambient norm over the variable parameter blocks (or of x - y)."""
         tot = 0.0
         rv, tv, pv = self.rot_col >= 0, self.trn_col >= 0, self.pt_col >= 0
-        for key, m in (("quat", rv), ("trans", tv), ("points", pv)):
+        blocks = [("quat", rv), ("trans", tv), ("points", pv)]
+        if self.S:
+            blocks += [("sq", self.sq_col >= 0), ("st", self.st_col >= 0)]
+        for key, m in blocks:
             a = x[key][m] if y is None else x[key][m] - y[key][m]
             tot += float((a * a).sum())
         for k, ent in enumerate(self.intr_cols):
@@ -246,8 +275,17 @@ class BAProblem:
         X = x["points"][self.obs_pt]
         RX = np.einsum("nij,nj->ni", R, X)
         Xc = RX + x["trans"][self.obs_cam]
+        R_cr = RY = None
         if self.rig is not None:      # X_c = R_cr (R_f X + t_f) + t_cr
-            Xc = np.einsum("nij,nj->ni", self.rig["R_cr"], Xc) + self.rig["t_cr"]
+            R_cr, t_cr = self.rig["R_cr"], self.rig["t_cr"]
+            os_ = self.rig["obs_sensor"]
+            if os_ is not None:       # unknown cam_from_rig of the non-reference sensors comes from the state
+                m = os_ >= 0
+                R_cr, t_cr = R_cr.copy(), t_cr.copy()
+                R_cr[m] = quat_rotmat(x["sq"])[os_[m]]
+                t_cr[m] = x["st"][os_[m]]
+            RY = np.einsum("nij,nj->ni", R_cr, Xc)
+            Xc = RY + t_cr
         valid = Xc[:, 2] > Z_EPS
         Xs = np.where(valid[:, None], Xc, np.array([0.0, 0.0, 1.0]))
         res = np.zeros((self.N, 2))
@@ -270,13 +308,17 @@ class BAProblem:
         if not want_jac:
             return res, None
         Jp[~valid] = 0.0
-        if self.rig is not None:      # chain through the constant cam_from_rig rotation
-            Jp = np.einsum("nij,njk->nik", Jp, self.rig["R_cr"])
+        Jsq = Jst = None
+        if self.rig is not None:
+            if self.S:                # d X_c / d(sensor rotation) = -2 [R_cr Y]x (left perturbation), d X_c / d t_cr = I
+                Jsq = np.einsum("nij,njk->nik", Jp, -2.0 * skew(RY))
+                Jst = Jp
+            Jp = np.einsum("nij,njk->nik", Jp, R_cr)      # chain the frame / point blocks through R_cr
         # d Xc / d delta (quaternion manifold, left perturbation angle 2|d|): -2 [R X]x
         Jrot = np.einsum("nij,njk->nik", Jp, -2.0 * skew(RX))
         Jtrn = Jp
         Jpt = np.einsum("nij,njk->nik", Jp, R)
-        return res, (Jrot, Jtrn, Jpt, Jk_all, valid)
+        return res, (Jrot, Jtrn, Jpt, Jk_all, valid, Jsq, Jst)
 
     def evaluate(self, x, want_jac):
         res, jac = self.residuals(x, want_jac)
@@ -287,7 +329,7 @@ class BAProblem:
         r = (res * w[:, None]).ravel()
         if not want_jac:
             return cost, r, None
-        Jrot, Jtrn, Jpt, Jk_all, valid = jac
+        Jrot, Jtrn, Jpt, Jk_all, valid, Jsq, Jst = jac
         rows_l, cols_l, vals_l = [], [], []
         row0 = 2 * np.arange(self.N)
 
@@ -307,6 +349,12 @@ class BAProblem:
         add_block(Jtrn, tc, tc >= 0)
         pc = self.pt_col[self.obs_pt]
         add_block(Jpt, pc, pc >= 0)
+        if Jsq is not None:
+            os_ = self.rig["obs_sensor"]
+            qc = np.where(os_ >= 0, self.sq_col[np.maximum(os_, 0)], -1)
+            tc2 = np.where(os_ >= 0, self.st_col[np.maximum(os_, 0)], -1)
+            add_block(Jsq, qc, qc >= 0)
+            add_block(Jst, tc2, tc2 >= 0)
         for k, (mk, jk) in Jk_all.items():
             idx = np.nonzero(mk)[0]
             vmask = valid[idx]
