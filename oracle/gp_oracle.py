@@ -49,10 +49,14 @@ class GPOptions:
 
 class GPProblem:
     def __init__(self, centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts: GPOptions, scales=None,
-                 obs_offset=None):
+                 obs_offset=None, rig_unknown=None):
         """``obs_offset`` [N,3]: known-rig term of RigBATAPairwiseDirectionError (cost_function.h:49-82) with the rig
         scale held at 1 (global_positioning.cc:493-497): r = t_obs - s (X - c_frame + t_rig), t_rig = R_cw^T t_cam_from_rig
-        (.cc:339-345)."""
+        (.cc:339-345).
+        ``rig_unknown`` = dict(obs_sensor [N] (-1: none), R_rw [N,3,3] rig_from_world rotation of the observation's frame,
+        centers [S,3]): RigUnknownBATAPairwiseDirectionError (cost_function.h:90-134, global_positioning.cc:347-364) --
+        the camera centre in the rig frame u_s of a sensor whose cam_from_rig is not known yet is an unknown block shared
+        by all its images:  r = t_obs - s (X - c_frame - R_rw^T u_s).  Oracle only so far (no device path)."""
         self.opts = opts
         self.C, self.P = len(centers), len(points)
         lens = np.diff(pt_obs_begin)
@@ -68,6 +72,11 @@ class GPProblem:
         self.loss_scale = np.where(cal[self.obs_cam], 1.0, 0.5)
         s0 = np.ones(self.N) if scales is None else np.asarray(scales, dtype=np.float64)[self.keep]
         self.x0 = dict(centers=np.array(centers, dtype=np.float64), points=np.array(points, dtype=np.float64), scales=s0)
+        self.ru = None
+        if rig_unknown is not None:
+            os_ = np.asarray(rig_unknown["obs_sensor"]).astype(np.int64)[self.keep]
+            self.ru = dict(obs_sensor=os_, R_rw=np.asarray(rig_unknown["R_rw"], dtype=np.float64)[self.keep])
+            self.x0["rig_centers"] = np.array(rig_unknown["centers"], dtype=np.float64)
         cam_used = np.zeros(self.C, bool); cam_used[self.obs_cam] = True
         pt_used = np.zeros(self.P, bool); pt_used[self.obs_pt] = True
         col = 0
@@ -83,10 +92,21 @@ class GPProblem:
         if opts.optimize_scales and self.N > 1:
             self.s_col[1:] = col + np.arange(self.N - 1)      # first scale constant (.cc:484-489)
             col += self.N - 1
+        self.u_col = np.zeros(0, dtype=np.int64)
+        if self.ru is not None:
+            S_ = len(self.x0["rig_centers"])
+            self.u_col = np.full(S_, -1)
+            used = np.zeros(S_, bool); used[self.ru["obs_sensor"][self.ru["obs_sensor"] >= 0]] = True
+            if opts.optimize_positions:      # the centres are randomised with the positions (.cc:440-453)
+                idx = np.nonzero(used)[0]
+                self.u_col[idx] = col + 3 * np.arange(len(idx)); col += 3 * len(idx)
         self.ncols = col
 
     def plus(self, x, delta):
         out = {k: v.copy() for k, v in x.items()}
+        uv = self.u_col >= 0
+        if uv.any():
+            out["rig_centers"][uv] += delta[self.u_col[uv][:, None] + np.arange(3)]
         cv = self.cam_col >= 0
         out["centers"][cv] += delta[self.cam_col[cv][:, None] + np.arange(3)]
         pv = self.pt_col >= 0
@@ -108,12 +128,21 @@ class GPProblem:
         for key, m in (("centers", self.cam_col >= 0), ("points", self.pt_col >= 0), ("scales", self.s_col >= 0)):
             a = x[key][m] if y is None else x[key][m] - y[key][m]
             tot += float((a * a).sum())
+        if (self.u_col >= 0).any():
+            m = self.u_col >= 0
+            a = x["rig_centers"][m] if y is None else x["rig_centers"][m] - y["rig_centers"][m]
+            tot += float((a * a).sum())
         return np.sqrt(tot)
 
     def evaluate(self, x, want_jac):
         d = x["points"][self.obs_pt] - x["centers"][self.obs_cam]
         if self.obs_off is not None:
             d = d + self.obs_off
+        if self.ru is not None:       # - R_rw^T u_sensor
+            os_ = self.ru["obs_sensor"]
+            mu = os_ >= 0
+            d = d.copy()
+            d[mu] -= np.einsum("nji,nj->ni", self.ru["R_rw"][mu], x["rig_centers"][os_[mu]])
         s = x["scales"]
         res = self.obs_dir - s[:, None] * d
         sq = (res * res).sum(1)
@@ -137,17 +166,24 @@ class GPProblem:
         m = self.s_col >= 0
         for k in range(3):     # dr/ds = -(X - c)
             rows.append(row0[m] + k); cols.append(self.s_col[m]); vals.append(-(w * d[:, k])[m])
+        if self.ru is not None and (self.u_col >= 0).any():     # dr/du = + s R_rw^T
+            os_ = self.ru["obs_sensor"]
+            uc = np.where(os_ >= 0, self.u_col[np.maximum(os_, 0)], -1)
+            m = uc >= 0
+            for k in range(3):
+                for j in range(3):
+                    rows.append(row0[m] + k); cols.append(uc[m] + j); vals.append((w * s)[m] * self.ru["R_rw"][m][:, j, k])
         J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(3 * self.N, self.ncols))
         return cost, r, J
 
 
 def solve_gp(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated=None, opts: GPOptions | None = None,
-             scales=None, verbose=False, obs_offset=None):
+             scales=None, verbose=False, obs_offset=None, rig_unknown=None):
     """Oracle counterpart of the ceres::Solve inside GlobalPositioner::Solve
     (global_positioning.cc:83) on already-initialised centres/points.
     Returns (state dict with centers, points, scales (valid observations only), LMSummary)."""
     opts = opts or GPOptions()
-    prob = GPProblem(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts, scales, obs_offset)
+    prob = GPProblem(centers, points, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, opts, scales, obs_offset, rig_unknown)
     if prob.N == 0 or prob.ncols == 0:
         return prob.x0, LMSummary(termination="empty problem")
     lm = LMOptions(max_num_iterations=opts.max_num_iterations, function_tolerance=opts.function_tolerance, verbose=verbose)

@@ -123,3 +123,32 @@ def test_optimised_rig_poses_oracle():
     # without the flag the same dictionary is the constant-rig problem
     q = B.BAProblem(*args, B.BAOptions(), rig=rig)
     assert q.S == 0 and "sq" not in q.x0
+
+
+def test_rig_unknown_bata_oracle():
+    """RigUnknownBATAPairwiseDirectionError (cost_function.h:90-134, global_positioning.cc:347-364): the camera centre in
+    the rig frame of a sensor without a known cam_from_rig is an unknown shared by its images.  Oracle only so far.
+    With u_s = -R_cr^T t_cr the term -R_rw^T u_s equals the known-rig offset R_cw^T t_cr, so the residual vanishes at
+    the ground truth; Jacobian against finite differences; the solve drives the cost to zero."""
+    rs = S.make_rig_scene(10, 3, 250, seed=12)
+    bear = S.bearings_from_scene(rs.images_scene())
+    t_obs, t_rig = E.rig_world_terms(rs.quat, rs.sensor_quat, rs.sensor_trans, bear, rs.obs_frame, rs.obs_sensor)
+    Rf = G.quat_xyzw_to_rotmat(rs.quat)
+    c_f = G.centers_from_pose(Rf, rs.trans)
+    u = -np.einsum("sji,sj->si", G.quat_xyzw_to_rotmat(rs.sensor_quat), rs.sensor_trans)
+    ru = dict(obs_sensor=np.where(rs.obs_sensor > 0, rs.obs_sensor.astype(np.int64), -1), R_rw=Rf[rs.obs_frame], centers=u)
+    pt = np.repeat(np.arange(rs.P), np.diff(rs.pt_obs_begin))
+    s = 1.0 / np.linalg.norm(rs.points[pt] - c_f[rs.obs_frame] + t_rig, axis=1)
+    p = GPO.GPProblem(c_f, rs.points, rs.pt_obs_begin, rs.obs_frame, t_obs, None, GPO.GPOptions(), s, rig_unknown=ru)
+    assert p.evaluate(p.x0, False)[0] < 1e-20
+    rng = np.random.default_rng(0)
+    ru2 = dict(ru, centers=u + rng.normal(size=u.shape) * 0.1)
+    c0, p0 = c_f + rng.normal(size=c_f.shape) * 0.3, rs.points + rng.normal(size=rs.points.shape) * 0.3
+    q = GPO.GPProblem(c0, p0, rs.pt_obs_begin, rs.obs_frame, t_obs, None, GPO.GPOptions(thres_loss_function=1e9), s, rig_unknown=ru2)
+    _, _, J = q.evaluate(q.x0, True)
+    assert J.shape[1] == 3 * rs.F + 3 * rs.P + (q.N - 1) + 3 * (rs.S - 1)
+    d = rng.normal(size=J.shape[1]) * 1e-6
+    r1, r0 = q.evaluate(q.plus(q.x0, d), False)[1], q.evaluate(q.plus(q.x0, -d), False)[1]
+    assert np.abs((r1 - r0) / 2 - J @ d).max() < 1e-12
+    x, summ = GPO.solve_gp(c0, p0, rs.pt_obs_begin, rs.obs_frame, t_obs, None, GPO.GPOptions(), None, rig_unknown=ru2)
+    assert summ.final_cost < 1e-12 * summ.initial_cost
