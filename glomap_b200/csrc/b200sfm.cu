@@ -26,7 +26,50 @@ int guarded(b200sfm_ctx* ctx, F&& f) {
   } catch (const std::bad_alloc&) {
     if (ctx) ctx->err = "host allocation failed";
     return B200SFM_ERR_CUDA;
+  } catch (const b200::InvalidInput& e) {
+    if (ctx) ctx->err = e.msg;
+    return B200SFM_ERR_INVALID_ARG;
+  } catch (const std::exception& e) {   // nothing may escape through the extern "C" boundary
+    if (ctx) ctx->err = std::string("internal error: ") + e.what();
+    return B200SFM_ERR_CUDA;
+  } catch (...) {
+    if (ctx) ctx->err = "internal error (unknown exception)";
+    return B200SFM_ERR_CUDA;
   }
+}
+
+// A rank that fails while its peers are inside a collective must not leave them blocked for ever: abort the
+// communicator (the peers' pending collectives then fail instead of waiting) before the status is returned.
+int finish(b200sfm_ctx* ctx, int rc) {
+  if (ctx && ctx->world > 1 && ctx->comm && (rc == B200SFM_ERR_CUDA || rc == B200SFM_ERR_NCCL)) {
+    if (nccl_api().CommAbort) nccl_api().CommAbort(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->err += " [communicator aborted]";
+  }
+  return rc;
+}
+
+// SPMD guard for the sharded create calls: every rank learns whether ANY rank holds an empty or invalid shard, so
+// all of them return the same status instead of one returning early and the others blocking in the next all-reduce.
+int agree_status(b200sfm_ctx* ctx, int local_rc) {
+  if (!ctx || ctx->world == 1 || !ctx->comm) return local_rc;
+  int agreed = local_rc;
+  int rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    b200::DevBuf<double> flag;
+    flag.alloc(1);
+    const double v = (double)local_rc;
+    B200_CUDA_OK(cudaMemcpyAsync(flag.p, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->allreduce_max(flag.p, 1);
+    double out = 0;
+    B200_CUDA_OK(cudaMemcpyAsync(&out, flag.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    agreed = (int)out;
+    return (int)B200SFM_OK;
+  });
+  if (rc != B200SFM_OK) return finish(ctx, rc);
+  if (agreed != B200SFM_OK && local_rc == B200SFM_OK) ctx->err = "another rank reported an empty or invalid shard";
+  return agreed;
 }
 
 int create_common(int device, b200sfm_ctx** out) {
@@ -149,25 +192,32 @@ int b200sfm_ba_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
                               b200sfm_ba_problem** out) {
   if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
   *out = nullptr;
-  if (C <= 0 || P <= 0 || N <= 0 || K <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
-  if (!pt_obs_begin || !obs_cam || !obs_xy || !cam_intr || !intr_model) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
-  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
-  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
-  for (int k = 0; k < K; ++k)
-    if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
-  return guarded(ctx, [&]() {
+  auto precheck = [&]() -> int {
+    if (C <= 0 || P <= 0 || N <= 0 || K <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
+    if (!pt_obs_begin || !obs_cam || !obs_xy || !cam_intr || !intr_model) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
+    if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+    if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+    for (int k = 0; k < K; ++k)
+      if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
+    return B200SFM_OK;
+  };
+  int rc = agree_status(ctx, precheck());
+  if (rc != B200SFM_OK) return rc;
+  b200sfm_ba_problem* p = nullptr;
+  rc = guarded(ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(ctx->device));
-    auto* p = new b200sfm_ba_problem();
-    try {
-      p->create(ctx, C, P, N, K, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, cam_const_mask,
-                min_num_view_per_track, nullptr);
-    } catch (...) {
-      delete p;
-      throw;
-    }
-    *out = p;
+    p = new b200sfm_ba_problem();
+    p->create(ctx, C, P, N, K, pt_obs_begin, obs_cam, obs_xy, cam_intr, intr_model, cam_const_mask,
+              min_num_view_per_track, nullptr);
     return (int)B200SFM_OK;
   });
+  rc = agree_status(ctx, finish(ctx, rc));
+  if (rc != B200SFM_OK) {
+    if (p) b200sfm_ba_problem_free(p);
+    return rc;
+  }
+  *out = p;
+  return B200SFM_OK;
 }
 
 int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_t N, int32_t K, int32_t S,
@@ -177,33 +227,40 @@ int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_
                                   int32_t min_num_view_per_track, b200sfm_ba_problem** out) {
   if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
   *out = nullptr;
-  if (F <= 0 || P <= 0 || N <= 0 || K <= 0 || S <= 0) { ctx->err = "empty problem (no frames / tracks / observations / sensors)"; return B200SFM_ERR_EMPTY; }
-  if (!pt_obs_begin || !obs_frame || !obs_sensor || !obs_xy || !sensor_quat_xyzw || !sensor_trans || !sensor_intr || !intr_model) {
-    ctx->err = "null input array";
-    return B200SFM_ERR_INVALID_ARG;
-  }
-  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
-  if (S > 65535 || (long long)F * S >= (1ll << 31) - 1) { ctx->err = "too many sensors (S <= 65535, F * S < 2^31)"; return B200SFM_ERR_INVALID_ARG; }
-  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
-  for (int k = 0; k < K; ++k)
-    if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
-  for (int i = 0; i < S; ++i)
-    if (sensor_intr[i] < 0 || sensor_intr[i] >= K) { ctx->err = "sensor_intr out of range"; return B200SFM_ERR_INVALID_ARG; }
-  for (int64_t o = 0; o < N; ++o)
-    if (obs_sensor[o] >= S || obs_frame[o] < 0 || obs_frame[o] >= F) { ctx->err = "obs_frame / obs_sensor out of range"; return B200SFM_ERR_INVALID_ARG; }
-  return guarded(ctx, [&]() {
-    B200_CUDA_OK(cudaSetDevice(ctx->device));
-    auto* p = new b200sfm_ba_problem();
-    try {
-      p->create(ctx, F, P, N, K, pt_obs_begin, obs_frame, obs_xy, nullptr, intr_model, frame_const_mask,
-                min_num_view_per_track, nullptr, S, obs_sensor, sensor_quat_xyzw, sensor_trans, sensor_intr);
-    } catch (...) {
-      delete p;
-      throw;
+  auto precheck = [&]() -> int {
+    if (F <= 0 || P <= 0 || N <= 0 || K <= 0 || S <= 0) { ctx->err = "empty problem (no frames / tracks / observations / sensors)"; return B200SFM_ERR_EMPTY; }
+    if (!pt_obs_begin || !obs_frame || !obs_sensor || !obs_xy || !sensor_quat_xyzw || !sensor_trans || !sensor_intr || !intr_model) {
+      ctx->err = "null input array";
+      return B200SFM_ERR_INVALID_ARG;
     }
-    *out = p;
+    if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+    if (S > 65535 || (long long)F * S >= (1ll << 31) - 1) { ctx->err = "too many sensors (S <= 65535, F * S < 2^31)"; return B200SFM_ERR_INVALID_ARG; }
+    if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+    for (int k = 0; k < K; ++k)
+      if (intr_model[k] < 0 || intr_model[k] > 3) { ctx->err = "unsupported camera model id " + std::to_string(intr_model[k]); return B200SFM_ERR_UNSUPPORTED; }
+    for (int i = 0; i < S; ++i)
+      if (sensor_intr[i] < 0 || sensor_intr[i] >= K) { ctx->err = "sensor_intr out of range"; return B200SFM_ERR_INVALID_ARG; }
+    for (int64_t o = 0; o < N; ++o)
+      if (obs_sensor[o] >= S || obs_frame[o] < 0 || obs_frame[o] >= F) { ctx->err = "obs_frame / obs_sensor out of range"; return B200SFM_ERR_INVALID_ARG; }
+    return B200SFM_OK;
+  };
+  int rc = agree_status(ctx, precheck());
+  if (rc != B200SFM_OK) return rc;
+  b200sfm_ba_problem* p = nullptr;
+  rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    p = new b200sfm_ba_problem();
+    p->create(ctx, F, P, N, K, pt_obs_begin, obs_frame, obs_xy, nullptr, intr_model, frame_const_mask,
+              min_num_view_per_track, nullptr, S, obs_sensor, sensor_quat_xyzw, sensor_trans, sensor_intr);
     return (int)B200SFM_OK;
   });
+  rc = agree_status(ctx, finish(ctx, rc));
+  if (rc != B200SFM_OK) {
+    if (p) b200sfm_ba_problem_free(p);
+    return rc;
+  }
+  *out = p;
+  return B200SFM_OK;
 }
 
 int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
@@ -249,7 +306,7 @@ int b200sfm_ba_problem_restore_state(b200sfm_ba_problem* p) {
 
 int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, b200sfm_lm_stats* stats) {
   if (!p || !opts) return B200SFM_ERR_INVALID_ARG;
-  return guarded(p->ctx, [&]() {
+  return finish(p->ctx, guarded(p->ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(p->ctx->device));
     if (opts->min_num_view_per_track != p->min_views) {
       p->ctx->err = "min_num_view_per_track differs from the value the problem was created with";
@@ -257,7 +314,7 @@ int b200sfm_ba_problem_solve(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts,
     }
     if (stats) std::memset(stats, 0, sizeof(*stats));
     return p->solve(*opts, stats);
-  });
+  }));
 }
 
 int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, double* cost) {
@@ -400,22 +457,29 @@ int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
                               const uint8_t* cam_const_mask, int32_t min_num_view_per_track, b200sfm_gp_problem** out) {
   if (!ctx || !out) return B200SFM_ERR_INVALID_ARG;
   *out = nullptr;
-  if (C <= 0 || P <= 0 || N <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
-  if (!pt_obs_begin || !obs_cam || !obs_dir) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
-  if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
-  if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
-  return guarded(ctx, [&]() {
+  auto precheck = [&]() -> int {
+    if (C <= 0 || P <= 0 || N <= 0) { ctx->err = "empty problem (no images / tracks / observations)"; return B200SFM_ERR_EMPTY; }
+    if (!pt_obs_begin || !obs_cam || !obs_dir) { ctx->err = "null input array"; return B200SFM_ERR_INVALID_ARG; }
+    if (N >= (1ll << 31)) { ctx->err = "N must be < 2^31 per rank"; return B200SFM_ERR_INVALID_ARG; }
+    if (pt_obs_begin[0] != 0 || pt_obs_begin[P] != N) { ctx->err = "pt_obs_begin must start at 0 and end at N"; return B200SFM_ERR_INVALID_ARG; }
+    return B200SFM_OK;
+  };
+  int rc = agree_status(ctx, precheck());
+  if (rc != B200SFM_OK) return rc;
+  b200sfm_gp_problem* p = nullptr;
+  rc = guarded(ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(ctx->device));
-    auto* p = new b200sfm_gp_problem();
-    try {
-      p->create(ctx, C, P, N, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, cam_const_mask, min_num_view_per_track);
-    } catch (...) {
-      delete p;
-      throw;
-    }
-    *out = p;
+    p = new b200sfm_gp_problem();
+    p->create(ctx, C, P, N, pt_obs_begin, obs_cam, obs_dir, cam_calibrated, cam_const_mask, min_num_view_per_track);
     return (int)B200SFM_OK;
   });
+  rc = agree_status(ctx, finish(ctx, rc));
+  if (rc != B200SFM_OK) {
+    if (p) b200sfm_gp_problem_free(p);
+    return rc;
+  }
+  *out = p;
+  return B200SFM_OK;
 }
 
 int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* obs_offset, const uint8_t* obs_calibrated) {
@@ -468,7 +532,7 @@ int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p) {
 
 int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* opts, b200sfm_lm_stats* stats) {
   if (!p || !opts) return B200SFM_ERR_INVALID_ARG;
-  return guarded(p->ctx, [&]() {
+  return finish(p->ctx, guarded(p->ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(p->ctx->device));
     if (opts->min_num_view_per_track != p->min_views) {
       p->ctx->err = "min_num_view_per_track differs from the value the problem was created with";
@@ -476,7 +540,7 @@ int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* opts,
     }
     if (stats) std::memset(stats, 0, sizeof(*stats));
     return p->solve(*opts, stats);
-  });
+  }));
 }
 
 void b200sfm_gp_problem_free(b200sfm_gp_problem* p) {
@@ -562,7 +626,7 @@ int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int3
     return (int)B200SFM_OK;
   });
   if (stats) *stats = st;
-  return rc;
+  return finish(ctx, rc);
 }
 
 }  // extern "C"

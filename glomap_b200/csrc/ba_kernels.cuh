@@ -20,6 +20,7 @@
 // reductions through shared memory.
 #pragma once
 #include "common.cuh"
+#include "pcg.cuh"
 
 namespace b200 {
 
@@ -468,9 +469,11 @@ __global__ void __launch_bounds__(128) ba_linearize_cams(BAView v, const double*
 // rows, Jacobi scaling is fixed at the first linearisation, max|gc| -> scal[1].
 __global__ void ba_finalize_cams(int C, double* __restrict__ U, double* __restrict__ gc,
                                  const unsigned char* __restrict__ cam_mask, double* __restrict__ jscale_c,
-                                 int set_jscale, double* __restrict__ scal) {
+                                 int set_jscale, double* __restrict__ scal, const double* __restrict__ gslots, int nslots) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double gmax = 0.0;
+  // per-rank max|g_p| travelled through the sum all-reduce in one slot per rank: fold them into scal[1]
+  if (blockIdx.x == 0 && threadIdx.x < nslots) gmax = gslots[threadIdx.x];
   if (c < C) {
     const int mask = cam_mask[c];
 #pragma unroll
@@ -634,8 +637,10 @@ __global__ void __launch_bounds__(kTile, B200_K3_MIN_CTAS) ba_schur_pass(BAView 
                                                           const double* __restrict__ points,
                                                           double* __restrict__ points_new, double radius,
                                                           double* __restrict__ bscal, const double* __restrict__ spk = nullptr,
-                                                          const double* __restrict__ dk = nullptr, int m_intr = 0) {
+                                                          const double* __restrict__ dk = nullptr, int m_intr = 0,
+                                                          const PcgCtl* __restrict__ ctl = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  if (ctl && ctl->done) return;   // the PCG stopping rule has fired: the queued iterations are no-ops
   K3Smem& sm = *reinterpret_cast<K3Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;

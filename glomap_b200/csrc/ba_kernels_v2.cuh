@@ -22,6 +22,7 @@
 // All arithmetic stays FP64.  Algorithmic bytes per mat-vec: 52 N + 80 P (A) + 76 N + 32 P (B).
 #pragma once
 #include "ba_kernels.cuh"
+#include "pcg.cuh"
 
 namespace b200 {
 
@@ -48,6 +49,42 @@ __global__ void ba2_pack_x(int C, const double* __restrict__ x, const double* __
   for (int k = 0; k < 3; ++k) {
     o[k] = R[k] * xc[0] + R[3 + k] * xc[1] + R[6 + k] * xc[2];
     o[3 + k] = R[k] * xc[3] + R[3 + k] * xc[4] + R[6 + k] * xc[5];
+  }
+}
+
+// Head of a PCG iteration fused with the packing of its search direction: p = z + beta p (pcg_direction) and
+// xp[c] = {R^T p_r, R^T p_t} for pass A, one thread per camera -- one launch instead of two per iteration.
+__global__ void __launch_bounds__(kPcgThreads) ba2_pcg_direction_pack(int nb, int nblk, int it, int min_it, double rel_tol,
+                                                                      const double* __restrict__ z, double* __restrict__ p,
+                                                                      double* __restrict__ yw,
+                                                                      const double* __restrict__ dots_pp,
+                                                                      const double* __restrict__ part_rz,
+                                                                      const double* __restrict__ part_rr,
+                                                                      double* __restrict__ dots_pub, PcgCtl* __restrict__ ctl,
+                                                                      const double* __restrict__ cam_rec,
+                                                                      double* __restrict__ xp) {
+  __shared__ double sh3[3];
+  double beta;
+  if (!pcg_direction_head(nblk, it, min_it, rel_tol, dots_pp, part_rz, part_rr, nullptr, dots_pub, ctl, sh3, beta)) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb) return;
+  double pv[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const size_t i = (size_t)c * 6 + k;
+    pv[k] = (it == 1) ? z[i] : z[i] + beta * p[i];
+    p[i] = pv[k];
+    yw[i] = 0.0;
+  }
+  const double* r = cam_rec + (size_t)c * kCamRec;
+  const double q[4] = {r[0], r[1], r[2], r[3]};
+  double R[9];
+  quat_to_R(q, R);
+  double* o = xp + (size_t)c * kXqStride;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[k] = R[k] * pv[0] + R[3 + k] * pv[1] + R[6 + k] * pv[2];
+    o[3 + k] = R[k] * pv[3] + R[3 + k] * pv[4] + R[6 + k] * pv[5];
   }
 }
 
@@ -237,8 +274,10 @@ template <int MODE>
 __global__ void __launch_bounds__(kTile, MODE == 0 ? B200_PA_MIN_CTAS : B200_K3_MIN_CTAS) ba2_pass_a(BAView v, BAViewV2 v2, const double* __restrict__ xp,
                                                                      const double* __restrict__ points,
                                                                      double* __restrict__ points_new, double radius,
-                                                                     double* __restrict__ bscal) {
+                                                                     double* __restrict__ bscal,
+                                                                     const PcgCtl* __restrict__ ctl) {
   extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  if (ctl && ctl->done) return;   // the PCG stopping rule has fired: the queued iterations are no-ops
   K3v2Smem& sm = *reinterpret_cast<K3v2Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int tid = threadIdx.x;
@@ -420,7 +459,8 @@ __global__ void ba2_point_rhs_z(BAView v, BAViewV2 v2) {
 // pass B (camera order): y_c -= [ 2 R sum (X x w) ; R sum w ],  w = A_o z_p
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
-                                                 double* __restrict__ y) {
+                                                 double* __restrict__ y, const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= v.n_segs) return;

@@ -29,16 +29,20 @@ __global__ void k_expand_obs_pt(int P, const unsigned* __restrict__ pt_begin, in
 __global__ void k_cam_keys(long long N, int VC, int smul, int min_views, const int* __restrict__ obs_cam,
                            const unsigned short* __restrict__ obs_sensor,
                            const int* __restrict__ obs_pt, const unsigned* __restrict__ pt_begin,
-                           int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ cam_count) {
+                           int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ cam_count,
+                           int* __restrict__ bad) {
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= N) return;
   const int pt = obs_pt[o];
   const bool valid = (int)(pt_begin[pt + 1] - pt_begin[pt]) >= min_views;
   const int cam = obs_cam[o] * smul + (obs_sensor ? (int)obs_sensor[o] : 0);
   const int C = VC;
-  keys[o] = valid ? cam : C;
+  // caller-supplied camera index out of range: flag it (-> B200SFM_ERR_INVALID_ARG) instead of writing out of bounds
+  const bool in_range = obs_cam[o] >= 0 && cam < C;
+  if (!in_range) *bad = 1;
+  keys[o] = (valid && in_range) ? cam : C;
   vals[o] = (int)o;
-  if (valid) atomicAdd(&cam_count[cam], 1);
+  if (valid && in_range) atomicAdd(&cam_count[cam], 1);
 }
 __global__ void k_seg_counts(int C, const int* __restrict__ cam_count, int* __restrict__ seg_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +156,8 @@ struct b200sfm_ba_problem {
   // linear system
   DevBuf<double> W, V, Vinv, gp, lin /* U | gc | cost */, Sd, Minv, jscale_c, jscale_p, Dc;
   // pcg
-  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dots, part;
+  DevBuf<double> px, pr, pz, pp, pq, yw, bvec;
+  b200::PcgHost pcgh;
   DevBuf<double> scal;   // [0] cost [1] gmax | [2..5] bscal | [6] cand cost | [8..12] cscal
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_k1 = 0, smem_k3 = 0;
@@ -195,6 +200,7 @@ struct b200sfm_ba_problem {
     for (int p = 0; p < P; ++p) {
       ptb[p] = (unsigned)h_pt_begin[p];
       const long long len = h_pt_begin[p + 1] - h_pt_begin[p];
+      if (len < 0) throw InvalidInput{"pt_obs_begin must be non-decreasing"};
       if (len >= min_views) n_obs_used += len;
       if (tile_pts > 0 && (tile_obs + len > kTile || tile_pts >= kTilePts)) {
         tiles.push_back(p);
@@ -248,6 +254,8 @@ struct b200sfm_ba_problem {
       cam_intr.upload(zeros.data(), C, s);
       B200_CUDA_OK(cudaStreamSynchronize(s));
     } else {
+      for (int c2 = 0; c2 < C; ++c2)
+        if (h_cam_intr[c2] < 0 || h_cam_intr[c2] >= K) throw InvalidInput{"cam_intr out of range"};
       cam_intr.upload(h_cam_intr, C, s);
     }
     intr_model.upload(h_intr_model, K, s);
@@ -258,12 +266,13 @@ struct b200sfm_ba_problem {
 
     B200_LAUNCH(ctx, k_expand_obs_pt, cdiv(P, 256), 256, 0, P, pt_begin.p, obs_pt.p);
     // camera order
-    DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off;
+    DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off, bad;
     keys.alloc(N); vals.alloc(N); keys_out.alloc(N); camord_obs.alloc(N);
     cam_count.alloc((size_t)VC + 1); seg_count.alloc((size_t)VC + 1); cam_begin.alloc((size_t)VC + 1); seg_off.alloc((size_t)VC + 1);
-    cam_count.zero(s); seg_count.zero(s);
+    bad.alloc(1);
+    cam_count.zero(s); seg_count.zero(s); bad.zero(s);
     B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, VC, smul, min_views, obs_cam.p, S > 0 ? obs_sensor.p : nullptr,
-                obs_pt.p, pt_begin.p, keys.p, vals.p, cam_count.p);
+                obs_pt.p, pt_begin.p, keys.p, vals.p, cam_count.p, bad.p);
     int end_bit = 1;
     while ((1ll << end_bit) <= VC) ++end_bit;
     size_t tmp_bytes = 0;
@@ -281,10 +290,12 @@ struct b200sfm_ba_problem {
     tb = tmp.bytes();
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, seg_count.p, seg_off.p, VC + 1, s);
     ctx->launches += 4;
-    int h_tot[2];
+    int h_tot[3];
     B200_CUDA_OK(cudaMemcpyAsync(&h_tot[0], cam_begin.p + VC, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(&h_tot[1], seg_off.p + VC, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[2], bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
+    if (h_tot[2]) throw InvalidInput{"obs_cam out of range [0, C)"};
     Nv = h_tot[0];
     n_segs = h_tot[1];
     seg_cam.alloc(std::max(n_segs, 1)); seg_begin.alloc(std::max(n_segs, 1)); seg_end.alloc(std::max(n_segs, 1));
@@ -320,7 +331,7 @@ struct b200sfm_ba_problem {
     intr_cand.alloc((size_t)K * B200SFM_INTR_STRIDE);
     cam_rec.alloc((size_t)C * kCamRec); intr_rec.alloc((size_t)K * kIntrRec);
     W.alloc((size_t)N * kWDoubles); V.alloc((size_t)P * 6); Vinv.alloc((size_t)P * 6); gp.alloc((size_t)P * 3);
-    lin.alloc((size_t)C * 27 + 2); Sd.alloc((size_t)C * 21); Minv.alloc((size_t)C * 21);
+    lin.alloc((size_t)C * 27 + 1 + (size_t)ctx->world);   // U | gc | cost | one max|g_p| slot per rank Sd.alloc((size_t)C * 27);   // Schur-Jacobi blocks | right-hand-side accumulator (one all-reduce for both) Minv.alloc((size_t)C * 21);
     jscale_c.alloc((size_t)C * 6); jscale_p.alloc((size_t)P * 3); Dc.alloc((size_t)C * 6);
     px.alloc((size_t)C * 6); pr.alloc((size_t)C * 6); pz.alloc((size_t)C * 6); pp.alloc((size_t)C * 6);
     pq.alloc((size_t)C * 6); yw.alloc((size_t)C * 6); bvec.alloc((size_t)C * 6);
@@ -444,12 +455,13 @@ struct b200sfm_ba_problem {
         B200_LAUNCH(ctx, ba_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p,
                     points[cur].p, huber_a);
     }
-    // cost travels with U|gc through one all-reduce
+    // cost and this rank's max|g_p| (own slot, zeros elsewhere) travel with U|gc through ONE sum all-reduce
     B200_CUDA_OK(cudaMemcpyAsync(cost_ptr(), scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    ctx->allreduce_sum(lin.p, (size_t)C * 27 + 1);
-    ctx->allreduce_max(scal.p + 1, 1);
+    B200_CUDA_OK(cudaMemcpyAsync(cost_ptr() + 1 + ctx->rank, scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    ctx->allreduce_sum(lin.p, (size_t)C * 27 + 1 + (size_t)ctx->world);
+    B200_CUDA_OK(cudaMemsetAsync(scal.p + 1, 0, sizeof(double), s));
     B200_LAUNCH(ctx, ba_finalize_cams, cdiv(C, 128), 128, 0, C, U(), gc(), cam_mask.p, jscale_c.p, first ? 1 : 0,
-                scal.p);
+                scal.p, cost_ptr() + 1, ctx->world);
     if (m_intr > 0) {
       // U_ck into the (local) border, U_kk / g_k per block (camera order)
       Buck.zero(s);
@@ -551,14 +563,21 @@ struct b200sfm_ba_problem {
     if (points_var) B200_LAUNCH(ctx, ba_damp_points, cdiv(P, 256), 256, 0, P, V.p, jscale_p.p, set_jscale_p ? 1 : 0, radius, Vinv.p);
     B200_LAUNCH(ctx, ba_damp_cams, cdiv(nC6, 256), 256, 0, C, U(), jscale_c.p, radius, Dc.p);
     const bool schur_jacobi = points_var && o.preconditioner == 1;
-    if (schur_jacobi) {
-      Sd.zero(s);
-      if (n_segs > 0) {
-        if (use_v2) B200_LAUNCH(ctx, ba2_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p);
-        else B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
-      }
-      ctx->allreduce_sum(Sd.p, (size_t)C * 21);
+    double* yrhs = Sd.p + (size_t)C * 21;   // W Vinv g_p accumulates next to Sd so that both share one all-reduce
+    Sd.zero(s);
+    if (schur_jacobi && n_segs > 0) {
+      if (use_v2) B200_LAUNCH(ctx, ba2_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p);
+      else B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
     }
+    if (points_var) {
+      if (use_v2) {
+        B200_LAUNCH(ctx, ba2_point_rhs_z, cdiv(P, 256), 256, 0, v, view2());
+        if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yrhs, nullptr);
+      } else {
+        B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yrhs, nullptr, nullptr, radius, nullptr);
+      }
+    }
+    if (schur_jacobi || points_var) ctx->allreduce_sum(Sd.p, (size_t)C * 27);
     B200_LAUNCH(ctx, ba_build_precond, cdiv(C, 128), 128, 0, C, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
     const int m = m_intr;
     const int npair = m * (m + 1) / 2, nacc = npair + m;
@@ -631,72 +650,62 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaMemcpyAsync(vvec.p, vv.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
       B200_CUDA_OK(cudaStreamSynchronize(s));   // vv is a local
     }
-    // right-hand side b = -(gc - W Vinv gp)
-    if (points_var) {
-      yw.zero(s);
-      if (use_v2) {
-        B200_LAUNCH(ctx, ba2_point_rhs_z, cdiv(P, 256), 256, 0, v, view2());
-        if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
-      } else {
-        B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yw.p, nullptr, nullptr, radius, nullptr);
-      }
-      ctx->allreduce_sum(yw.p, nC6);
-    }
-    B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yw.p : nullptr, bvec.p);
+    // right-hand side b = -(gc - W Vinv gp)   (W Vinv gp was accumulated above, next to Sd)
+    B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yrhs : nullptr, bvec.p);
     if (m > 0) B200_LAUNCH(ctx, ba_border_rhs, cdiv(nC6, 256), 256, 0, C, m, Bmat.p, vvec.p, jscale_c.p, bvec.p);
-    // ---- PCG ------------------------------------------------------------------
+    // ---- PCG (loop control on the device, iterations queued ahead of the read-back: pcg.cuh) --------
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(C, kPcgThreads);
-    if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
-    if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
-    double* part_pq = part.p;
-    double* part_rz = part.p + nblk;
-    double* part_rr = part.p + 2 * (size_t)nblk;
-    B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
-    B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaStreamSynchronize(s));
-    const double rr0 = ctx->h_scal[2];
+    pcgh.ensure(max_it, (size_t)nblk * 3);
+    double* part_pq = pcgh.d_part;
+    double* part_rz = pcgh.d_part + nblk;
+    double* part_rr = pcgh.d_part + 2 * (size_t)nblk;
+    PcgCtl* ctl = pcgh.d_ctl;
     StepResult res;
-    int it = 0;
-    if (rr0 > 0.0 && std::isfinite(rr0)) {
-      const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * rr0;
-      for (it = 1; it <= max_it; ++it) {
-        double* d_prev = dots.p + (size_t)(it - 1) * 4;
-        double* d_it = dots.p + (size_t)it * 4;
-        if (points_var) {
-          cudaEvent_t e0 = nullptr, e1 = nullptr;
-          if (profile) {
-            e0 = timer_mv.next();
-            e1 = timer_mv.next();
-            B200_CUDA_OK(cudaEventRecord(e0, s));
+    const size_t mv_ev0 = timer_mv.used;
+    PcgResult pr_ = pcgh.run(
+        s, max_it,
+        [&]() { B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
+        [&](int it) {
+          double* d_pp = pcgh.dots(it - 2);
+          double* d_pub = pcgh.dots(it - 1);
+          double* d_it = pcgh.dots(it);
+          if (points_var && use_v2)
+            B200_LAUNCH(ctx, ba2_pcg_direction_pack, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance,
+                        pz.p, pp.p, yw.p, d_pp, part_rz, part_rr, d_pub, ctl, cam_rec.p, xq.p);
+          else
+            B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
+                        pp.p, yw.p, d_pp, part_rz, part_rr, nullptr, d_pub, ctl);
+          if (points_var) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (profile) {
+              e0 = timer_mv.next();
+              e1 = timer_mv.next();
+              B200_CUDA_OK(cudaEventRecord(e0, s));
+            }
+            if (use_v2) {
+              B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
+              if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p, ctl);
+            } else {
+              B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr, nullptr,
+                          nullptr, 0, ctl);
+            }
+            if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
+            ctx->allreduce_sum(yw.p, nC6);
           }
-          if (use_v2) {
-            B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, pp.p, cam_rec.p, xq.p);
-            B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr);
-            if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p);
-          } else {
-            B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr);
+          B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, part_pq, ctl);
+          if (m > 0) {   // q -= B Ck^-1 B^T p
+            B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, pp.p, part_bt.p);
+            B200_LAUNCH(ctx, pcg_border_apply, nblk, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, pp.p, pq.p, part_pq, nullptr);
           }
-          if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
-          ctx->allreduce_sum(yw.p, nC6);
-        }
-        B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, part_pq);
-        if (m > 0) {   // q -= B Ck^-1 B^T p
-          B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, pp.p, part_bt.p);
-          B200_LAUNCH(ctx, pcg_border_apply, nblk, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, pp.p, pq.p, part_pq, nullptr);
-        }
-        B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq,
-                    part_rz, part_rr, d_it);
-        B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, C, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
-        B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        B200_CUDA_OK(cudaStreamSynchronize(s));
-        const double rr = ctx->h_scal[2];
-        if (!std::isfinite(rr)) { res.finite = false; break; }
-        if (it >= o.pcg_min_iterations && rr <= tol2) break;
-      }
-      if (it > max_it) it = max_it;
-    }
+          B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
+                      part_rr, d_it, ctl);
+        },
+        [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
+    res.finite = pr_.finite;
+    const int it = pr_.iters;
+    // the queued-ahead iterations after the stopping rule fired were no-ops: keep only the real mat-vecs in the timer
+    if (profile && points_var) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);
     res.pcg_iters = it;
     // ---- back-substitution + candidate ------------------------------------------
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));
@@ -735,7 +744,7 @@ struct b200sfm_ba_problem {
     }
     if (points_var && use_v2) {
       B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
-      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p);
+      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
       const int nb = std::min(cdiv(n_tiles, 256), 296);
       B200_LAUNCH(ctx, ba2_sum4_stage1, nb, 256, 0, n_tiles, bpart.p, bpart2.p);
       B200_LAUNCH(ctx, ba_colsum, 4, 256, 0, nb, 4, bpart2.p, scal.p + 2);

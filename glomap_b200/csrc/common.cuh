@@ -51,6 +51,10 @@ struct CudaError {
   int line;
   CudaError(std::string m, int l) : msg(std::move(m)), line(l) {}
 };
+// caller-supplied indices out of range (found on the host or by a device-side check): B200SFM_ERR_INVALID_ARG
+struct InvalidInput {
+  std::string msg;
+};
 
 // ---------------------------------------------------------------------------
 // TMA 1-D bulk copies (cp.async.bulk) + mbarrier.  The W tiles are contiguous

@@ -17,6 +17,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;   // optional: error path only
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& err) {
@@ -31,6 +32,7 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    CommAbort = (decltype(CommAbort))dlsym(lib, "ncclCommAbort");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) {
@@ -62,11 +64,13 @@ struct b200sfm_ctx {
 
   void allreduce_sum(double* buf, size_t n) {
     if (world == 1 || n == 0) return;
+    if (!comm) throw NcclError{"communicator was aborted after an earlier failure"};
     ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclFloat64, ncclSum, comm, stream);
     if (r != ncclSuccess) throw NcclError{std::string("ncclAllReduce(sum): ") + nccl_api().GetErrorString(r)};
   }
   void allreduce_max(double* buf, size_t n) {
     if (world == 1 || n == 0) return;
+    if (!comm) throw NcclError{"communicator was aborted after an earlier failure"};
     ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclFloat64, ncclMax, comm, stream);
     if (r != ncclSuccess) throw NcclError{std::string("ncclAllReduce(max): ") + nccl_api().GetErrorString(r)};
   }

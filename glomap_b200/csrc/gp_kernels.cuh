@@ -301,9 +301,11 @@ __global__ void __launch_bounds__(128) gp_linearize_cams(GPView v, int with_schu
 __global__ void gp_finalize_cams(int C, const double* __restrict__ out16, const unsigned char* __restrict__ cam_const,
                                  double* __restrict__ jscale_c, int set_js, double radius, int with_schur,
                                  double* __restrict__ U, double* __restrict__ gc, double* __restrict__ Dc,
-                                 double* __restrict__ Minv, double* __restrict__ scal) {
+                                 double* __restrict__ Minv, double* __restrict__ scal,
+                                 const double* __restrict__ gslots, int nslots) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double gmax = 0.0;
+  if (blockIdx.x == 0 && threadIdx.x < nslots) gmax = gslots[threadIdx.x];   // per-rank max|g_X| slots (sum all-reduced)
   if (c < C) {
     const double* o = out16 + (size_t)c * 16;
     const double diag = o[9];
@@ -371,8 +373,10 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
                                                        const double* __restrict__ points,
                                                        const double* __restrict__ scales, double huber_a, double radius,
                                                        double* __restrict__ dX, double* __restrict__ ds,
-                                                       double* __restrict__ bscal) {
+                                                       double* __restrict__ bscal,
+                                                       const PcgCtl* __restrict__ ctl = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
+  if (ctl && ctl->done) return;   // the PCG stopping rule has fired: the queued iterations are no-ops
   G3Smem& sm = *reinterpret_cast<G3Smem*>(smem_raw);
   const int tile = blockIdx.x;
   const int p0 = v.tile_pt_begin[tile], p1 = v.tile_pt_begin[tile + 1];

@@ -28,7 +28,8 @@ struct b200sfm_gp_problem {
   DevBuf<double> cen4;
   // linear system
   DevBuf<double> M, bw, jscale_s, Vinv, gX, Dp, jscale_p, out16, U, gc, Dc, Minv, jscale_c;
-  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dots, part, dX, ds, scal;
+  DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dX, ds, scal;
+  b200::PcgHost pcgh;
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_g1 = 0, smem_g3 = 0;
 
@@ -71,6 +72,7 @@ struct b200sfm_gp_problem {
     for (int p = 0; p < P; ++p) {
       ptb[p] = (unsigned)h_pt_begin[p];
       const long long len = h_pt_begin[p + 1] - h_pt_begin[p];
+      if (len < 0) throw InvalidInput{"pt_obs_begin must be non-decreasing"};
       if (len >= min_views) {
         if (first_valid_obs < 0) first_valid_obs = h_pt_begin[p];
         n_obs_used += len;
@@ -97,12 +99,13 @@ struct b200sfm_gp_problem {
     if (h_cam_const) cam_const_base.upload(h_cam_const, C, s);
     else cam_const_base.zero(s);
     B200_LAUNCH(ctx, k_expand_obs_pt, cdiv(P, 256), 256, 0, P, pt_begin.p, obs_pt.p);
-    DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off;
+    DevBuf<int> keys, vals, keys_out, cam_count, seg_count, cam_begin, seg_off, bad;
     keys.alloc(N); vals.alloc(N); keys_out.alloc(N); camord_obs.alloc(N);
     cam_count.alloc((size_t)C + 1); seg_count.alloc((size_t)C + 1); cam_begin.alloc((size_t)C + 1); seg_off.alloc((size_t)C + 1);
-    cam_count.zero(s); seg_count.zero(s);
+    bad.alloc(1);
+    cam_count.zero(s); seg_count.zero(s); bad.zero(s);
     B200_LAUNCH(ctx, k_cam_keys, cdiv(N, 256), 256, 0, N, C, 1, min_views, obs_cam.p, nullptr, obs_pt.p, pt_begin.p, keys.p, vals.p,
-                cam_count.p);
+                cam_count.p, bad.p);
     int end_bit = 1;
     while ((1ll << end_bit) <= C) ++end_bit;
     size_t tmp_bytes = 0, scan_bytes = 0;
@@ -118,10 +121,12 @@ struct b200sfm_gp_problem {
     tb = tmp.bytes();
     cub::DeviceScan::ExclusiveSum(tmp.p, tb, seg_count.p, seg_off.p, C + 1, s);
     ctx->launches += 12;
-    int h_tot[2];
+    int h_tot[3];
     B200_CUDA_OK(cudaMemcpyAsync(&h_tot[0], cam_begin.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(&h_tot[1], seg_off.p + C, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(&h_tot[2], bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
+    if (h_tot[2]) throw InvalidInput{"obs_cam out of range [0, C)"};
     Nv = h_tot[0];
     n_segs = h_tot[1];
     seg_cam.alloc(std::max(n_segs, 1)); seg_begin.alloc(std::max(n_segs, 1)); seg_end.alloc(std::max(n_segs, 1));
@@ -135,7 +140,7 @@ struct b200sfm_gp_problem {
     cen4.alloc((size_t)C * 4);
     M.alloc((size_t)N * kMDoubles); bw.alloc((size_t)N * 4); jscale_s.alloc(N);
     Vinv.alloc((size_t)P * 6); gX.alloc((size_t)P * 3); Dp.alloc(P); jscale_p.alloc(P);
-    out16.alloc((size_t)C * 16 + 2); U.alloc((size_t)C * 6); gc.alloc((size_t)C * 3); Dc.alloc((size_t)C * 3);
+    out16.alloc((size_t)C * 16 + 1 + (size_t)ctx->world);   // per camera 16 | cost | one max|g_X| slot per rank U.alloc((size_t)C * 6); gc.alloc((size_t)C * 3); Dc.alloc((size_t)C * 3);
     Minv.alloc((size_t)C * 6); jscale_c.alloc(C);
     px.alloc((size_t)C * 3); pr.alloc((size_t)C * 3); pz.alloc((size_t)C * 3); pp.alloc((size_t)C * 3);
     pq.alloc((size_t)C * 3); yw.alloc((size_t)C * 3); bvec.alloc((size_t)C * 3);
@@ -221,11 +226,13 @@ struct b200sfm_gp_problem {
     const bool schur_jacobi = points_var && o.preconditioner == 1;
     if (n_segs > 0)
       B200_LAUNCH(ctx, gp_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, schur_jacobi ? 1 : 0, out16.p);
+    // cost and this rank's max|g_X| (own slot) travel with the camera blocks through ONE sum all-reduce
     B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)C * 16, scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    ctx->allreduce_sum(out16.p, (size_t)C * 16 + 1);
-    ctx->allreduce_max(scal.p + 1, 1);
+    B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)C * 16 + 1 + ctx->rank, scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    ctx->allreduce_sum(out16.p, (size_t)C * 16 + 1 + (size_t)ctx->world);
+    B200_CUDA_OK(cudaMemsetAsync(scal.p + 1, 0, sizeof(double), s));
     B200_LAUNCH(ctx, gp_finalize_cams, cdiv(C, 128), 128, 0, C, out16.p, cam_const.p, jscale_c.p, first ? 1 : 0, radius,
-                schur_jacobi ? 1 : 0, U.p, gc.p, Dc.p, Minv.p, scal.p);
+                schur_jacobi ? 1 : 0, U.p, gc.p, Dc.p, Minv.p, scal.p, out16.p + (size_t)C * 16 + 1, ctx->world);
     // rhs  (constant points have Vinv = 0 from G1, so the same passes apply)
     {
       yw.zero(s);
@@ -234,51 +241,43 @@ struct b200sfm_gp_problem {
       ctx->allreduce_sum(yw.p, nC3);
     }
     B200_LAUNCH(ctx, k_rhs, cdiv(nC3, 256), 256, 0, nC3, gc.p, yw.p, bvec.p);
-    // PCG (3x3 blocks)
+    // PCG (3x3 blocks; loop control on the device, pcg.cuh)
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(C, kPcgThreads);
-    if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
-    if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
-    double *part_pq = part.p, *part_rz = part.p + nblk, *part_rr = part.p + 2 * (size_t)nblk;
-    B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
-    B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, out16.p + (size_t)C * 16, sizeof(double), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 9, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaStreamSynchronize(s));
+    pcgh.ensure(max_it, (size_t)nblk * 3);
+    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
+    PcgCtl* ctl = pcgh.d_ctl;
     StepResult res;
-    res.cost = ctx->h_scal[8];
-    res.gmax = ctx->h_scal[9];
-    const double rr0 = ctx->h_scal[2];
-    int it = 0;
-    if (rr0 > 0.0 && std::isfinite(rr0)) {
-      const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * rr0;
-      for (it = 1; it <= max_it; ++it) {
-        double* d_prev = dots.p + (size_t)(it - 1) * 4;
-        double* d_it = dots.p + (size_t)it * 4;
-        {
+    const size_t mv_ev0 = timer_mv.used;
+    PcgResult pr_ = pcgh.run(
+        s, max_it,
+        [&]() { B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
+        [&](int it) {
+          double* d_pub = pcgh.dots(it - 1);
+          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
+                      pp.p, yw.p, pcgh.dots(it - 2), part_rz, part_rr, nullptr, d_pub, ctl);
           cudaEvent_t m0 = nullptr, m1 = nullptr;
           if (profile) {
             m0 = timer_mv.next(); m1 = timer_mv.next();
             B200_CUDA_OK(cudaEventRecord(m0, s));
           }
           B200_LAUNCH(ctx, gp_schur_pass<0>, n_tiles, kTile, smem_g3, v, pp.p, yw.p, nullptr, nullptr, nullptr, 0.0, radius,
-                      nullptr, nullptr, nullptr);
+                      nullptr, nullptr, nullptr, ctl);
           if (profile) B200_CUDA_OK(cudaEventRecord(m1, s));
           ctx->allreduce_sum(yw.p, nC3);
-        }
-        B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, C, U.p, Dc.p, pp.p, yw.p, pq.p, part_pq);
-        B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq,
-                    part_rz, part_rr, d_it);
-        B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, C, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
-        B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        B200_CUDA_OK(cudaStreamSynchronize(s));
-        const double rr = ctx->h_scal[2];
-        if (!std::isfinite(rr)) { res.finite = false; break; }
-        if (it >= o.pcg_min_iterations && rr <= tol2) break;
-      }
-      if (it > max_it) it = max_it;
-    }
+          B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, C, U.p, Dc.p, pp.p, yw.p, pq.p, part_pq, ctl);
+          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq,
+                      part_rz, part_rr, pcgh.dots(it), ctl);
+        },
+        [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
+    if (profile) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, out16.p + (size_t)C * 16, sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 9, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    res.cost = ctx->h_scal[8];
+    res.gmax = ctx->h_scal[9];
+    res.finite = pr_.finite;
+    const int it = pr_.iters;
     res.pcg_iters = it;
     // back-substitution (dX, ds) + step scalars
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));

@@ -1,23 +1,43 @@
 // pcg.cuh -- block-preconditioned conjugate gradients on the reduced camera
-// system, entirely stream-ordered on the device (no host sync inside an
-// iteration).  The reference factors this system with CHOLMOD
-// (bundle_adjustment.cc:94-96, global_positioning.cc:551-559); north_star
-// mandates PCG with one all-reduce per mat-vec.
+// system with the loop control ON THE DEVICE.  The reference factors this system
+// with CHOLMOD (bundle_adjustment.cc:94-96, global_positioning.cc:551-559);
+// north_star mandates PCG with one all-reduce per mat-vec.
+//
+// Control flow.  A PcgCtl record in device memory holds the convergence state.
+// The first kernel of iteration `it` (pcg_direction) re-sums the partial inner
+// products of iteration it-1 in a fixed order, evaluates the stopping rule and,
+// when it fires, sets ctl->done; every later kernel of the solve starts with
+// `if (ctl->done) return`.  The host therefore never has to wait for an
+// iteration before it launches the next one: it keeps `depth` iterations queued
+// ahead of the one whose control record it has read back (PcgHost::run), so the
+// GPU does not idle on a device->host->device round trip per iteration (at 8
+// GPUs that round trip was ~2/3 of the step).  depth = 1 is
+// the classic "synchronise every iteration" loop.
 //
 // All inner products are DETERMINISTIC: every CTA writes its partial sum to
 // part[which][blockIdx.x] and the consuming kernel re-sums the partials in a
-// fixed order.  With replicated camera-sized vectors this makes alpha, beta and
-// the convergence test bit-identical on every rank, so all ranks take the same
-// control-flow decisions without an extra collective.
+// fixed order.  With replicated camera-sized vectors alpha, beta and the
+// stopping rule are bit-identical on every rank, all ranks set `done` in the
+// same iteration and launch the same number of collectives.
 //
-// Scalars: dots[it][0] = p.q, dots[it][1] = r.z after iteration it,
-// dots[it][2] = r.r after iteration it (it = 0: initial values).
+// Scalars: dots[k][0] = p.q of iteration k, dots[k][1] = r.z and dots[k][2] =
+// r.r after k iterations (k = 0: initial values).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr int kPcgThreads = 128;
+
+struct PcgCtl {
+  int done;     // 0 running, 1 converged, 2 non-finite residual, 3 iteration cap
+  int iters;    // iterations whose update is part of x
+  int pad0, pad1;
+  double tol2;  // rel_tol^2 * reference
+  double rr0;   // |r_0|^2
+};
 
 // fixed-order sum of n partials by the first warp of the CTA; result broadcast
 // through shared memory to all threads.
@@ -43,9 +63,11 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_apply_diag(int nb, const doub
                                                               const double* __restrict__ D,
                                                               const double* __restrict__ p,
                                                               const double* __restrict__ yw, double* __restrict__ q,
-                                                              double* __restrict__ part_pq) {
+                                                              double* __restrict__ part_pq,
+                                                              const PcgCtl* __restrict__ ctl) {
   constexpr int NP = B * (B + 1) / 2;
   __shared__ double scratch[32];
+  if (ctl->done) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double pq = 0.0;
   if (c < nb) {
@@ -66,6 +88,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_apply_diag(int nb, const doub
 }
 
 // alpha = rz / pq; x += alpha p; r -= alpha q; z = Minv r; partial r.z, r.r
+//   dots_prev = dots[it-1] (r.z published by pcg_direction of this iteration), dots_it = dots[it] (receives p.q)
 template <int B>
 __global__ void __launch_bounds__(kPcgThreads) pcg_update(int nb, int nblk, const double* __restrict__ Minv,
                                                           const double* __restrict__ p, const double* __restrict__ q,
@@ -73,10 +96,12 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update(int nb, int nblk, cons
                                                           double* __restrict__ z, const double* __restrict__ dots_prev,
                                                           const double* __restrict__ part_pq,
                                                           double* __restrict__ part_rz, double* __restrict__ part_rr,
-                                                          double* __restrict__ dots_it) {
+                                                          double* __restrict__ dots_it,
+                                                          const PcgCtl* __restrict__ ctl) {
   constexpr int NP = B * (B + 1) / 2;
   __shared__ double scratch[32];
   __shared__ double sh;
+  if (ctl->done) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const double pq = sum_partials(part_pq, nblk, &sh);
   const double rz = dots_prev[1];
@@ -106,43 +131,78 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_update(int nb, int nblk, cons
   write_partial(rr, part_rr, scratch);
 }
 
-// beta = rz_new / rz; p = z + beta p; clears the mat-vec accumulator yw;
-// CTA 0 publishes dots[it][1] = r.z, dots[it][2] = r.r
-template <int B>
-__global__ void __launch_bounds__(kPcgThreads) pcg_direction(int nb, int nblk, const double* __restrict__ z,
-                                                             double* __restrict__ p, double* __restrict__ yw,
-                                                             const double* __restrict__ dots_prev,
-                                                             const double* __restrict__ part_rz,
-                                                             const double* __restrict__ part_rr,
-                                                             double* __restrict__ dots_it) {
-  __shared__ double sh, sh2;
-  const double rzn = sum_partials(part_rz, nblk, &sh);
-  if (blockIdx.x == 0) {
-    const double rr = sum_partials(part_rr, nblk, &sh2);
-    if (threadIdx.x == 0) {
-      dots_it[1] = rzn;
-      dots_it[2] = rr;
+// Head of iteration `it` (>= 1), executed identically by every CTA: publish r.z / r.r after it-1 iterations, evaluate
+// the stopping rule on them and return beta.  Returns false when the solve is over (ctl->done set by CTA 0).
+//   dots_pub = dots[it-1]; dots_pp = dots[it-2] (it >= 2); part_ref: optional partials of the convergence reference
+//   (warm-started solves measure against |b|^2 instead of |r_0|^2)
+__device__ __forceinline__ bool pcg_direction_head(int nblk, int it, int min_it, double rel_tol,
+                                                   const double* __restrict__ dots_pp,
+                                                   const double* __restrict__ part_rz,
+                                                   const double* __restrict__ part_rr,
+                                                   const double* __restrict__ part_ref, double* __restrict__ dots_pub,
+                                                   PcgCtl* __restrict__ ctl, double* sh3, double& beta) {
+  if (ctl->done) return false;   // set by an earlier launch only (this launch decides below, identically in every CTA)
+  const double rzn = sum_partials(part_rz, nblk, sh3);
+  const double rr = sum_partials(part_rr, nblk, sh3 + 1);
+  double tol2;
+  bool stop;
+  int code = 1;
+  if (it == 1) {
+    const double ref2 = part_ref ? sum_partials(part_ref, nblk, sh3 + 2) : rr;
+    tol2 = rel_tol * rel_tol * ref2;
+    stop = !(ref2 > 0.0) || !isfinite(rr) || (min_it <= 0 && rr <= tol2);
+    if (!isfinite(rr)) code = 2;
+    beta = 0.0;
+  } else {
+    tol2 = ctl->tol2;
+    stop = !isfinite(rr) || (it - 1 >= min_it && rr <= tol2);
+    if (!isfinite(rr)) code = 2;
+    const double rz = dots_pp[1];
+    beta = (rz > 0.0) ? rzn / rz : 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    dots_pub[1] = rzn;
+    dots_pub[2] = rr;
+    if (it == 1) {
+      ctl->tol2 = tol2;
+      ctl->rr0 = rr;
+    }
+    if (stop) {
+      ctl->iters = it - 1;
+      ctl->done = code;
     }
   }
-  const double rz = dots_prev[1];
-  const double beta = (rz > 0.0) ? rzn / rz : 0.0;
+  return !stop;
+}
+
+// p = z + beta p (it == 1: p = z); clears the mat-vec accumulator yw
+template <int B>
+__global__ void __launch_bounds__(kPcgThreads) pcg_direction(int nb, int nblk, int it, int min_it, double rel_tol,
+                                                             const double* __restrict__ z, double* __restrict__ p,
+                                                             double* __restrict__ yw, const double* __restrict__ dots_pp,
+                                                             const double* __restrict__ part_rz,
+                                                             const double* __restrict__ part_rr,
+                                                             const double* __restrict__ part_ref,
+                                                             double* __restrict__ dots_pub, PcgCtl* __restrict__ ctl) {
+  __shared__ double sh3[3];
+  double beta;
+  if (!pcg_direction_head(nblk, it, min_it, rel_tol, dots_pp, part_rz, part_rr, part_ref, dots_pub, ctl, sh3, beta)) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < nb) {
 #pragma unroll
     for (int k = 0; k < B; ++k) {
       const size_t i = (size_t)c * B + k;
-      p[i] = z[i] + beta * p[i];
+      p[i] = (it == 1) ? z[i] : z[i] + beta * p[i];
       if (yw) yw[i] = 0.0;
     }
   }
 }
 
-// x = 0; r = b; z = Minv r; p = z; yw = 0; partial r.z, r.r
+// x = 0; r = b; z = Minv r; partial r.z, r.r   (p is set by pcg_direction of iteration 1)
 template <int B>
 __global__ void __launch_bounds__(kPcgThreads) pcg_init(int nb, const double* __restrict__ Minv,
                                                         const double* __restrict__ b, double* __restrict__ x,
                                                         double* __restrict__ r, double* __restrict__ z,
-                                                        double* __restrict__ p, double* __restrict__ yw,
                                                         double* __restrict__ part_rz, double* __restrict__ part_rr) {
   constexpr int NP = B * (B + 1) / 2;
   __shared__ double scratch[32];
@@ -158,7 +218,6 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_init(int nb, const double* __
       rv[k] = b[i];
       x[i] = 0.0;
       r[i] = rv[k];
-      if (yw) yw[i] = 0.0;
       rr += rv[k] * rv[k];
     }
     sym_packed_mul<B>(m, rv, zv);
@@ -166,7 +225,6 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_init(int nb, const double* __
     for (int k = 0; k < B; ++k) {
       const size_t i = (size_t)c * B + k;
       z[i] = zv[k];
-      p[i] = zv[k];
       rz += rv[k] * zv[k];
     }
   }
@@ -174,18 +232,103 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_init(int nb, const double* __
   write_partial(rr, part_rr, scratch);
 }
 
-// dots0[1] = sum part_rz, dots0[2] = sum part_rr   (single CTA)
-__global__ void __launch_bounds__(kPcgThreads) pcg_publish_init(int nblk, const double* __restrict__ part_rz,
-                                                                const double* __restrict__ part_rr,
-                                                                double* __restrict__ dots0) {
-  __shared__ double sh, sh2;
-  const double rz = sum_partials(part_rz, nblk, &sh);
-  const double rr = sum_partials(part_rr, nblk, &sh2);
+// After the last launched iteration: the cap was reached without the stopping rule firing (single CTA).
+__global__ void __launch_bounds__(kPcgThreads) pcg_finalize(int nblk, int launched, const double* __restrict__ part_rr,
+                                                            PcgCtl* __restrict__ ctl) {
+  __shared__ double sh;
+  if (ctl->done) return;
+  const double rr = sum_partials(part_rr, nblk, &sh);
   if (threadIdx.x == 0) {
-    dots0[0] = 0.0;
-    dots0[1] = rz;
-    dots0[2] = rr;
+    ctl->iters = launched;
+    ctl->done = isfinite(rr) ? 3 : 2;
   }
 }
+
+// ---------------------------------------------------------------------------
+// host side: speculative launch of the iterations
+// ---------------------------------------------------------------------------
+struct PcgResult {
+  int iters = 0;
+  int launched = 0;
+  bool finite = true;
+  double rr0 = 0;
+};
+
+struct PcgHost {
+  static constexpr int kMaxDepth = 8;
+  PcgCtl* h_slots = nullptr;   // pinned
+  cudaEvent_t ev[kMaxDepth + 1] = {};
+  PcgCtl* d_ctl = nullptr;
+  double* d_dots = nullptr;
+  double* d_part = nullptr;
+  size_t n_dots = 0, n_part = 0;
+  int depth = 2;
+
+  PcgHost() = default;
+  PcgHost(const PcgHost&) = delete;
+  PcgHost& operator=(const PcgHost&) = delete;
+  ~PcgHost() {
+    if (h_slots) cudaFreeHost(h_slots);
+    for (auto e : ev)
+      if (e) cudaEventDestroy(e);
+    if (d_ctl) cudaFree(d_ctl);
+    if (d_dots) cudaFree(d_dots);
+    if (d_part) cudaFree(d_part);
+  }
+  // dots: (max_it + 2) x 4 doubles; part: n_part doubles (caller's layout)
+  void ensure(int max_it, size_t part_doubles) {
+    if (!h_slots) {
+      B200_CUDA_OK(cudaMallocHost(&h_slots, sizeof(PcgCtl) * (kMaxDepth + 1)));
+      for (auto& e : ev) B200_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      B200_CUDA_OK(cudaMalloc(&d_ctl, sizeof(PcgCtl)));
+      const char* d = getenv("B200SFM_PCG_DEPTH");
+      if (d) depth = std::min(std::max(atoi(d), 1), (int)kMaxDepth);
+    }
+    const size_t need = (size_t)(max_it + 2) * 4;
+    if (n_dots < need) {
+      if (d_dots) cudaFree(d_dots);
+      B200_CUDA_OK(cudaMalloc(&d_dots, need * sizeof(double)));
+      n_dots = need;
+    }
+    if (n_part < part_doubles) {
+      if (d_part) cudaFree(d_part);
+      B200_CUDA_OK(cudaMalloc(&d_part, part_doubles * sizeof(double)));
+      n_part = part_doubles;
+    }
+  }
+  double* dots(int k) const { return d_dots + (size_t)std::max(k, 0) * 4; }
+
+  // init(): launches the kernels that leave r, z and the partial r.z / r.r of iteration 0;
+  // iter(it): launches iteration it = direction(it), mat-vec (+ all-reduce), apply_diag, update(it);
+  // final(launched): launches pcg_finalize.
+  template <class Init, class Iter, class Final>
+  PcgResult run(cudaStream_t s, int max_it, Init&& init, Iter&& iter, Final&& final) {
+    B200_CUDA_OK(cudaMemsetAsync(d_ctl, 0, sizeof(PcgCtl), s));
+    init();
+    const int nslots = depth + 1;
+    int launched = 0;
+    for (int it = 1; it <= max_it; ++it) {
+      if (it > depth) {
+        const int slot = (it - depth) % nslots;
+        B200_CUDA_OK(cudaEventSynchronize(ev[slot]));
+        if (h_slots[slot].done) break;
+      }
+      iter(it);
+      const int slot = it % nslots;
+      B200_CUDA_OK(cudaMemcpyAsync(&h_slots[slot], d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaEventRecord(ev[slot], s));
+      launched = it;
+    }
+    final(launched);
+    B200_CUDA_OK(cudaMemcpyAsync(&h_slots[0], d_ctl, sizeof(PcgCtl), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    PcgResult r;
+    r.iters = h_slots[0].iters;
+    r.launched = launched;
+    r.finite = h_slots[0].done != 2;
+    r.rr0 = h_slots[0].rr0;
+    return r;
+  }
+};
 
 }  // namespace b200

@@ -14,6 +14,7 @@
 // Node vectors [n][3] are replicated on every rank; edges are sharded.
 #pragma once
 #include "common.cuh"
+#include "pcg.cuh"
 
 namespace b200 {
 
@@ -221,7 +222,8 @@ __global__ void ra_scatter(RAView v, const double* __restrict__ w, int square, c
 
 // y += L(w^p) x :  t = w (x_j - x_i); y_j += t; y_i -= t
 __global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square, const double* __restrict__ x,
-                             double* __restrict__ y) {
+                             double* __restrict__ y, const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;   // the PCG stopping rule has fired: the queued iterations are no-ops
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= v.E) return;
   const int i = v.ei[e], j = v.ej[e];

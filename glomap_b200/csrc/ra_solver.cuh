@@ -22,7 +22,8 @@ struct b200sfm_ra_problem {
   bool has_grav = false;
   long long rows_total = 0;
   DevBuf<double> Rrel, w_edge, theta, res, w, b, z, u;
-  DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, dots, part, scal;
+  DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, part, scal;
+  b200::PcgHost pcgh;
 
   b200::RAView view() {
     b200::RAView v;
@@ -130,56 +131,43 @@ struct b200sfm_ra_problem {
     B200_CUDA_OK(cudaStreamSynchronize(s));   // host vectors go out of scope
   }
 
-  // x = L(w^p)^-1 rhs_vec by PCG (result in px); returns iterations
+  // x = L(w^p)^-1 rhs_vec by PCG (result in px); returns iterations.  Loop control on the device (pcg.cuh).
   int pcg_solve(const b200sfm_ra_opts& o, int square, const double* rhs_vec, bool& finite, bool warm = false) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     RAView v = view();
     const int nblk = cdiv(n, kPcgThreads);
     const int max_it = std::max(1, o.pcg_max_iterations);
-    if (dots.n < (size_t)(max_it + 2) * 4) dots.alloc((size_t)(max_it + 2) * 4);
-    if (part.n < (size_t)nblk * 3) part.alloc((size_t)nblk * 3);
-    double *part_pq = part.p, *part_rz = part.p + nblk, *part_rr = part.p + 2 * (size_t)nblk;
+    pcgh.ensure(max_it, (size_t)nblk * 3);
+    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
+    PcgCtl* ctl = pcgh.d_ctl;
     const int egrid = cdiv(std::max<long long>(E, 1), 256);
-    if (warm) {
-      // r0 = b - L x_prev (ADMM x-updates change little between iterations)
-      yw.zero(s);
-      if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, px.p, yw.p);
-      ctx->allreduce_sum(yw.p, (size_t)n * 3);
-      B200_LAUNCH(ctx, ra_pcg_init_warm, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, yw.p, pr.p, pz.p, pp.p, part_pq, part_rz, part_rr);
-      B200_LAUNCH(ctx, ra_publish_warm, 1, kPcgThreads, 0, nblk, part_pq, part_rz, part_rr, dots.p);
-    } else {
-      B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, pp.p, yw.p, part_rz, part_rr);
-      B200_LAUNCH(ctx, pcg_publish_init, 1, kPcgThreads, 0, nblk, part_rz, part_rr, dots.p);
-    }
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, dots.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    B200_CUDA_OK(cudaStreamSynchronize(s));
-    const double rr0 = ctx->h_scal[2];
-    const double ref2 = warm ? ctx->h_scal[3] : rr0;
-    int it = 0;
-    finite = std::isfinite(rr0);
-    if (!(ref2 > 0.0) || !finite) return 0;
-    const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance * ref2;
-    if (rr0 <= tol2) return 0;
-    const int check_every = 4;   // convergence is polled every few iterations (host sync)
-    for (it = 1; it <= max_it; ++it) {
-      double* d_prev = dots.p + (size_t)(it - 1) * 4;
-      double* d_it = dots.p + (size_t)it * 4;
-      if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, pp.p, yw.p);
-      ctx->allreduce_sum(yw.p, (size_t)n * 3);
-      B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq);
-      B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_prev, part_pq, part_rz,
-                  part_rr, d_it);
-      B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk, pz.p, pp.p, yw.p, d_prev, part_rz, part_rr, d_it);
-      if (it % check_every == 0 || it == max_it) {
-        B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, d_it, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        B200_CUDA_OK(cudaStreamSynchronize(s));
-        const double rr = ctx->h_scal[2];
-        if (!std::isfinite(rr)) { finite = false; break; }
-        if (rr <= tol2) break;
-      }
-    }
-    return std::min(it, max_it);
+    PcgResult r = pcgh.run(
+        s, max_it,
+        [&]() {
+          if (warm) {
+            // r0 = b - L x_prev (ADMM x-updates change little between iterations); reference = |b|^2 (partials in part_pq)
+            yw.zero(s);
+            if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, px.p, yw.p, nullptr);
+            ctx->allreduce_sum(yw.p, (size_t)n * 3);
+            B200_LAUNCH(ctx, ra_pcg_init_warm, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, yw.p, pr.p, pz.p, pp.p, part_pq, part_rz, part_rr);
+          } else {
+            B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, part_rz, part_rr);
+          }
+        },
+        [&](int it) {
+          double* d_pub = pcgh.dots(it - 1);
+          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk, it, 0, o.pcg_rel_tolerance, pz.p, pp.p, yw.p,
+                      pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
+          if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, pp.p, yw.p, ctl);
+          ctx->allreduce_sum(yw.p, (size_t)n * 3);
+          B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq, ctl);
+          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
+                      part_rr, pcgh.dots(it), ctl);
+        },
+        [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
+    finite = r.finite;
+    return r.iters;
   }
 
   // weights w -> Laplacian diagonal + preconditioner, rhs = A^T diag(w^p) vec

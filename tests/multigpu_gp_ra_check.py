@@ -18,7 +18,7 @@ def _p(a):
     return a.ctypes.data_as(ct.c_void_p)
 
 
-def gp_solve(ctx, sc, t_obs, c0, X0, a, b):
+def gp_solve(ctx, sc, t_obs, c0, X0, a, b, fixed_iters=0):
     """b200sfm_gp_solve on the point range [a, b) of the scene."""
     o0, o1 = int(sc.pt_obs_begin[a]), int(sc.pt_obs_begin[b])
     ptb = np.ascontiguousarray(sc.pt_obs_begin[a:b + 1] - o0, np.int64)
@@ -30,6 +30,7 @@ def gp_solve(ctx, sc, t_obs, c0, X0, a, b):
     opts.solver_options.pcg_max_iterations = 3000
     opts.solver_options.function_tolerance = 1e-12
     opts.solver_options.max_num_iterations = 200
+    opts.fixed_num_iterations = fixed_iters
     co = opts.to_c()
     st = _lib.LMStats()
     rc = ctx.lib.b200sfm_gp_solve(ctx.handle, ct.byref(co), sc.C, b - a, o1 - o0, _p(ptb), _p(cam), _p(dirs), None, None,
@@ -64,6 +65,14 @@ def main():
     c0 = 100 * rng.uniform(-1, 1, size=(sc.C, 3)); X0 = 100 * rng.uniform(-1, 1, size=(sc.P, 3))
     a, b = D.shard_range(sc.P, 500, rank, world)
     cen, st = gp_solve(ctx, sc, t_obs, c0, X0, a, b)
+    # trajectory parity.  From the reference's random start (100 U(-1,1), global_positioning.cc:123-165) the first LM
+    # iterations are chaotic: the 1e-16 differences of a different summation order are amplified until line-search /
+    # accept decisions flip, so iteration COUNTS from a random start are not comparable (round 1 saw 39 vs 15 to the
+    # same cost).  The comparable quantity is the cost after a fixed number of iterations from a start inside the
+    # basin of attraction (ground truth perturbed by 1 %): it must agree to rounding.
+    cg = G.centers_from_pose(G.quat_xyzw_to_rotmat(sc.quat), sc.trans)
+    c_near = cg + 0.1 * rng.normal(size=cg.shape); X_near = sc.points + 0.03 * rng.normal(size=sc.points.shape)
+    gtraj = [gp_solve(ctx, sc, t_obs, c_near, X_near, a, b, fixed_iters=k)[1].final_cost for k in (1, 2, 3, 5)]
     # ---- RA -----------------------------------------------------------------------------------
     vg = S.make_random_view_graph(400, 14, seed=9, noise_deg=1.0, outlier_ratio=0.05)
     lo, hi = D.shard_range(vg.E, 64, rank, world)
@@ -71,13 +80,16 @@ def main():
     if rank == 0:
         one = E.Context(local)
         cen1, st1 = gp_solve(one, sc, t_obs, c0, X0, 0, sc.P)
+        gtraj1 = [gp_solve(one, sc, t_obs, c_near, X_near, 0, sc.P, fixed_iters=k)[1].final_cost for k in (1, 2, 3, 5)]
+        print("GP cost after k LM iterations, multi vs single:", list(zip(gtraj, gtraj1)))
+        ok_traj = all(abs(a_ - b_) <= 1e-8 * b_ for a_, b_ in zip(gtraj, gtraj1))
         s_, R_, t_ = G.umeyama_sim3(cen, cen1)
         gerr = np.linalg.norm((s_ * (R_ @ cen.T)).T + t_ - cen1, axis=1).max() / np.abs(cen1).max()
         th1, rst1 = ra_solve(one, vg, np.zeros((vg.n_images, 3)), 0, vg.E)
         rerr = np.abs(G.so3_exp(th) - G.so3_exp(th1)).max()
         print(f"GP multi({world})/single: its {st.iterations}/{st1.iterations} cost {st.final_cost:.10e}/{st1.final_cost:.10e} centre rel err {gerr:.2e}")
         print(f"RA multi({world})/single: L1 {rst.l1_iterations}/{rst1.l1_iterations} IRLS {rst.irls_iterations}/{rst1.irls_iterations} max |dR| {rerr:.2e}")
-        ok = (abs(st.final_cost - st1.final_cost) <= 1e-6 * max(st1.final_cost, 1e-12) + 1e-9 and gerr < 1e-5 and
+        ok = (ok_traj and abs(st.final_cost - st1.final_cost) <= 1e-6 * max(st1.final_cost, 1e-12) + 1e-9 and gerr < 1e-5 and
               (rst.l1_iterations, rst.irls_iterations) == (rst1.l1_iterations, rst1.irls_iterations) and rerr < 1e-7)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -9,8 +9,7 @@ import pytest
 from glomap_b200 import estimators as E, geometry as G, synthetic as S
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200SFM_UNVERIFIED_TESTS") != "1", reason="not yet validated on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,oi", [("const_intr", False), ("opt_intr", True)])

@@ -12,8 +12,7 @@ import pytest
 
 from glomap_b200 import geometry as G, mapper as M, synthetic as S
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200SFM_UNVERIFIED_TESTS") != "1", reason="not yet validated on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 def test_mapper_recovers_the_scene():
