@@ -213,6 +213,78 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
     for (int b = 0; b < 3; ++b) o.Jp[3 * a + b] = J[3 * a] * R[b] + J[3 * a + 1] * R[3 + b] + J[3 * a + 2] * R[6 + b];
 }
 
+// Lean per-observation core of design v2 (both traversal orders): everything downstream is rho' * (unscaled
+// Jacobian products), so sqrt(rho') is never formed -- one reciprocal and, for outliers only, one rsqrt:
+//   J   = d(pixel)/d(X_frame)  2x3, unscaled (chained through the constant cam_from_rig of a known rig)
+//   e   = pixel residual, rho0 = rho(|e|^2), rho1 = rho'(|e|^2)  (Huber; corrector with rho'' <= 0 => rows * sqrt(rho'))
+//   RX  = R X (the rotated point, for the rotation block), R = R(q)
+// valid == false (point behind the camera): the observation contributes nothing (ObsLin convention).
+struct ObsCore {
+  double J[6], e[2], rho0, rho1, RX[3], R[9];
+  bool valid;
+};
+__device__ __forceinline__ void obs_core(const double4& q4, const double4& t4, const double* __restrict__ ir,
+                                         const double* __restrict__ sr, double X0, double X1, double X2, double2 xy,
+                                         double huber_a, ObsCore& o) {
+  const double q[4] = {q4.x, q4.y, q4.z, q4.w};
+  quat_to_R(q, o.R);
+  o.RX[0] = o.R[0] * X0 + o.R[1] * X1 + o.R[2] * X2;
+  o.RX[1] = o.R[3] * X0 + o.R[4] * X1 + o.R[5] * X2;
+  o.RX[2] = o.R[6] * X0 + o.R[7] * X1 + o.R[8] * X2;
+  double xc = o.RX[0] + t4.x, yc = o.RX[1] + t4.y, zc = o.RX[2] + t4.z;
+  if (sr) sensor_apply(sr, xc, yc, zc);
+  o.valid = zc > kZEps;
+  if (!o.valid) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.J[k] = 0.0;
+    o.e[0] = o.e[1] = 0.0;
+    o.rho0 = 0.0;
+    o.rho1 = 0.0;
+    return;
+  }
+  double px, py;
+  project_jac(ir, xc, yc, zc, px, py, o.J);
+  if (sr) {   // chain through the constant cam_from_rig rotation: J <- J R_cr
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const double j0 = o.J[3 * a], j1 = o.J[3 * a + 1], j2 = o.J[3 * a + 2];
+      o.J[3 * a] = j0 * sr[0] + j1 * sr[3] + j2 * sr[6];
+      o.J[3 * a + 1] = j0 * sr[1] + j1 * sr[4] + j2 * sr[7];
+      o.J[3 * a + 2] = j0 * sr[2] + j1 * sr[5] + j2 * sr[8];
+    }
+  }
+  o.e[0] = px - xy.x;
+  o.e[1] = py - xy.y;
+  const double s = o.e[0] * o.e[0] + o.e[1] * o.e[1];
+  const double b = huber_a * huber_a;
+  if (s > b) {   // Ceres HuberLoss: rho = 2 a sqrt(s) - a^2, rho' = a / sqrt(s)
+    const double t = rsqrt(s);
+    o.rho1 = fmax(2.2250738585072014e-308, huber_a * t);
+    o.rho0 = 2.0 * huber_a * (s * t) - b;
+  } else {
+    o.rho0 = s;
+    o.rho1 = 1.0;
+  }
+}
+// point block J_pt = J R (2x3, unscaled) -> A = rho' J_pt^T J_pt (packed symmetric), b = rho' J_pt^T e
+__device__ __forceinline__ void obs_point_blocks(const ObsCore& o, double Jp[6], double A[6], double b[3]) {
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Jp[3 * a + c] = o.J[3 * a] * o.R[c] + o.J[3 * a + 1] * o.R[3 + c] + o.J[3 * a + 2] * o.R[6 + c];
+  const double s0 = o.rho1 * Jp[0], s1 = o.rho1 * Jp[1], s2 = o.rho1 * Jp[2];
+  const double s3 = o.rho1 * Jp[3], s4 = o.rho1 * Jp[4], s5 = o.rho1 * Jp[5];
+  A[0] = s0 * Jp[0] + s3 * Jp[3];
+  A[1] = s0 * Jp[1] + s3 * Jp[4];
+  A[2] = s0 * Jp[2] + s3 * Jp[5];
+  A[3] = s1 * Jp[1] + s4 * Jp[4];
+  A[4] = s1 * Jp[2] + s4 * Jp[5];
+  A[5] = s2 * Jp[2] + s5 * Jp[5];
+  b[0] = s0 * o.e[0] + s3 * o.e[1];
+  b[1] = s1 * o.e[0] + s4 * o.e[1];
+  b[2] = s2 * o.e[0] + s5 * o.e[1];
+}
+
 // ---------------------------------------------------------------------------
 // camera / intrinsics records
 // ---------------------------------------------------------------------------

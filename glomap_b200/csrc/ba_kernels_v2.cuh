@@ -108,36 +108,43 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
   for (int k = 0; k < 21; ++k) U[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) g[k] = 0.0;
+  const int cmask = (int)(__double_as_longlong(t4c.w) & 0xff);
+  const bool tvar = !(cmask & 2), rvar = !(cmask & 1);
   double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
   for (int i = b + lane; i < e; i += 32, row += kJcDoubles * 32) {
     const int pt = ld_stream(v.pt_c + i);
     const double2 xy = ld_stream(v.xy_c + i);
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
-    ObsLin o;
-    linearize_obs(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
-    st_stream(row, o.Jp[0] * o.Jp[0] + o.Jp[3] * o.Jp[3]);
-    st_stream(row + 32, o.Jp[0] * o.Jp[1] + o.Jp[3] * o.Jp[4]);
-    st_stream(row + 64, o.Jp[0] * o.Jp[2] + o.Jp[3] * o.Jp[5]);
-    st_stream(row + 96, o.Jp[1] * o.Jp[1] + o.Jp[4] * o.Jp[4]);
-    st_stream(row + 128, o.Jp[1] * o.Jp[2] + o.Jp[4] * o.Jp[5]);
-    st_stream(row + 160, o.Jp[2] * o.Jp[2] + o.Jp[5] * o.Jp[5]);
+    ObsCore o;
+    obs_core(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
+    double Jp[6], A[6], bo[3];
+    obs_point_blocks(o, Jp, A, bo);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) st_stream(row + 32 * k, A[k]);
     st_stream(row + 192, X0);
     st_stream(row + 224, X1);
     st_stream(row + 256, X2);
+    // camera blocks: J_t = J, J_r = J (-2 [R X]x)  (EigenQuaternionManifold: left perturbation of angle 2|d|), masked;
+    // U += rho' Jc^T Jc, g += rho' Jc^T e
     double Jc[2][6];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        Jc[a][k] = o.Jr[3 * a + k];
-        Jc[a][3 + k] = o.Jt[3 * a + k];
-      }
+    for (int a = 0; a < 2; ++a) {
+      const double j0 = o.J[3 * a], j1 = o.J[3 * a + 1], j2 = o.J[3 * a + 2];
+      Jc[a][0] = rvar ? -2.0 * (j1 * o.RX[2] - j2 * o.RX[1]) : 0.0;
+      Jc[a][1] = rvar ? -2.0 * (j2 * o.RX[0] - j0 * o.RX[2]) : 0.0;
+      Jc[a][2] = rvar ? -2.0 * (j0 * o.RX[1] - j1 * o.RX[0]) : 0.0;
+      Jc[a][3] = tvar ? j0 : 0.0;
+      Jc[a][4] = tvar ? j1 : 0.0;
+      Jc[a][5] = tvar ? j2 : 0.0;
+    }
+    const double e0 = o.rho1 * o.e[0], e1 = o.rho1 * o.e[1];
     int idx = 0;
 #pragma unroll
     for (int i2 = 0; i2 < 6; ++i2) {
+      const double s0 = o.rho1 * Jc[0][i2], s1 = o.rho1 * Jc[1][i2];
 #pragma unroll
-      for (int j = i2; j < 6; ++j) U[idx++] += Jc[0][i2] * Jc[0][j] + Jc[1][i2] * Jc[1][j];
-      g[i2] += Jc[0][i2] * o.r[0] + Jc[1][i2] * o.r[1];
+      for (int j = i2; j < 6; ++j) U[idx++] += s0 * Jc[0][j] + s1 * Jc[1][j];
+      g[i2] += Jc[0][i2] * e0 + Jc[1][i2] * e1;
     }
   }
 #pragma unroll

@@ -13,6 +13,7 @@
 
 #include "ba_kernels.cuh"
 #include "ba_kernels_v2.cuh"
+#include "ba_kernels_v3.cuh"
 #include "filter_kernels.cuh"
 #include "context.cuh"
 #include "pcg.cuh"
@@ -144,6 +145,20 @@ struct b200sfm_ba_problem {
   size_t smem_ki = 0;
   // design v2 (compact rows, camera-order second pass)
   bool use_v2 = false;
+  // point side of v2 in the ELL-32 layout (ba_kernels_v3.cuh): one thread per point
+  bool use_ell = false;
+  int ell_groups = 0, ell_ctas = 0, ell_bpart_rows = 0;
+  long long ell_rows = 0;
+  DevBuf<int> ell_row0, ell_pt, ell_len, ell_slot, ell_cam;
+  DevBuf<double2> ell_xy;
+  DevBuf<unsigned short> ell_sensor;
+  DevBuf<double> ell_A, ell_part;
+  b200::EllView ell_view() {
+    b200::EllView e;
+    e.n_groups = ell_groups; e.row0 = ell_row0.p; e.pt = ell_pt.p; e.len = ell_len.p; e.cam = ell_cam.p; e.xy = ell_xy.p;
+    e.sensor = S > 0 ? ell_sensor.p : nullptr; e.A = ell_A.p;
+    return e;
+  }
   DevBuf<double> Jc, z4, xq, bpart, bpart2;
   size_t smem_k3v2 = 0;
   b200::BAViewV2 view2() {
@@ -324,6 +339,38 @@ struct b200sfm_ba_problem {
       n_rows_padded = h_rows;
     }
 
+    // ELL-32 point-order structure (ba_kernels_v3.cuh): windows of 1024 points sorted by track length, 32 per group
+    {
+      using Sort = cub::BlockRadixSort<unsigned, kEllWindow, 1, int>;
+      const int n_win = cdiv(P, kEllWindow);
+      ell_groups = n_win * (kEllWindow / 32);
+      ell_ctas = cdiv((long long)ell_groups * 32, kEllThreads);
+      ell_pt.alloc((size_t)ell_groups * 32); ell_len.alloc((size_t)ell_groups * 32); ell_slot.alloc(P);
+      ell_row0.alloc((size_t)ell_groups + 1);
+      DevBuf<int> grows;
+      grows.alloc((size_t)ell_groups + 1);
+      grows.zero(s);
+      B200_LAUNCH(ctx, (ell_sort_window<Sort>), n_win, kEllWindow, 0, P, min_views, pt_begin.p, ell_pt.p, ell_len.p, ell_slot.p, grows.p);
+      size_t need = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, grows.p, ell_row0.p, ell_groups + 1, s);
+      DevBuf<unsigned char> tmp3;
+      tmp3.alloc(need + 16);
+      size_t tb3 = tmp3.bytes();
+      cub::DeviceScan::ExclusiveSum(tmp3.p, tb3, grows.p, ell_row0.p, ell_groups + 1, s);
+      ctx->launches += 1;
+      int h_rows = 0;
+      B200_CUDA_OK(cudaMemcpyAsync(&h_rows, ell_row0.p + ell_groups, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      ell_rows = h_rows;
+      const size_t cells = (size_t)std::max<long long>(ell_rows, 1) * 32;
+      ell_cam.alloc(cells); ell_xy.alloc(cells); ell_A.alloc(cells * 6);
+      if (S > 0) ell_sensor.alloc(cells);
+      ell_part.alloc((size_t)ell_ctas * 4 + 8);
+      ell_bpart_rows = ell_ctas;
+      B200_LAUNCH(ctx, ell_scatter_obs, cdiv(N, 256), 256, 0, N, min_views, obs_pt.p, pt_begin.p, obs_cam.p, obs_xy.p,
+                  S > 0 ? obs_sensor.p : nullptr, ell_slot.p, ell_row0.p, ell_cam.p, ell_xy.p, S > 0 ? ell_sensor.p : nullptr);
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // temporaries go out of scope
+    }
     for (int i = 0; i < 2; ++i) {
       quat[i].alloc((size_t)C * 4); trans[i].alloc((size_t)C * 3); points[i].alloc((size_t)P * 3);
     }
@@ -358,7 +405,7 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(ba2_pass_a<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXqStride);
-    bpart.alloc((size_t)std::max(n_tiles, 1) * 4);
+    bpart.alloc((size_t)std::max(std::max(n_tiles, ell_bpart_rows), 1) * 4);
     bpart2.alloc(296 * 4);
     smem_ki = sizeof(KISmem) + 128;
     B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
@@ -413,13 +460,24 @@ struct b200sfm_ba_problem {
                 cam_intr.p, cam_mask.p, (which == cur ? intr.p : intr_cand.p), intr_model.p, cam_rec.p, intr_rec.p);
   }
 
+  // robust cost of points[which] under the current records -> scal[6] (this rank's shard)
+  void launch_cost(int which, double huber_a) {
+    using namespace b200;
+    if (use_ell) {
+      B200_LAUNCH(ctx, ba3_cost, ell_ctas, kEllThreads, 0, view(), ell_view(), cam_rec.p, intr_rec.p, points[which].p, huber_a, ell_part.p);
+      B200_LAUNCH(ctx, ba3_reduce_partials, 1, 256, 0, ell_ctas, ell_part.p, nullptr, scal.p + 6, nullptr);
+    } else {
+      const int grid = std::min(cdiv(N, 256), 148 * 8);
+      B200_LAUNCH(ctx, ba_cost, grid, 256, 0, view(), cam_rec.p, intr_rec.p, points[which].p, huber_a, scal.p + 6);
+    }
+  }
+
   // robust cost of state `which` -> host (synchronises)
   double eval_cost(int which, double huber_a) {
     using namespace b200;
     build_records(which);
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 6, 0, sizeof(double), ctx->stream));
-    const int grid = std::min(cdiv(N, 256), 148 * 8);
-    B200_LAUNCH(ctx, ba_cost, grid, 256, 0, view(), cam_rec.p, intr_rec.p, points[which].p, huber_a, scal.p + 6);
+    launch_cost(which, huber_a);
     ctx->allreduce_sum(scal.p + 6, 1);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p + 6, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -440,7 +498,11 @@ struct b200sfm_ba_problem {
       e1 = timer_lin.next();
       B200_CUDA_OK(cudaEventRecord(e0, s));
     }
-    if (use_v2)
+    if (use_ell) {
+      B200_LAUNCH(ctx, ba3_linearize_points, ell_ctas, kEllThreads, 0, v, ell_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a,
+                  points_var ? 1 : 0, ell_part.p, ell_part.p + ell_ctas);
+      B200_LAUNCH(ctx, ba3_reduce_partials, 1, 256, 0, ell_ctas, ell_part.p, ell_part.p + ell_ctas, scal.p, scal.p + 1);
+    } else if (use_v2)
       B200_LAUNCH(ctx, ba_linearize_points<true>, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
                   points_var ? 1 : 0, scal.p);
     else
@@ -684,7 +746,11 @@ struct b200sfm_ba_problem {
               B200_CUDA_OK(cudaEventRecord(e0, s));
             }
             if (use_v2) {
-              B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
+              if (use_ell)
+                B200_LAUNCH(ctx, ba3_pass_a<0>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius,
+                            nullptr, ctl);
+              else
+                B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
               if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p, ctl);
             } else {
               B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr, nullptr,
@@ -744,9 +810,14 @@ struct b200sfm_ba_problem {
     }
     if (points_var && use_v2) {
       B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
-      B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
-      const int nb = std::min(cdiv(n_tiles, 256), 296);
-      B200_LAUNCH(ctx, ba2_sum4_stage1, nb, 256, 0, n_tiles, bpart.p, bpart2.p);
+      const int nrow_part = use_ell ? ell_ctas : n_tiles;
+      if (use_ell)
+        B200_LAUNCH(ctx, ba3_pass_a<2>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
+                    bpart.p, nullptr);
+      else
+        B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
+      const int nb = std::min(cdiv(nrow_part, 256), 296);
+      B200_LAUNCH(ctx, ba2_sum4_stage1, nb, 256, 0, nrow_part, bpart.p, bpart2.p);
       B200_LAUNCH(ctx, ba_colsum, 4, 256, 0, nb, 4, bpart2.p, scal.p + 2);
     } else if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
@@ -757,8 +828,7 @@ struct b200sfm_ba_problem {
     B200_LAUNCH(ctx, ba_update_cams, cdiv(C, 128), 128, 0, C, quat[cur].p, trans[cur].p, px.p, gc(), pr.p, Dc.p, jscale_c.p,
                 quat[nxt].p, trans[nxt].p, scal.p + 8);
     build_records(nxt);
-    const int grid = std::min(cdiv(N, 256), 148 * 8);
-    B200_LAUNCH(ctx, ba_cost, grid, 256, 0, v, cam_rec.p, intr_rec.p, points[nxt].p, o.thres_loss_function, scal.p + 6);
+    launch_cost(nxt, o.thres_loss_function);
     // bscal[0..3] + cand cost are per-shard partial sums; cscal[8..12] is replicated but summed
     // with atomics (rank-dependent rounding): all-reduce everything and average the replicated
     // part so that every rank takes bit-identical accept/reject decisions.
@@ -822,6 +892,7 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaStreamSynchronize(s));
     }
     use_v2 = (m_intr == 0) && (o.design != 1);   // v2 (compact rows) unless the intrinsics border needs W
+    use_ell = use_v2 && !(getenv("B200SFM_ELL") && atoi(getenv("B200SFM_ELL")) == 0);   // point side: one thread per point
     // v2: keep z4 (written by pass A, gathered by pass B) in the persisting part of L2
     const bool l2_persist = use_v2 && !(getenv("B200SFM_L2_PERSIST") && atoi(getenv("B200SFM_L2_PERSIST")) == 0);
     if (l2_persist) l2_persist_window(s, ctx->device, z4.p, z4.bytes());

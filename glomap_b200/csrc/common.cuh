@@ -30,6 +30,15 @@ namespace b200 {
 #ifndef B200_PB_MIN_CTAS
 #define B200_PB_MIN_CTAS 9
 #endif
+#ifndef B200_E1_MIN_CTAS   // ELL point-side linearisation (one thread per point): CTAs of 128 threads per SM
+#define B200_E1_MIN_CTAS 4
+#endif
+#ifndef B200_EA_MIN_CTAS   // ELL pass A (mat-vec)
+#define B200_EA_MIN_CTAS 8
+#endif
+#ifndef B200_EA2_MIN_CTAS  // ELL pass A, back-substitution epilogue
+#define B200_EA2_MIN_CTAS 6
+#endif
 #ifndef B200_STREAM_HINTS  // evict-first loads/stores on the once-per-pass streams so the gathered arrays stay in L2
 #define B200_STREAM_HINTS 1
 #endif
