@@ -378,7 +378,9 @@ struct b200sfm_ba_problem {
     intr_cand.alloc((size_t)K * B200SFM_INTR_STRIDE);
     cam_rec.alloc((size_t)C * kCamRec); intr_rec.alloc((size_t)K * kIntrRec);
     W.alloc((size_t)N * kWDoubles); V.alloc((size_t)P * 6); Vinv.alloc((size_t)P * 6); gp.alloc((size_t)P * 3);
-    lin.alloc((size_t)C * 27 + 1 + (size_t)ctx->world);   // U | gc | cost | one max|g_p| slot per rank Sd.alloc((size_t)C * 27);   // Schur-Jacobi blocks | right-hand-side accumulator (one all-reduce for both) Minv.alloc((size_t)C * 21);
+    lin.alloc((size_t)C * 27 + 1 + (size_t)ctx->world);   // U | gc | cost | one max|g_p| slot per rank
+    Sd.alloc((size_t)C * 27);                              // Schur-Jacobi blocks | right-hand-side accumulator (one all-reduce for both)
+    Minv.alloc((size_t)C * 21);
     jscale_c.alloc((size_t)C * 6); jscale_p.alloc((size_t)P * 3); Dc.alloc((size_t)C * 6);
     px.alloc((size_t)C * 6); pr.alloc((size_t)C * 6); pz.alloc((size_t)C * 6); pp.alloc((size_t)C * 6);
     pq.alloc((size_t)C * 6); yw.alloc((size_t)C * 6); bvec.alloc((size_t)C * 6);

@@ -140,7 +140,8 @@ struct b200sfm_gp_problem {
     cen4.alloc((size_t)C * 4);
     M.alloc((size_t)N * kMDoubles); bw.alloc((size_t)N * 4); jscale_s.alloc(N);
     Vinv.alloc((size_t)P * 6); gX.alloc((size_t)P * 3); Dp.alloc(P); jscale_p.alloc(P);
-    out16.alloc((size_t)C * 16 + 1 + (size_t)ctx->world);   // per camera 16 | cost | one max|g_X| slot per rank U.alloc((size_t)C * 6); gc.alloc((size_t)C * 3); Dc.alloc((size_t)C * 3);
+    out16.alloc((size_t)C * 16 + 1 + (size_t)ctx->world);   // per camera 16 | cost | one max|g_X| slot per rank
+    U.alloc((size_t)C * 6); gc.alloc((size_t)C * 3); Dc.alloc((size_t)C * 3);
     Minv.alloc((size_t)C * 6); jscale_c.alloc(C);
     px.alloc((size_t)C * 3); pr.alloc((size_t)C * 3); pz.alloc((size_t)C * 3); pp.alloc((size_t)C * 3);
     pq.alloc((size_t)C * 3); yw.alloc((size_t)C * 3); bvec.alloc((size_t)C * 3);

@@ -14,7 +14,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <array>
 #include <map>
+#include <queue>
 #include <random>
 #include <string>
 #include <vector>
@@ -25,13 +27,54 @@
 namespace b200sfm_shim {
 using namespace b200host;
 
-inline b200sfm_ctx* DefaultContext(int device = 0) {
-  static b200sfm_ctx* ctx = nullptr;
-  if (!ctx && b200sfm_create(device, &ctx) != B200SFM_OK) {
-    std::fprintf(stderr, "b200sfm: no CUDA device / context creation failed (there is no CPU fallback)\n");
-    ctx = nullptr;
+// One context per CUDA device, created on first use.  `gpu_index` is the reference's option string
+// (bundle_adjustment.h:24, global_positioning.h:42: "-1" = the default device, otherwise the first index of a
+// comma-separated list -- the reference hands the list to Ceres/cuDSS, which uses one device as well).
+inline b200sfm_ctx* DefaultContext(const std::string& gpu_index = "-1") {
+  static std::map<int, b200sfm_ctx*> ctxs;
+  int device = 0;
+  try {
+    device = std::stoi(gpu_index);
+  } catch (...) {
+    device = -1;
   }
+  if (device < 0) device = 0;
+  auto it = ctxs.find(device);
+  if (it != ctxs.end()) return it->second;
+  b200sfm_ctx* ctx = nullptr;
+  if (b200sfm_create(device, &ctx) != B200SFM_OK) {
+    std::fprintf(stderr, "b200sfm: no CUDA device %d / context creation failed (there is no CPU fallback)\n", device);
+    return nullptr;   // not cached: a later call may name a valid device
+  }
+  ctxs[device] = ctx;
   return ctx;
+}
+
+// small quaternion helpers (xyzw, Eigen coeffs() order)
+inline void QuatMul(const double* a, const double* b, double* o) {   // o = a (x) b
+  const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const double y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  const double z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+inline void QuatConj(const double* a, double* o) { o[0] = -a[0]; o[1] = -a[1]; o[2] = -a[2]; o[3] = a[3]; }
+// colmap::AverageQuaternions with unit weights: dominant eigenvector of sum q q^T (sign-invariant), by power iteration
+inline void AverageQuaternions(const std::vector<std::array<double, 4>>& qs, double* out) {
+  double M[4][4] = {};
+  for (const auto& q : qs)
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) M[r][c] += q[r] * q[c];
+  double v[4] = {qs[0][0], qs[0][1], qs[0][2], qs[0][3]};
+  for (int it = 0; it < 200; ++it) {
+    double u[4] = {0, 0, 0, 0};
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) u[r] += M[r][c] * v[c];
+    const double n = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
+    if (!(n > 0)) break;
+    for (int k = 0; k < 4; ++k) v[k] = u[k] / n;
+  }
+  for (int k = 0; k < 4; ++k) out[k] = v[k];
 }
 
 inline void QuatToR(const double* q, double R[9]) {
@@ -85,7 +128,7 @@ class BundleAdjuster {
              std::unordered_map<track_t, Track>& tracks) {
     if (images.empty()) { std::fprintf(stderr, "Number of images = 0\n"); return false; }     // .cc:17-20
     if (tracks.empty()) { std::fprintf(stderr, "Number of tracks = 0\n"); return false; }     // .cc:21-24
-    b200sfm_ctx* ctx = DefaultContext();
+    b200sfm_ctx* ctx = DefaultContext(options_.gpu_index);
     if (!ctx) return false;
     // frames / cameras / tracks in sorted-id order
     std::map<frame_t, Frame*> fsorted;
@@ -105,7 +148,7 @@ class BundleAdjuster {
       for (int k = 0; k < 4; ++k) quat[4 * i + k] = f->RigFromWorld().rotation.coeffs_data()[k];
       for (int k = 0; k < 3; ++k) trans[3 * i + k] = f->RigFromWorld().translation[k];
     }
-    if (C > 0) mask[0] = 3;                                                                   // .cc:261-266 (first frame)
+    // the gauge frame is chosen below, once it is known which frames carry observations (.cc:252-266)
     for (auto& [id, c] : csorted) {
       const int k = cidx[id];
       intr_model[k] = c->model_id;
@@ -148,7 +191,11 @@ class BundleAdjuster {
     std::vector<double> obs_xy, points(3 * (size_t)P);
     int p = 0;
     for (auto& [id, t] : tsorted) {
+      // .cc:122: the track is skipped on ITS observation count; observations of missing images are dropped afterwards
+      // (.cc:125), so the device gets min_num_view_per_track = 1 and a skipped track simply carries no observation
+      const bool keep = (int)t->observations.size() >= options_.min_num_view_per_track;
       for (const auto& ob : t->observations) {
+        if (!keep) break;
         auto it = images.find(ob.first);
         if (it == images.end()) continue;                                                     // .cc:125
         obs_cam.push_back(fidx[it->second.frame_id]);
@@ -160,12 +207,18 @@ class BundleAdjuster {
       for (int k = 0; k < 3; ++k) points[3 * (size_t)p + k] = t->xyz[k];
       ++p;
     }
+    {   // .cc:252-266: the first frame (map order; here sorted-id order) that HAS a parameter block is held constant
+      std::vector<uint8_t> used(C, 0);
+      for (int32_t f : obs_cam) used[f] = 1;
+      for (int i = 0; i < C; ++i)
+        if (used[i]) { mask[i] = 3; break; }
+    }
     b200sfm_ba_opts o;
     b200sfm_ba_default_opts(&o);
     o.optimize_rig_poses = options_.optimize_rig_poses; o.optimize_rotations = options_.optimize_rotations;
     o.optimize_translation = options_.optimize_translation; o.optimize_intrinsics = options_.optimize_intrinsics;
     o.optimize_principal_point = options_.optimize_principal_point; o.optimize_points = options_.optimize_points;
-    o.min_num_view_per_track = options_.min_num_view_per_track;
+    o.min_num_view_per_track = 1;   // the track-length rule was applied above, on track.observations.size()
     o.max_num_iterations = options_.solver_options.max_num_iterations;
     o.thres_loss_function = options_.thres_loss_function;
     o.function_tolerance = options_.solver_options.function_tolerance;
@@ -238,7 +291,7 @@ class GlobalPositioner {
       std::fprintf(stderr, "b200sfm: only ONLY_POINTS is implemented\n");
       return false;
     }
-    b200sfm_ctx* ctx = DefaultContext();
+    b200sfm_ctx* ctx = DefaultContext(options_.gpu_index);
     if (!ctx) return false;
     std::map<frame_t, Frame*> fsorted;
     for (auto& [id, f] : frames) fsorted[id] = &f;
@@ -276,7 +329,9 @@ class GlobalPositioner {
     std::vector<double> obs_dir, points(3 * (size_t)P);
     int p = 0;
     for (auto& [id, t] : tsorted) {
+      const bool keep = (int)t->observations.size() >= options_.min_num_view_per_track;        // .cc:257-258
       for (const auto& ob : t->observations) {
+        if (!keep) break;
         auto it = images.find(ob.first);
         if (it == images.end() || !it->second.IsRegistered()) continue;                      // .cc:279-282
         const auto& b = it->second.features_undist[ob.second];
@@ -319,7 +374,8 @@ class GlobalPositioner {
     b200sfm_gp_opts o;
     b200sfm_gp_default_opts(&o);
     o.optimize_positions = options_.optimize_positions; o.optimize_points = options_.optimize_points;
-    o.optimize_scales = options_.optimize_scales; o.min_num_view_per_track = options_.min_num_view_per_track;
+    o.optimize_scales = options_.optimize_scales;
+    o.min_num_view_per_track = 1;   // the track-length rule was applied above, on track.observations.size()
     o.max_num_iterations = options_.solver_options.max_num_iterations;
     o.thres_loss_function = options_.thres_loss_function;
     o.function_tolerance = options_.solver_options.function_tolerance;
@@ -374,13 +430,116 @@ class RotationEstimator {
   explicit RotationEstimator(const RotationEstimatorOptions& options) : options_(options) {}
   b200sfm_ra_stats summary{};
 
+  // InitializeFromMaximumSpanningTree (global_rotation_averaging.cc:87-138 + math/tree.cc:78-153): Kruskal on
+  // (max #inliers - #inliers), BFS from the first registered image, composition of the relative rotations along the
+  // tree, then ConvertRotationsFromImageToRig (rotation_initializer.cc:7-120) for trivial frames and calibrated rigs:
+  // rig_from_world = average over the frame's images of cam_from_rig^-1 * cam_from_world.  Images are enumerated in
+  // sorted-id order (the reference: unordered_map order), so the root is the smallest registered image id.
+  void InitializeFromMaximumSpanningTree(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
+                                         std::unordered_map<frame_t, Frame>& frames,
+                                         std::unordered_map<image_t, Image>& images) {
+    auto registered = [&](const Image& im) {
+      auto f = frames.find(im.frame_id);
+      return f != frames.end() && f->second.is_registered;
+    };
+    std::map<image_t, int> idx;
+    std::vector<image_t> ids;
+    {
+      std::map<image_t, const Image*> isorted;
+      for (const auto& [id, im] : images) isorted[id] = &im;
+      for (const auto& [id, im] : isorted)
+        if (registered(*im)) { idx[id] = (int)ids.size(); ids.push_back(id); }
+    }
+    const int n = (int)ids.size();
+    if (n == 0) return;
+    struct Edge { double w; int a, b; const ImagePair* pr; };
+    std::map<image_pair_t, const ImagePair*> psorted;
+    double max_w = 0;
+    for (const auto& [id, pr] : view_graph.image_pairs)
+      if (pr.is_valid) { psorted[id] = &pr; max_w = std::max(max_w, (double)pr.inliers.size()); }   // tree.cc:93-100 (INLIER_NUM)
+    std::vector<Edge> edges;
+    for (const auto& [id, pr] : psorted) {
+      auto a = idx.find(pr->image_id1), b = idx.find(pr->image_id2);
+      if (a == idx.end() || b == idx.end()) continue;                                         // tree.cc:113-116
+      edges.push_back({max_w - (double)pr->inliers.size(), a->second, b->second, pr});
+    }
+    std::stable_sort(edges.begin(), edges.end(), [](const Edge& x, const Edge& y) { return x.w < y.w; });
+    std::vector<int> uf(n);
+    for (int i = 0; i < n; ++i) uf[i] = i;
+    auto find = [&](int x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+    std::vector<std::vector<std::pair<int, const ImagePair*>>> adj(n);
+    for (const Edge& e : edges) {
+      const int ra = find(e.a), rb = find(e.b);
+      if (ra == rb) continue;
+      uf[ra] = rb;
+      adj[e.a].push_back({e.b, e.pr});
+      adj[e.b].push_back({e.a, e.pr});
+    }
+    // BFS from index 0; cam_from_world rotation of the root = identity (default-constructed, .cc:112)
+    std::vector<std::array<double, 4>> q(n, {{0, 0, 0, 1}});
+    std::vector<char> seen(n, 0);
+    std::queue<int> bfs;
+    bfs.push(0);
+    seen[0] = 1;
+    while (!bfs.empty()) {
+      const int cur = bfs.front();
+      bfs.pop();
+      for (const auto& [nb, pr] : adj[cur]) {
+        if (seen[nb]) continue;
+        seen[nb] = 1;
+        const double* r21 = pr->cam2_from_cam1.rotation.coeffs_data();
+        if (pr->image_id1 == ids[nb]) {          // 1_R_w = 2_R_1^T * 2_R_w   (.cc:125-129)
+          double inv[4];
+          QuatConj(r21, inv);
+          QuatMul(inv, q[cur].data(), q[nb].data());
+        } else {                                 // 2_R_w = 2_R_1 * 1_R_w     (.cc:130-134)
+          QuatMul(r21, q[cur].data(), q[nb].data());
+        }
+        bfs.push(nb);
+      }
+    }
+    // ConvertRotationsFromImageToRig: per frame, average cam_from_rig^-1 * cam_from_world over its estimated images
+    std::map<frame_t, std::vector<std::array<double, 4>>> per_frame;
+    for (int i = 0; i < n; ++i) {
+      if (!seen[i]) continue;                    // not reached by the tree: not estimated (rotation_initializer.cc:101-102)
+      const Image& im = images.at(ids[i]);
+      std::array<double, 4> r = q[i];
+      if (!im.HasTrivialFrame()) {
+        Rig& rig = rigs[frames[im.frame_id].RigId()];
+        if (!b200host_adapt::IsRefSensor(rig, im.camera_id)) {
+          if (!b200host_adapt::HasCamFromRig(rig, im.camera_id)) continue;                    // .cc:108-111
+          const Rigid3d c = b200host_adapt::CamFromRig(rig, im.camera_id);
+          double inv[4];
+          QuatConj(c.rotation.coeffs_data(), inv);
+          QuatMul(inv, q[i].data(), r.data());
+        }
+      }
+      per_frame[im.frame_id].push_back(r);
+    }
+    for (auto& [fid, qs] : per_frame) {
+      double avg[4];
+      AverageQuaternions(qs, avg);
+      double* out = frames[fid].RigFromWorld().rotation.coeffs_data();
+      for (int k = 0; k < 4; ++k) out[k] = avg[k];
+    }
+  }
+
   // global_rotation_averaging.cc:40-85 (3-DoF frames and, with use_gravity, 1-DoF frames that carry a gravity
-  // prior; trivial frames and known rigs -- unknown cam_from_rig rotations are not estimated).  The spanning-tree initialisation is expected from the
-  // caller when skip_initialization is false (host-side, math/tree.cc).
+  // prior; trivial frames and known rigs -- unknown cam_from_rig rotations are not estimated).
   bool EstimateRotations(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
                          std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images) {
+    if (options_.use_gravity) {   // .cc:47-59: gravity-aligned averaging needs every rig calibrated
+      for (auto& [rig_id, rig] : rigs)
+        if (!b200host_adapt::AllSensorsCalibrated(rig)) {
+          std::fprintf(stderr, "Rig %u has an uncalibrated sensor, but the gravity aligned rotation is requested. "
+                               "Please add the rig calibration.\n", (unsigned)rig_id);
+          return false;
+        }
+    }
     b200sfm_ctx* ctx = DefaultContext();
     if (!ctx) return false;
+    if (!options_.skip_initialization && !options_.use_gravity)                               // .cc:60-63
+      InitializeFromMaximumSpanningTree(view_graph, rigs, frames, images);
     std::map<frame_t, Frame*> fsorted;
     for (auto& [id, f] : frames)
       if (f.is_registered) fsorted[id] = &f;

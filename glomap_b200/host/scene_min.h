@@ -14,6 +14,15 @@ namespace b200host_adapt {
 inline glomap::Rigid3d CamFromRig(glomap::Rig& rig, glomap::camera_t camera_id) {
   return rig.SensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id));
 }
+inline bool AllSensorsCalibrated(const glomap::Rig& rig) {
+  for (const auto& [sensor_id, sensor] : rig.NonRefSensors())
+    if (!sensor.has_value()) return false;
+  return true;
+}
+inline bool IsRefSensor(const glomap::Rig& rig, glomap::camera_t camera_id) { return rig.RefSensorId().id == camera_id; }
+inline bool HasCamFromRig(const glomap::Rig& rig, glomap::camera_t camera_id) {
+  return rig.MaybeSensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id)).has_value();
+}
 // GravityInfo::GetRAlign() (scene/frame.h:16) as row-major doubles
 inline void RAlignRowMajor(const glomap::Frame& f, double out[9]) {
   const Eigen::Matrix3d& R = f.gravity_info.GetRAlign();
@@ -56,9 +65,11 @@ struct Camera {
   std::vector<double> params;
   bool has_prior_focal_length = true;
 };
-struct Rig {   // colmap::Rig: one reference sensor (identity) + sensors with a cam_from_rig
+struct Rig {   // colmap::Rig: one reference sensor (identity) + non-reference sensors, calibrated (cam_from_rig) or not yet
   rig_t rig_id = 0;
-  std::map<camera_t, Rigid3d> cam_from_rig;
+  camera_t ref_camera_id = 0;                    // RefSensorId().id
+  std::map<camera_t, Rigid3d> cam_from_rig;      // calibrated non-reference sensors (MaybeSensorFromRig has a value)
+  std::vector<camera_t> uncalibrated;            // non-reference sensors without a cam_from_rig yet
   Rigid3d SensorFromRig(camera_t camera_id) const {
     auto it = cam_from_rig.find(camera_id);
     return it == cam_from_rig.end() ? Rigid3d{} : it->second;
@@ -117,6 +128,7 @@ struct ImagePair {
   image_t image_id1 = 0, image_id2 = 0;
   bool is_valid = true;
   double weight = -1;
+  std::vector<int> inliers;                      // scene/image_pair.h: indices of the inlier matches
   Rigid3d cam2_from_cam1;
 };
 struct ViewGraph {
@@ -130,6 +142,10 @@ inline image_pair_t ImagePairToPairId(image_t a, image_t b) {   // colmap::Image
 }  // namespace b200host
 namespace b200host_adapt {
 inline b200host::Rigid3d CamFromRig(b200host::Rig& rig, b200host::camera_t camera_id) { return rig.SensorFromRig(camera_id); }
+// every non-reference sensor of the rig has a cam_from_rig (global_rotation_averaging.cc:47-59)
+inline bool AllSensorsCalibrated(const b200host::Rig& rig) { return rig.uncalibrated.empty(); }
+inline bool IsRefSensor(const b200host::Rig& rig, b200host::camera_t camera_id) { return camera_id == rig.ref_camera_id; }
+inline bool HasCamFromRig(const b200host::Rig& rig, b200host::camera_t camera_id) { return rig.cam_from_rig.count(camera_id) != 0; }
 inline void RAlignRowMajor(const b200host::Frame& f, double out[9]) {
   for (int k = 0; k < 9; ++k) out[k] = f.gravity_info.R_align[k];
 }

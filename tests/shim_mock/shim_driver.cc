@@ -24,11 +24,11 @@ int main() {
     Camera cam; cam.camera_id = c; cam.model_id = 0; cam.params = {500.0 + c, 320.0, 240.0}; cam.has_prior_focal_length = (c != 2);
     cameras[c] = cam;
   }
-  Rig rig1; rig1.rig_id = 1;
+  Rig rig1; rig1.rig_id = 1; rig1.ref_camera_id = 1;
   Rigid3d c2r; SetQuat(c2r.rotation, 0.2, 1.0, -0.3, 0.35); c2r.translation = {{0.4, -0.1, 0.05}};
   rig1.cam_from_rig[2] = c2r;
   rigs[1] = rig1;
-  Rig rig2; rig2.rig_id = 2; rigs[2] = rig2;
+  Rig rig2; rig2.rig_id = 2; rig2.ref_camera_id = 3; rigs[2] = rig2;
   // frames 10, 20, 30 (rig 1) and 40 (rig 2)
   for (int k = 0; k < 4; ++k) {
     Frame f; f.frame_id = 10 * (k + 1); f.rig_id = k < 3 ? 1 : 2;
@@ -63,6 +63,7 @@ int main() {
   const image_t pr[5][2] = {{101, 102}, {101, 201}, {102, 301}, {202, 302}, {301, 401}};
   for (int k = 0; k < 5; ++k) {
     ImagePair p; p.image_id1 = pr[k][0]; p.image_id2 = pr[k][1]; p.weight = 1.0 + k;
+    p.inliers.assign(10 + k, 0);
     SetQuat(p.cam2_from_cam1.rotation, 1.0, 0.1 * k, -0.2, 0.2 + 0.1 * k);
     vg.image_pairs[ImagePairToPairId(pr[k][0], pr[k][1])] = p;
   }
@@ -75,6 +76,7 @@ int main() {
   GlobalPositioner gp(go);
   if (!gp.Solve(vg, rigs, cameras, frames, images, tracks)) return 2;
   RotationEstimatorOptions ro;
+  ro.skip_initialization = true;   // the flattening checks start from the frames' own rotations
   RotationEstimator ra(ro);
   if (!ra.EstimateRotations(vg, rigs, frames, images)) return 3;
   // gravity-aligned rotation averaging: frames 20 and 40 carry a gravity prior
@@ -94,6 +96,16 @@ int main() {
   Track tr; tr.track_id = 1; tr.observations = {{401, 0}, {401, 1}, {401, 2}}; t2[1] = tr;
   BundleAdjuster ba2(bo);
   if (!ba2.Solve(rigs, c2, f2, i2, t2)) return 4;
+  // maximum-spanning-tree initialisation inside EstimateRotations (global_rotation_averaging.cc:60-63): the mock
+  // records the initial theta the device solver would start from
+  for (auto& [id, f] : frames) { f.rig_from_world.rotation = Quaternion(); f.gravity_info.has_gravity = false; }
+  RotationEstimatorOptions rm;   // skip_initialization = false (the reference default)
+  RotationEstimator ram(rm);
+  if (!ram.EstimateRotations(vg, rigs, frames, images)) return 6;
+  // use_gravity with an uncalibrated rig sensor must be refused (.cc:47-59)
+  rigs[1].uncalibrated.push_back(9);
+  RotationEstimator rag2(rg);
+  if (rag2.EstimateRotations(vg, rigs, frames, images)) return 7;
   std::printf("shim driver ok\n");
   return 0;
 }

@@ -54,7 +54,7 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     calls = calls[1:]
     assert [c["_name"] for c in calls] == ["ba_problem_create_rig", "ba_problem_set_state", "ba_problem_solve",
                                            "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
-                                           "ra_solve_gravity", "ba_solve"]
+                                           "ra_solve_gravity", "ba_solve", "ra_solve"]
     # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
     img_ids = [101, 102, 201, 202, 301, 302, 401]
     kimg = {i: k for k, i in enumerate(img_ids)}
@@ -68,7 +68,7 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     obs = [o for t in order for o in tracks[t]]
     # ---- BA: known-rig entry -----------------------------------------------------------------------------------
     ba = calls[0]
-    assert ba["dims"].tolist() == [4, 3, 12, 3, 3, 3]                            # F P N K S min_views
+    assert ba["dims"].tolist() == [4, 3, 12, 3, 3, 1]                            # F P N K S min_views (1: the shim applied the rule itself)
     assert ba["pt_obs_begin"].tolist() == [0, 4, 8, 12]
     assert ba["obs_frame"].tolist() == [frame_of[i] for i, _ in obs]
     assert ba["obs_sensor"].tolist() == [sensor_of[i] for i, _ in obs]
@@ -134,3 +134,22 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     one = calls[8]
     assert one["dims"].tolist() == [1, 1, 3, 1] and one["obs_cam"].tolist() == [0, 0, 0] and one["cam_intr"].tolist() == [0]
     assert one["flags"].tolist() == [1, 1, 0]
+    # ---- InitializeFromMaximumSpanningTree inside EstimateRotations (.cc:60-63, 87-138; math/tree.cc:78-153) -------------
+    # inliers = 10 + k: Kruskal keeps all five pairs (a forest: 202-302 is not connected to the root 101); BFS from 101
+    mst = calls[9]
+    q21 = np.array([_quat(1.0, 0.1 * k, -0.2, 0.2 + 0.1 * k) for k in range(5)])
+    Rrel = G.quat_xyzw_to_rotmat(q21)
+    R = {101: np.eye(3)}
+    R[102] = Rrel[0] @ R[101]            # pair (101,102): 2_R_w = 2_R_1 1_R_w
+    R[201] = Rrel[1] @ R[101]
+    R[301] = Rrel[2] @ R[102]
+    R[401] = Rrel[4] @ R[301]
+
+    def avg(Rs_):
+        qs = np.array([G.rotmat_to_quat_xyzw(r[None])[0] for r in Rs_])
+        w, v = np.linalg.eigh(qs.T @ qs)
+        return G.quat_xyzw_to_rotmat(v[:, -1][None])[0]
+
+    want = [avg([R[101], Rs[1].T @ R[102]]), R[201], R[301], R[401]]       # frame 10 averages its two images (rotation_initializer.cc:95-117)
+    got = G.so3_exp(mst["theta"].reshape(-1, 3))
+    assert np.abs(got - np.array(want)).max() < 1e-12, np.abs(got - np.array(want)).max()
