@@ -263,6 +263,26 @@ int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_
   return B200SFM_OK;
 }
 
+int b200sfm_ba_problem_set_sensor_variable(b200sfm_ba_problem* p, const uint8_t* sensor_variable) {
+  if (!p || !sensor_variable) return B200SFM_ERR_INVALID_ARG;
+  if (p->S <= 0) { p->ctx->err = "the problem has no rig sensors (b200sfm_ba_problem_create_rig)"; return B200SFM_ERR_INVALID_ARG; }
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->set_sensor_variable(sensor_variable);
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_get_sensor_poses(b200sfm_ba_problem* p, double* sensor_quat_xyzw, double* sensor_trans) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  if (p->S <= 0) { p->ctx->err = "the problem has no rig sensors (b200sfm_ba_problem_create_rig)"; return B200SFM_ERR_INVALID_ARG; }
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->get_sensor_poses(sensor_quat_xyzw, sensor_trans);
+    return (int)B200SFM_OK;
+  });
+}
+
 int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
                                  const double* trans, const double* points) {
   if (!p || !intr_params || !quat_xyzw || !trans || !points) return B200SFM_ERR_INVALID_ARG;

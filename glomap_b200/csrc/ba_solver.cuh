@@ -14,6 +14,7 @@
 #include "ba_kernels.cuh"
 #include "ba_kernels_v2.cuh"
 #include "ba_kernels_v3.cuh"
+#include "ba_kernels_ext.cuh"
 #include "filter_kernels.cuh"
 #include "context.cuh"
 #include "pcg.cuh"
@@ -135,14 +136,21 @@ struct b200sfm_ba_problem {
   DevBuf<unsigned char> cam_mask_base, cam_mask;
   // state + candidate + snapshot
   DevBuf<double> quat[2], trans[2], points[2], intr, intr_cand, quat_saved, trans_saved, points_saved, intr_saved;
-  // shared-intrinsics border (optimize_intrinsics)
-  int m_intr = 0;
+  // extended path (ba_kernels_ext.cuh): intrinsics blocks and unknown cam_from_rig poses as pseudo-camera blocks
+  // appended to the frames: block f | C + k | C + K + s;  CB = C + K + S.  nbk = blocks in the current solve.
+  int CB = 0, nbk = 0;
+  bool ext = false, ext_k = false, ext_s = false;
   std::vector<int> h_intr_model;
   std::vector<b200::IntrVarRec> h_ivar;
-  std::vector<double> h_intr, h_intr_cand, h_ukk, h_js_k, h_Dk, h_gk, h_bk, h_CkInv, h_dk;
   DevBuf<b200::IntrVarRec> ivar;
-  DevBuf<double> Buck, Bmat, spk, part_seg, intr_out, part_tile, tile_sum, CkInv, vvec, part_bt, tvec, dkv;
-  size_t smem_ki = 0;
+  std::vector<unsigned char> h_sensor_var;       // [S] caller's request (b200sfm_ba_problem_set_sensor_variable)
+  DevBuf<unsigned char> sensor_var;
+  DevBuf<double> sens_q[2], sens_t[2], sens_q_saved, sens_t_saved;   // cam_from_rig state (indexed like quat/trans by cur)
+  b200::ExtView ext_view() {
+    b200::ExtView e;
+    e.C = C; e.K = K; e.S = S; e.ivar = ivar.p; e.sensor_var = (ext_s && S > 0) ? sensor_var.p : nullptr;
+    return e;
+  }
   // design v2 (compact rows, camera-order second pass)
   bool use_v2 = false;
   // point side of v2 in the ELL-32 layout (ba_kernels_v3.cuh): one thread per point
@@ -177,9 +185,10 @@ struct b200sfm_ba_problem {
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_k1 = 0, smem_k3 = 0;
 
+  // lin = U[CB][21] | gc[CB][6] | cost | one max|g_p| slot per rank  (fixed layout; a solve uses the first nbk blocks)
   double* U() { return lin.p; }
-  double* gc() { return lin.p + (size_t)C * 21; }
-  double* cost_ptr() { return lin.p + (size_t)C * 27; }
+  double* gc() { return lin.p + (size_t)CB * 21; }
+  double* cost_ptr() { return lin.p + (size_t)CB * 27; }
 
   BAView view() {
     BAView v;
@@ -201,6 +210,8 @@ struct b200sfm_ba_problem {
               const double* h_sensor_t = nullptr, const int32_t* h_sensor_intr = nullptr) {
     using namespace b200;
     ctx = c; C = C_; P = P_; N = N_; K = K_; min_views = min_views_; S = S_;
+    CB = C + K + S;
+    nbk = C;
     const int smul = std::max(S, 1);
     const int VC = C * smul;
     cudaStream_t s = ctx->stream;
@@ -231,7 +242,8 @@ struct b200sfm_ba_problem {
 
     obs_cam.alloc(N); obs_pt.alloc(N); obs_xy.alloc(N); pt_begin.alloc((size_t)P + 1);
     tile_pt_begin.alloc(tiles.size()); cam_intr.alloc(C); intr_model.alloc(K);
-    cam_mask_base.alloc(C); cam_mask.alloc(C);
+    cam_mask_base.alloc(CB); cam_mask.alloc(CB);   // the extra blocks carry no mask (zero)
+    cam_mask_base.zero(s); cam_mask.zero(s);
     obs_cam.upload(h_obs_cam, N, s);
     obs_xy.upload(reinterpret_cast<const double2*>(h_obs_xy), N, s);
     pt_begin.upload(ptb.data(), (size_t)P + 1, s);
@@ -261,6 +273,13 @@ struct b200sfm_ba_problem {
       sensor_rec.upload(rec.data(), rec.size(), s);
       sensor_intr.alloc(S);
       sensor_intr.upload(h_sensor_intr, S, s);
+      for (int i = 0; i < 2; ++i) { sens_q[i].alloc((size_t)S * 4); sens_t[i].alloc((size_t)S * 3); }
+      sens_q[0].upload(h_sensor_q, (size_t)S * 4, s);
+      sens_t[0].upload(h_sensor_t, (size_t)S * 3, s);
+      B200_LAUNCH(ctx, b200::k_normalize_quat, b200::cdiv(S, 256), 256, 0, S, sens_q[0].p);
+      sensor_var.alloc(S);
+      sensor_var.zero(s);
+      h_sensor_var.assign(S, 0);
       obs_sensor.alloc(N);
       obs_sensor.upload(h_obs_sensor, N, s);
       B200_CUDA_OK(cudaStreamSynchronize(s));   // rec is a local
@@ -276,7 +295,6 @@ struct b200sfm_ba_problem {
     intr_model.upload(h_intr_model, K, s);
     this->h_intr_model.assign(h_intr_model, h_intr_model + K);
     if (h_cam_mask) cam_mask_base.upload(h_cam_mask, C, s);
-    else cam_mask_base.zero(s);
     if (st) st->h2d_bytes += N * 20 + ((long long)P + 1) * 4 + (long long)tiles.size() * 4 + (long long)C * 5 + K * 4;
 
     B200_LAUNCH(ctx, k_expand_obs_pt, cdiv(P, 256), 256, 0, P, pt_begin.p, obs_pt.p);
@@ -378,12 +396,13 @@ struct b200sfm_ba_problem {
     intr_cand.alloc((size_t)K * B200SFM_INTR_STRIDE);
     cam_rec.alloc((size_t)C * kCamRec); intr_rec.alloc((size_t)K * kIntrRec);
     W.alloc((size_t)N * kWDoubles); V.alloc((size_t)P * 6); Vinv.alloc((size_t)P * 6); gp.alloc((size_t)P * 3);
-    lin.alloc((size_t)C * 27 + 1 + (size_t)ctx->world);   // U | gc | cost | one max|g_p| slot per rank
-    Sd.alloc((size_t)C * 27);                              // Schur-Jacobi blocks | right-hand-side accumulator (one all-reduce for both)
-    Minv.alloc((size_t)C * 21);
-    jscale_c.alloc((size_t)C * 6); jscale_p.alloc((size_t)P * 3); Dc.alloc((size_t)C * 6);
-    px.alloc((size_t)C * 6); pr.alloc((size_t)C * 6); pz.alloc((size_t)C * 6); pp.alloc((size_t)C * 6);
-    pq.alloc((size_t)C * 6); yw.alloc((size_t)C * 6); bvec.alloc((size_t)C * 6);
+    lin.alloc((size_t)CB * 27 + 1 + (size_t)ctx->world);   // U | gc | cost | one max|g_p| slot per rank
+    Sd.alloc((size_t)CB * 27);                              // Schur-Jacobi blocks | right-hand-side accumulator (one all-reduce for both)
+    Minv.alloc((size_t)CB * 21);
+    jscale_c.alloc((size_t)CB * 6); jscale_p.alloc((size_t)P * 3); Dc.alloc((size_t)CB * 6);
+    px.alloc((size_t)CB * 6); pr.alloc((size_t)CB * 6); pz.alloc((size_t)CB * 6); pp.alloc((size_t)CB * 6);
+    pq.alloc((size_t)CB * 6); yw.alloc((size_t)CB * 6); bvec.alloc((size_t)CB * 6);
+    ivar.alloc(K);
     scal.alloc(16);
     smem_k1 = sizeof(K1Smem) + 128;
     smem_k3 = sizeof(K3Smem) + 128;
@@ -409,9 +428,6 @@ struct b200sfm_ba_problem {
     Jc.alloc((size_t)std::max<long long>(n_rows_padded, 32) * kJcDoubles); z4.alloc((size_t)P * 4); xq.alloc((size_t)C * kXqStride);
     bpart.alloc((size_t)std::max(std::max(n_tiles, ell_bpart_rows), 1) * 4);
     bpart2.alloc(296 * 4);
-    smem_ki = sizeof(KISmem) + 128;
-    B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ki));
-    B200_CUDA_OK(cudaFuncSetAttribute(ba_intr_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaStreamSynchronize(s));   // temporaries go out of scope
   }
 
@@ -439,6 +455,11 @@ struct b200sfm_ba_problem {
     if (!quat_saved.p) {
       quat_saved.alloc((size_t)C * 4); trans_saved.alloc((size_t)C * 3); points_saved.alloc((size_t)P * 3);
       intr_saved.alloc((size_t)K * B200SFM_INTR_STRIDE);
+      if (S > 0) { sens_q_saved.alloc((size_t)S * 4); sens_t_saved.alloc((size_t)S * 3); }
+    }
+    if (S > 0) {
+      B200_CUDA_OK(cudaMemcpyAsync(sens_q_saved.p, sens_q[cur].p, sens_q_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+      B200_CUDA_OK(cudaMemcpyAsync(sens_t_saved.p, sens_t[cur].p, sens_t_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     }
     B200_CUDA_OK(cudaMemcpyAsync(quat_saved.p, quat[cur].p, quat_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(trans_saved.p, trans[cur].p, trans_saved.bytes(), cudaMemcpyDeviceToDevice, s));
@@ -452,6 +473,11 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaMemcpyAsync(trans[cur].p, trans_saved.p, trans_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(points[cur].p, points_saved.p, points_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(intr.p, intr_saved.p, intr_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    if (S > 0) {
+      B200_CUDA_OK(cudaMemcpyAsync(sens_q[cur].p, sens_q_saved.p, sens_q_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+      B200_CUDA_OK(cudaMemcpyAsync(sens_t[cur].p, sens_t_saved.p, sens_t_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+      B200_LAUNCH(ctx, b200::bax_build_sensor_rec, b200::cdiv(S, 256), 256, 0, S, sens_q[cur].p, sens_t[cur].p, sensor_intr.p, sensor_rec.p);
+    }
     return true;
   }
 
@@ -460,6 +486,21 @@ struct b200sfm_ba_problem {
     using namespace b200;
     B200_LAUNCH(ctx, ba_build_records, cdiv(std::max(C, K), 256), 256, 0, C, K, quat[which].p, trans[which].p,
                 cam_intr.p, cam_mask.p, (which == cur ? intr.p : intr_cand.p), intr_model.p, cam_rec.p, intr_rec.p);
+    // cam_from_rig poses: constant unless a sensor is an unknown of this solve; the records are rebuilt either way
+    // (S is small) so that a state accepted by an earlier optimize_rig_poses solve stays in effect
+    if (S > 0)
+      B200_LAUNCH(ctx, bax_build_sensor_rec, cdiv(S, 256), 256, 0, S, sens_q[which].p, sens_t[which].p,
+                  sensor_intr.p, sensor_rec.p);
+  }
+  void set_sensor_variable(const uint8_t* h_var) {
+    h_sensor_var.assign(h_var, h_var + S);
+    sensor_var.upload(h_sensor_var.data(), S, ctx->stream);
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  void get_sensor_poses(double* h_q, double* h_t) {
+    if (h_q) sens_q[cur].download(h_q, (size_t)S * 4, ctx->stream);
+    if (h_t) sens_t[cur].download(h_t, (size_t)S * 3, ctx->stream);
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
 
   // robust cost of points[which] under the current records -> scal[6] (this rank's shard)
@@ -512,52 +553,28 @@ struct b200sfm_ba_problem {
                   points_var ? 1 : 0, scal.p);
     if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
     if (n_segs > 0) {
-      if (use_v2)
-        B200_LAUNCH(ctx, ba2_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, intr_rec.p,
-                    points[cur].p, huber_a);
+      const int sgrid = cdiv((long long)n_segs * 32, 128);
+      if (ext) {
+        B200_LAUNCH(ctx, bax_linearize_blocks<0>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+        if (ext_k) B200_LAUNCH(ctx, bax_linearize_blocks<1>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+        if (ext_s) B200_LAUNCH(ctx, bax_linearize_blocks<2>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+      } else if (use_v2)
+        B200_LAUNCH(ctx, ba2_linearize_cams, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
       else
-        B200_LAUNCH(ctx, ba_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p,
-                    points[cur].p, huber_a);
+        B200_LAUNCH(ctx, ba_linearize_cams, sgrid, 128, 0, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a);
     }
     // cost and this rank's max|g_p| (own slot, zeros elsewhere) travel with U|gc through ONE sum all-reduce
     B200_CUDA_OK(cudaMemcpyAsync(cost_ptr(), scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(cost_ptr() + 1 + ctx->rank, scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    ctx->allreduce_sum(lin.p, (size_t)C * 27 + 1 + (size_t)ctx->world);
+    ctx->allreduce_sum(lin.p, (size_t)CB * 27 + 1 + (size_t)ctx->world);
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 1, 0, sizeof(double), s));
-    B200_LAUNCH(ctx, ba_finalize_cams, cdiv(C, 128), 128, 0, C, U(), gc(), cam_mask.p, jscale_c.p, first ? 1 : 0,
+    B200_LAUNCH(ctx, ba_finalize_cams, cdiv(nbk, 128), 128, 0, nbk, U(), gc(), cam_mask.p, jscale_c.p, first ? 1 : 0,
                 scal.p, cost_ptr() + 1, ctx->world);
-    if (m_intr > 0) {
-      // U_ck into the (local) border, U_kk / g_k per block (camera order)
-      Buck.zero(s);
-      if (n_segs > 0) {
-        B200_LAUNCH(ctx, ba_intr_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, cam_rec.p, intr_rec.p, ivar.p,
-                    points[cur].p, huber_a, m_intr, Buck.p, part_seg.p);
-        B200_LAUNCH(ctx, ba_intr_reduce_segs, K, 256, 0, n_segs, seg_intr.p, part_seg.p, intr_out.p);
-      } else {
-        intr_out.zero(s);
-      }
-      ctx->allreduce_sum(intr_out.p, (size_t)K * 20);
-      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, intr_out.p, (size_t)K * 20 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, cost_ptr(), sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 1, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     cost = ctx->h_scal[0];
     gmax = ctx->h_scal[1];
-    if (m_intr > 0) {
-      h_ukk.assign(ctx->h_scal + 64, ctx->h_scal + 64 + (size_t)K * 20);
-      h_gk.assign(m_intr, 0.0);
-      if (first) h_js_k.assign(m_intr, 1.0);
-      for (int k = 0; k < K; ++k) {
-        const b200::IntrVarRec& iv = h_ivar[k];
-        for (int a = 0; a < iv.mb; ++a) {
-          const double d = h_ukk[(size_t)k * 20 + (a * kMaxBlockDof - a * (a - 1) / 2)];   // packed (a,a) of a 5x5
-          if (first) h_js_k[iv.col0 + a] = 1.0 / (1.0 + std::sqrt(std::max(d, 0.0)));
-          h_gk[iv.col0 + a] = h_ukk[(size_t)k * 20 + 15 + a];
-          gmax = std::max(gmax, std::fabs(h_gk[iv.col0 + a]));
-        }
-      }
-    }
   }
 
   // ---- track filters on the resident arrays (glomap/processors/track_filter.cc) -----------------
@@ -617,17 +634,46 @@ struct b200sfm_ba_problem {
     bool finite = true;
   };
 
+  // mat-vec of the extended path: yw = (J^T J - W Vinv W^T) p over all nbk blocks (ba_kernels_ext.cuh); the damping
+  // is added by pcg_apply_diag.  x == nullptr: right-hand-side mode (z4 already holds Vinv g_p).
+  void ext_matvec(const double* x, double* y, double huber_a, double radius, bool points_var, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    BAView v = view();
+    ExtView ex = ext_view();
+    const int sgrid = cdiv((long long)n_segs * 32, 128);
+    if (x && points_var) {
+#define B200_EXT_A(WK, WS)                                                                                              \
+  B200_LAUNCH(ctx, (bax_pass_a<0, WK, WS>), ell_ctas, kEllThreads, 0, v, ell_view(), ex, view2(), cam_rec.p, intr_rec.p, x, \
+              points[cur].p, nullptr, huber_a, radius, nullptr, ctl)
+      if (ext_k && ext_s) B200_EXT_A(true, true);
+      else if (ext_k) B200_EXT_A(true, false);
+      else if (ext_s) B200_EXT_A(false, true);
+      else B200_EXT_A(false, false);
+#undef B200_EXT_A
+    }
+    if (n_segs > 0) {
+#define B200_EXT_B(WK, WS)                                                                                              \
+  B200_LAUNCH(ctx, (bax_pass_b<WK, WS>), sgrid, 128, 0, v, ex, view2(), cam_rec.p, intr_rec.p, points[cur].p, x, huber_a, y, ctl)
+      if (ext_k && ext_s) B200_EXT_B(true, true);
+      else if (ext_k) B200_EXT_B(true, false);
+      else if (ext_s) B200_EXT_B(false, true);
+      else B200_EXT_B(false, false);
+#undef B200_EXT_B
+    }
+  }
+
   // One trust-region step at the current linearisation: damping, preconditioner,
   // PCG on the reduced camera system, back-substitution, candidate + its cost.
   StepResult compute_step(const b200sfm_ba_opts& o, double radius, bool points_var, bool set_jscale_p, bool profile) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     BAView v = view();
-    const int nC6 = C * 6;
+    const int nB6 = nbk * 6;
     if (points_var) B200_LAUNCH(ctx, ba_damp_points, cdiv(P, 256), 256, 0, P, V.p, jscale_p.p, set_jscale_p ? 1 : 0, radius, Vinv.p);
-    B200_LAUNCH(ctx, ba_damp_cams, cdiv(nC6, 256), 256, 0, C, U(), jscale_c.p, radius, Dc.p);
-    const bool schur_jacobi = points_var && o.preconditioner == 1;
-    double* yrhs = Sd.p + (size_t)C * 21;   // W Vinv g_p accumulates next to Sd so that both share one all-reduce
+    B200_LAUNCH(ctx, ba_damp_cams, cdiv(nB6, 256), 256, 0, nbk, U(), jscale_c.p, radius, Dc.p);
+    // Schur-Jacobi blocks need the stored A_o rows of the fast path; the extended path preconditions with block-Jacobi
+    const bool schur_jacobi = points_var && o.preconditioner == 1 && !ext;
+    double* yrhs = Sd.p + (size_t)CB * 21;   // W Vinv g_p accumulates next to Sd so that both share one all-reduce
     Sd.zero(s);
     if (schur_jacobi && n_segs > 0) {
       if (use_v2) B200_LAUNCH(ctx, ba2_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p);
@@ -636,90 +682,21 @@ struct b200sfm_ba_problem {
     if (points_var) {
       if (use_v2) {
         B200_LAUNCH(ctx, ba2_point_rhs_z, cdiv(P, 256), 256, 0, v, view2());
-        if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yrhs, nullptr);
+        if (ext) ext_matvec(nullptr, yrhs, o.thres_loss_function, radius, true, nullptr);
+        else if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yrhs, nullptr);
       } else {
         B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yrhs, nullptr, nullptr, radius, nullptr);
       }
+    } else if (ext) {
+      z4.zero(s);   // constant points: no Schur term, pass B still applies J^T J
     }
-    if (schur_jacobi || points_var) ctx->allreduce_sum(Sd.p, (size_t)C * 27);
-    B200_LAUNCH(ctx, ba_build_precond, cdiv(C, 128), 128, 0, C, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
-    const int m = m_intr;
-    const int npair = m * (m + 1) / 2, nacc = npair + m;
-    if (m > 0) {
-      // border B = U_ck - W_c Vinv W_k^T, Ck = U_kk + D_k - W_k Vinv W_k^T, b_k
-      B200_CUDA_OK(cudaMemcpyAsync(Bmat.p, Buck.p, Buck.bytes(), cudaMemcpyDeviceToDevice, s));
-      if (points_var) {
-        B200_LAUNCH(ctx, ba_intr_points, n_tiles, kTile, smem_ki, v, cam_rec.p, intr_rec.p, ivar.p, points[cur].p,
-                    o.thres_loss_function, m, spk.p, Bmat.p, part_tile.p);
-        B200_LAUNCH(ctx, ba_colsum, nacc, 256, 0, n_tiles, nacc, part_tile.p, tile_sum.p);
-      } else {
-        tile_sum.zero(s);
-        spk.zero(s);
-      }
-      ctx->allreduce_sum(Bmat.p, (size_t)C * 6 * m);
-      ctx->allreduce_sum(tile_sum.p, nacc);
-      B200_LAUNCH(ctx, ba_border_mask, cdiv(nC6, 256), 256, 0, C, m, jscale_c.p, Bmat.p);
-      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, tile_sum.p, nacc * sizeof(double), cudaMemcpyDeviceToHost, s));
-      B200_CUDA_OK(cudaStreamSynchronize(s));
-      const double* ts = ctx->h_scal + 64;
-      std::vector<double> Ck((size_t)m * m, 0.0);
-      h_Dk.assign(m, 0.0);
-      h_bk.assign(m, 0.0);
-      for (int k = 0; k < K; ++k) {
-        const b200::IntrVarRec& iv = h_ivar[k];
-        for (int a = 0; a < iv.mb; ++a)
-          for (int c2 = a; c2 < iv.mb; ++c2) {
-            const double u = h_ukk[(size_t)k * 20 + (a * kMaxBlockDof - a * (a - 1) / 2) + (c2 - a)];
-            Ck[(size_t)(iv.col0 + a) * m + iv.col0 + c2] = u;
-            Ck[(size_t)(iv.col0 + c2) * m + iv.col0 + a] = u;
-          }
-      }
-      for (int a = 0; a < m; ++a) {
-        const double d = Ck[(size_t)a * m + a], js2 = h_js_k[a] * h_js_k[a];
-        h_Dk[a] = std::min(std::max(d * js2, 1e-6), 1e32) / (radius * js2);
-        for (int c2 = 0; c2 <= a; ++c2) {   // Schur part: pair (a, c2), c2 <= a
-          const double sv = ts[a * (a + 1) / 2 + c2];
-          Ck[(size_t)a * m + c2] -= sv;
-          if (c2 != a) Ck[(size_t)c2 * m + a] -= sv;
-        }
-        Ck[(size_t)a * m + a] += h_Dk[a];
-        h_bk[a] = -(h_gk[a] - ts[npair + a]);
-      }
-      // invert Ck (SPD, tiny) by Gauss-Jordan with partial pivoting
-      h_CkInv.assign((size_t)m * m, 0.0);
-      for (int a = 0; a < m; ++a) h_CkInv[(size_t)a * m + a] = 1.0;
-      for (int col = 0; col < m; ++col) {
-        int piv = col;
-        for (int r = col + 1; r < m; ++r)
-          if (std::fabs(Ck[(size_t)r * m + col]) > std::fabs(Ck[(size_t)piv * m + col])) piv = r;
-        if (piv != col)
-          for (int c2 = 0; c2 < m; ++c2) {
-            std::swap(Ck[(size_t)piv * m + c2], Ck[(size_t)col * m + c2]);
-            std::swap(h_CkInv[(size_t)piv * m + c2], h_CkInv[(size_t)col * m + c2]);
-          }
-        const double d = Ck[(size_t)col * m + col];
-        const double inv = d != 0.0 ? 1.0 / d : 0.0;
-        for (int c2 = 0; c2 < m; ++c2) { Ck[(size_t)col * m + c2] *= inv; h_CkInv[(size_t)col * m + c2] *= inv; }
-        for (int r = 0; r < m; ++r) {
-          if (r == col) continue;
-          const double f = Ck[(size_t)r * m + col];
-          if (f == 0.0) continue;
-          for (int c2 = 0; c2 < m; ++c2) { Ck[(size_t)r * m + c2] -= f * Ck[(size_t)col * m + c2]; h_CkInv[(size_t)r * m + c2] -= f * h_CkInv[(size_t)col * m + c2]; }
-        }
-      }
-      std::vector<double> vv(m, 0.0);
-      for (int a = 0; a < m; ++a)
-        for (int c2 = 0; c2 < m; ++c2) vv[a] += h_CkInv[(size_t)a * m + c2] * h_bk[c2];
-      B200_CUDA_OK(cudaMemcpyAsync(CkInv.p, h_CkInv.data(), (size_t)m * m * sizeof(double), cudaMemcpyHostToDevice, s));
-      B200_CUDA_OK(cudaMemcpyAsync(vvec.p, vv.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
-      B200_CUDA_OK(cudaStreamSynchronize(s));   // vv is a local
-    }
+    if (schur_jacobi || points_var) ctx->allreduce_sum(Sd.p, (size_t)CB * 27);
+    B200_LAUNCH(ctx, ba_build_precond, cdiv(nbk, 128), 128, 0, nbk, U(), Dc.p, schur_jacobi ? Sd.p : nullptr, Minv.p);
     // right-hand side b = -(gc - W Vinv gp)   (W Vinv gp was accumulated above, next to Sd)
-    B200_LAUNCH(ctx, k_rhs, cdiv(nC6, 256), 256, 0, nC6, gc(), points_var ? yrhs : nullptr, bvec.p);
-    if (m > 0) B200_LAUNCH(ctx, ba_border_rhs, cdiv(nC6, 256), 256, 0, C, m, Bmat.p, vvec.p, jscale_c.p, bvec.p);
+    B200_LAUNCH(ctx, k_rhs, cdiv(nB6, 256), 256, 0, nB6, gc(), points_var ? yrhs : nullptr, bvec.p);
     // ---- PCG (loop control on the device, iterations queued ahead of the read-back: pcg.cuh) --------
     const int max_it = std::max(1, o.pcg_max_iterations);
-    const int nblk = cdiv(C, kPcgThreads);
+    const int nblk = cdiv(nbk, kPcgThreads);
     pcgh.ensure(max_it, (size_t)nblk * 3);
     double* part_pq = pcgh.d_part;
     double* part_rz = pcgh.d_part + nblk;
@@ -727,27 +704,30 @@ struct b200sfm_ba_problem {
     PcgCtl* ctl = pcgh.d_ctl;
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
+    const bool has_mv = points_var || ext;   // an observation pass per iteration (else S = U + D is block diagonal)
     PcgResult pr_ = pcgh.run(
         s, max_it,
-        [&]() { B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
+        [&]() { B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, nbk, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
         [&](int it) {
           double* d_pp = pcgh.dots(it - 2);
           double* d_pub = pcgh.dots(it - 1);
           double* d_it = pcgh.dots(it);
-          if (points_var && use_v2)
-            B200_LAUNCH(ctx, ba2_pcg_direction_pack, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance,
+          if (points_var && use_v2 && !ext)
+            B200_LAUNCH(ctx, ba2_pcg_direction_pack, nblk, kPcgThreads, 0, nbk, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance,
                         pz.p, pp.p, yw.p, d_pp, part_rz, part_rr, d_pub, ctl, cam_rec.p, xq.p);
           else
-            B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
+            B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, nbk, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
                         pp.p, yw.p, d_pp, part_rz, part_rr, nullptr, d_pub, ctl);
-          if (points_var) {
+          if (has_mv) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (profile) {
               e0 = timer_mv.next();
               e1 = timer_mv.next();
               B200_CUDA_OK(cudaEventRecord(e0, s));
             }
-            if (use_v2) {
+            if (ext) {
+              ext_matvec(pp.p, yw.p, o.thres_loss_function, radius, points_var, ctl);
+            } else if (use_v2) {
               if (use_ell)
                 B200_LAUNCH(ctx, ba3_pass_a<0>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius,
                             nullptr, ctl);
@@ -759,71 +739,59 @@ struct b200sfm_ba_problem {
                           nullptr, 0, ctl);
             }
             if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
-            ctx->allreduce_sum(yw.p, nC6);
+            ctx->allreduce_sum(yw.p, nB6);
           }
-          B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, C, U(), Dc.p, pp.p, points_var ? yw.p : nullptr, pq.p, part_pq, ctl);
-          if (m > 0) {   // q -= B Ck^-1 B^T p
-            B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, pp.p, part_bt.p);
-            B200_LAUNCH(ctx, pcg_border_apply, nblk, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, pp.p, pq.p, part_pq, nullptr);
-          }
-          B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
+          // extended path: J^T J is inside yw already, only the damping is added here
+          B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, nbk, ext ? nullptr : U(), Dc.p, pp.p, has_mv ? yw.p : nullptr, pq.p,
+                      part_pq, ctl);
+          B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, nbk, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
                       part_rr, d_it, ctl);
         },
         [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
     res.finite = pr_.finite;
-    const int it = pr_.iters;
     // the queued-ahead iterations after the stopping rule fired were no-ops: keep only the real mat-vecs in the timer
-    if (profile && points_var) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);
-    res.pcg_iters = it;
+    if (profile && has_mv) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);
+    res.pcg_iters = pr_.iters;
     // ---- back-substitution + candidate ------------------------------------------
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));
     const int nxt = cur ^ 1;
-    double gk_dot = 0, dk_D = 0, dk_norm2 = 0, xk_norm2 = 0;
-    if (m > 0) {
-      // dk = Ck^-1 (b_k - B^T dc); candidate intrinsics
-      B200_LAUNCH(ctx, pcg_border_dots, nblk, kPcgThreads, 0, C, m, Bmat.p, px.p, part_bt.p);
-      B200_LAUNCH(ctx, pcg_border_apply, 1, kPcgThreads, 0, C, m, nblk, Bmat.p, CkInv.p, part_bt.p, px.p, nullptr, nullptr, tvec.p);
-      B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 64, tvec.p, m * sizeof(double), cudaMemcpyDeviceToHost, s));
-      B200_CUDA_OK(cudaStreamSynchronize(s));
-      h_dk.assign(m, 0.0);
-      for (int a = 0; a < m; ++a)
-        for (int c2 = 0; c2 < m; ++c2) h_dk[a] += h_CkInv[(size_t)a * m + c2] * (h_bk[c2] - ctx->h_scal[64 + c2]);
-      h_intr_cand = h_intr;
-      for (int k = 0; k < K; ++k) {
-        const b200::IntrVarRec& iv = h_ivar[k];
-        for (int a = 0; a < iv.mb; ++a) h_intr_cand[(size_t)k * B200SFM_INTR_STRIDE + iv.pidx[a]] += h_dk[iv.col0 + a];
-        if (iv.mb > 0) {
-          static const int npar[4] = {3, 4, 4, 5};
-          for (int j = 0; j < npar[h_intr_model[k]]; ++j) {
-            const double x0 = h_intr[(size_t)k * B200SFM_INTR_STRIDE + j];
-            xk_norm2 += x0 * x0;
-          }
-        }
-      }
-      for (int a = 0; a < m; ++a) {
-        gk_dot += h_gk[a] * h_dk[a];
-        dk_D += h_Dk[a] * h_dk[a] * h_dk[a];
-        dk_norm2 += h_dk[a] * h_dk[a];
-      }
-      B200_CUDA_OK(cudaMemcpyAsync(dkv.p, h_dk.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
-      B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, h_intr_cand.data(), h_intr_cand.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (ext) {
+      B200_LAUNCH(ctx, bax_update_extras, cdiv(std::max(K + S, 1), 128), 128, 0, ext_view(), ivar.p, intr_model.p, intr.p, intr_cand.p,
+                  S > 0 ? sens_q[cur].p : nullptr, S > 0 ? sens_t[cur].p : nullptr, S > 0 ? sens_q[nxt].p : nullptr,
+                  S > 0 ? sens_t[nxt].p : nullptr, px.p, gc(), pr.p, Dc.p, jscale_c.p, 1, scal.p + 8);
     } else {
       B200_CUDA_OK(cudaMemcpyAsync(intr_cand.p, intr.p, intr.bytes(), cudaMemcpyDeviceToDevice, s));
+      if (S > 0) {   // the cam_from_rig poses follow `cur` like the frame poses: the candidate buffer mirrors them
+        B200_CUDA_OK(cudaMemcpyAsync(sens_q[nxt].p, sens_q[cur].p, sens_q[cur].bytes(), cudaMemcpyDeviceToDevice, s));
+        B200_CUDA_OK(cudaMemcpyAsync(sens_t[nxt].p, sens_t[cur].p, sens_t[cur].bytes(), cudaMemcpyDeviceToDevice, s));
+      }
     }
     if (points_var && use_v2) {
-      B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
       const int nrow_part = use_ell ? ell_ctas : n_tiles;
-      if (use_ell)
-        B200_LAUNCH(ctx, ba3_pass_a<2>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
-                    bpart.p, nullptr);
-      else
-        B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
+      if (ext) {
+        ExtView ex = ext_view();
+#define B200_EXT_A2(WK, WS)                                                                                                  \
+  B200_LAUNCH(ctx, (bax_pass_a<2, WK, WS>), ell_ctas, kEllThreads, 0, v, ell_view(), ex, view2(), cam_rec.p, intr_rec.p, px.p, \
+              points[cur].p, points[nxt].p, o.thres_loss_function, radius, bpart.p, nullptr)
+        if (ext_k && ext_s) B200_EXT_A2(true, true);
+        else if (ext_k) B200_EXT_A2(true, false);
+        else if (ext_s) B200_EXT_A2(false, true);
+        else B200_EXT_A2(false, false);
+#undef B200_EXT_A2
+      } else {
+        B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
+        if (use_ell)
+          B200_LAUNCH(ctx, ba3_pass_a<2>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
+                      bpart.p, nullptr);
+        else
+          B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
+      }
       const int nb = std::min(cdiv(nrow_part, 256), 296);
       B200_LAUNCH(ctx, ba2_sum4_stage1, nb, 256, 0, nrow_part, bpart.p, bpart2.p);
       B200_LAUNCH(ctx, ba_colsum, 4, 256, 0, nb, 4, bpart2.p, scal.p + 2);
     } else if (points_var) {
       B200_LAUNCH(ctx, ba_schur_pass<2>, n_tiles, kTile, smem_k3, v, px.p, nullptr, points[cur].p, points[nxt].p, radius,
-                  scal.p + 2, spk.p, dkv.p, m);
+                  scal.p + 2);
     } else {
       B200_CUDA_OK(cudaMemcpyAsync(points[nxt].p, points[cur].p, points[cur].bytes(), cudaMemcpyDeviceToDevice, s));
     }
@@ -839,12 +807,12 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaStreamSynchronize(s));
     double* h = ctx->h_scal;
     for (int k = 8; k <= 12; ++k) h[k] /= (double)ctx->world;
-    const double g_dot_d = h[8] + h[2] + gk_dot;
-    const double dDd = h[10] + h[3] + dk_D;
+    const double g_dot_d = h[8] + h[2];
+    const double dDd = h[10] + h[3];
     res.model_cost_change = 0.5 * (-g_dot_d + h[9] + dDd);
     res.cand_cost = h[6];
-    res.step_norm = std::sqrt(h[11] + h[4] + dk_norm2);
-    res.x_norm = std::sqrt(h[12] + h[5] + xk_norm2);
+    res.step_norm = std::sqrt(h[11] + h[4]);
+    res.x_norm = std::sqrt(h[12] + h[5]);
     if (!std::isfinite(res.model_cost_change) || !std::isfinite(res.cand_cost)) res.finite = false;
     return res;
   }
@@ -853,48 +821,39 @@ struct b200sfm_ba_problem {
   int solve(const b200sfm_ba_opts& o, b200sfm_lm_stats* st) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
-    if (o.optimize_rig_poses) {
-      ctx->err = "optimize_rig_poses: unknown cam_from_rig blocks are not supported (known rigs: b200sfm_ba_problem_create_rig)";
-      return B200SFM_ERR_UNSUPPORTED;
-    }
-    m_intr = 0;
-    if (o.optimize_intrinsics) {
-      // variable parameters per block: all but the principal point unless optimize_principal_point
-      // (SubsetManifold, bundle_adjustment.cc:273-286); order = ascending parameter index
-      static const int nfoc[4][3] = {{0, -1, -1}, {0, 1, -1}, {0, 3, -1}, {0, 3, 4}};
-      static const int pp[4][2] = {{1, 2}, {2, 3}, {1, 2}, {1, 2}};
+    // ---- which parameter blocks beyond the frame poses are unknowns of this solve ------------------------------
+    // intrinsics (bundle_adjustment.cc:273-293): optimize_principal_point -> no manifold is set at all, EVERY parameter
+    // of every camera is variable; else optimize_intrinsics -> SubsetManifold holding the principal point; else constant
+    {
+      static const int nfoc[4][3] = {{0, -1, -1}, {0, 1, -1}, {0, 3, -1}, {0, 3, 4}};   // focal + distortion parameter indices
+      static const int pp[4][2] = {{1, 2}, {2, 3}, {1, 2}, {1, 2}};                      // principal point indices
       h_ivar.assign(K, b200::IntrVarRec{});
+      ext_k = false;
+      const bool all_var = o.optimize_principal_point != 0, foc_var = o.optimize_intrinsics != 0 || all_var;
       for (int k = 0; k < K; ++k) {
         std::vector<int> idx;
-        for (int j = 0; j < 3; ++j)
-          if (nfoc[h_intr_model[k]][j] >= 0) idx.push_back(nfoc[h_intr_model[k]][j]);
-        if (o.optimize_principal_point) { idx.push_back(pp[h_intr_model[k]][0]); idx.push_back(pp[h_intr_model[k]][1]); }
+        if (foc_var)
+          for (int j = 0; j < 3; ++j)
+            if (nfoc[h_intr_model[k]][j] >= 0) idx.push_back(nfoc[h_intr_model[k]][j]);
+        if (all_var) { idx.push_back(pp[h_intr_model[k]][0]); idx.push_back(pp[h_intr_model[k]][1]); }
         std::sort(idx.begin(), idx.end());
-        h_ivar[k].col0 = m_intr;
+        h_ivar[k].col0 = 0;
         h_ivar[k].mb = (int)idx.size();
         for (size_t j = 0; j < idx.size(); ++j) h_ivar[k].pidx[j] = idx[j];
-        m_intr += (int)idx.size();
+        ext_k = ext_k || !idx.empty();
       }
-      if (m_intr > kMaxIntrDof) {
-        ctx->err = "optimize_intrinsics: " + std::to_string(m_intr) + " variable intrinsics parameters exceed the dense-border limit (" +
-                   std::to_string(kMaxIntrDof) + "); per-image intrinsics are not supported yet";
-        m_intr = 0;
-        return B200SFM_ERR_UNSUPPORTED;
-      }
-      const int m = m_intr, nacc = m * (m + 1) / 2 + m;
-      ivar.alloc(K);
       B200_CUDA_OK(cudaMemcpyAsync(ivar.p, h_ivar.data(), K * sizeof(b200::IntrVarRec), cudaMemcpyHostToDevice, s));
-      Buck.alloc((size_t)C * 6 * m); Bmat.alloc((size_t)C * 6 * m); spk.alloc((size_t)P * 3 * m);
-      part_seg.alloc((size_t)std::max(n_segs, 1) * 20); intr_out.alloc((size_t)K * 20);
-      part_tile.alloc((size_t)n_tiles * nacc); tile_sum.alloc(nacc); CkInv.alloc((size_t)m * m); vvec.alloc(m);
-      part_bt.alloc((size_t)cdiv(C, kPcgThreads) * m); tvec.alloc(m); dkv.alloc(m);
-      if ((size_t)K * 20 + 64 > (size_t)b200sfm_ctx::kHScal) { ctx->err = "too many intrinsics blocks"; return B200SFM_ERR_UNSUPPORTED; }
-      h_intr.resize((size_t)K * B200SFM_INTR_STRIDE);
-      B200_CUDA_OK(cudaMemcpyAsync(h_intr.data(), intr.p, h_intr.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-      B200_CUDA_OK(cudaStreamSynchronize(s));
     }
-    use_v2 = (m_intr == 0) && (o.design != 1);   // v2 (compact rows) unless the intrinsics border needs W
-    use_ell = use_v2 && !(getenv("B200SFM_ELL") && atoi(getenv("B200SFM_ELL")) == 0);   // point side: one thread per point
+    // unknown cam_from_rig (optimize_rig_poses, bundle_adjustment.cc:162-180,296-308): the sensors the caller marked
+    // (b200sfm_ba_problem_set_sensor_variable; the reference: every non-reference sensor)
+    ext_s = false;
+    if (o.optimize_rig_poses && S > 0)
+      for (int i = 0; i < S; ++i) ext_s = ext_s || h_sensor_var[i] != 0;
+    ext = ext_k || ext_s;
+    nbk = ext ? CB : C;
+    B200_CUDA_OK(cudaStreamSynchronize(s));   // h_ivar upload
+    use_v2 = ext || (o.design != 1);          // v1 (W blocks + atomics) only on request, constant intrinsics
+    use_ell = use_v2 && (ext || !(getenv("B200SFM_ELL") && atoi(getenv("B200SFM_ELL")) == 0));   // point side: one thread per point
     // v2: keep z4 (written by pass A, gathered by pass B) in the persisting part of L2
     const bool l2_persist = use_v2 && !(getenv("B200SFM_L2_PERSIST") && atoi(getenv("B200SFM_L2_PERSIST")) == 0);
     if (l2_persist) l2_persist_window(s, ctx->device, z4.p, z4.bytes());
@@ -943,7 +902,6 @@ struct b200sfm_ba_problem {
       if (rel > 1e-3) {
         cur ^= 1;
         std::swap(intr.p, intr_cand.p);   // the candidate intrinsics become current (buffers have equal size)
-        if (m_intr > 0) h_intr = h_intr_cand;
         ++local.num_successful_steps;
         linearize(o.thres_loss_function, points_var, false, profile, cost, gmax);
         radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));

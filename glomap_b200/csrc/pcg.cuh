@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_apply_diag(int nb, const doub
   if (c < nb) {
     double a[NP], pv[B], out[B];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) a[k] = A[(size_t)c * NP + k];
+    for (int k = 0; k < NP; ++k) a[k] = A ? A[(size_t)c * NP + k] : 0.0;   // A == nullptr: the mat-vec already holds A p
 #pragma unroll
     for (int k = 0; k < B; ++k) pv[k] = p[(size_t)c * B + k];
     sym_packed_mul<B>(a, pv, out);

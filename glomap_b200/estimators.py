@@ -155,7 +155,9 @@ class BAProblem:
                                                         ct.byref(h))
             _lib.check(ctx.handle, rc)
             self.handle = h
+            self.S = scene.S
             return
+        self.S = 0
         self._keep = [_c(scene.pt_obs_begin, np.int64), _c(scene.obs_cam, np.int32), _c(scene.obs_xy, np.float64),
                       _c(scene.cam_intr, np.int32), _c(scene.intr_model, np.int32)]
         rc = self.lib.b200sfm_ba_problem_create(ctx.handle, self.C, self.P, self.N, self.K, *[_ptr(a) for a in self._keep],
@@ -172,6 +174,17 @@ class BAProblem:
         pts = np.empty((self.P, 3))
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_get_state(self.handle, _ptr(intr), _ptr(quat), _ptr(trans), _ptr(pts)))
         return intr, quat, trans, pts
+
+    def set_sensor_variable(self, sensor_variable):
+        """optimize_rig_poses: the sensors whose cam_from_rig is an unknown (bundle_adjustment.cc:296-308: every
+        non-reference camera sensor); effective when options.optimize_rig_poses is set."""
+        v = _c(sensor_variable, np.uint8)
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_set_sensor_variable(self.handle, _ptr(v)))
+
+    def get_sensor_poses(self):
+        q = np.empty((self.S, 4)); t = np.empty((self.S, 3))
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_get_sensor_poses(self.handle, _ptr(q), _ptr(t)))
+        return q, t
 
     def save_state(self):
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_save_state(self.handle))
@@ -260,8 +273,14 @@ class BundleAdjuster:
             prob = BAProblem(ctx, scene, self.options_.min_num_view_per_track, cam_const_mask)
             try:
                 prob.set_state(scene.intr_params, scene.quat, scene.trans, scene.points)
+                if self.options_.optimize_rig_poses:
+                    # bundle_adjustment.cc:296-308: the cam_from_rig of every non-reference sensor is an unknown
+                    ref = getattr(scene, "sensor_is_ref", np.arange(scene.S) == 0)
+                    prob.set_sensor_variable((~np.asarray(ref, bool)).astype(np.uint8))
                 self.summary = prob.solve(self.options_)
                 scene.intr_params, scene.quat, scene.trans, scene.points = prob.get_state()
+                if self.options_.optimize_rig_poses:
+                    scene.sensor_quat, scene.sensor_trans = prob.get_sensor_poses()
             finally:
                 prob.free()
             return bool(self.summary.usable)

@@ -113,7 +113,7 @@ typedef struct {
  * + the inherited ceres::Solver::Options the reference sets
  * (optimization_base.h:18-23), + the PCG knobs of this implementation. */
 typedef struct {
-  int32_t optimize_rig_poses;        /* must be 0: non-trivial rigs unsupported (B200SFM_ERR_UNSUPPORTED) */
+  int32_t optimize_rig_poses;        /* unknown cam_from_rig of the sensors marked with b200sfm_ba_problem_set_sensor_variable */
   int32_t optimize_rotations;        /* default 1 */
   int32_t optimize_translation;      /* default 1 */
   int32_t optimize_intrinsics;       /* default 1 in the reference; shared blocks, <= 12 variable parameters in total */
@@ -188,6 +188,12 @@ int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_
                                   const double* sensor_trans /*[S][3]*/, const int32_t* sensor_intr /*[S]*/,
                                   const int32_t* intr_model, const uint8_t* frame_const_mask,
                                   int32_t min_num_view_per_track, b200sfm_ba_problem** out);
+/* optimize_rig_poses (bundle_adjustment.cc:162-180,296-308, colmap::RigReprojErrorCostFunctor): mark the sensors whose
+ * cam_from_rig is an UNKNOWN of the following solves (the reference: every non-reference camera sensor); takes effect
+ * when b200sfm_ba_opts::optimize_rig_poses is set.  sensor_variable[S]: 1 = unknown.  The optimised poses are read
+ * back with b200sfm_ba_problem_get_sensor_poses (quat_xyzw [S][4] / trans [S][3], either may be NULL). */
+int b200sfm_ba_problem_set_sensor_variable(b200sfm_ba_problem* p, const uint8_t* sensor_variable);
+int b200sfm_ba_problem_get_sensor_poses(b200sfm_ba_problem* p, double* sensor_quat_xyzw, double* sensor_trans);
 int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr_params, const double* quat_xyzw,
                                  const double* trans, const double* points);
 int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr_params, double* quat_xyzw, double* trans,

@@ -215,7 +215,10 @@ class BAProblem:
         used_intr[self.rig["obs_intr"] if self.rig is not None else self.cam_intr[self.obs_cam]] = True
         for k in range(self.K):
             ent = []
-            if opts.optimize_intrinsics and used_intr[k]:
+            # bundle_adjustment.cc:273-293: optimize_principal_point -> no manifold and no constant block is set, EVERY
+            # parameter is variable (whatever optimize_intrinsics says); else optimize_intrinsics -> SubsetManifold that
+            # holds the principal point; else the block is constant
+            if (opts.optimize_intrinsics or opts.optimize_principal_point) and used_intr[k]:
                 foc, pp, extra = MODEL_LAYOUT[int(self.intr_model[k])]
                 idxs = list(foc) + list(extra) + (list(pp) if opts.optimize_principal_point else [])
                 for i in sorted(idxs):

@@ -110,6 +110,15 @@ int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr, cons
   dump_call("ba_problem_set_state");
   return B200SFM_OK;
 }
+int b200sfm_ba_problem_set_sensor_variable(b200sfm_ba_problem* p, const uint8_t* v) {
+  (void)p; (void)v;
+  dump_call("ba_problem_set_sensor_variable");
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_get_sensor_poses(b200sfm_ba_problem* p, double* q, double* t) {
+  (void)p; (void)q; (void)t;
+  return B200SFM_OK;
+}
 int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr, double* q, double* t, double* pts) {
   (void)p; (void)intr; (void)q; (void)t; (void)pts;
   return B200SFM_OK;

@@ -159,3 +159,47 @@ def test_rig_rotation_averaging_over_frames():
     assert np.abs(R - G.so3_exp(th)).max() < 1e-7
     err = G.rotation_angle_deg(R @ np.swapaxes(R[:1], -1, -2), Rf @ np.swapaxes(Rf[:1], -1, -2))
     assert err.max() < 1.0
+
+
+# ---- unknown cam_from_rig: optimize_rig_poses (bundle_adjustment.cc:162-180,296-308, RigReprojErrorCostFunctor) ----------
+def _perturbed_rig(rs, seed=1):
+    init = S.perturb_rig_scene(rs)
+    rng = np.random.default_rng(seed)
+    init.sensor_quat = init.sensor_quat.copy(); init.sensor_trans = init.sensor_trans.copy()
+    init.sensor_quat[1:] = G.rotmat_to_quat_xyzw_fast(G.so3_exp(rng.normal(size=(rs.S - 1, 3)) * 0.01) @
+                                                      G.quat_xyzw_to_rotmat(init.sensor_quat[1:]))
+    init.sensor_trans[1:] += rng.normal(size=(rs.S - 1, 3)) * 0.02
+    return init
+
+
+@pytest.mark.parametrize("with_intr", [False, True])
+def test_optimised_rig_poses_track_oracle(with_intr):
+    """The shape of the reference's own NonTrivialUnknownRig test (global_mapper_test.cc:128): 3 cameras per rig, the
+    cam_from_rig of the two non-reference sensors unknown and shared by all frames; device vs oracle iteration by
+    iteration, with and without the (shared, per-sensor) intrinsics refined in the same solve."""
+    rs = S.make_rig_scene(12, 3, 600, seed=14, pixel_sigma=0.3, model=S.SIMPLE_RADIAL)
+    init = _perturbed_rig(rs)
+    mask = E.first_frame_mask(rs.F)
+    ok, dev, st = _device(init, mask, optimize_intrinsics=with_intr, optimize_rig_poses=True)
+    rig = init.rig_dict()
+    x, summ = B.solve_ba(init.quat, init.trans, init.points, rs.pt_obs_begin, rs.obs_frame, rs.obs_xy, np.zeros(rs.F, np.int32),
+                         rs.intr_model, init.intr_params, B.BAOptions(optimize_intrinsics=with_intr, optimize_rig_poses=True), mask,
+                         rig=rig)
+    assert ok and st.usable
+    assert st.iterations == summ.iterations, (st.iterations, summ.iterations)
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-7 * summ.final_cost
+    assert np.abs(G.quat_xyzw_to_rotmat(dev.sensor_quat) - G.quat_xyzw_to_rotmat(x["sq"])).max() < 1e-6
+    assert np.abs(dev.sensor_trans - x["st"]).max() < 1e-6
+    assert np.array_equal(dev.sensor_quat[0], init.sensor_quat[0]) and np.array_equal(dev.sensor_trans[0], init.sensor_trans[0])
+    assert np.abs(dev.quat - x["quat"]).max() < 1e-6 and np.abs(dev.points - x["points"]).max() < 1e-5
+
+
+def test_optimised_rig_poses_recover_the_extrinsics_noise_free():
+    rs = S.make_rig_scene(10, 3, 500, seed=4, model=S.SIMPLE_RADIAL)
+    init = _perturbed_rig(rs)
+    ok, dev, st = _device(init, E.first_frame_mask(rs.F), tol=1e-10, optimize_intrinsics=False, optimize_rig_poses=True)
+    assert ok and st.final_cost < 1e-10 * st.initial_cost
+    assert np.abs(G.quat_xyzw_to_rotmat(dev.sensor_quat) - G.quat_xyzw_to_rotmat(rs.sensor_quat)).max() < 1e-5
+    s = np.linalg.norm(dev.sensor_trans[1]) / np.linalg.norm(rs.sensor_trans[1])      # nothing metric is fixed: up to scale
+    assert np.abs(dev.sensor_trans[1:] - s * rs.sensor_trans[1:]).max() < 1e-5 and abs(s - 1) < 0.05
