@@ -109,6 +109,8 @@ PROTOTYPES = {
     "b200sfm_gp_solve": (c_int32, [c_void_p, P(GPOpts), c_int32, c_int32, c_int64] + [c_void_p] * 8 + [P(LMStats)]),
     "b200sfm_gp_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 5 + [c_int32, P(c_void_p)]),
     "b200sfm_gp_problem_set_rig_terms": (c_int32, [c_void_p, c_void_p, c_void_p]),
+    "b200sfm_gp_problem_set_rig_unknown": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200sfm_gp_problem_get_rig_unknown": (c_int32, [c_void_p, c_void_p]),
     "b200sfm_gp_problem_set_state": (c_int32, [c_void_p] * 4),
     "b200sfm_gp_problem_get_state": (c_int32, [c_void_p] * 4),
     "b200sfm_gp_problem_save_state": (c_int32, [c_void_p]),

@@ -511,6 +511,30 @@ int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* obs_of
   });
 }
 
+int b200sfm_gp_problem_set_rig_unknown(b200sfm_gp_problem* p, int32_t num_unknown_sensors, const int32_t* obs_unknown_sensor,
+                                       const double* frame_rot, const double* centers) {
+  if (!p || num_unknown_sensors <= 0 || !obs_unknown_sensor || !frame_rot || !centers) return B200SFM_ERR_INVALID_ARG;
+  for (long long o = 0; o < p->N; ++o)
+    if (obs_unknown_sensor[o] < -1 || obs_unknown_sensor[o] >= num_unknown_sensors) {
+      p->ctx->err = "obs_unknown_sensor out of range";
+      return B200SFM_ERR_INVALID_ARG;
+    }
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->set_rig_unknown(num_unknown_sensors, obs_unknown_sensor, frame_rot, centers);
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_gp_problem_get_rig_unknown(b200sfm_gp_problem* p, double* centers) {
+  if (!p || !centers || p->n_us <= 0) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->get_rig_unknown(centers);
+    return (int)B200SFM_OK;
+  });
+}
+
 int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* centers, const double* points, const double* scales) {
   if (!p || !centers || !points || !scales) return B200SFM_ERR_INVALID_ARG;
   return guarded(p->ctx, [&]() {

@@ -36,6 +36,13 @@ struct GPView {
   const double* obs_dir;          // [N][3] world-rotated unit bearings
   const double* obs_off;          // [N][3] or nullptr: known-rig offset R_cw^T t_cam_from_rig (RigBATA, rig scale = 1)
   const unsigned char* obs_cal;   // [N] or nullptr: prior-focal flag of the observing CAMERA (overrides the per-frame flag)
+  // unknown cam_from_rig (RigUnknownBATAPairwiseDirectionError, cost_function.h:90-136, global_positioning.cc:347-364):
+  //   r = t_obs - s (X - c_frame - R_rw^T u_s),  u_s = the camera centre of sensor s in the rig frame, an unknown shared by
+  //   all images of the sensor.  The S_u unknown sensors are pseudo-camera blocks C .. C + S_u - 1 of the reduced system;
+  //   the current -R_rw^T u_s is folded into obs_off before every evaluation (gp_dyn_offsets).
+  int n_us;                       // S_u (0: none)
+  const int* obs_us;              // [N] unknown-sensor index of the observing image, -1: none
+  const double* frame_rot;        // [C][9] rig_from_world rotations (row-major), constants of global positioning
   const unsigned* pt_begin;
   const int* tile_pt_begin;
   const int* camord_obs;
@@ -102,6 +109,65 @@ __device__ __forceinline__ void gp_obs(const double t[3], double s, const double
   o.M[5] = ws2 * (1.0 - k * o.d[2] * o.d[2]);
 #pragma unroll
   for (int i = 0; i < 3; ++i) o.b[i] = ws * (o.r[i] - k * o.d[i] * o.dr);
+}
+
+// obs_off[o] = static known-rig offset (or 0) - R_rw^T u_s  for the observations of unknown sensors
+__global__ void gp_dyn_offsets(long long N, const int* __restrict__ obs_cam, const int* __restrict__ obs_us,
+                               const double* __restrict__ frame_rot, const double* __restrict__ ucen,
+                               const double* __restrict__ off_static, double* __restrict__ off) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= N) return;
+  double f0 = 0, f1 = 0, f2 = 0;
+  if (off_static) { f0 = off_static[3 * o]; f1 = off_static[3 * o + 1]; f2 = off_static[3 * o + 2]; }
+  const int su = obs_us[o];
+  if (su >= 0) {
+    const double* R = frame_rot + 9 * (size_t)obs_cam[o];
+    const double u0 = ucen[3 * su], u1 = ucen[3 * su + 1], u2 = ucen[3 * su + 2];
+    f0 -= R[0] * u0 + R[3] * u1 + R[6] * u2;   // R^T u
+    f1 -= R[1] * u0 + R[4] * u1 + R[7] * u2;
+    f2 -= R[2] * u0 + R[5] * u1 + R[8] * u2;
+  }
+  off[3 * o] = f0; off[3 * o + 1] = f1; off[3 * o + 2] = f2;
+}
+
+// Blocks of the unknown sensors (dr/du_s = s R_rw^T = (dr/dc) R_rw^T):
+//   out16[C + su][0..5] += R M_o R^T, [6..8] += R b_o, [9] += w s^2      (one thread per observation, CTA-level sums)
+__global__ void __launch_bounds__(256) gp_linearize_sensors(GPView v, double* __restrict__ out16) {
+  __shared__ double scratch[32];
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int su = -1;
+  double val[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (o < v.N) {
+    su = v.obs_us[o];
+    const int pt = v.obs_pt[o];
+    if ((int)(v.pt_begin[pt + 1] - v.pt_begin[pt]) < v.min_views) su = -1;
+    if (su >= 0) {
+      const double* R = v.frame_rot + 9 * (size_t)v.obs_cam[o];
+      const double* m = v.M + kMDoubles * (size_t)o;
+      const double M[3][3] = {{m[0], m[1], m[2]}, {m[1], m[3], m[4]}, {m[2], m[4], m[5]}};
+      double T[3][3];   // R M
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) T[r][c] = R[3 * r] * M[0][c] + R[3 * r + 1] * M[1][c] + R[3 * r + 2] * M[2][c];
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c) val[idx++] = T[r][0] * R[3 * c] + T[r][1] * R[3 * c + 1] + T[r][2] * R[3 * c + 2];
+      const double4 bw = *reinterpret_cast<const double4*>(v.bw + 4 * (size_t)o);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) val[6 + r] = R[3 * r] * bw.x + R[3 * r + 1] * bw.y + R[3 * r + 2] * bw.z;
+      val[9] = bw.w;
+    }
+  }
+  for (int s2 = 0; s2 < v.n_us; ++s2) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const double t = block_sum(su == s2 ? val[k] : 0.0, scratch);
+      if (threadIdx.x == 0 && t != 0.0) atomicAdd(&out16[(size_t)(v.C + s2) * 16 + k], t);
+    }
+  }
 }
 
 // centre records [C][4] = (c, loss scale)
@@ -358,6 +424,24 @@ __global__ void gp_finalize_cams(int C, const double* __restrict__ out16, const 
 //           writes dX[P][3], ds[N]; bscal[0] += g.delta (points+scales part),
 //           bscal[1] += delta^T D delta (points + scales)
 // ---------------------------------------------------------------------------
+// the centre displacement an observation sees: x_c, plus R_rw^T x_u when its sensor's cam_from_rig centre is an unknown
+__device__ __forceinline__ void gp_x_eff(const GPView& v, const double* __restrict__ x, size_t oi, double xe[3]) {
+  const int cam = v.obs_cam[oi];
+  xe[0] = x[3 * (size_t)cam];
+  xe[1] = x[3 * (size_t)cam + 1];
+  xe[2] = x[3 * (size_t)cam + 2];
+  if (v.n_us > 0) {
+    const int su = v.obs_us[oi];
+    if (su >= 0) {
+      const double* R = v.frame_rot + 9 * (size_t)cam;
+      const double* xu = x + 3 * (size_t)(v.C + su);
+      xe[0] += R[0] * xu[0] + R[3] * xu[1] + R[6] * xu[2];
+      xe[1] += R[1] * xu[0] + R[4] * xu[1] + R[7] * xu[2];
+      xe[2] += R[2] * xu[0] + R[5] * xu[1] + R[8] * xu[2];
+    }
+  }
+}
+
 struct G3Smem {
   alignas(128) double Mt[kTile * kMDoubles];
   double t[3][kTile + 1];
@@ -406,12 +490,7 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
       }
       double xc[3] = {0, 0, 0};
       const bool active = tid < nc;
-      if (active) {
-        const int cam = v.obs_cam[(size_t)o0 + c0 + tid];
-        xc[0] = x[3 * (size_t)cam];
-        xc[1] = x[3 * (size_t)cam + 1];
-        xc[2] = x[3 * (size_t)cam + 2];
-      }
+      if (active) gp_x_eff(v, x, (size_t)o0 + c0 + tid, xc);
       mbar_wait(&sm.mbar, phase);
       phase ^= 1;
       double t0 = 0, t1 = 0, t2 = 0;
@@ -499,8 +578,9 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
           GPObs o;
           double js = v.jscale_s[oi];
           gp_obs(t, s, c4, X, huber_a, svar, js, false, radius, js, o);
-          const double q[3] = {sm.z[0][pl] - x[3 * (size_t)cam], sm.z[1][pl] - x[3 * (size_t)cam + 1],
-                               sm.z[2][pl] - x[3 * (size_t)cam + 2]};
+          double xe[3];
+          gp_x_eff(v, x, oi, xe);
+          const double q[3] = {sm.z[0][pl] - xe[0], sm.z[1][pl] - xe[1], sm.z[2][pl] - xe[2]};
           const double dq = o.d[0] * q[0] + o.d[1] * q[1] + o.d[2] * q[2];
           const double rq = o.r[0] * q[0] + o.r[1] * q[1] + o.r[2] * q[2];
           if (svar) {
@@ -540,14 +620,33 @@ __global__ void __launch_bounds__(kTile) gp_schur_pass(GPView v, const double* _
       const size_t oi = (size_t)o0 + c0 + tid;
       const int cam = v.obs_cam[oi];
       const int pl = v.obs_pt[oi] - p0;
-      const double z0 = sm.z[0][pl], z1 = sm.z[1][pl], z2 = sm.z[2][pl];
+      double z0 = sm.z[0][pl], z1 = sm.z[1][pl], z2 = sm.z[2][pl];
+      const bool pvalid2 = (int)(sm.pb[pl + 1] - sm.pb[pl]) >= v.min_views;
+      if (v.n_us > 0 && MODE == 0 && pvalid2) {
+        // unknown sensors: the direct term is applied here too (y = M (x_eff + z): pcg_apply_diag then adds D x only),
+        // because x_eff = x_c + R^T x_u differs per observation
+        double xe[3];
+        gp_x_eff(v, x, oi, xe);
+        z0 += xe[0]; z1 += xe[1]; z2 += xe[2];
+      }
       if (z0 != 0.0 || z1 != 0.0 || z2 != 0.0) {
         const double2* mr = reinterpret_cast<const double2*>(sm.Mt + tid * kMDoubles);
         const double2 m0 = mr[0], m1 = mr[1], m2 = mr[2];
         double* yc = y + 3 * (size_t)cam;
-        atomicAdd(&yc[0], m0.x * z0 + m0.y * z1 + m1.x * z2);
-        atomicAdd(&yc[1], m0.y * z0 + m1.y * z1 + m2.x * z2);
-        atomicAdd(&yc[2], m1.x * z0 + m2.x * z1 + m2.y * z2);
+        const double a0 = m0.x * z0 + m0.y * z1 + m1.x * z2;
+        const double a1 = m0.y * z0 + m1.y * z1 + m2.x * z2;
+        const double a2 = m1.x * z0 + m2.x * z1 + m2.y * z2;
+        atomicAdd(&yc[0], a0);
+        atomicAdd(&yc[1], a1);
+        atomicAdd(&yc[2], a2);
+        const int su = v.n_us > 0 ? v.obs_us[oi] : -1;
+        if (su >= 0) {   // y_u += R (M z)
+          const double* R = v.frame_rot + 9 * (size_t)cam;
+          double* yu = y + 3 * (size_t)(v.C + su);
+          atomicAdd(&yu[0], R[0] * a0 + R[1] * a1 + R[2] * a2);
+          atomicAdd(&yu[1], R[3] * a0 + R[4] * a1 + R[5] * a2);
+          atomicAdd(&yu[2], R[6] * a0 + R[7] * a1 + R[8] * a2);
+        }
       }
     }
   }
@@ -563,7 +662,8 @@ __global__ void gp_apply_step(GPView v, double alpha, const double* __restrict__
                               const double* __restrict__ dc, const double* __restrict__ dX,
                               const double* __restrict__ ds, const double* __restrict__ jscale_c, int count_cams,
                               double* __restrict__ centers_new, double* __restrict__ points_new,
-                              double* __restrict__ scales_new, double* __restrict__ nscal) {
+                              double* __restrict__ scales_new, double* __restrict__ nscal,
+                              const double* __restrict__ ucen, double* __restrict__ ucen_new) {
   __shared__ double scratch[32];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double a0 = 0, a1 = 0;
@@ -597,6 +697,16 @@ __global__ void gp_apply_step(GPView v, double alpha, const double* __restrict__
     if (var && count_cams) {
       a0 += d * d;
       a1 += co * co;
+    }
+  }
+  if (i < (long long)v.n_us * 3) {   // unknown cam_from_rig centres: blocks C .. C + S_u - 1
+    const bool var = jscale_c[v.C + i / 3] >= 0.0;
+    const double uo = ucen[i];
+    const double d = var ? alpha * dc[(long long)v.C * 3 + i] : 0.0;
+    ucen_new[i] = uo + d;
+    if (var && count_cams) {
+      a0 += d * d;
+      a1 += uo * uo;
     }
   }
   a0 = block_sum(a0, scratch);

@@ -22,6 +22,10 @@ struct b200sfm_gp_problem {
   DevBuf<unsigned char> obs_cal;
   DevBuf<unsigned char> calibrated, cam_const_base, cam_const;
   bool has_calibrated = false;
+  // unknown cam_from_rig centres (RigUnknownBATA): S_u pseudo-camera blocks behind the C frames; CB = C + S_u
+  int n_us = 0, CB = 0;
+  DevBuf<int> obs_us;
+  DevBuf<double> frame_rot, ucen[2], ucen_saved, off_static, off_dyn;
   // state / candidate / snapshot
   DevBuf<double> centers[2], points[2], scales[2], centers_saved, points_saved, scales_saved;
   int cur = 0;
@@ -39,7 +43,8 @@ struct b200sfm_gp_problem {
     v.const_obs = (ctx->rank == 0) ? first_valid_obs : -1;
     v.scales_var = scales_var ? 1 : 0;
     v.obs_cam = obs_cam.p; v.obs_pt = obs_pt.p; v.obs_dir = obs_dir.p; v.pt_begin = pt_begin.p;
-    v.obs_off = obs_off.p; v.obs_cal = obs_cal.p;
+    v.obs_off = n_us > 0 ? off_dyn.p : obs_off.p; v.obs_cal = obs_cal.p;
+    v.n_us = n_us; v.obs_us = obs_us.p; v.frame_rot = frame_rot.p;
     v.tile_pt_begin = tile_pt_begin.p; v.camord_obs = camord_obs.p; v.pt_c = pt_c.p;
     v.seg_cam = seg_cam.p; v.seg_begin = seg_begin.p; v.seg_end = seg_end.p;
     v.M = M.p; v.bw = bw.p; v.jscale_s = jscale_s.p; v.Vinv = Vinv.p; v.gX = gX.p; v.Dp = Dp.p; v.jscale_p = jscale_p.p;
@@ -54,6 +59,44 @@ struct b200sfm_gp_problem {
     if (h_cal) { obs_cal.alloc(N); obs_cal.upload(h_cal, N, s); }
     else obs_cal.release();
     B200_CUDA_OK(cudaStreamSynchronize(s));
+  }
+
+  // unknown cam_from_rig: h_obs_us[N] (-1: the observing image's sensor is the reference sensor / calibrated),
+  // h_frame_rot[C][9] rig_from_world rotations, h_ucen[S_u][3] initial centres.  Re-sizes the camera-block arrays.
+  void set_rig_unknown(int S_u, const int32_t* h_obs_us, const double* h_frame_rot, const double* h_ucen) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    n_us = S_u;
+    CB = C + n_us;
+    obs_us.alloc(N); obs_us.upload(h_obs_us, N, s);
+    frame_rot.alloc((size_t)C * 9); frame_rot.upload(h_frame_rot, (size_t)C * 9, s);
+    for (int i = 0; i < 2; ++i) ucen[i].alloc((size_t)n_us * 3);
+    ucen[cur].upload(h_ucen, (size_t)n_us * 3, s);
+    off_dyn.alloc((size_t)N * 3);
+    alloc_blocks();
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  void get_rig_unknown(double* h_ucen) {
+    ucen[cur].download(h_ucen, (size_t)n_us * 3, ctx->stream);
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  // fold -R_rw^T u_s of state `which` into the per-observation offsets
+  void dyn_offsets(int which) {
+    using namespace b200;
+    if (n_us > 0)
+      B200_LAUNCH(ctx, gp_dyn_offsets, cdiv(N, 256), 256, 0, N, obs_cam.p, obs_us.p, frame_rot.p, ucen[which].p,
+                  obs_off.p /* static known-rig offsets or nullptr */, off_dyn.p);
+  }
+  // per-block arrays of the reduced system (CB blocks of 3)
+  void alloc_blocks() {
+    cudaStream_t s = ctx->stream;
+    out16.alloc((size_t)CB * 16 + 1 + (size_t)ctx->world);   // per block 16 | cost | one max|g_X| slot per rank
+    U.alloc((size_t)CB * 6); gc.alloc((size_t)CB * 3); Dc.alloc((size_t)CB * 3);
+    Minv.alloc((size_t)CB * 6); jscale_c.alloc(CB);
+    px.alloc((size_t)CB * 3); pr.alloc((size_t)CB * 3); pz.alloc((size_t)CB * 3); pp.alloc((size_t)CB * 3);
+    pq.alloc((size_t)CB * 3); yw.alloc((size_t)CB * 3); bvec.alloc((size_t)CB * 3);
+    cam_const.alloc(CB);   // [0, C): frames (k_eff_mask); the unknown-sensor blocks are always variable (.cc:440-453)
+    cam_const.zero(s);
   }
 
   void create(b200sfm_ctx* c, int C_, int P_, long long N_, const int64_t* h_pt_begin, const int32_t* h_obs_cam,
@@ -89,7 +132,7 @@ struct b200sfm_gp_problem {
     tiles.push_back(P);
     n_tiles = (int)tiles.size() - 1;
     obs_cam.alloc(N); obs_pt.alloc(N); obs_dir.alloc((size_t)N * 3); pt_begin.alloc((size_t)P + 1);
-    tile_pt_begin.alloc(tiles.size()); calibrated.alloc(C); cam_const_base.alloc(C); cam_const.alloc(C);
+    tile_pt_begin.alloc(tiles.size()); calibrated.alloc(C); cam_const_base.alloc(C);
     obs_cam.upload(h_obs_cam, N, s);
     obs_dir.upload(h_obs_dir, (size_t)N * 3, s);
     pt_begin.upload(ptb.data(), (size_t)P + 1, s);
@@ -140,11 +183,8 @@ struct b200sfm_gp_problem {
     cen4.alloc((size_t)C * 4);
     M.alloc((size_t)N * kMDoubles); bw.alloc((size_t)N * 4); jscale_s.alloc(N);
     Vinv.alloc((size_t)P * 6); gX.alloc((size_t)P * 3); Dp.alloc(P); jscale_p.alloc(P);
-    out16.alloc((size_t)C * 16 + 1 + (size_t)ctx->world);   // per camera 16 | cost | one max|g_X| slot per rank
-    U.alloc((size_t)C * 6); gc.alloc((size_t)C * 3); Dc.alloc((size_t)C * 3);
-    Minv.alloc((size_t)C * 6); jscale_c.alloc(C);
-    px.alloc((size_t)C * 3); pr.alloc((size_t)C * 3); pz.alloc((size_t)C * 3); pp.alloc((size_t)C * 3);
-    pq.alloc((size_t)C * 3); yw.alloc((size_t)C * 3); bvec.alloc((size_t)C * 3);
+    CB = C;
+    alloc_blocks();
     dX.alloc((size_t)P * 3); ds.alloc(N); scal.alloc(16);
     smem_g1 = sizeof(G1Smem) + 128;
     smem_g3 = sizeof(G3Smem) + 128;
@@ -176,6 +216,10 @@ struct b200sfm_gp_problem {
     B200_CUDA_OK(cudaMemcpyAsync(centers_saved.p, centers[cur].p, centers_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(points_saved.p, points[cur].p, points_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(scales_saved.p, scales[cur].p, scales_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    if (n_us > 0) {
+      if (!ucen_saved.p) ucen_saved.alloc((size_t)n_us * 3);
+      B200_CUDA_OK(cudaMemcpyAsync(ucen_saved.p, ucen[cur].p, ucen_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    }
   }
   bool restore_state() {
     if (!centers_saved.p) return false;
@@ -183,6 +227,8 @@ struct b200sfm_gp_problem {
     B200_CUDA_OK(cudaMemcpyAsync(centers[cur].p, centers_saved.p, centers_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(points[cur].p, points_saved.p, points_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     B200_CUDA_OK(cudaMemcpyAsync(scales[cur].p, scales_saved.p, scales_saved.bytes(), cudaMemcpyDeviceToDevice, s));
+    if (n_us > 0 && ucen_saved.p)
+      B200_CUDA_OK(cudaMemcpyAsync(ucen[cur].p, ucen_saved.p, ucen_saved.bytes(), cudaMemcpyDeviceToDevice, s));
     return true;
   }
 
@@ -190,6 +236,7 @@ struct b200sfm_gp_problem {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     B200_LAUNCH(ctx, gp_build_records, cdiv(C, 256), 256, 0, C, centers[which].p, has_calibrated ? calibrated.p : nullptr, cen4.p);
+    dyn_offsets(which);
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 6, 0, sizeof(double), s));
     const int grid = std::min(cdiv(N, 256), 148 * 8);
     B200_LAUNCH(ctx, gp_cost, grid, 256, 0, v, cen4.p, points[which].p, scales[which].p, huber_a, scal.p + 6);
@@ -212,8 +259,9 @@ struct b200sfm_gp_problem {
                           bool profile) {
     using namespace b200;
     cudaStream_t s = ctx->stream;
-    const int nC3 = C * 3;
+    const int nC3 = CB * 3;   // frames + unknown-sensor blocks
     B200_LAUNCH(ctx, gp_build_records, cdiv(C, 256), 256, 0, C, centers[cur].p, has_calibrated ? calibrated.p : nullptr, cen4.p);
+    dyn_offsets(cur);
     B200_CUDA_OK(cudaMemsetAsync(scal.p, 0, 16 * sizeof(double), s));
     out16.zero(s);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -224,16 +272,18 @@ struct b200sfm_gp_problem {
     B200_LAUNCH(ctx, gp_linearize_points, n_tiles, kTile, smem_g1, v, cen4.p, points[cur].p, scales[cur].p,
                 o.thres_loss_function, radius, first ? 1 : 0, points_var ? 1 : 0, scal.p);
     if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
-    const bool schur_jacobi = points_var && o.preconditioner == 1;
+    // Schur-Jacobi blocks only without unknown sensors (their frame / sensor cross terms are not block diagonal)
+    const bool schur_jacobi = points_var && o.preconditioner == 1 && n_us == 0;
     if (n_segs > 0)
       B200_LAUNCH(ctx, gp_linearize_cams, cdiv((long long)n_segs * 32, 128), 128, 0, v, schur_jacobi ? 1 : 0, out16.p);
+    if (n_us > 0) B200_LAUNCH(ctx, gp_linearize_sensors, cdiv(N, 256), 256, 0, v, out16.p);
     // cost and this rank's max|g_X| (own slot) travel with the camera blocks through ONE sum all-reduce
-    B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)C * 16, scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)C * 16 + 1 + ctx->rank, scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
-    ctx->allreduce_sum(out16.p, (size_t)C * 16 + 1 + (size_t)ctx->world);
+    B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)CB * 16, scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(out16.p + (size_t)CB * 16 + 1 + ctx->rank, scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    ctx->allreduce_sum(out16.p, (size_t)CB * 16 + 1 + (size_t)ctx->world);
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 1, 0, sizeof(double), s));
-    B200_LAUNCH(ctx, gp_finalize_cams, cdiv(C, 128), 128, 0, C, out16.p, cam_const.p, jscale_c.p, first ? 1 : 0, radius,
-                schur_jacobi ? 1 : 0, U.p, gc.p, Dc.p, Minv.p, scal.p, out16.p + (size_t)C * 16 + 1, ctx->world);
+    B200_LAUNCH(ctx, gp_finalize_cams, cdiv(CB, 128), 128, 0, CB, out16.p, cam_const.p, jscale_c.p, first ? 1 : 0, radius,
+                schur_jacobi ? 1 : 0, U.p, gc.p, Dc.p, Minv.p, scal.p, out16.p + (size_t)CB * 16 + 1, ctx->world);
     // rhs  (constant points have Vinv = 0 from G1, so the same passes apply)
     {
       yw.zero(s);
@@ -244,7 +294,7 @@ struct b200sfm_gp_problem {
     B200_LAUNCH(ctx, k_rhs, cdiv(nC3, 256), 256, 0, nC3, gc.p, yw.p, bvec.p);
     // PCG (3x3 blocks; loop control on the device, pcg.cuh)
     const int max_it = std::max(1, o.pcg_max_iterations);
-    const int nblk = cdiv(C, kPcgThreads);
+    const int nblk = cdiv(CB, kPcgThreads);
     pcgh.ensure(max_it, (size_t)nblk * 3);
     double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
     PcgCtl* ctl = pcgh.d_ctl;
@@ -252,10 +302,10 @@ struct b200sfm_gp_problem {
     const size_t mv_ev0 = timer_mv.used;
     PcgResult pr_ = pcgh.run(
         s, max_it,
-        [&]() { B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, C, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
+        [&]() { B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, CB, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
         [&](int it) {
           double* d_pub = pcgh.dots(it - 1);
-          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, C, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
+          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, CB, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
                       pp.p, yw.p, pcgh.dots(it - 2), part_rz, part_rr, nullptr, d_pub, ctl);
           cudaEvent_t m0 = nullptr, m1 = nullptr;
           if (profile) {
@@ -266,13 +316,14 @@ struct b200sfm_gp_problem {
                       nullptr, nullptr, nullptr, ctl);
           if (profile) B200_CUDA_OK(cudaEventRecord(m1, s));
           ctx->allreduce_sum(yw.p, nC3);
-          B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, C, U.p, Dc.p, pp.p, yw.p, pq.p, part_pq, ctl);
-          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, C, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq,
+          // unknown sensors: the pass already applied the direct term per observation (A = nullptr)
+          B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, CB, n_us > 0 ? nullptr : U.p, Dc.p, pp.p, yw.p, pq.p, part_pq, ctl);
+          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, CB, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq,
                       part_rz, part_rr, pcgh.dots(it), ctl);
         },
         [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
     if (profile) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);
-    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, out16.p + (size_t)C * 16, sizeof(double), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, out16.p + (size_t)CB * 16, sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 9, scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     res.cost = ctx->h_scal[8];
@@ -284,7 +335,7 @@ struct b200sfm_gp_problem {
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 2, 0, 14 * sizeof(double), s));
     B200_LAUNCH(ctx, gp_schur_pass<2>, n_tiles, kTile, smem_g3, v, px.p, nullptr, cen4.p, points[cur].p, scales[cur].p,
                 o.thres_loss_function, radius, dX.p, ds.p, scal.p + 2);
-    B200_LAUNCH(ctx, gp_cam_scalars, cdiv(nC3, 256), 256, 0, C, px.p, pr.p, Dc.p, jscale_c.p, scal.p + 8);
+    B200_LAUNCH(ctx, gp_cam_scalars, cdiv(nC3, 256), 256, 0, CB, px.p, pr.p, Dc.p, jscale_c.p, scal.p + 8);
     ctx->allreduce_sum(scal.p + 2, 8);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal, scal.p, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
@@ -304,9 +355,10 @@ struct b200sfm_gp_problem {
     cudaStream_t s = ctx->stream;
     const int nxt = cur ^ 1;
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 12, 0, 2 * sizeof(double), s));
-    const long long nthreads = std::max<long long>(N, std::max<long long>((long long)P * 3, (long long)C * 3));
+    const long long nthreads = std::max<long long>(N, std::max<long long>((long long)P * 3, (long long)CB * 3));
     B200_LAUNCH(ctx, gp_apply_step, cdiv(nthreads, 256), 256, 0, v, alpha, centers[cur].p, points[cur].p, scales[cur].p, px.p,
-                dX.p, ds.p, jscale_c.p, ctx->rank == 0 ? 1 : 0, centers[nxt].p, points[nxt].p, scales[nxt].p, scal.p + 12);
+                dX.p, ds.p, jscale_c.p, ctx->rank == 0 ? 1 : 0, centers[nxt].p, points[nxt].p, scales[nxt].p, scal.p + 12,
+                n_us > 0 ? ucen[cur].p : nullptr, n_us > 0 ? ucen[nxt].p : nullptr);
     cand_cost = eval_cost(nxt, v, huber_a);
     // points/scales norms are per-shard, camera norms replicated: reduce the former only approximately matters
     ctx->allreduce_sum(scal.p + 12, 2);

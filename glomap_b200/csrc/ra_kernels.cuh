@@ -242,6 +242,101 @@ __global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square,
   }
 }
 
+// ---------------------------------------------------------------------------
+// CSR-by-node form of the same operators (3-DoF frames without gravity): every node owns the list of its incident
+// edges, so the weighted Laplacian is a GATHER -- one warp per node, register accumulation, one store per node, no
+// atomics (the edge-parallel ra_laplacian costs 6 FP64 RED per edge and ran at 0.12 of the HBM roofline).  The
+// incidence list is sorted (node, edge id): the summation order is fixed, results are run-to-run identical.
+//   inc_val[s] = edge id | (1u << 31 if the node is the edge's image 1, whose block in A is -I);  inc_other[s] = the
+//   node at the other end (-1: the gauge pseudo-edge, which has no other end);  w_inc[s] = w_e^p in incidence order
+//   (refreshed once per linear system by ra_node_setup, so the mat-vec streams 12 B per incidence).
+// ---------------------------------------------------------------------------
+struct RACsr {
+  int n;
+  const int* begin;        // [n + 1]
+  const unsigned* val;     // [n_inc]
+  const int* other;        // [n_inc]
+  double* w_inc;           // [n_inc]
+};
+
+__global__ void ra_csr_count(long long E, const int* __restrict__ ei, const int* __restrict__ ej, int n,
+                             int* __restrict__ cnt, int* __restrict__ keys, unsigned* __restrict__ vals) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int i = ei[e], j = ej[e];
+  atomicAdd(&cnt[j], 1);
+  keys[2 * e] = j;
+  vals[2 * e] = (unsigned)e;
+  if (i >= 0) {
+    atomicAdd(&cnt[i], 1);
+    keys[2 * e + 1] = i;
+    vals[2 * e + 1] = (unsigned)e | 0x80000000u;
+  } else {
+    keys[2 * e + 1] = n;   // sorts behind every real node
+    vals[2 * e + 1] = 0;
+  }
+}
+__global__ void ra_csr_other(int n_inc, const unsigned* __restrict__ val, const int* __restrict__ ei,
+                             const int* __restrict__ ej, int* __restrict__ other) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_inc) return;
+  const unsigned v = val[s];
+  const unsigned e = v & 0x7fffffffu;
+  other[s] = (v >> 31) ? ej[e] : ei[e];
+}
+
+// per linear system: w_inc, Laplacian diagonal deg[n][3], rhs = A^T diag(w^p) vec   (replaces ra_scatter)
+__global__ void __launch_bounds__(128) ra_node_setup(RACsr c, const double* __restrict__ w, int square,
+                                                     const double* __restrict__ vec, double* __restrict__ rhs,
+                                                     double* __restrict__ deg) {
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= c.n) return;
+  const int b = c.begin[node], e = c.begin[node + 1];
+  double d = 0, r0 = 0, r1 = 0, r2 = 0;
+  for (int s = b + lane; s < e; s += 32) {
+    const unsigned v = c.val[s];
+    const unsigned ed = v & 0x7fffffffu;
+    double we = w[ed];
+    if (square) we *= we;
+    c.w_inc[s] = we;
+    d += we;
+    const double sg = (v >> 31) ? -we : we;
+    r0 += sg * vec[3 * (size_t)ed];
+    r1 += sg * vec[3 * (size_t)ed + 1];
+    r2 += sg * vec[3 * (size_t)ed + 2];
+  }
+  d = warp_sum(d); r0 = warp_sum(r0); r1 = warp_sum(r1); r2 = warp_sum(r2);
+  if (lane == 0) {
+    deg[3 * (size_t)node] = deg[3 * (size_t)node + 1] = deg[3 * (size_t)node + 2] = d;
+    rhs[3 * (size_t)node] = r0; rhs[3 * (size_t)node + 1] = r1; rhs[3 * (size_t)node + 2] = r2;
+  }
+}
+
+// y_n = sum_{e ~ n} w_e (x_n - x_other)
+__global__ void __launch_bounds__(128) ra_laplacian_csr(RACsr c, const double* __restrict__ x, double* __restrict__ y,
+                                                        const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;   // the PCG stopping rule has fired: the queued iterations are no-ops
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= c.n) return;
+  const int b = c.begin[node], e = c.begin[node + 1];
+  const double x0 = x[3 * (size_t)node], x1 = x[3 * (size_t)node + 1], x2 = x[3 * (size_t)node + 2];
+  double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+  for (int s = b + lane; s < e; s += 32) {
+    const double we = ld_stream(c.w_inc + s);
+    const int o = ld_stream(c.other + s);
+    double o0 = 0, o1 = 0, o2 = 0;
+    if (o >= 0) { o0 = x[3 * (size_t)o]; o1 = x[3 * (size_t)o + 1]; o2 = x[3 * (size_t)o + 2]; }
+    a0 += we * (x0 - o0);
+    a1 += we * (x1 - o1);
+    a2 += we * (x2 - o2);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { y[3 * (size_t)node] = a0; y[3 * (size_t)node + 1] = a1; y[3 * (size_t)node + 2] = a2; }
+}
+
 // Minv (packed 3x3 diagonal) = 1/deg ; nodes without edges get identity
 __global__ void ra_build_precond(int n, const double* __restrict__ deg, double* __restrict__ Minv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

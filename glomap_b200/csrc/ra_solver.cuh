@@ -3,6 +3,8 @@
 // SetupLinearSystem / SolveL1Regression / SolveIRLS sequence; the L1 solver is
 // colmap::LeastAbsoluteDeviationSolver restated in oracle/ra_oracle.py).
 #pragma once
+#include <cub/cub.cuh>
+
 #include "context.cuh"
 #include "pcg.cuh"
 #include "ra_kernels.cuh"
@@ -24,6 +26,17 @@ struct b200sfm_ra_problem {
   DevBuf<double> Rrel, w_edge, theta, res, w, b, z, u;
   DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, part, scal;
   b200::PcgHost pcgh;
+  // CSR-by-node incidence lists (3-DoF frames without gravity): gather form of the Laplacian, see ra_kernels.cuh
+  bool use_csr = false;
+  int n_inc = 0;
+  DevBuf<int> inc_begin, inc_other;
+  DevBuf<unsigned> inc_val;
+  DevBuf<double> w_inc;
+  b200::RACsr csr() {
+    b200::RACsr c;
+    c.n = n; c.begin = inc_begin.p; c.val = inc_val.p; c.other = inc_other.p; c.w_inc = w_inc.p;
+    return c;
+  }
 
   b200::RAView view() {
     b200::RAView v;
@@ -128,7 +141,46 @@ struct b200sfm_ra_problem {
       E_total = (long long)(tot[0] + 0.5);
       rows_total = (long long)(tot[1] + 0.5);
     }
+    // incidence lists by node (device radix sort on (node, edge id): deterministic summation order)
+    use_csr = !has_grav && E > 0 && !(getenv("B200SFM_RA_CSR") && atoi(getenv("B200SFM_RA_CSR")) == 0);
+    if (use_csr) {
+      DevBuf<int> cnt, keys, keys_out;
+      DevBuf<unsigned> vals;
+      cnt.alloc((size_t)n + 1); keys.alloc((size_t)2 * E); keys_out.alloc((size_t)2 * E); vals.alloc((size_t)2 * E);
+      inc_val.alloc((size_t)2 * E); inc_begin.alloc((size_t)n + 1);
+      cnt.zero(s);
+      B200_LAUNCH(ctx, ra_csr_count, cdiv(E, 256), 256, 0, E, ei.p, ej.p, n, cnt.p, keys.p, vals.p);
+      int end_bit = 1;
+      while ((1ll << end_bit) <= n) ++end_bit;
+      size_t sort_bytes = 0, scan_bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys.p, keys_out.p, vals.p, inc_val.p, (int)(2 * E), 0, end_bit, s);
+      cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt.p, inc_begin.p, n + 1, s);
+      DevBuf<unsigned char> tmp;
+      tmp.alloc(std::max(sort_bytes, scan_bytes) + 16);
+      size_t tb = tmp.bytes();
+      cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_out.p, vals.p, inc_val.p, (int)(2 * E), 0, end_bit, s);
+      tb = tmp.bytes();
+      cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, inc_begin.p, n + 1, s);
+      ctx->launches += 4;
+      int h_inc = 0;
+      B200_CUDA_OK(cudaMemcpyAsync(&h_inc, inc_begin.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      n_inc = h_inc;
+      inc_other.alloc((size_t)std::max(n_inc, 1)); w_inc.alloc((size_t)std::max(n_inc, 1));
+      B200_LAUNCH(ctx, ra_csr_other, cdiv(std::max(n_inc, 1), 256), 256, 0, n_inc, inc_val.p, ei.p, ej.p, inc_other.p);
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // sort temporaries go out of scope
+    }
     B200_CUDA_OK(cudaStreamSynchronize(s));   // host vectors go out of scope
+  }
+
+  // y = L(w^p) x over this rank's edges (then all-reduced by the caller); weights as prepared by prepare_system
+  void laplacian(const b200::RAView& v, int square, const double* x, double* y, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    if (use_csr) {
+      B200_LAUNCH(ctx, ra_laplacian_csr, cdiv((long long)n * 32, 128), 128, 0, csr(), x, y, ctl);
+    } else if (E > 0) {
+      B200_LAUNCH(ctx, ra_laplacian, cdiv(std::max<long long>(E, 1), 256), 256, 0, v, w.p, square, x, y, ctl);
+    }
   }
 
   // x = L(w^p)^-1 rhs_vec by PCG (result in px); returns iterations.  Loop control on the device (pcg.cuh).
@@ -141,14 +193,13 @@ struct b200sfm_ra_problem {
     pcgh.ensure(max_it, (size_t)nblk * 3);
     double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
     PcgCtl* ctl = pcgh.d_ctl;
-    const int egrid = cdiv(std::max<long long>(E, 1), 256);
     PcgResult r = pcgh.run(
         s, max_it,
         [&]() {
           if (warm) {
             // r0 = b - L x_prev (ADMM x-updates change little between iterations); reference = |b|^2 (partials in part_pq)
             yw.zero(s);
-            if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, px.p, yw.p, nullptr);
+            laplacian(v, square, px.p, yw.p, nullptr);
             ctx->allreduce_sum(yw.p, (size_t)n * 3);
             B200_LAUNCH(ctx, ra_pcg_init_warm, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, yw.p, pr.p, pz.p, pp.p, part_pq, part_rz, part_rr);
           } else {
@@ -159,7 +210,7 @@ struct b200sfm_ra_problem {
           double* d_pub = pcgh.dots(it - 1);
           B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk, it, 0, o.pcg_rel_tolerance, pz.p, pp.p, yw.p,
                       pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
-          if (E > 0) B200_LAUNCH(ctx, ra_laplacian, egrid, 256, 0, v, w.p, square, pp.p, yw.p, ctl);
+          laplacian(v, square, pp.p, yw.p, ctl);
           ctx->allreduce_sum(yw.p, (size_t)n * 3);
           B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq, ctl);
           B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
@@ -175,9 +226,13 @@ struct b200sfm_ra_problem {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     RAView v = view();
-    deg.zero(s);
-    B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 3 * sizeof(double), s));
-    if (E > 0) B200_LAUNCH(ctx, ra_scatter, cdiv(E, 256), 256, 0, v, w.p, square, vec, rhs.p, deg.p);
+    if (use_csr) {   // gather form: also refreshes the incidence-ordered weights the mat-vec streams
+      B200_LAUNCH(ctx, ra_node_setup, cdiv((long long)n * 32, 128), 128, 0, csr(), w.p, square, vec, rhs.p, deg.p);
+    } else {
+      deg.zero(s);
+      B200_CUDA_OK(cudaMemsetAsync(rhs.p, 0, (size_t)n * 3 * sizeof(double), s));
+      if (E > 0) B200_LAUNCH(ctx, ra_scatter, cdiv(E, 256), 256, 0, v, w.p, square, vec, rhs.p, deg.p);
+    }
     ctx->allreduce_sum(rhs.p, (size_t)n * 3);
     ctx->allreduce_sum(deg.p, (size_t)n * 3);
     B200_LAUNCH(ctx, ra_build_precond, cdiv(n, 256), 256, 0, n, deg.p, Minv.p);

@@ -362,6 +362,11 @@ class PositioningProblem:
     sensor_quat: np.ndarray | None = None      # [S,4] cam_from_rig rotations
     sensor_trans: np.ndarray | None = None     # [S,3] cam_from_rig translations (rig scale 1)
     sensor_calibrated: np.ndarray | None = None  # [S] has_prior_focal_length of the sensor's camera
+    # unknown cam_from_rig translations (global_positioning.cc:347-364, RigUnknownBATA): the camera centre in the rig
+    # frame of these sensors is an unknown shared by their images; sensor_trans is ignored for them on input and holds
+    # the estimated cam_from_rig translation (-R_cr c_cr, ConvertResults .cc:578-582) on return
+    sensor_unknown: np.ndarray | None = None     # [S] bool
+    rig_centers: np.ndarray | None = None        # [S,3] initial / estimated centres (rows of known sensors unused)
 
     @property
     def C(self):
@@ -432,8 +437,11 @@ class GlobalPositioner:
         st = LMStats()
         if prob.obs_sensor is not None:
             # RigBATA with constant rig scale: resident-problem path + per-observation rig terms
-            t_obs, t_rig = rig_world_terms(prob.quat, prob.sensor_quat, prob.sensor_trans, prob.bearings, prob.obs_cam,
-                                           prob.obs_sensor)
+            unk = None if prob.sensor_unknown is None else np.asarray(prob.sensor_unknown, bool)
+            st_in = np.array(prob.sensor_trans, dtype=np.float64, copy=True)
+            if unk is not None and unk.any():
+                st_in[unk] = 0.0                                         # no known offset for these images
+            t_obs, t_rig = rig_world_terms(prob.quat, prob.sensor_quat, st_in, prob.bearings, prob.obs_cam, prob.obs_sensor)
             t_obs, t_rig = _c(t_obs, np.float64), _c(t_rig, np.float64)
             ocal = None if prob.sensor_calibrated is None else _c(
                 np.asarray(prob.sensor_calibrated)[np.asarray(prob.obs_sensor)], np.uint8)
@@ -445,9 +453,30 @@ class GlobalPositioner:
             _lib.check(ctx.handle, rc)
             try:
                 _lib.check(ctx.handle, lib.b200sfm_gp_problem_set_rig_terms(h, _ptr(t_rig), _ptr(ocal)))
+                ucen = None
+                if unk is not None and unk.any():
+                    from . import geometry as geo
+                    uidx = np.full(len(unk), -1, np.int32)
+                    uidx[unk] = np.arange(int(unk.sum()), dtype=np.int32)
+                    obs_us = _c(uidx[np.asarray(prob.obs_sensor)], np.int32)
+                    frot = _c(geo.quat_xyzw_to_rotmat(np.asarray(prob.quat, np.float64)).reshape(-1, 9), np.float64)
+                    if prob.rig_centers is None or (o.generate_random_positions and o.optimize_positions):
+                        rc0 = np.zeros((len(unk), 3))
+                        rc0[unk] = self.rng.uniform(-1, 1, size=(int(unk.sum()), 3))       # .cc:440-453
+                        prob.rig_centers = rc0
+                    ucen = _c(np.asarray(prob.rig_centers, np.float64)[unk], np.float64)
+                    _lib.check(ctx.handle, lib.b200sfm_gp_problem_set_rig_unknown(h, int(unk.sum()), _ptr(obs_us), _ptr(frot), _ptr(ucen)))
                 _lib.check(ctx.handle, lib.b200sfm_gp_problem_set_state(h, _ptr(cen), _ptr(pts), _ptr(sc)))
                 _lib.check(ctx.handle, lib.b200sfm_gp_problem_solve(h, ct.byref(co), ct.byref(st)))
                 _lib.check(ctx.handle, lib.b200sfm_gp_problem_get_state(h, _ptr(cen), _ptr(pts), _ptr(sc)))
+                if ucen is not None:
+                    from . import geometry as geo
+                    _lib.check(ctx.handle, lib.b200sfm_gp_problem_get_rig_unknown(h, _ptr(ucen)))
+                    prob.rig_centers = np.array(prob.rig_centers, dtype=np.float64, copy=True)
+                    prob.rig_centers[unk] = ucen
+                    Rs = geo.quat_xyzw_to_rotmat(np.asarray(prob.sensor_quat, np.float64))
+                    prob.sensor_trans = np.array(prob.sensor_trans, dtype=np.float64, copy=True)
+                    prob.sensor_trans[unk] = -np.einsum("sij,sj->si", Rs[unk], ucen)    # ConvertResults .cc:578-582
             finally:
                 lib.b200sfm_gp_problem_free(h)
             self.summary = st

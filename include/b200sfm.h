@@ -281,6 +281,15 @@ int b200sfm_gp_problem_create(b200sfm_ctx* ctx, int32_t C, int32_t P, int64_t N,
  * .cc:313-316).  NULL/NULL restores the trivial-frame behaviour. */
 int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* obs_offset /*[N][3]*/,
                                      const uint8_t* obs_calibrated /*[N] or NULL*/);
+/* Unknown cam_from_rig in global positioning -- RigUnknownBATAPairwiseDirectionError (glomap/estimators/cost_function.h:
+ * 90-136, call site global_positioning.cc:347-364): for the images of a sensor whose cam_from_rig translation is not
+ * known yet,  r = t_obs - s (X - c_frame - R_rw^T u_s)  with u_s (3 doubles, "cam_from_rig_center") an unknown shared by
+ * all images of the sensor.  obs_unknown_sensor[N]: index in [0, S_u) or -1 for observations of reference / calibrated
+ * sensors; frame_rot[C][9]: rig_from_world rotations, row-major; centers[S_u][3]: initial values (the reference draws
+ * U(-1,1)^3, global_positioning.cc:440-453) -- read back with b200sfm_gp_problem_get_rig_unknown. */
+int b200sfm_gp_problem_set_rig_unknown(b200sfm_gp_problem* p, int32_t num_unknown_sensors, const int32_t* obs_unknown_sensor,
+                                       const double* frame_rot, const double* centers);
+int b200sfm_gp_problem_get_rig_unknown(b200sfm_gp_problem* p, double* centers);
 int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* centers, const double* points, const double* scales);
 int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* centers, double* points, double* scales);
 int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p);

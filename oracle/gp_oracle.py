@@ -97,9 +97,9 @@ class GPProblem:
             S_ = len(self.x0["rig_centers"])
             self.u_col = np.full(S_, -1)
             used = np.zeros(S_, bool); used[self.ru["obs_sensor"][self.ru["obs_sensor"] >= 0]] = True
-            if opts.optimize_positions:      # the centres are randomised with the positions (.cc:440-453)
-                idx = np.nonzero(used)[0]
-                self.u_col[idx] = col + 3 * np.arange(len(idx)); col += 3 * len(idx)
+            # always variable: .cc:440-453 only RANDOMISES them with optimize_positions, nothing sets them constant
+            idx = np.nonzero(used)[0]
+            self.u_col[idx] = col + 3 * np.arange(len(idx)); col += 3 * len(idx)
         self.ncols = col
 
     def plus(self, x, delta):

@@ -203,3 +203,40 @@ def test_optimised_rig_poses_recover_the_extrinsics_noise_free():
     assert np.abs(G.quat_xyzw_to_rotmat(dev.sensor_quat) - G.quat_xyzw_to_rotmat(rs.sensor_quat)).max() < 1e-5
     s = np.linalg.norm(dev.sensor_trans[1]) / np.linalg.norm(rs.sensor_trans[1])      # nothing metric is fixed: up to scale
     assert np.abs(dev.sensor_trans[1:] - s * rs.sensor_trans[1:]).max() < 1e-5 and abs(s - 1) < 0.05
+
+
+def test_rig_unknown_bata_matches_oracle():
+    """RigUnknownBATAPairwiseDirectionError (cost_function.h:90-136, global_positioning.cc:347-364): sensor 0 is the
+    reference sensor, sensor 1 is calibrated (RigBATA offset), the camera centre of sensor 2 in the rig frame is an
+    unknown shared by all its images.  Same start as the oracle, tight PCG: same initial / final cost, same centres."""
+    rs = S.make_rig_scene(14, 3, 500, seed=11, pixel_sigma=0.3)
+    bear = S.bearings_from_scene(rs.images_scene())
+    rng = np.random.default_rng(4)
+    Rf = G.quat_xyzw_to_rotmat(rs.quat)
+    cen0 = G.centers_from_pose(Rf, rs.trans) + rng.normal(size=(rs.F, 3)) * 0.3
+    pts0 = rs.points + rng.normal(size=rs.points.shape) * 0.3
+    u_gt = -np.einsum("sji,sj->si", G.quat_xyzw_to_rotmat(rs.sensor_quat), rs.sensor_trans)     # centre in the rig frame
+    unk = np.array([False, False, True])
+    u0 = np.zeros((3, 3)); u0[2] = u_gt[2] + rng.normal(size=3) * 0.1
+    opts = E.GlobalPositionerOptions(generate_random_positions=False, generate_random_points=False, generate_scales=True)
+    opts.solver_options.pcg_rel_tolerance = 1e-12
+    opts.solver_options.pcg_max_iterations = 3000
+    prob = E.PositioningProblem(rs.quat, rs.pt_obs_begin, rs.obs_frame, bear, centers=cen0.copy(), points=pts0.copy(),
+                                obs_sensor=rs.obs_sensor, sensor_quat=rs.sensor_quat, sensor_trans=rs.sensor_trans.copy(),
+                                sensor_unknown=unk, rig_centers=u0.copy())
+    gp = E.GlobalPositioner(opts)
+    assert gp.Solve(prob)
+    st_known = rs.sensor_trans.copy(); st_known[2] = 0.0
+    t_obs, t_rig = E.rig_world_terms(rs.quat, rs.sensor_quat, st_known, bear, rs.obs_frame, rs.obs_sensor)
+    ru = dict(obs_sensor=np.where(rs.obs_sensor == 2, 0, -1).astype(np.int64), R_rw=Rf[rs.obs_frame], centers=u0[2:3].copy())
+    x, summ = GPO.solve_gp(cen0, pts0, rs.pt_obs_begin, rs.obs_frame, t_obs, None, GPO.GPOptions(), None, obs_offset=t_rig,
+                           rig_unknown=ru)
+    st = gp.summary
+    assert abs(st.initial_cost - summ.initial_cost) <= 1e-10 * summ.initial_cost
+    assert abs(st.final_cost - summ.final_cost) <= 1e-6 * max(summ.final_cost, 1e-12), (st.final_cost, summ.final_cost)
+    assert np.abs(prob.centers - x["centers"]).max() < 1e-5
+    assert np.abs(prob.rig_centers[2] - x["rig_centers"][0]).max() < 1e-5
+    # ConvertResults (.cc:578-582): the estimated centre becomes the cam_from_rig translation -R_cr u
+    want_t = -G.quat_xyzw_to_rotmat(rs.sensor_quat[2:3])[0] @ prob.rig_centers[2]
+    assert np.abs(prob.sensor_trans[2] - want_t).max() < 1e-12
+    assert np.array_equal(prob.sensor_trans[:2], rs.sensor_trans[:2])
