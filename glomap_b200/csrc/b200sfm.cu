@@ -673,4 +673,43 @@ int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int3
   return finish(ctx, rc);
 }
 
+int b200sfm_ra_solve_rig(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int32_t n_cams, int64_t n_edges,
+                         const int32_t* ei, const int32_t* ej, const int32_t* eci, const int32_t* ecj, const double* R_rel,
+                         const double* edge_w, const int32_t* cam_frames_begin, const int32_t* cam_frames,
+                         int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats) {
+  if (!ctx || !opts || !theta) return B200SFM_ERR_INVALID_ARG;
+  if (n_frames <= 0) { ctx->err = "no frames"; return B200SFM_ERR_EMPTY; }
+  if (n_cams <= 0 || !eci || !ecj || !cam_frames_begin || !cam_frames) { ctx->err = "no unknown cameras (use b200sfm_ra_solve)"; return B200SFM_ERR_INVALID_ARG; }
+  if (n_edges < 0 || (n_edges > 0 && (!ei || !ej || !R_rel))) { ctx->err = "null edge array"; return B200SFM_ERR_INVALID_ARG; }
+  if (fixed_frame < 0 || fixed_frame >= n_frames) { ctx->err = "fixed_frame out of range"; return B200SFM_ERR_INVALID_ARG; }
+  const int n = n_frames + n_cams;
+  for (int64_t e = 0; e < n_edges; ++e) {
+    if (ei[e] < 0 || ei[e] >= n_frames || ej[e] < 0 || ej[e] >= n_frames) { ctx->err = "edge index out of range"; return B200SFM_ERR_INVALID_ARG; }
+    if ((eci[e] != -1 && (eci[e] < n_frames || eci[e] >= n)) || (ecj[e] != -1 && (ecj[e] < n_frames || ecj[e] >= n))) {
+      ctx->err = "camera node out of range (must be -1 or in [n_frames, n_frames + n_cams))";
+      return B200SFM_ERR_INVALID_ARG;
+    }
+  }
+  if (cam_frames_begin[0] != 0) { ctx->err = "cam_frames_begin must start at 0"; return B200SFM_ERR_INVALID_ARG; }
+  for (int c = 0; c < n_cams; ++c)
+    if (cam_frames_begin[c + 1] < cam_frames_begin[c]) { ctx->err = "cam_frames_begin must be non-decreasing"; return B200SFM_ERR_INVALID_ARG; }
+  for (int k = 0; k < cam_frames_begin[n_cams]; ++k)
+    if (cam_frames[k] < 0 || cam_frames[k] >= n_frames) { ctx->err = "cam_frames out of range"; return B200SFM_ERR_INVALID_ARG; }
+  if (ctx->world > 1) { ctx->err = "unknown cam_from_rig rotations: single-process contexts only"; return B200SFM_ERR_UNSUPPORTED; }
+  b200sfm_ra_stats st{};
+  int rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    b200sfm_ra_problem p;
+    p.create(ctx, n, n_edges, ei, ej, R_rel, edge_w, opts->use_weight, fixed_frame, theta, nullptr, n_cams, eci, ecj,
+             cam_frames_begin, cam_frames);
+    int r = p.solve(*opts, &st);
+    if (r != B200SFM_OK) return r;
+    p.theta.download(theta, (size_t)n * 3, ctx->stream);
+    B200_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return (int)B200SFM_OK;
+  });
+  if (stats) *stats = st;
+  return finish(ctx, rc);
+}
+
 }  // extern "C"

@@ -32,6 +32,11 @@ struct RAView {
   const unsigned char* node_grav;   // [n] or nullptr
   const double* angle_rel;          // [E] y angle of R_rel (both-gravity pairs / gravity gauge), or nullptr
   const double* xz_err;             // [E] x^2 + z^2 of log(R_rel) (.cc:330-337), or nullptr
+  // unknown cam_from_rig rotations (.cc:173-245): nodes [n_frames, n) are the sensors that are not calibrated yet; an
+  // edge adds -I at eci and +I at ecj (.cc:425-440) and its residual uses R_k = R_cam R_frame (.cc:726-736)
+  int n_frames;                     // == n without unknown cameras
+  const int* eci;                   // [E] node of image 1's camera, -1: calibrated / reference sensor; nullptr: none
+  const int* ecj;                   // [E]
 };
 
 // which rows / coefficients an edge has
@@ -165,10 +170,27 @@ __global__ void ra_residuals(RAView v, const double* __restrict__ theta, int mod
   double Rj[9], T[9], M[9], r[3];
   const double tj[3] = {theta[3 * (size_t)j], theta[3 * (size_t)j + 1], theta[3 * (size_t)j + 2]};
   aa_to_R(tj, Rj);
+  const int ci = (v.eci && i >= 0) ? v.eci[e] : -1, cj = (v.ecj && i >= 0) ? v.ecj[e] : -1;
+  if (cj >= 0) {   // R_2 = R_cam2 R_frame2 (.cc:733-736)
+    const double tc[3] = {theta[3 * (size_t)cj], theta[3 * (size_t)cj + 1], theta[3 * (size_t)cj + 2]};
+    double Rc[9], P[9];
+    aa_to_R(tc, Rc);
+    mat3_mul(Rc, Rj, P);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rj[k] = P[k];
+  }
   if (i >= 0) {
     const double ti[3] = {theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2]};
     double Ri[9];
     aa_to_R(ti, Ri);
+    if (ci >= 0) {   // R_1 = R_cam1 R_frame1 (.cc:726-730)
+      const double tc[3] = {theta[3 * (size_t)ci], theta[3 * (size_t)ci + 1], theta[3 * (size_t)ci + 2]};
+      double Rc[9], P[9];
+      aa_to_R(tc, Rc);
+      mat3_mul(Rc, Ri, P);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Ri[k] = P[k];
+    }
     mat3_mul(Rrel, Ri, T);
   } else {
 #pragma unroll
@@ -204,18 +226,28 @@ __global__ void ra_scatter(RAView v, const double* __restrict__ w, int square, c
   double we = w[e];
   if (square) we *= we;
   const EdgeRows er = edge_rows(v, i, j);
+  const int nci = (v.eci && i >= 0) ? v.eci[e] : -1, ncj = (v.ecj && i >= 0) ? v.ecj[e] : -1;
+  const bool same_frame = i == j;   // only with unknown cameras: the -I and +I on the frame cancel (.cc:300-304 keeps the pair)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (er.y_only && k != 1) continue;
     const double a = we * vec[3 * e + k];
     const double cj = coef(er.gj, k);
-    if (cj != 0.0) {
+    if (cj != 0.0 && !same_frame) {
       atomicAdd(&out[3 * (size_t)j + k], a);
       if (deg) atomicAdd(&deg[3 * (size_t)j + k], we);
     }
-    if (i >= 0 && coef(er.gi, k) != 0.0) {
+    if (i >= 0 && coef(er.gi, k) != 0.0 && !same_frame) {
       atomicAdd(&out[3 * (size_t)i + k], -a);
       if (deg) atomicAdd(&deg[3 * (size_t)i + k], we);
+    }
+    if (ncj >= 0) {
+      atomicAdd(&out[3 * (size_t)ncj + k], a);
+      if (deg) atomicAdd(&deg[3 * (size_t)ncj + k], we);
+    }
+    if (nci >= 0) {
+      atomicAdd(&out[3 * (size_t)nci + k], -a);
+      if (deg) atomicAdd(&deg[3 * (size_t)nci + k], we);
     }
   }
 }
@@ -230,15 +262,21 @@ __global__ void ra_laplacian(RAView v, const double* __restrict__ w, int square,
   double we = w[e];
   if (square) we *= we;
   const EdgeRows er = edge_rows(v, i, j);
+  const int nci = (v.eci && i >= 0) ? v.eci[e] : -1, ncj = (v.ecj && i >= 0) ? v.ecj[e] : -1;
+  const bool same_frame = i == j;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (er.y_only && k != 1) continue;
-    const double cj = coef(er.gj, k), ci = (i >= 0) ? coef(er.gi, k) : 0.0;
+    const double cj = same_frame ? 0.0 : coef(er.gj, k), ci = (i >= 0 && !same_frame) ? coef(er.gi, k) : 0.0;
     double t = cj * x[3 * (size_t)j + k];
     if (ci != 0.0) t -= x[3 * (size_t)i + k];
+    if (ncj >= 0) t += x[3 * (size_t)ncj + k];
+    if (nci >= 0) t -= x[3 * (size_t)nci + k];
     t *= we;
     if (cj != 0.0) atomicAdd(&y[3 * (size_t)j + k], t);
     if (ci != 0.0) atomicAdd(&y[3 * (size_t)i + k], -t);
+    if (ncj >= 0) atomicAdd(&y[3 * (size_t)ncj + k], t);
+    if (nci >= 0) atomicAdd(&y[3 * (size_t)nci + k], -t);
   }
 }
 
@@ -382,12 +420,16 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
     const double we = w[e];
     const double kappa = 1.0 / rho;
     const EdgeRows er = edge_rows(v, i, j);
+    const int nci = (v.eci && i >= 0) ? v.eci[e] : -1, ncj = (v.ecj && i >= 0) ? v.ecj[e] : -1;
+    const bool same_frame = i == j;   // unknown cameras only: the frame coefficients cancel
     double r3[3] = {0, 0, 0}, s3[3] = {0, 0, 0}, u3[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (er.y_only && k != 1) continue;   // this row does not exist
-      double a = coef(er.gj, k) * x[3 * (size_t)j + k];
-      if (i >= 0) a -= coef(er.gi, k) * x[3 * (size_t)i + k];
+      double a = same_frame ? 0.0 : coef(er.gj, k) * x[3 * (size_t)j + k];
+      if (i >= 0 && !same_frame) a -= coef(er.gi, k) * x[3 * (size_t)i + k];
+      if (ncj >= 0) a += x[3 * (size_t)ncj + k];
+      if (nci >= 0) a -= x[3 * (size_t)nci + k];
       a *= we;
       const double bo = b[3 * e + k], zo = z[3 * e + k], uo = u[3 * e + k];
       const double vv = a - bo + uo;
@@ -406,15 +448,25 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (er.y_only && k != 1) continue;
-      if (coef(er.gj, k) != 0.0) {
+      if (coef(er.gj, k) != 0.0 && !same_frame) {
         atomicAdd(&rhs[3 * (size_t)j + k], r3[k]);
         atomicAdd(&svec[3 * (size_t)j + k], s3[k]);
         atomicAdd(&uvec[3 * (size_t)j + k], u3[k]);
       }
-      if (i >= 0 && coef(er.gi, k) != 0.0) {
+      if (i >= 0 && coef(er.gi, k) != 0.0 && !same_frame) {
         atomicAdd(&rhs[3 * (size_t)i + k], -r3[k]);
         atomicAdd(&svec[3 * (size_t)i + k], -s3[k]);
         atomicAdd(&uvec[3 * (size_t)i + k], -u3[k]);
+      }
+      if (ncj >= 0) {
+        atomicAdd(&rhs[3 * (size_t)ncj + k], r3[k]);
+        atomicAdd(&svec[3 * (size_t)ncj + k], s3[k]);
+        atomicAdd(&uvec[3 * (size_t)ncj + k], u3[k]);
+      }
+      if (nci >= 0) {
+        atomicAdd(&rhs[3 * (size_t)nci + k], -r3[k]);
+        atomicAdd(&svec[3 * (size_t)nci + k], -s3[k]);
+        atomicAdd(&uvec[3 * (size_t)nci + k], -u3[k]);
       }
     }
   }
@@ -431,12 +483,17 @@ __global__ void ra_admm_step(RAView v, const double* __restrict__ w, const doubl
 // UpdateGlobalRotations (.cc:631-640): theta <- log(exp(theta) exp(-step));
 // sums[0] += |step_i| (ComputeAverageStepSize .cc:758-772), sums[1] += |step|^2,
 // sums[2] = NaN flag
-__global__ void ra_update(int n, double* __restrict__ theta, const double* __restrict__ step, double* __restrict__ sums,
-                          const unsigned char* __restrict__ node_grav) {
+__global__ void ra_update(int n, int n_frames, double* __restrict__ theta, const double* __restrict__ step,
+                          double* __restrict__ sums, const unsigned char* __restrict__ node_grav) {
   __shared__ double scratch[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double s1 = 0, s2 = 0, bad = 0;
-  if (i < n) {
+  if (i >= n_frames && i < n) {   // unknown-camera node: updated by ra_update_cams; only |step|^2 / NaN are accounted here
+    const double d[3] = {step[3 * (size_t)i], step[3 * (size_t)i + 1], step[3 * (size_t)i + 2]};
+    s2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    if (isnan(s2)) bad = 1.0;
+  }
+  if (i < n_frames) {
     const double d[3] = {step[3 * (size_t)i], step[3 * (size_t)i + 1], step[3 * (size_t)i + 2]};
     const double nd[3] = {-d[0], -d[1], -d[2]};
     const double t[3] = {theta[3 * (size_t)i], theta[3 * (size_t)i + 1], theta[3 * (size_t)i + 2]};
@@ -467,6 +524,81 @@ __global__ void ra_update(int n, double* __restrict__ theta, const double* __res
     atomicAdd(&sums[1], s2);
     if (bad > 0) atomicAdd(&sums[2], bad);
   }
+}
+
+// Unknown cam_from_rig rotations (.cc:646-693): for every frame f that holds an image of camera c the updated rotation
+// is R_c R_f exp(-step_c) R_f^T (R_f = the frame's ALREADY UPDATED rotation); the new R_c is the quaternion average
+// (colmap::AverageQuaternions, unit weights: dominant eigenvector of sum q q^T) over those frames.  One warp per camera.
+__global__ void __launch_bounds__(128) ra_update_cams(int n_frames, int n_cams, double* __restrict__ theta,
+                                                      const double* __restrict__ step, const int* __restrict__ cf_begin,
+                                                      const int* __restrict__ cf_list) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= n_cams) return;
+  const size_t node = (size_t)n_frames + c;
+  const double tc[3] = {theta[3 * node], theta[3 * node + 1], theta[3 * node + 2]};
+  const double ns[3] = {-step[3 * node], -step[3 * node + 1], -step[3 * node + 2]};
+  double Rc[9], Ru[9];
+  aa_to_R(tc, Rc);
+  aa_to_R(ns, Ru);
+  double M[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // packed symmetric 4x4 of sum q q^T
+  double q0[4] = {0, 0, 0, 1};
+  bool have0 = false;
+  for (int s = cf_begin[c] + lane; s < cf_begin[c + 1]; s += 32) {
+    const int f = cf_list[s];
+    const double tf[3] = {theta[3 * (size_t)f], theta[3 * (size_t)f + 1], theta[3 * (size_t)f + 2]};
+    double Rf[9], A[9], B[9], P[9];
+    aa_to_R(tf, Rf);
+    mat3_mul(Rc, Rf, A);        // R_c R_f
+    mat3_mul(A, Ru, B);         // R_c R_f R_upd
+#pragma unroll
+    for (int i = 0; i < 3; ++i)   // P = B R_f^T
+#pragma unroll
+      for (int j = 0; j < 3; ++j) P[3 * i + j] = B[3 * i] * Rf[3 * j] + B[3 * i + 1] * Rf[3 * j + 1] + B[3 * i + 2] * Rf[3 * j + 2];
+    double q[4];   // Eigen::Quaterniond(Matrix3d)
+    const double t = P[0] + P[4] + P[8];
+    if (t > 0.0) {
+      double tt = sqrt(t + 1.0);
+      q[3] = 0.5 * tt;
+      tt = 0.5 / tt;
+      q[0] = (P[7] - P[5]) * tt; q[1] = (P[2] - P[6]) * tt; q[2] = (P[3] - P[1]) * tt;
+    } else {
+      int i = 0;
+      if (P[4] > P[0]) i = 1;
+      if (P[8] > P[4 * i]) i = 2;
+      const int j = (i + 1) % 3, k = (i + 2) % 3;
+      double tt = sqrt(P[4 * i] - P[4 * j] - P[4 * k] + 1.0);
+      q[i] = 0.5 * tt;
+      tt = 0.5 / tt;
+      q[3] = (P[3 * k + j] - P[3 * j + k]) * tt; q[j] = (P[3 * j + i] + P[3 * i + j]) * tt; q[k] = (P[3 * k + i] + P[3 * i + k]) * tt;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a; b < 4; ++b) M[idx++] += q[a] * q[b];
+    if (!have0) { q0[0] = q[0]; q0[1] = q[1]; q0[2] = q[2]; q0[3] = q[3]; have0 = true; }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) M[k] = warp_sum(M[k]);
+  if (lane != 0 || cf_begin[c + 1] == cf_begin[c]) return;
+  // dominant eigenvector by power iteration from the first quaternion (the averaged rotations are estimates of one
+  // rotation: the gap to the second eigenvalue is large)
+  const double S[4][4] = {{M[0], M[1], M[2], M[3]}, {M[1], M[4], M[5], M[6]}, {M[2], M[5], M[7], M[8]}, {M[3], M[6], M[8], M[9]}};
+  double v[4] = {q0[0], q0[1], q0[2], q0[3]};
+  for (int it = 0; it < 200; ++it) {
+    double u[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) u[a] = S[a][0] * v[0] + S[a][1] * v[1] + S[a][2] * v[2] + S[a][3] * v[3];
+    const double nn = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]);
+    if (!(nn > 0.0)) break;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[a] = u[a] / nn;
+  }
+  double R[9], out[3];
+  quat_to_R(v, R);
+  R_to_aa(R, out);
+  theta[3 * node] = out[0]; theta[3 * node + 1] = out[1]; theta[3 * node + 2] = out[2];
 }
 
 // |a|^2, |b|^2 of node vectors: per-CTA partials (deterministic two-stage sum)

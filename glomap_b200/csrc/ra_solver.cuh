@@ -13,7 +13,9 @@ struct b200sfm_ra_problem {
   template <class T>
   using DevBuf = b200::DevBuf<T>;
   b200sfm_ctx* ctx = nullptr;
-  int n = 0;
+  int n = 0;              // nodes: frames followed by the unknown cam_from_rig rotations
+  int n_frames = 0, n_cams = 0;
+  DevBuf<int> eci, ecj, cf_begin, cf_list;
   long long E = 0;        // local edges (+1 gauge pseudo-edge on rank 0)
   long long E_real = 0;
   long long E_total = 0;  // valid edges over all ranks
@@ -44,13 +46,18 @@ struct b200sfm_ra_problem {
     v.node_grav = has_grav ? node_grav.p : nullptr;
     v.angle_rel = has_grav ? angle_rel.p : nullptr;
     v.xz_err = has_grav ? xz_err.p : nullptr;
+    v.n_frames = n_frames; v.eci = n_cams > 0 ? eci.p : nullptr; v.ecj = n_cams > 0 ? ecj.p : nullptr;
     return v;
   }
 
   void create(b200sfm_ctx* c, int n_, long long E_, const int32_t* h_ei, const int32_t* h_ej, const double* h_Rrel,
-              const double* h_w, int use_weight, int fixed_, const double* h_theta, const uint8_t* h_grav = nullptr) {
+              const double* h_w, int use_weight, int fixed_, const double* h_theta, const uint8_t* h_grav = nullptr,
+              int n_cams_ = 0, const int32_t* h_eci = nullptr, const int32_t* h_ecj = nullptr,
+              const int32_t* h_cf_begin = nullptr, const int32_t* h_cf_list = nullptr) {
     using namespace b200;
     ctx = c; n = n_; E_real = E_; fixed = fixed_;
+    n_cams = n_cams_;
+    n_frames = n - n_cams;
     cudaStream_t s = ctx->stream;
     const bool gauge_here = ctx->rank == 0;
     E = E_real + (gauge_here ? 1 : 0);
@@ -121,6 +128,18 @@ struct b200sfm_ra_problem {
       node_grav.alloc(n); angle_rel.alloc(Ea); xz_err.alloc(Ea);
       node_grav.upload(h_grav, n, s); angle_rel.upload(h_ang.data(), E, s); xz_err.upload(h_xz.data(), E, s);
     }
+    if (n_cams > 0) {
+      std::vector<int> hci(h_eci, h_eci + E_real), hcj(h_ecj, h_ecj + E_real);
+      if (gauge_here) { hci.push_back(-1); hcj.push_back(-1); }
+      eci.alloc(Ea); ecj.alloc(Ea);
+      eci.upload(hci.data(), E, s); ecj.upload(hcj.data(), E, s);
+      cf_begin.alloc((size_t)n_cams + 1);
+      cf_begin.upload(h_cf_begin, (size_t)n_cams + 1, s);
+      const int n_cf = h_cf_begin[n_cams];
+      cf_list.alloc((size_t)std::max(n_cf, 1));
+      cf_list.upload(h_cf_list, n_cf, s);
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // hci / hcj are locals
+    }
     ei.alloc(Ea); ej.alloc(Ea); Rrel.alloc(Ea * 9); w_edge.alloc(Ea); flags.alloc(4);
     ei.upload(hi.data(), E, s); ej.upload(hj.data(), E, s); Rrel.upload(hr.data(), (size_t)E * 9, s); w_edge.upload(hw.data(), E, s);
     theta.alloc((size_t)n * 3);
@@ -142,7 +161,7 @@ struct b200sfm_ra_problem {
       rows_total = (long long)(tot[1] + 0.5);
     }
     // incidence lists by node (device radix sort on (node, edge id): deterministic summation order)
-    use_csr = !has_grav && E > 0 && !(getenv("B200SFM_RA_CSR") && atoi(getenv("B200SFM_RA_CSR")) == 0);
+    use_csr = !has_grav && n_cams == 0 && E > 0 && !(getenv("B200SFM_RA_CSR") && atoi(getenv("B200SFM_RA_CSR")) == 0);
     if (use_csr) {
       DevBuf<int> cnt, keys, keys_out;
       DevBuf<unsigned> vals;
@@ -243,10 +262,12 @@ struct b200sfm_ra_problem {
     using namespace b200;
     cudaStream_t s = ctx->stream;
     B200_CUDA_OK(cudaMemsetAsync(scal.p + 8, 0, 4 * sizeof(double), s));
-    B200_LAUNCH(ctx, ra_update, cdiv(n, 256), 256, 0, n, theta.p, px.p, scal.p + 8, has_grav ? node_grav.p : nullptr);
+    B200_LAUNCH(ctx, ra_update, cdiv(n, 256), 256, 0, n, n_frames, theta.p, px.p, scal.p + 8, has_grav ? node_grav.p : nullptr);
+    if (n_cams > 0)   // after the frames: the averaging uses the updated frame rotations (.cc:646-693)
+      B200_LAUNCH(ctx, ra_update_cams, cdiv((long long)n_cams * 32, 128), 128, 0, n_frames, n_cams, theta.p, px.p, cf_begin.p, cf_list.p);
     B200_CUDA_OK(cudaMemcpyAsync(ctx->h_scal + 8, scal.p + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
-    avg = ctx->h_scal[8] / n;
+    avg = ctx->h_scal[8] / n_frames;   // ComputeAverageStepSize runs over the frames (.cc:758-772)
     norm = std::sqrt(ctx->h_scal[9]);
     bad = ctx->h_scal[10] > 0 || !std::isfinite(ctx->h_scal[9]);
   }

@@ -577,6 +577,33 @@ def rig_view_graph(vg, img_frame, img_sensor, sensor_quat, R_gt_frames=None):
                      np.asarray(vg.weight)[keep].copy(), R_gt)
 
 
+def rig_view_graph_unknown(vg, img_frame, img_sensor, sensor_quat, sensor_known):
+    """Rigs with sensors whose cam_from_rig is NOT known yet (global_rotation_averaging.cc:173-245,274-309,425-440): the
+    unknowns are the frame rotations followed by one rotation per uncalibrated sensor.  An image pair contributes
+    R_rel = R_c2r2^T R_21 R_c1r1 with the identity for an uncalibrated sensor, -I / +I blocks on its frames and on the
+    uncalibrated cameras; a pair inside one frame is dropped only when both sensors are calibrated (.cc:300-304).
+    Returns dict(n_frames, n_cams, ei, ej, eci, ecj, R_rel, weight, cam_of_sensor [S] (-1 or node index),
+    cam_frames_begin, cam_frames)."""
+    from . import geometry as geo
+    img_frame, img_sensor = np.asarray(img_frame), np.asarray(img_sensor)
+    known = np.asarray(sensor_known, bool)
+    n_frames = int(img_frame.max()) + 1
+    cam_idx = np.full(len(known), -1, np.int64)
+    cam_idx[~known] = n_frames + np.arange(int((~known).sum()))
+    Rs = geo.quat_xyzw_to_rotmat(np.asarray(sensor_quat, dtype=np.float64)).copy()
+    Rs[~known] = np.eye(3)
+    fi, fj = img_frame[vg.ei], img_frame[vg.ej]
+    si, sj = img_sensor[vg.ei], img_sensor[vg.ej]
+    keep = ~((fi == fj) & known[si] & known[sj])
+    R_rel = np.einsum("nji,njk,nkl->nil", Rs[sj[keep]], vg.R_rel[keep], Rs[si[keep]])
+    frames_of = [np.unique(img_frame[img_sensor == s_]) for s_ in np.nonzero(~known)[0]]
+    cfb = np.concatenate([[0], np.cumsum([len(f) for f in frames_of])]).astype(np.int32)
+    return dict(n_frames=n_frames, n_cams=int((~known).sum()), ei=fi[keep].astype(np.int32), ej=fj[keep].astype(np.int32),
+                eci=cam_idx[si[keep]].astype(np.int32), ecj=cam_idx[sj[keep]].astype(np.int32), R_rel=R_rel,
+                weight=np.asarray(vg.weight)[keep].copy(), cam_of_sensor=cam_idx, cam_frames_begin=cfb,
+                cam_frames=(np.concatenate(frames_of) if frames_of else np.zeros(0)).astype(np.int32))
+
+
 class RotationEstimator:
     """glomap::RotationEstimator (global_rotation_averaging.h:77-87)."""
 
@@ -639,6 +666,27 @@ class RotationEstimator:
         R = geo.so3_exp(theta)
         R[hg] = R_align[hg] @ R[hg]                                                       # ConvertResults .cc:787-793
         return bool(st.usable), R
+
+
+def estimate_rotations_rig_unknown(est: "RotationEstimator", g: dict, R_frames0, R_cams0, fixed: int = 0):
+    """RotationEstimator::EstimateRotations over the flattening of rig_view_graph_unknown: returns
+    (ok, R_frames [F,3,3], R_cams [n_cams,3,3] = the estimated cam_from_rig rotations, .cc:805-813)."""
+    from . import geometry as geo
+    ctx = est.ctx or default_context()
+    co = est.options_.to_c()
+    st = _lib.RAStats()
+    theta = _c(np.concatenate([geo.so3_log(np.asarray(R_frames0, np.float64)), geo.so3_log(np.asarray(R_cams0, np.float64))]), np.float64)
+    a = [_c(g["ei"], np.int32), _c(g["ej"], np.int32), _c(g["eci"], np.int32), _c(g["ecj"], np.int32),
+         _c(g["R_rel"].reshape(-1, 9), np.float64), _c(g["weight"], np.float64), _c(g["cam_frames_begin"], np.int32),
+         _c(g["cam_frames"], np.int32)]
+    rc = ctx.lib.b200sfm_ra_solve_rig(ctx.handle, ct.byref(co), g["n_frames"], g["n_cams"], len(a[0]), *[_ptr(x) for x in a], fixed,
+                                      _ptr(theta), ct.byref(st))
+    est.summary = st
+    if rc == 4:
+        return False, None, None
+    _lib.check(ctx.handle, rc)
+    R = geo.so3_exp(theta)
+    return bool(st.usable), R[:g["n_frames"]], R[g["n_frames"]:]
 
 
 def get_align_rot(gravity) -> np.ndarray:

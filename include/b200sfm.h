@@ -359,6 +359,18 @@ int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int3
                              const uint8_t* frame_has_gravity, int32_t fixed_frame, double* theta,
                              b200sfm_ra_stats* stats);
 
+/* Rotation averaging with UNKNOWN cam_from_rig rotations (glomap/estimators/global_rotation_averaging.cc:173-245 the
+ * unknown layout, :425-440 the extra -I / +I blocks, :646-693 the update with colmap::AverageQuaternions over the frames
+ * of each camera, :726-736 residuals with R_k = R_cam R_frame, :805-813 the estimated rotations).
+ *   theta [n_frames + n_cams][3]: frame rotations followed by the cam_from_rig rotations of the sensors that are not
+ *   calibrated (initial values in, result out);  eci/ecj [E]: node index (>= n_frames) of the camera of image 1 / 2 or -1;
+ *   R_rel carries the calibrated cam_from_rig factors (:305-309);  cam_frames (CSR over the n_cams cameras): the frames that
+ *   hold an image of the camera.  A pair inside one frame is kept when a camera of it is unknown (:300-304). */
+int b200sfm_ra_solve_rig(b200sfm_ctx* ctx, const b200sfm_ra_opts* opts, int32_t n_frames, int32_t n_cams, int64_t n_edges,
+                         const int32_t* ei, const int32_t* ej, const int32_t* eci, const int32_t* ecj, const double* R_rel,
+                         const double* edge_w, const int32_t* cam_frames_begin, const int32_t* cam_frames,
+                         int32_t fixed_frame, double* theta, b200sfm_ra_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -398,3 +398,124 @@ def estimate_rotations_gravity(n, ei, ej, R_rel, R0, has_gravity, R_align, opts:
     R = np.stack([R_align[i] @ node_R(i) if hg[i] else node_R(i) for i in range(n)])   # ConvertResults (.cc:787-799)
     info["fixed"] = fixed
     return R, info
+
+
+# ---------------------------------------------------------------------------
+# Unknown cam_from_rig rotations (non-trivial rigs whose sensors are not calibrated yet)
+# ---------------------------------------------------------------------------
+def average_quaternions(R_list):
+    """colmap::AverageQuaternions with unit weights (UPSTREAM-UNVERIFIED restatement): the eigenvector of
+    sum q q^T with the largest eigenvalue, returned as a rotation matrix."""
+    qs = []
+    for R in R_list:
+        # Eigen::Quaterniond(Matrix3d): the same branch structure as R_to_aa's first half
+        t = np.trace(R)
+        q = np.zeros(4)
+        if t > 0:
+            tt = np.sqrt(t + 1.0); q[3] = 0.5 * tt; tt = 0.5 / tt
+            q[0] = (R[2, 1] - R[1, 2]) * tt; q[1] = (R[0, 2] - R[2, 0]) * tt; q[2] = (R[1, 0] - R[0, 1]) * tt
+        else:
+            i = 0
+            if R[1, 1] > R[0, 0]:
+                i = 1
+            if R[2, 2] > R[i, i]:
+                i = 2
+            j, k = (i + 1) % 3, (i + 2) % 3
+            tt = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+            q[i] = 0.5 * tt; tt = 0.5 / tt
+            q[3] = (R[k, j] - R[j, k]) * tt; q[j] = (R[j, i] + R[i, j]) * tt; q[k] = (R[k, i] + R[i, k]) * tt
+        qs.append(q)
+    qs = np.array(qs)
+    w, v = np.linalg.eigh(qs.T @ qs)
+    x, y, z, ww = v[:, -1] / np.linalg.norm(v[:, -1])
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * ww), 2 * (x * z + y * ww)],
+                     [2 * (x * y + z * ww), 1 - 2 * (x * x + z * z), 2 * (y * z - x * ww)],
+                     [2 * (x * z - y * ww), 2 * (y * z + x * ww), 1 - 2 * (x * x + y * y)]])
+
+
+def estimate_rotations_rig_unknown(n_frames, n_cams, ei, ej, eci, ecj, R_rel, theta0, cam_frames, opts: RAOptions | None = None,
+                                   fixed=0, edge_weight=None):
+    """RotationEstimator with unknown cam_from_rig rotations (global_rotation_averaging.cc:173-245 unknown layout,
+    :425-440 rows, :646-693 update with quaternion averaging, :726-736 residuals).
+      unknowns: theta [n_frames + n_cams, 3] = frame rotations followed by the cam_from_rig rotations of the sensors that
+      are not calibrated; edge e: frames (ei, ej), unknown-camera nodes (eci, ecj) as indices into theta or -1;
+      R_rel already carries the KNOWN cam_from_rig factors (:305-309); cam_frames[c] = frames that hold an image of
+      unknown camera c (:660-671).  Row e of A: -I at ei, +I at ej, -I at eci, +I at ecj (same-frame pairs cancel)."""
+    o = opts or RAOptions()
+    ei = np.asarray(ei, np.int64); ej = np.asarray(ej, np.int64); eci = np.asarray(eci, np.int64); ecj = np.asarray(ecj, np.int64)
+    E, n = len(ei), n_frames + n_cams
+    theta = np.array(theta0, dtype=np.float64)
+    theta_fixed0 = theta[fixed].copy()
+    rows, cols, vals = [], [], []
+    for nodes, sgn in ((ei, -1.0), (ej, 1.0), (eci, -1.0), (ecj, 1.0)):
+        m = nodes >= 0
+        idx = np.nonzero(m)[0]
+        for k in range(3):
+            rows.append(3 * idx + k); cols.append(3 * nodes[m] + k); vals.append(np.full(len(idx), sgn))
+    rows.append(3 * E + np.arange(3)); cols.append(3 * fixed + np.arange(3)); vals.append(np.ones(3))
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(3 * E + 3, 3 * n))
+    A.sum_duplicates()
+    w_rows = np.ones(3 * E + 3)
+    if o.use_weight and edge_weight is not None:
+        w_rows[:3 * E] = np.repeat(np.where(np.asarray(edge_weight) >= 0, edge_weight, 1.0), 3)
+
+    def residuals(th):
+        R1, R2 = aa_to_R(th[ei]), aa_to_R(th[ej])
+        m = eci >= 0
+        if m.any():
+            R1[m] = aa_to_R(th[eci[m]]) @ R1[m]          # R_1 = R_cam1 R_frame1 (:726-730)
+        m = ecj >= 0
+        if m.any():
+            R2[m] = aa_to_R(th[ecj[m]]) @ R2[m]
+        r_e = -R_to_aa(np.swapaxes(R2, -1, -2) @ R_rel @ R1)
+        r_g = R_to_aa(aa_to_R(theta_fixed0[None]).transpose(0, 2, 1) @ aa_to_R(th[fixed][None]))[0]
+        return np.concatenate([r_e.ravel(), r_g])
+
+    def update(th, step):
+        out = th.copy()
+        out[:n_frames] = R_to_aa(aa_to_R(th[:n_frames]) @ aa_to_R(-step[:n_frames]))      # frames first (:631-644)
+        Rf = aa_to_R(out[:n_frames])
+        for c in range(n_cams):                                                              # :675-693
+            R_ori = aa_to_R(th[n_frames + c][None])[0]
+            R_upd = aa_to_R(-step[n_frames + c][None])[0]
+            prods = [R_ori @ Rf[f] @ R_upd @ Rf[f].T for f in cam_frames[c]]
+            out[n_frames + c] = R_to_aa(average_quaternions(prods)[None])[0]
+        return out
+
+    info = dict(l1_iterations=0, irls_iterations=0, admm_iterations=0)
+    res = residuals(theta)
+    if o.max_num_l1_iterations > 0:
+        Aw = (sp.diags(w_rows) @ A).tocsc()
+        last_norm = curr_norm = 0.0
+        for it in range(o.max_num_l1_iterations):
+            last_norm = curr_norm
+            step, n_admm = l1_admm(Aw, w_rows * res, max_iter=10)
+            info["admm_iterations"] += n_admm
+            curr_norm = np.linalg.norm(step)
+            st = step.reshape(n, 3)
+            theta = update(theta, st)
+            res = residuals(theta)
+            info["l1_iterations"] += 1
+            avg = np.linalg.norm(st[:n_frames], axis=1).sum() / n_frames                  # frames only (:758-772)
+            if avg < o.l1_step_convergence_threshold or abs(last_norm - curr_norm) < EPS:
+                break
+    if o.max_num_irls_iterations > 0:
+        sigma = np.radians(o.irls_loss_parameter_sigma)
+        for it in range(o.max_num_irls_iterations):
+            err2 = (res[:3 * E].reshape(E, 3) ** 2).sum(1)
+            if o.weight_type == "GEMAN_MCCLURE":
+                tmp = err2 + sigma * sigma
+                w = sigma * sigma / (tmp * tmp)
+            else:
+                with np.errstate(divide="ignore"):
+                    w = err2 ** ((0.5 - 2) / 2)
+            W = sp.diags(np.concatenate([np.repeat(w, 3), np.ones(3)]) * w_rows)
+            AtW = A.T @ W
+            step = spla.splu((AtW @ A).tocsc()).solve(AtW @ res)
+            st = step.reshape(n, 3)
+            theta = update(theta, st)
+            res = residuals(theta)
+            info["irls_iterations"] += 1
+            if np.linalg.norm(st[:n_frames], axis=1).sum() / n_frames < o.irls_step_convergence_threshold:
+                break
+    return theta, info

@@ -217,6 +217,15 @@ int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double 
 }
 int b200sfm_gp_problem_save_state(b200sfm_gp_problem* p) { (void)p; return B200SFM_OK; }
 int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p) { (void)p; return B200SFM_OK; }
+int b200sfm_ra_solve_rig(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t nf, int32_t nc, int64_t ne, const int32_t* ei,
+                         const int32_t* ej, const int32_t* eci, const int32_t* ecj, const double* R, const double* w,
+                         const int32_t* cfb, const int32_t* cf, int32_t fixed, double* theta, b200sfm_ra_stats* st) {
+  (void)ctx; (void)o; (void)nf; (void)nc; (void)ne; (void)ei; (void)ej; (void)eci; (void)ecj; (void)R; (void)w; (void)cfb; (void)cf;
+  (void)fixed; (void)theta;
+  dump_call("ra_solve_rig");
+  if (st) { memset(st, 0, sizeof(*st)); st->usable = 1; }
+  return B200SFM_OK;
+}
 int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t n, int64_t E, const int32_t* ei, const int32_t* ej,
                              const double* R, const double* w, const uint8_t* hg, int32_t fixed, double* theta, b200sfm_ra_stats* st) {
   (void)ctx; (void)o; (void)w;

@@ -240,3 +240,40 @@ def test_rig_unknown_bata_matches_oracle():
     want_t = -G.quat_xyzw_to_rotmat(rs.sensor_quat[2:3])[0] @ prob.rig_centers[2]
     assert np.abs(prob.sensor_trans[2] - want_t).max() < 1e-12
     assert np.array_equal(prob.sensor_trans[:2], rs.sensor_trans[:2])
+
+
+def test_rotation_averaging_with_unknown_cam_from_rig():
+    """global_rotation_averaging.cc:173-245,425-440,646-693: sensor 1 of a 3-camera rig is calibrated, sensor 2 is not --
+    its cam_from_rig rotation is an extra 3-dof node shared by all frames, updated by quaternion averaging over the
+    frames.  Device vs oracle (same L1 / IRLS iteration counts, same rotations), and recovery of the extrinsic rotation."""
+    rs = S.make_rig_scene(16, 3, 10, seed=13)
+    Ri, _ = rs.image_poses()
+    rng = np.random.default_rng(6)
+    n_img = rs.F * rs.S
+    ei, ej = np.triu_indices(n_img, 1)
+    sel = rng.uniform(size=len(ei)) < 0.3
+    ei, ej = ei[sel].astype(np.int32), ej[sel].astype(np.int32)
+    noise = G.so3_exp(rng.normal(size=(len(ei), 3)) * np.radians(0.3))
+    R_rel = noise @ Ri[ej] @ np.swapaxes(Ri[ei], -1, -2)
+    vg_img = S.ViewGraph(n_img, ei, ej, R_rel, np.ones(len(ei)), Ri)
+    img_frame = np.repeat(np.arange(rs.F), rs.S)
+    img_sensor = np.tile(np.arange(rs.S), rs.F)
+    known = np.array([True, True, False])
+    g = E.rig_view_graph_unknown(vg_img, img_frame, img_sensor, rs.sensor_quat, known)
+    assert g["n_cams"] == 1 and (g["eci"] >= rs.F).any() and ((g["ei"] == g["ej"]) & ((g["eci"] >= 0) | (g["ecj"] >= 0))).any()
+    Rf = G.quat_xyzw_to_rotmat(rs.quat)
+    Rs = G.quat_xyzw_to_rotmat(rs.sensor_quat)
+    R_f0 = G.so3_exp(rng.normal(size=(rs.F, 3)) * 0.03) @ Rf
+    R_f0[0] = Rf[0]
+    R_c0 = np.eye(3)[None]                                   # no prior: the reference starts from zero (.cc:238-242)
+    est = E.RotationEstimator(E.RotationEstimatorOptions(pcg_rel_tolerance=1e-12))
+    ok, R_frames, R_cams = E.estimate_rotations_rig_unknown(est, g, R_f0, R_c0)
+    assert ok
+    cam_frames = [g["cam_frames"][g["cam_frames_begin"][c]:g["cam_frames_begin"][c + 1]] for c in range(g["n_cams"])]
+    theta0 = np.concatenate([G.so3_log(R_f0), G.so3_log(R_c0)])
+    th, info = RO.estimate_rotations_rig_unknown(g["n_frames"], g["n_cams"], g["ei"], g["ej"], g["eci"], g["ecj"], g["R_rel"],
+                                                 theta0, cam_frames)
+    assert (est.summary.l1_iterations, est.summary.irls_iterations) == (info["l1_iterations"], info["irls_iterations"])
+    assert np.abs(R_frames - G.so3_exp(th[:rs.F])).max() < 1e-7
+    assert np.abs(R_cams - G.so3_exp(th[rs.F:])).max() < 1e-7
+    assert G.rotation_angle_deg(R_cams, Rs[2:3]).max() < 0.5          # the extrinsic rotation is recovered (0.3 deg noise)
