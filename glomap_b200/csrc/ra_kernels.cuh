@@ -375,6 +375,114 @@ __global__ void __launch_bounds__(128) ra_laplacian_csr(RACsr c, const double* _
   if (lane == 0) { y[3 * (size_t)node] = a0; y[3 * (size_t)node + 1] = a1; y[3 * (size_t)node + 2] = a2; }
 }
 
+// ---------------------------------------------------------------------------
+// Two-level preconditioner for the weighted Laplacian (3-DoF frames without gravity, large graphs):
+//     M^-1 = D^-1 + P (P^T L P)^-1 P^T,     P = piecewise-constant prolongation over aggregates of ~256 nodes
+// (greedy breadth-first clusters, built once per problem on the host: the graph does not change between the linear
+// systems, only the weights do).  Jacobi alone needs O(graph diameter) iterations -- 350 at forcing tolerance 1e-2 on the
+// 100 k-frame lattice of config 5, 24.5 k per rotation-averaging solve; the coarse space
+// removes the smooth error components and brings that to ~17 (measured with the same construction in scipy).
+// The coarse matrix (n_c <= 1024, dense) is re-assembled and inverted in place whenever the weights change
+// (Gauss-Jordan, one elimination kernel + one pivot kernel per column); its application is a dense mat-vec.
+// ---------------------------------------------------------------------------
+struct RACoarse {
+  int nc;
+  const int* agg_of;      // [n]
+  const int* agg_begin;   // [nc + 1]
+  const int* agg_nodes;   // [n] nodes grouped by aggregate
+  double* Ac;             // [nc][nc]  coarse matrix, then its inverse
+  double* rc;             // [nc][3]
+  double* zc;             // [nc][3]
+};
+
+__global__ void ra_coarse_assemble(long long E, const int* __restrict__ ei, const int* __restrict__ ej,
+                                   const double* __restrict__ w, int square, const int* __restrict__ agg_of, int nc,
+                                   double* __restrict__ Ac) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int i = ei[e], j = ej[e];
+  double we = w[e];
+  if (square) we *= we;
+  const int b = agg_of[j];
+  if (i < 0) {   // gauge rows: + w on the fixed frame
+    atomicAdd(&Ac[(size_t)b * nc + b], we);
+    return;
+  }
+  const int a = agg_of[i];
+  if (a == b) return;   // the edge lives inside one aggregate: P^T L P sees nothing of it
+  atomicAdd(&Ac[(size_t)a * nc + a], we);
+  atomicAdd(&Ac[(size_t)b * nc + b], we);
+  atomicAdd(&Ac[(size_t)a * nc + b], -we);
+  atomicAdd(&Ac[(size_t)b * nc + a], -we);
+}
+// in-place Gauss-Jordan inversion of the SPD coarse matrix, column k:  (1) every entry outside row / column k
+__global__ void ra_gj_eliminate(int nc, int k, double* __restrict__ A) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nc || i == k || j == k) return;
+  A[(size_t)i * nc + j] -= A[(size_t)i * nc + k] * A[(size_t)k * nc + j] / A[(size_t)k * nc + k];
+}
+//   (2) row k, column k and the pivot   (single CTA)
+__global__ void ra_gj_pivot(int nc, int k, double* __restrict__ A) {
+  const double p = A[(size_t)k * nc + k];
+  __syncthreads();
+  for (int t = threadIdx.x; t < nc; t += blockDim.x) {
+    if (t == k) continue;
+    A[(size_t)k * nc + t] /= p;
+    A[(size_t)t * nc + k] /= -p;
+  }
+  if (threadIdx.x == 0) A[(size_t)k * nc + k] = 1.0 / p;
+}
+// rc = P^T r   (one warp per aggregate)
+__global__ void __launch_bounds__(128) ra_coarse_restrict(RACoarse c, const double* __restrict__ r,
+                                                          const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= c.nc) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int t = c.agg_begin[a] + lane; t < c.agg_begin[a + 1]; t += 32) {
+    const size_t node = (size_t)c.agg_nodes[t];
+    s0 += r[3 * node]; s1 += r[3 * node + 1]; s2 += r[3 * node + 2];
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { c.rc[3 * a] = s0; c.rc[3 * a + 1] = s1; c.rc[3 * a + 2] = s2; }
+}
+// zc = Ac^-1 rc (one warp per row); part[blockIdx.x] = this CTA's share of rc . zc (= r . P zc, the coarse part of r.z)
+__global__ void __launch_bounds__(128) ra_coarse_solve(RACoarse c, double* __restrict__ part_rz_extra,
+                                                       const PcgCtl* __restrict__ ctl) {
+  __shared__ double sh[4];
+  if (ctl && ctl->done) return;
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double dot = 0.0;
+  if (a < c.nc) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    const double* row = c.Ac + (size_t)a * c.nc;
+    for (int b = lane; b < c.nc; b += 32) {
+      const double m = row[b];
+      s0 += m * c.rc[3 * b]; s1 += m * c.rc[3 * b + 1]; s2 += m * c.rc[3 * b + 2];
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+      c.zc[3 * a] = s0; c.zc[3 * a + 1] = s1; c.zc[3 * a + 2] = s2;
+      dot = s0 * c.rc[3 * a] + s1 * c.rc[3 * a + 1] + s2 * c.rc[3 * a + 2];
+    }
+  }
+  if (lane == 0) sh[wid] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) part_rz_extra[blockIdx.x] = sh[0] + sh[1] + sh[2] + sh[3];
+}
+// z += P zc
+__global__ void ra_coarse_prolong(int n, RACoarse c, double* __restrict__ z, const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = c.agg_of[i];
+  z[3 * (size_t)i] += c.zc[3 * a];
+  z[3 * (size_t)i + 1] += c.zc[3 * a + 1];
+  z[3 * (size_t)i + 2] += c.zc[3 * a + 2];
+}
+
 // Minv (packed 3x3 diagonal) = 1/deg ; nodes without edges get identity
 __global__ void ra_build_precond(int n, const double* __restrict__ deg, double* __restrict__ Minv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

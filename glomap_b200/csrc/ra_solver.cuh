@@ -34,6 +34,16 @@ struct b200sfm_ra_problem {
   DevBuf<int> inc_begin, inc_other;
   DevBuf<unsigned> inc_val;
   DevBuf<double> w_inc;
+  // two-level preconditioner (ra_kernels.cuh): aggregates built on the host at create()
+  bool use_2lvl = false;
+  int nc = 0, nblk_c = 0;
+  DevBuf<int> agg_of, agg_begin, agg_nodes;
+  DevBuf<double> Ac, rc, zc;
+  b200::RACoarse coarse() {
+    b200::RACoarse c;
+    c.nc = nc; c.agg_of = agg_of.p; c.agg_begin = agg_begin.p; c.agg_nodes = agg_nodes.p; c.Ac = Ac.p; c.rc = rc.p; c.zc = zc.p;
+    return c;
+  }
   b200::RACsr csr() {
     b200::RACsr c;
     c.n = n; c.begin = inc_begin.p; c.val = inc_val.p; c.other = inc_other.p; c.w_inc = w_inc.p;
@@ -160,6 +170,54 @@ struct b200sfm_ra_problem {
       E_total = (long long)(tot[0] + 0.5);
       rows_total = (long long)(tot[1] + 0.5);
     }
+    // aggregates of the two-level preconditioner: greedy breadth-first clusters over the LOCAL edge list (all ranks hold
+    // the same list only when world == 1: the coarse space is used by single-process contexts)
+    {
+      const char* env = getenv("B200SFM_RA_2LVL");
+      const int min_nodes = env ? (atoi(env) > 0 ? 0 : 1 << 30) : 20000;   // default: large graphs only; =1 forces, =0 disables
+      use_2lvl = !has_grav && n_cams == 0 && ctx->world == 1 && E_real > 0 && n >= std::max(min_nodes, 64);
+    }
+    if (use_2lvl) {
+      const int target = std::max(32, (n + 399) / 400);   // ~400 aggregates, never more than 1024
+      std::vector<int> deg_h((size_t)n + 1, 0);
+      for (long long e = 0; e < E_real; ++e) { ++deg_h[hi[e] + 1]; ++deg_h[hj[e] + 1]; }
+      for (int i = 0; i < n; ++i) deg_h[i + 1] += deg_h[i];
+      std::vector<int> adj((size_t)deg_h[n]), fill(deg_h.begin(), deg_h.end() - 1);
+      for (long long e = 0; e < E_real; ++e) { adj[fill[hi[e]]++] = hj[e]; adj[fill[hj[e]]++] = hi[e]; }
+      std::vector<int> agg((size_t)n, -1), queue;
+      queue.reserve(target + 8);
+      int na = 0;
+      for (int seed = 0; seed < n; ++seed) {
+        if (agg[seed] >= 0) continue;
+        queue.clear();
+        queue.push_back(seed);
+        agg[seed] = na;
+        int cnt = 1;
+        for (size_t head = 0; head < queue.size() && cnt < target; ++head) {
+          const int u = queue[head];
+          for (int t = deg_h[u]; t < deg_h[u + 1] && cnt < target; ++t) {
+            const int v2 = adj[t];
+            if (agg[v2] < 0) { agg[v2] = na; ++cnt; queue.push_back(v2); }
+          }
+        }
+        ++na;
+      }
+      if (na > 1024 || na < 2) {
+        use_2lvl = false;   // pathological graph (many tiny components): Jacobi only
+      } else {
+        nc = na;
+        std::vector<int> ab((size_t)nc + 1, 0), an((size_t)n);
+        for (int i = 0; i < n; ++i) ++ab[agg[i] + 1];
+        for (int a = 0; a < nc; ++a) ab[a + 1] += ab[a];
+        std::vector<int> f2(ab.begin(), ab.end() - 1);
+        for (int i = 0; i < n; ++i) an[f2[agg[i]]++] = i;
+        agg_of.alloc(n); agg_begin.alloc((size_t)nc + 1); agg_nodes.alloc(n);
+        agg_of.upload(agg.data(), n, s); agg_begin.upload(ab.data(), (size_t)nc + 1, s); agg_nodes.upload(an.data(), n, s);
+        Ac.alloc((size_t)nc * nc); rc.alloc((size_t)nc * 3); zc.alloc((size_t)nc * 3);
+        nblk_c = cdiv((long long)nc * 32, 128);
+        B200_CUDA_OK(cudaStreamSynchronize(s));   // host vectors are locals
+      }
+    }
     // incidence lists by node (device radix sort on (node, edge id): deterministic summation order)
     use_csr = !has_grav && n_cams == 0 && E > 0 && !(getenv("B200SFM_RA_CSR") && atoi(getenv("B200SFM_RA_CSR")) == 0);
     if (use_csr) {
@@ -208,9 +266,12 @@ struct b200sfm_ra_problem {
     cudaStream_t s = ctx->stream;
     RAView v = view();
     const int nblk = cdiv(n, kPcgThreads);
+    // partial sums: nblk per-CTA Jacobi partials followed by nblk_c coarse partials (r.z only; zero for p.q and r.r)
+    const int nblk_t = nblk + (use_2lvl ? nblk_c : 0);
     const int max_it = std::max(1, o.pcg_max_iterations);
-    pcgh.ensure(max_it, (size_t)nblk * 3);
-    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
+    pcgh.ensure(max_it, (size_t)nblk_t * 3);
+    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk_t, *part_rr = pcgh.d_part + 2 * (size_t)nblk_t;
+    if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
     PcgCtl* ctl = pcgh.d_ctl;
     PcgResult r = pcgh.run(
         s, max_it,
@@ -224,18 +285,20 @@ struct b200sfm_ra_problem {
           } else {
             B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, part_rz, part_rr);
           }
+          if (use_2lvl) coarse_correct(pr.p, pz.p, part_rz + nblk, nullptr);
         },
         [&](int it) {
           double* d_pub = pcgh.dots(it - 1);
-          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk, it, 0, o.pcg_rel_tolerance, pz.p, pp.p, yw.p,
+          B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk_t, it, 0, o.pcg_rel_tolerance, pz.p, pp.p, yw.p,
                       pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
           laplacian(v, square, pp.p, yw.p, ctl);
           ctx->allreduce_sum(yw.p, (size_t)n * 3);
           B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq, ctl);
-          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
+          B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk_t, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
                       part_rr, pcgh.dots(it), ctl);
+          if (use_2lvl) coarse_correct(pr.p, pz.p, part_rz + nblk, ctl);
         },
-        [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
+        [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk_t, launched, part_rr, ctl); });
     finite = r.finite;
     return r.iters;
   }
@@ -255,6 +318,22 @@ struct b200sfm_ra_problem {
     ctx->allreduce_sum(rhs.p, (size_t)n * 3);
     ctx->allreduce_sum(deg.p, (size_t)n * 3);
     B200_LAUNCH(ctx, ra_build_precond, cdiv(n, 256), 256, 0, n, deg.p, Minv.p);
+    if (use_2lvl) {   // coarse matrix P^T L(w^p) P, inverted in place
+      Ac.zero(s);
+      B200_LAUNCH(ctx, ra_coarse_assemble, cdiv(std::max<long long>(E, 1), 256), 256, 0, E, ei.p, ej.p, w.p, square, agg_of.p, nc, Ac.p);
+      const dim3 g2(cdiv(nc, 128), nc);
+      for (int k = 0; k < nc; ++k) {
+        B200_LAUNCH(ctx, ra_gj_eliminate, g2, 128, 0, nc, k, Ac.p);
+        B200_LAUNCH(ctx, ra_gj_pivot, 1, 256, 0, nc, k, Ac.p);
+      }
+    }
+  }
+  // z += P Ac^-1 P^T r and the coarse share of r.z (partials behind the nblk Jacobi partials)
+  void coarse_correct(double* r, double* z, double* part_rz_extra, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    B200_LAUNCH(ctx, ra_coarse_restrict, nblk_c, 128, 0, coarse(), r, ctl);
+    B200_LAUNCH(ctx, ra_coarse_solve, nblk_c, 128, 0, coarse(), part_rz_extra, ctl);
+    B200_LAUNCH(ctx, ra_coarse_prolong, cdiv(n, 256), 256, 0, n, coarse(), z, ctl);
   }
 
   // theta <- theta (+) step(px); returns (avg step, |step|, nan?)
