@@ -361,7 +361,7 @@ def run_b200(args):
         assert ok
         return ba.summary.as_dict(), dt
 
-    for _ in range(min(args.warmup, 1) if args.workload == "config4" else args.warmup):
+    for _ in range(min(args.warmup, 3)):
         e2e_step()
     e2e_walls = []
     for _ in range(args.e2e_steps):

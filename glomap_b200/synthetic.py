@@ -115,7 +115,8 @@ def make_intrinsics(C: int, model: int, focal: float, image_size: int, num_intri
     intr_params = np.zeros((K, INTR_STRIDE))
     half = image_size / 2
     for k in range(K):
-        f = focal * (1 + 0.02 * (k - (K - 1) / 2))
+        # a few shared blocks: 2 % steps around `focal`; many (per-image) blocks: bounded +-10 % variation
+        f = focal * (1 + 0.02 * (k - (K - 1) / 2)) if K <= 8 else focal * (1 + 0.1 * np.sin(1.7 * k))
         if model == SIMPLE_PINHOLE:
             intr_params[k, :3] = [f, half, half]
         elif model == PINHOLE:
