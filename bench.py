@@ -179,14 +179,14 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def gpu_parity(ctx, E, cb):
+def gpu_parity(ctx, E, cb, pcg_tol):
     """The CUDA path on the CPU arm's own problem (same generator, seed and start, all LM iterations to Ceres'
     termination at the bench's PCG forcing tolerance): final cost and LM iteration count against the exact-solve
     CPU port, and the time both take to reach it."""
     import torch
     sc, init, mask = _cpu_problem()
     opts = E.BundleAdjusterOptions(optimize_intrinsics=False)
-    opts.solver_options.pcg_rel_tolerance = 0.1
+    opts.solver_options.pcg_rel_tolerance = pcg_tol
     opts.solver_options.pcg_max_iterations = 200
     prob = E.BAProblem(ctx, sc, 3, mask)
     prob.set_state(init.intr_params, init.quat, init.trans, init.points)
@@ -199,7 +199,7 @@ def gpu_parity(ctx, E, cb):
     prob.free()
     rec = {"workload": CPU_SAMPLE, "same_problem_as_cpu_arm": True,
            "gpu": {"lm_iterations": st["iterations"], "pcg_iterations": st["pcg_iterations"], "initial_cost": st["initial_cost"],
-                   "final_cost": st["final_cost"], "ms": st["ms_total"], "pcg_rel_tolerance": 0.1}}
+                   "final_cost": st["final_cost"], "ms": st["ms_total"], "pcg_rel_tolerance": pcg_tol}}
     ns = (cb or {}).get("natural_solve")
     if ns:
         rec["cpu"] = ns
@@ -299,29 +299,43 @@ def run_b200(args):
         li_bytes = 168 * sc.N + 96 * sc.P + 64 * C
         mv_name, mv_model = "ba_schur_pass<0> (implicit-Schur mat-vec, design v1)", "152*N + 56*P + 96*C per launch"
         li_model = "168*N + 96*P + 64*C per launch"
-    else:
-        # design v2: pass A streams A_o rows in point order (48 B + 2 x 4 B indices), per point X 24 + CSR 4 + Vinv 48
-        # + z 32; pass B streams {A_o, X} rows in camera order (72 B + 4 B index) and gathers z once per point (32 B)
+        li_name = "ba_linearize_points<false> (Jacobian + point Schur blocks, design v1)"
+    elif os.environ.get("B200SFM_ELL") == "0":
+        # design v2, tile kernels: pass A streams A_o rows in point order (48 B + 2 x 4 B indices), per point X 24 + CSR 4 +
+        # Vinv 48 + z 32; pass B streams {A_o, X} rows in camera order (72 B + 4 B index) and gathers z once per point (32 B)
         mv_bytes = 132 * sc.N + 140 * sc.P + 160 * C
         li_bytes = 72 * sc.N + 96 * sc.P + 64 * C
-        mv_name = "ba2_pack_x + ba2_pass_a<0> + ba2_pass_b (implicit-Schur mat-vec, design v2: two streaming passes)"
+        mv_name = "ba2_pcg_direction_pack + ba2_pass_a<0> + ba2_pass_b (implicit-Schur mat-vec, design v2, tile kernels)"
         mv_model, li_model = "132*N + 140*P + 160*C per mat-vec", "72*N + 96*P + 64*C per launch"
+        li_name = "ba_linearize_points<true> (Jacobian + point Schur blocks, tile kernel)"
+    else:
+        # design v2 with the point side in the ELL-32 layout (one thread per point): pass A streams A_o (48 B) + camera index
+        # (4 B) per observation and, per point, slot -> point id 4 + length 4 + X 24 + Vinv 48 + z 32; pass B as above
+        mv_bytes = 128 * sc.N + 144 * sc.P + 160 * C
+        # linearisation: reads xy 16 + camera index 4, writes A_o 48 per observation; per point id 4 + length 4 + X 24 + V 48 + g 24
+        li_bytes = 68 * sc.N + 104 * sc.P + 64 * C
+        mv_name = "ba2_pcg_direction_pack + ba3_pass_a<0> + ba2_pass_b (implicit-Schur mat-vec, design v2, ELL-32 point side)"
+        mv_model, li_model = "128*N + 144*P + 160*C per mat-vec", "68*N + 104*P + 64*C per launch"
+        li_name = "ba3_linearize_points (Jacobian + point Schur blocks, one thread per point)"
     roof_mv = {"kernel": mv_name, "bound": "hbm",
                "achieved": mv_bytes / (ms_mv / max(n_mv, 1) * 1e-3) / 1e9 if n_mv else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_mv, "avg_ms": ms_mv / max(n_mv, 1),
                "bytes_model": mv_model}
-    roof_li = {"kernel": "ba_linearize_points (Jacobian + point Schur blocks)", "bound": "hbm",
+    roof_li = {"kernel": li_name, "bound": "hbm",
                "achieved": li_bytes / (ms_li / max(n_li, 1) * 1e-3) / 1e9 if n_li else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_li, "avg_ms": ms_li / max(n_li, 1),
                "bytes_model": li_model}
-    # DRAM traffic per launch from the committed `ncu --set full` capture (same workload, 1 GPU)
+    # DRAM traffic per launch: from the committed `ncu --set full` capture of the same kernels on the same workload (1 GPU);
+    # the record carries the commit it was captured at -- null when no capture of this layout is committed
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if tr.get("workload") == args.workload and world == 1:
-            d = tr["design1" if args.design == 1 else "design2"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        key = "design1" if args.design == 1 else ("design2_tiles" if os.environ.get("B200SFM_ELL") == "0" else "design2_ell")
+        if tr.get("workload") == args.workload and world == 1 and key in tr:
+            d = tr[key]
             roof_mv["traffic"] = sum(d["dram_bytes_per_launch"][k] for k in d["matvec_kernels"])
             roof_li["traffic"] = d["dram_bytes_per_launch"][d["linearize_kernel"]]
             roof_mv["traffic_source"] = roof_li["traffic_source"] = d["source"]
+            roof_mv["traffic_captured_at_commit"] = roof_li["traffic_captured_at_commit"] = d.get("commit")
     except Exception:
         pass
     roof_mv["algorithmic_bytes"], roof_li["algorithmic_bytes"] = mv_bytes, li_bytes
@@ -383,7 +397,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(3, args.cpu_lm_iters)
     if rank == 0 and world == 1 and not args.no_parity:
-        parity = gpu_parity(ctx, E, cb)
+        parity = gpu_parity(ctx, E, cb, args.pcg_tol)
 
     if rank == 0:
         line = {
@@ -420,7 +434,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config4", choices=list(WORKLOADS))
     ap.add_argument("--lm-iters", type=int, default=20, help="cap on LM iterations per solve (natural termination)")
-    ap.add_argument("--pcg-tol", type=float, default=0.1, help="PCG forcing tolerance (Ceres eta default 0.1)")
+    ap.add_argument("--pcg-tol", type=float, default=0.05,
+                    help="PCG forcing tolerance: 0.05 keeps the LM iteration count within +-1 of the exact-solve CPU arm "
+                         "(profiles/r2_tolerance_sweep.md); looser values buy cheaper but MORE LM iterations and would inflate the metric")
     ap.add_argument("--pcg-max", type=int, default=200)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-lm-iters", type=int, default=1, help="LM iterations of the CPU port per step / sample")

@@ -697,7 +697,7 @@ struct b200sfm_ba_problem {
     // ---- PCG (loop control on the device, iterations queued ahead of the read-back: pcg.cuh) --------
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(nbk, kPcgThreads);
-    pcgh.ensure(max_it, (size_t)nblk * 3);
+    pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
     double* part_pq = pcgh.d_part;
     double* part_rz = pcgh.d_part + nblk;
     double* part_rr = pcgh.d_part + 2 * (size_t)nblk;

@@ -295,7 +295,7 @@ struct b200sfm_gp_problem {
     // PCG (3x3 blocks; loop control on the device, pcg.cuh)
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(CB, kPcgThreads);
-    pcgh.ensure(max_it, (size_t)nblk * 3);
+    pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
     double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
     PcgCtl* ctl = pcgh.d_ctl;
     StepResult res;

@@ -263,6 +263,14 @@ struct PcgHost {
   double* d_part = nullptr;
   size_t n_dots = 0, n_part = 0;
   int depth = 2;
+  bool depth_from_env = false;
+  // Iterations queued ahead of the read-back.  One GPU: the mat-vec (0.6 ms at config 4) dwarfs the 15 us round trip and
+  // every queued-ahead no-op iteration after convergence costs more than it hides (measured: 57.7 ms / step at depth 1,
+  // 58.1 ms at depth 2), so the loop synchronises every iteration.  Several GPUs: the per-iteration work shrinks with
+  // 1 / world while the round trip does not, and an all-reduce sits in every iteration -- two iterations are kept in flight.
+  void configure(int world) {
+    if (!depth_from_env) depth = world > 1 ? 2 : 1;
+  }
 
   PcgHost() = default;
   PcgHost(const PcgHost&) = delete;
@@ -276,14 +284,18 @@ struct PcgHost {
     if (d_part) cudaFree(d_part);
   }
   // dots: (max_it + 2) x 4 doubles; part: n_part doubles (caller's layout)
-  void ensure(int max_it, size_t part_doubles) {
+  void ensure(int max_it, size_t part_doubles, int world = 1) {
     if (!h_slots) {
       B200_CUDA_OK(cudaMallocHost(&h_slots, sizeof(PcgCtl) * (kMaxDepth + 1)));
       for (auto& e : ev) B200_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       B200_CUDA_OK(cudaMalloc(&d_ctl, sizeof(PcgCtl)));
       const char* d = getenv("B200SFM_PCG_DEPTH");
-      if (d) depth = std::min(std::max(atoi(d), 1), (int)kMaxDepth);
+      if (d) {
+        depth = std::min(std::max(atoi(d), 1), (int)kMaxDepth);
+        depth_from_env = true;
+      }
     }
+    configure(world);
     const size_t need = (size_t)(max_it + 2) * 4;
     if (n_dots < need) {
       if (d_dots) cudaFree(d_dots);

@@ -269,7 +269,7 @@ struct b200sfm_ra_problem {
     // partial sums: nblk per-CTA Jacobi partials followed by nblk_c coarse partials (r.z only; zero for p.q and r.r)
     const int nblk_t = nblk + (use_2lvl ? nblk_c : 0);
     const int max_it = std::max(1, o.pcg_max_iterations);
-    pcgh.ensure(max_it, (size_t)nblk_t * 3);
+    pcgh.ensure(max_it, (size_t)nblk_t * 3, ctx->world);
     double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk_t, *part_rr = pcgh.d_part + 2 * (size_t)nblk_t;
     if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
     PcgCtl* ctl = pcgh.d_ctl;
