@@ -10,11 +10,18 @@
 
 namespace {
 
+cudaStream_t pool_stream(const b200sfm_ctx* ctx) {
+  static const bool dist_pool = !(getenv("B200SFM_ASYNC_ALLOC_DIST") && atoi(getenv("B200SFM_ASYNC_ALLOC_DIST")) == 0);
+  return ctx && (ctx->world == 1 || dist_pool) ? ctx->stream : nullptr;
+}
+
 template <class F>
 int guarded(b200sfm_ctx* ctx, F&& f) {
-  // stream-ordered allocation only for single-process contexts: with NCCL the buffers stay plain cudaMalloc
-  // memory (the pool + NCCL combination has not been exercised on this code path)
-  b200::AllocScope alloc_scope(ctx && ctx->world == 1 ? ctx->stream : nullptr);
+  // device buffers come from the stream-ordered pool of the context's stream (cudaMallocAsync): a repeated one-shot call
+  // re-uses its ~30 buffers instead of paying cudaMalloc / cudaFree (a device-wide synchronisation each) -- at 8 GPUs that
+  // setup was 2/3 of the end-to-end call.  NCCL takes pool memory as ordinary send / receive buffers.
+  // B200SFM_ASYNC_ALLOC_DIST=0 restores plain cudaMalloc for multi-rank contexts.
+  b200::AllocScope alloc_scope(pool_stream(ctx));
   try {
     return f();
   } catch (const b200::CudaError& e) {
@@ -396,7 +403,7 @@ void b200sfm_ba_problem_free(b200sfm_ba_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
-  b200::AllocScope alloc_scope(p->ctx->world == 1 ? p->ctx->stream : nullptr);   // back to the stream-ordered pool
+  b200::AllocScope alloc_scope(pool_stream(p->ctx));   // back to the stream-ordered pool
   delete p;
 }
 
@@ -591,7 +598,7 @@ void b200sfm_gp_problem_free(b200sfm_gp_problem* p) {
   if (!p) return;
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
-  b200::AllocScope alloc_scope(p->ctx->world == 1 ? p->ctx->stream : nullptr);   // back to the stream-ordered pool
+  b200::AllocScope alloc_scope(pool_stream(p->ctx));   // back to the stream-ordered pool
   delete p;
 }
 

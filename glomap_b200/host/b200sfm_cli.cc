@@ -69,7 +69,7 @@ static int RunRotationAverager(int argc, char** argv) {
     bool ok = true;
     for (int i = 0; i < 4 && ok; ++i) {                                   // QW QX QY QZ -> coeffs (x,y,z,w) (pose_io.cc:64-68)
       if (!std::getline(ls, item, ' ')) { ok = false; break; }
-      pr.cam2_from_cam1.rotation.coeffs_data()[(i + 3) % 4] = std::stod(item);
+      pr.cam2_from_cam1.rotation.coeffs().data()[(i + 3) % 4] = std::stod(item);
     }
     for (int i = 0; i < 3 && ok; ++i) {
       if (!std::getline(ls, item, ' ')) { ok = false; break; }
@@ -123,13 +123,13 @@ static int RunRotationAverager(int argc, char** argv) {
     while (!bfs.empty()) {
       image_t c = bfs.front(); bfs.pop();
       double Rc[9];
-      QuatToR(frames[c].RigFromWorld().rotation.coeffs_data(), Rc);
+      QuatToR(frames[c].RigFromWorld().rotation.coeffs().data(), Rc);
       for (image_t nb : adj[c]) {
         if (seen.count(nb)) continue;
         seen.insert(nb);
         const ImagePair& pr = view_graph.image_pairs[ImagePairToPairId(c, nb)];
         double Rr[9], Rn[9];
-        QuatToR(pr.cam2_from_cam1.rotation.coeffs_data(), Rr);
+        QuatToR(pr.cam2_from_cam1.rotation.coeffs().data(), Rr);
         for (int i = 0; i < 3; ++i)
           for (int j = 0; j < 3; ++j) {
             double s = 0;
@@ -146,7 +146,7 @@ static int RunRotationAverager(int argc, char** argv) {
           q[i] = 0.5 * t; t = 0.5 / t;
           q[3] = (Rn[3 * k + j] - Rn[3 * j + k]) * t; q[j] = (Rn[3 * j + i] + Rn[3 * i + j]) * t; q[k] = (Rn[3 * k + i] + Rn[3 * i + k]) * t;
         }
-        for (int k = 0; k < 4; ++k) frames[nb].RigFromWorld().rotation.coeffs_data()[k] = q[k];
+        for (int k = 0; k < 4; ++k) frames[nb].RigFromWorld().rotation.coeffs().data()[k] = q[k];
         bfs.push(nb);
       }
     }
@@ -160,7 +160,7 @@ static int RunRotationAverager(int argc, char** argv) {
   for (image_t id : ids) {
     if (!images[id].IsRegistered()) continue;
     out << images[id].file_name;
-    const double* c = frames[id].RigFromWorld().rotation.coeffs_data();
+    const double* c = frames[id].RigFromWorld().rotation.coeffs().data();
     for (int i = 0; i < 4; ++i) out << " " << c[(i + 3) % 4];
     out << "\n";
   }
@@ -219,7 +219,7 @@ static int RunFlat(int argc, char** argv, bool is_ba) {
   for (int64_t i = 0; i < p.C; ++i) {
     Frame f;
     f.frame_id = (frame_t)(i + 1);
-    for (int k = 0; k < 4; ++k) f.RigFromWorld().rotation.coeffs_data()[k] = p.quat[4 * i + k];
+    for (int k = 0; k < 4; ++k) f.RigFromWorld().rotation.coeffs().data()[k] = p.quat[4 * i + k];
     for (int k = 0; k < 3; ++k) f.RigFromWorld().translation[k] = p.trans[3 * i + k];
     frames[f.frame_id] = f;
     Image im;
@@ -265,7 +265,7 @@ static int RunFlat(int argc, char** argv, bool is_ba) {
   if (!ok) { std::cerr << "solve failed\n"; return 1; }
   for (int64_t i = 0; i < p.C; ++i) {
     const Frame& f = frames[(frame_t)(i + 1)];
-    for (int k = 0; k < 4; ++k) p.quat[4 * i + k] = f.RigFromWorld().rotation.coeffs_data()[k];
+    for (int k = 0; k < 4; ++k) p.quat[4 * i + k] = f.RigFromWorld().rotation.coeffs().data()[k];
     for (int k = 0; k < 3; ++k) p.trans[3 * i + k] = f.RigFromWorld().translation[k];
   }
   for (int64_t t = 0; t < p.P; ++t)

@@ -145,13 +145,13 @@ class BundleAdjuster {
     std::vector<uint8_t> mask(C, 0);
     for (auto& [id, f] : fsorted) {
       const int i = fidx[id];
-      for (int k = 0; k < 4; ++k) quat[4 * i + k] = f->RigFromWorld().rotation.coeffs_data()[k];
+      for (int k = 0; k < 4; ++k) quat[4 * i + k] = f->RigFromWorld().rotation.coeffs().data()[k];
       for (int k = 0; k < 3; ++k) trans[3 * i + k] = f->RigFromWorld().translation[k];
     }
     // the gauge frame is chosen below, once it is known which frames carry observations (.cc:252-266)
     for (auto& [id, c] : csorted) {
       const int k = cidx[id];
-      intr_model[k] = c->model_id;
+      intr_model[k] = static_cast<int32_t>(c->model_id);   // colmap::CameraModelId is an enum class
       for (size_t j = 0; j < c->params.size() && j < B200SFM_INTR_STRIDE; ++j) intr[(size_t)k * B200SFM_INTR_STRIDE + j] = c->params[j];
     }
     // sensors = (rig, camera) pairs in sorted order; trivial frames use the identity cam_from_rig
@@ -174,7 +174,7 @@ class BundleAdjuster {
         for (auto& [iid, im] : images)
           if (frames[im.frame_id].RigId() == key.first && im.camera_id == key.second) { trivial = im.HasTrivialFrame(); break; }
         if (!trivial) cfr = b200host_adapt::CamFromRig(rigs[key.first], key.second);
-        for (int k = 0; k < 4; ++k) sensor_q.push_back(cfr.rotation.coeffs_data()[k]);
+        for (int k = 0; k < 4; ++k) sensor_q.push_back(cfr.rotation.coeffs().data()[k]);
         for (int k = 0; k < 3; ++k) sensor_t.push_back(cfr.translation[k]);
         sensor_intr.push_back(cidx[key.second]);
       }
@@ -243,7 +243,7 @@ class BundleAdjuster {
     if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ba_solve: %s\n", b200sfm_last_error(ctx)); return false; }
     for (auto& [id, f] : fsorted) {                                                           // results in place (.cc:140-146)
       const int i = fidx[id];
-      for (int k = 0; k < 4; ++k) f->RigFromWorld().rotation.coeffs_data()[k] = quat[4 * i + k];
+      for (int k = 0; k < 4; ++k) f->RigFromWorld().rotation.coeffs().data()[k] = quat[4 * i + k];
       for (int k = 0; k < 3; ++k) f->RigFromWorld().translation[k] = trans[3 * i + k];
     }
     p = 0;
@@ -303,7 +303,7 @@ class GlobalPositioner {
     std::vector<uint8_t> calibrated(C, 1);
     for (auto& [id, f] : fsorted) {
       const int i = fidx[id];
-      QuatToR(f->RigFromWorld().rotation.coeffs_data(), &Rm[9 * (size_t)i]);
+      QuatToR(f->RigFromWorld().rotation.coeffs().data(), &Rm[9 * (size_t)i]);
       for (int k = 0; k < 3; ++k) {
         if (options_.generate_random_positions && options_.optimize_positions) {
           centers[3 * i + k] = 100.0 * U(random_generator_);                                  // .cc:158-159
@@ -348,7 +348,7 @@ class GlobalPositioner {
             return false;
           }
           double Rs[9], bb[3], tt[3];
-          QuatToR(cfr.rotation.coeffs_data(), Rs);
+          QuatToR(cfr.rotation.coeffs().data(), Rs);
           for (int k = 0; k < 3; ++k) {   // R_cr^T b, R_cr^T t_cr
             bb[k] = Rs[k] * b[0] + Rs[3 + k] * b[1] + Rs[6 + k] * b[2];
             tt[k] = Rs[k] * cfr.translation[0] + Rs[3 + k] * cfr.translation[1] + Rs[6 + k] * cfr.translation[2];
@@ -487,7 +487,7 @@ class RotationEstimator {
       for (const auto& [nb, pr] : adj[cur]) {
         if (seen[nb]) continue;
         seen[nb] = 1;
-        const double* r21 = pr->cam2_from_cam1.rotation.coeffs_data();
+        const double* r21 = pr->cam2_from_cam1.rotation.coeffs().data();
         if (pr->image_id1 == ids[nb]) {          // 1_R_w = 2_R_1^T * 2_R_w   (.cc:125-129)
           double inv[4];
           QuatConj(r21, inv);
@@ -510,7 +510,7 @@ class RotationEstimator {
           if (!b200host_adapt::HasCamFromRig(rig, im.camera_id)) continue;                    // .cc:108-111
           const Rigid3d c = b200host_adapt::CamFromRig(rig, im.camera_id);
           double inv[4];
-          QuatConj(c.rotation.coeffs_data(), inv);
+          QuatConj(c.rotation.coeffs().data(), inv);
           QuatMul(inv, q[i].data(), r.data());
         }
       }
@@ -519,7 +519,7 @@ class RotationEstimator {
     for (auto& [fid, qs] : per_frame) {
       double avg[4];
       AverageQuaternions(qs, avg);
-      double* out = frames[fid].RigFromWorld().rotation.coeffs_data();
+      double* out = frames[fid].RigFromWorld().rotation.coeffs().data();
       for (int k = 0; k < 4; ++k) out[k] = avg[k];
     }
   }
@@ -548,7 +548,7 @@ class RotationEstimator {
     const int n = (int)fsorted.size();
     if (n == 0) return false;
     std::vector<double> theta(3 * (size_t)n);
-    for (auto& [id, f] : fsorted) QuatToAngleAxis(f->RigFromWorld().rotation.coeffs_data(), &theta[3 * (size_t)fidx[id]]);   // .cc:223-224
+    for (auto& [id, f] : fsorted) QuatToAngleAxis(f->RigFromWorld().rotation.coeffs().data(), &theta[3 * (size_t)fidx[id]]);   // .cc:223-224
     // use_gravity (.cc:207-217): a frame with a gravity prior keeps theta = (0, phi, 0), phi = RotUpToAngle(R_align^T R);
     // the first such frame (sorted-id order) is the fixed one
     std::vector<uint8_t> has_gravity(n, 0);
@@ -562,7 +562,7 @@ class RotationEstimator {
         double* Ra = &R_align[9 * (size_t)i];
         b200host_adapt::RAlignRowMajor(*f, Ra);
         double R0[9], M[9], q[4], aa[3];
-        QuatToR(f->RigFromWorld().rotation.coeffs_data(), R0);
+        QuatToR(f->RigFromWorld().rotation.coeffs().data(), R0);
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) M[3 * r + c] = Ra[r] * R0[c] + Ra[3 + r] * R0[3 + c] + Ra[6 + r] * R0[6 + c];   // R_align^T R
         RToQuat(M, q);
@@ -584,7 +584,7 @@ class RotationEstimator {
       const auto f1 = fidx.find(i1->second.frame_id), f2 = fidx.find(i2->second.frame_id);
       if (f1 == fidx.end() || f2 == fidx.end()) continue;                                     // .cc:365-368
       double R[9];
-      QuatToR(pr->cam2_from_cam1.rotation.coeffs_data(), R);
+      QuatToR(pr->cam2_from_cam1.rotation.coeffs().data(), R);
       // known rigs: the unknowns are the frame rotations, R_rel = R_c2r2^T R_21 R_c1r1 (.cc:274-309); an image
       // pair inside one frame is a self loop and is skipped (.cc:300-303)
       const bool rig1 = !i1->second.HasTrivialFrame(), rig2 = !i2->second.HasTrivialFrame();
@@ -592,7 +592,7 @@ class RotationEstimator {
       if (rig1) {
         const Rigid3d c = b200host_adapt::CamFromRig(rigs[frames[i1->second.frame_id].RigId()], i1->second.camera_id);
         double Rc[9], T[9];
-        QuatToR(c.rotation.coeffs_data(), Rc);
+        QuatToR(c.rotation.coeffs().data(), Rc);
         for (int r = 0; r < 3; ++r)
           for (int k = 0; k < 3; ++k) T[3 * r + k] = R[3 * r] * Rc[k] + R[3 * r + 1] * Rc[3 + k] + R[3 * r + 2] * Rc[6 + k];
         std::copy(T, T + 9, R);
@@ -600,7 +600,7 @@ class RotationEstimator {
       if (rig2) {
         const Rigid3d c = b200host_adapt::CamFromRig(rigs[frames[i2->second.frame_id].RigId()], i2->second.camera_id);
         double Rc[9], T[9];
-        QuatToR(c.rotation.coeffs_data(), Rc);
+        QuatToR(c.rotation.coeffs().data(), Rc);
         for (int r = 0; r < 3; ++r)   // Rc^T R
           for (int k = 0; k < 3; ++k) T[3 * r + k] = Rc[r] * R[k] + Rc[3 + r] * R[3 + k] + Rc[6 + r] * R[6 + k];
         std::copy(T, T + 9, R);
@@ -642,7 +642,7 @@ class RotationEstimator {
     if (!summary.usable) return false;                                                        // NaN (.cc:508-512,590-593)
     for (auto& [id, f] : fsorted) {                                                           // ConvertResults (.cc:787-798)
       const int i = fidx[id];
-      double* qout = f->RigFromWorld().rotation.coeffs_data();
+      double* qout = f->RigFromWorld().rotation.coeffs().data();
       if (has_gravity[i]) {   // R = R_align * AngleToRotUp(phi)
         double qa[4], Ry[9], M[9];
         AngleAxisToQuat(&theta[3 * (size_t)i], qa);
@@ -654,7 +654,7 @@ class RotationEstimator {
       } else {
         AngleAxisToQuat(&theta[3 * (size_t)i], qout);
       }
-      f->RigFromWorld().translation = {{0, 0, 0}};
+      for (int k = 0; k < 3; ++k) f->RigFromWorld().translation[k] = 0.0;                     // Vector3d::Zero() (.cc:795)
     }
     return true;
   }

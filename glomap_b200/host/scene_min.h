@@ -50,10 +50,12 @@ using track_t = uint64_t;
 using image_pair_t = uint64_t;
 using feature_t = uint32_t;
 
-struct Quaternion {   // Eigen::Quaterniond: coeffs() is (x, y, z, w)
+struct Quaternion {   // Eigen::Quaterniond: coeffs() is (x, y, z, w); the shim only uses coeffs().data()
   double c[4] = {0, 0, 0, 1};
-  double* coeffs_data() { return c; }
-  const double* coeffs_data() const { return c; }
+  struct Coeffs { double* p; double* data() const { return p; } };
+  struct ConstCoeffs { const double* p; const double* data() const { return p; } };
+  Coeffs coeffs() { return Coeffs{c}; }
+  ConstCoeffs coeffs() const { return ConstCoeffs{c}; }
 };
 struct Rigid3d {
   Quaternion rotation;

@@ -153,3 +153,15 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     want = [avg([R[101], Rs[1].T @ R[102]]), R[201], R[301], R[401]]       # frame 10 averages its two images (rotation_initializer.cc:95-117)
     got = G.so3_exp(mst["theta"].reshape(-1, 3))
     assert np.abs(got - np.array(want)).max() < 1e-12, np.abs(got - np.array(want)).max()
+
+
+def test_shim_typechecks_against_the_glomap_api():
+    """inside a glomap build the shim is compiled with -DB200SFM_WITH_GLOMAP against the real scene
+    types.  Those need Eigen + COLMAP (absent here), so the branch is type-checked against tests/shim_mock/glomap_stub, which
+    restates the members the shim touches with their real spellings and types (Eigen::Quaterniond::coeffs().data(),
+    Eigen::Vector3d, enum class CameraModelId, sensor_t, std::optional<Rigid3d> MaybeSensorFromRig, Frame::is_registered)."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DB200SFM_WITH_GLOMAP",
+                        "-I" + os.path.join(ROOT, "tests", "shim_mock", "glomap_stub"), "-I" + os.path.join(ROOT, "glomap_b200", "host"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "shim_mock", "shim_typecheck.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
