@@ -44,6 +44,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (C, P, mean track len, chunk)
+    "config5": (0, 0, 0.0, 0),                      # rotation averaging on the 100k-frame lattice: dispatched to bench_secondary
     "config4": (10_000, 2_000_000, 10.0, 50_000),   # 10k cams / 2M pts / 20M obs  (the metric's config)
     "config2": (1_000, 200_000, 10.0, 25_000),      # 1k cams / 200k pts / 2M obs
     "tiny": (200, 20_000, 8.0, 2_500),
@@ -444,6 +445,13 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the config-2 GPU-vs-CPU-port parity record")
     ap.add_argument("--design", type=int, default=0, help="BA data layout: 0 auto (v2), 1 = v1 (W blocks + atomics), 2 = v2")
     args = ap.parse_args()
+    if args.workload == "config5":
+        # BASELINE.json config 5 (100 k-frame view graph): rotation averaging, the secondary metric of SURVEY.md 8(d)
+        # (edges/s per L1 / IRLS iteration).  Single GPU; the line is printed by bench_secondary.py in the same JSON style.
+        import bench_secondary as B2
+        B2.bench_ra(argparse.Namespace(frames=100_000, neighbours=100, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
+                                       pcg_tol=1e-6))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

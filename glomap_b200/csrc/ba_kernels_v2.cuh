@@ -111,8 +111,24 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
   const int cmask = (int)(__double_as_longlong(t4c.w) & 0xff);
   const bool tvar = !(cmask & 2), rvar = !(cmask & 1);
   double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
+  // index -> point gather -> ~400 instructions is latency-bound (ncu r2: long-scoreboard 6.8 stalled warps per issue at 16
+  // resident warps): rows of iteration + 2 and the point of iteration + 1 are prefetched into L1 meanwhile
+  int pt_next = (b + lane < e) ? ld_stream(v.pt_c + b + lane) : 0;
+  if (b + lane + 32 < e) {
+    prefetch_l1(v.pt_c + b + lane + 32);
+    prefetch_l1(v.xy_c + b + lane + 32);
+  }
   for (int i = b + lane; i < e; i += 32, row += kJcDoubles * 32) {
-    const int pt = ld_stream(v.pt_c + i);
+    const int pt = pt_next;
+    if (i + 64 < e) {
+      prefetch_l1(v.pt_c + i + 64);
+      prefetch_l1(v.xy_c + i + 64);
+    }
+    if (i + 32 < e) {
+      pt_next = ld_stream(v.pt_c + i + 32);
+      prefetch_l1(points + 3 * (size_t)pt_next);
+      prefetch_l1(points + 3 * (size_t)pt_next + 2);
+    }
     const double2 xy = ld_stream(v.xy_c + i);
     const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
     ObsCore o;

@@ -82,7 +82,11 @@ __global__ void ell_scatter_obs(long long N, int min_views, const int* __restric
 }
 
 // ---- linearisation, point side -----------------------------------------------------------------------------------
-// residual, Jacobian wrt the point, Huber; A_o rows -> ell.A; V_p, g_p per point; per-CTA partial cost / max|g_p|.
+// residual, Jacobian wrt the point, Huber; A_o rows -> ell.A; V_p, g_p per point; per-WARP partial cost / max|g_p|
+// (no CTA barrier: the warps of a CTA own groups of different length and would wait for the longest one).
+// The per-observation chain  camera index -> camera record -> ~260 instructions  is latency-bound at 16-20 resident
+// warps (ncu r2: long-scoreboard 12.3 stalled warps per issue, 21 % issue-active); the index / pixel rows of iteration
+// j + 2 and the camera record of iteration j + 1 are therefore prefetched into L1 while observation j is computed.
 __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_points(BAView v, EllView ell,
                                                                                const double* __restrict__ cam_rec,
                                                                                const double* __restrict__ intr_rec,
@@ -90,7 +94,6 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
                                                                                double huber_a, int points_var,
                                                                                double* __restrict__ part_cost,
                                                                                double* __restrict__ part_gmax) {
-  __shared__ double scratch[32];
   const int slot = blockIdx.x * kEllThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int g = slot >> 5;
@@ -104,11 +107,24 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       X0 = points[3 * (size_t)pt]; X1 = points[3 * (size_t)pt + 1]; X2 = points[3 * (size_t)pt + 2];
     }
     double V[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
-#pragma unroll 2
+    if (nrow > 1) {
+      prefetch_l1(ell.cam + ((size_t)r0 + 1) * 32 + lane);
+      prefetch_l1(ell.xy + ((size_t)r0 + 1) * 32 + lane);
+    }
+    int cam_next = (mylen > 0) ? ld_stream(ell.cam + (size_t)r0 * 32 + lane) : 0;
     for (int j = 0; j < nrow; ++j) {
-      if (j >= mylen) continue;
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
-      const int cam = ld_stream(ell.cam + idx);
+      const int cam = cam_next;
+      if (j + 2 < nrow) {   // rows of iteration j + 2 (one 128-B line of indices, four of pixels per warp)
+        prefetch_l1(ell.cam + idx + 64);
+        prefetch_l1(ell.xy + idx + 64);
+      }
+      if (j + 1 < mylen) {  // index of iteration j + 1 (prefetched one iteration ago) -> its camera record on the way
+        cam_next = ld_stream(ell.cam + idx + 32);
+        prefetch_l1(cam_rec + (size_t)cam_next * kCamRec);
+        prefetch_l1(cam_rec + (size_t)cam_next * kCamRec + 4);
+      }
+      if (j >= mylen) continue;
       const double2 xy = ld_stream(ell.xy + idx);
       const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
       const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
@@ -139,10 +155,13 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       }
     }
   }
-  cost = block_sum(cost, scratch);
-  if (threadIdx.x == 0) part_cost[blockIdx.x] = cost;
-  gmax = block_max(gmax, scratch);
-  if (threadIdx.x == 0) part_gmax[blockIdx.x] = gmax;
+  // one partial per warp (slot >> 5 == global warp index; the padding warps of the last CTA write zeros)
+  cost = warp_sum(cost);
+  gmax = warp_max(gmax);
+  if (lane == 0) {
+    part_cost[slot >> 5] = cost;
+    part_gmax[slot >> 5] = gmax;
+  }
 }
 
 // cost only (trial point of the LM step), same traversal: per-CTA partial costs
@@ -195,7 +214,7 @@ __global__ void __launch_bounds__(kEllThreads) ba3_cost(BAView v, EllView ell, c
 }
 
 // out[0] = sum part_a (fixed order), out[1] = max part_b (optional)   -- single CTA
-__global__ void __launch_bounds__(256) ba3_reduce_partials(int n, const double* __restrict__ part_a,
+__global__ void __launch_bounds__(1024) ba3_reduce_partials(int n, const double* __restrict__ part_a,
                                                            const double* __restrict__ part_b, double* __restrict__ out_sum,
                                                            double* __restrict__ out_max) {
   __shared__ double scratch[32];

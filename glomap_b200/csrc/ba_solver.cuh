@@ -383,7 +383,7 @@ struct b200sfm_ba_problem {
       const size_t cells = (size_t)std::max<long long>(ell_rows, 1) * 32;
       ell_cam.alloc(cells); ell_xy.alloc(cells); ell_A.alloc(cells * 6);
       if (S > 0) ell_sensor.alloc(cells);
-      ell_part.alloc((size_t)ell_ctas * 4 + 8);
+      ell_part.alloc((size_t)ell_ctas * (kEllThreads / 32) * 2 + 8);
       ell_bpart_rows = ell_ctas;
       B200_LAUNCH(ctx, ell_scatter_obs, cdiv(N, 256), 256, 0, N, min_views, obs_pt.p, pt_begin.p, obs_cam.p, obs_xy.p,
                   S > 0 ? obs_sensor.p : nullptr, ell_slot.p, ell_row0.p, ell_cam.p, ell_xy.p, S > 0 ? ell_sensor.p : nullptr);
@@ -542,9 +542,10 @@ struct b200sfm_ba_problem {
       B200_CUDA_OK(cudaEventRecord(e0, s));
     }
     if (use_ell) {
+      const int nwp = ell_ctas * (kEllThreads / 32);   // one partial per warp
       B200_LAUNCH(ctx, ba3_linearize_points, ell_ctas, kEllThreads, 0, v, ell_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a,
-                  points_var ? 1 : 0, ell_part.p, ell_part.p + ell_ctas);
-      B200_LAUNCH(ctx, ba3_reduce_partials, 1, 256, 0, ell_ctas, ell_part.p, ell_part.p + ell_ctas, scal.p, scal.p + 1);
+                  points_var ? 1 : 0, ell_part.p, ell_part.p + nwp);
+      B200_LAUNCH(ctx, ba3_reduce_partials, 1, 1024, 0, nwp, ell_part.p, ell_part.p + nwp, scal.p, scal.p + 1);
     } else if (use_v2)
       B200_LAUNCH(ctx, ba_linearize_points<true>, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
                   points_var ? 1 : 0, scal.p);

@@ -28,10 +28,10 @@ namespace b200 {
 #define B200_PB_PREFETCH 1
 #endif
 #ifndef B200_PB_MIN_CTAS
-#define B200_PB_MIN_CTAS 9
+#define B200_PB_MIN_CTAS 7   // r2 sweep: 7 -> 0.575, 9 -> 0.583, 12 -> 0.693 ms per mat-vec
 #endif
 #ifndef B200_E1_MIN_CTAS   // ELL point-side linearisation (one thread per point): CTAs of 128 threads per SM
-#define B200_E1_MIN_CTAS 4
+#define B200_E1_MIN_CTAS 5   // 96 registers, no spills: 20 warps / SM (sweep r2: 3 -> 0.707, 4 -> 0.707, 5 -> 0.680, 6 -> 0.804 ms)
 #endif
 #ifndef B200_EA_MIN_CTAS   // ELL pass A (mat-vec)
 #define B200_EA_MIN_CTAS 8
@@ -119,6 +119,9 @@ __device__ __forceinline__ void tma_load_1d_stream(void* smem_dst, const void* g
   tma_load_1d(smem_dst, gsrc, bytes, bar);
 #endif
 }
+// software prefetch into L1 (no register is tied up while the line travels): used one / two loop iterations ahead of
+// the dependent index -> record gathers of the linearisation kernels
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // 256-bit read-only gather (LDG.E.256, sm_100): p must be 32-B aligned
 __device__ __forceinline__ void ld_nc_256(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));

@@ -35,7 +35,7 @@ struct b200sfm_ra_problem {
   DevBuf<unsigned> inc_val;
   DevBuf<double> w_inc;
   // two-level preconditioner (ra_kernels.cuh): aggregates built on the host at create()
-  bool use_2lvl = false;
+  bool use_2lvl = false, coarse_l1_valid = false;
   int nc = 0, nblk_c = 0;
   DevBuf<int> agg_of, agg_begin, agg_nodes;
   DevBuf<double> Ac, rc, zc;
@@ -270,6 +270,9 @@ struct b200sfm_ra_problem {
     const int nblk_t = nblk + (use_2lvl ? nblk_c : 0);
     const int max_it = std::max(1, o.pcg_max_iterations);
     pcgh.ensure(max_it, (size_t)nblk_t * 3, ctx->world);
+    // a rotation-averaging PCG iteration is ~10 small kernels (~100 us at 100 k frames): the read-back round trip is a fifth
+    // of it even on one GPU, so two iterations are always kept in flight here
+    if (!pcgh.depth_from_env) pcgh.depth = 2;
     double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk_t, *part_rr = pcgh.d_part + 2 * (size_t)nblk_t;
     if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
     PcgCtl* ctl = pcgh.d_ctl;
@@ -318,7 +321,10 @@ struct b200sfm_ra_problem {
     ctx->allreduce_sum(rhs.p, (size_t)n * 3);
     ctx->allreduce_sum(deg.p, (size_t)n * 3);
     B200_LAUNCH(ctx, ra_build_precond, cdiv(n, 256), 256, 0, n, deg.p, Minv.p);
-    if (use_2lvl) {   // coarse matrix P^T L(w^p) P, inverted in place
+    // coarse matrix P^T L(w^p) P, inverted in place.  The L1 stage keeps the weights of the rows fixed (w_edge, .cc:488-489):
+    // its five outer iterations share one inverse
+    if (use_2lvl && !(square == 1 && coarse_l1_valid)) {
+      coarse_l1_valid = square == 1;
       Ac.zero(s);
       B200_LAUNCH(ctx, ra_coarse_assemble, cdiv(std::max<long long>(E, 1), 256), 256, 0, E, ei.p, ej.p, w.p, square, agg_of.p, nc, Ac.p);
       const dim3 g2(cdiv(nc, 128), nc);
