@@ -107,24 +107,62 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       X0 = points[3 * (size_t)pt]; X1 = points[3 * (size_t)pt + 1]; X2 = points[3 * (size_t)pt + 2];
     }
     double V[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0};
-    if (nrow > 1) {
-      prefetch_l1(ell.cam + ((size_t)r0 + 1) * 32 + lane);
-      prefetch_l1(ell.xy + ((size_t)r0 + 1) * 32 + lane);
+#if B200_E1_PIPE
+    // software pipeline in registers: while observation j is computed, the camera record of j + 1 and the index / pixel
+    // of j + 2 are already in flight (they are issued BEFORE the arithmetic of j in program order; the A_o stores of j
+    // cannot be reordered with later loads by the compiler, so without this the warp sees every latency in sequence)
+    int camB = 0;
+    double2 xyA = make_double2(0, 0), xyB = xyA;
+    double4 qA = make_double4(0, 0, 0, 1), tA = make_double4(0, 0, 0, 0);
+    if (mylen > 0) {
+      const size_t i0 = (size_t)r0 * 32 + lane;
+      const int camA = ld_stream(ell.cam + i0);
+      xyA = ld_stream(ell.xy + i0);
+      if (mylen > 1) {
+        camB = ld_stream(ell.cam + i0 + 32);
+        xyB = ld_stream(ell.xy + i0 + 32);
+      }
+      qA = *reinterpret_cast<const double4*>(cam_rec + (size_t)camA * kCamRec);
+      tA = *reinterpret_cast<const double4*>(cam_rec + (size_t)camA * kCamRec + 4);
     }
-    int cam_next = (mylen > 0) ? ld_stream(ell.cam + (size_t)r0 * 32 + lane) : 0;
     for (int j = 0; j < nrow; ++j) {
+      if (j >= mylen) break;   // tracks are sorted by length inside a window: a lane is done when its own track is
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
-      const int cam = cam_next;
-      if (j + 2 < nrow) {   // rows of iteration j + 2 (one 128-B line of indices, four of pixels per warp)
-        prefetch_l1(ell.cam + idx + 64);
-        prefetch_l1(ell.xy + idx + 64);
+      double4 qB = qA, tB = tA;
+      int camC = 0;
+      double2 xyC = xyB;
+      if (j + 1 < mylen) {
+        qB = *reinterpret_cast<const double4*>(cam_rec + (size_t)camB * kCamRec);
+        tB = *reinterpret_cast<const double4*>(cam_rec + (size_t)camB * kCamRec + 4);
       }
-      if (j + 1 < mylen) {  // index of iteration j + 1 (prefetched one iteration ago) -> its camera record on the way
-        cam_next = ld_stream(ell.cam + idx + 32);
-        prefetch_l1(cam_rec + (size_t)cam_next * kCamRec);
-        prefetch_l1(cam_rec + (size_t)cam_next * kCamRec + 4);
+      if (j + 2 < mylen) {
+        camC = ld_stream(ell.cam + idx + 64);
+        xyC = ld_stream(ell.xy + idx + 64);
       }
+      const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
+      const double* ir = intr_rec + (size_t)obs_intr_idx(tA, sr) * kIntrRec;
+      ObsCore o;
+      obs_core(qA, tA, ir, sr, X0, X1, X2, xyA, huber_a, o);
+      cost += 0.5 * o.rho0;
+      if (points_var) {
+        double Jp[6], A[6], b[3];
+        obs_point_blocks(o, Jp, A, b);
+        double* row = ell.A + ((size_t)r0 + j) * (6 * 32) + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          st_stream(row + 32 * k, A[k]);
+          V[k] += A[k];
+        }
+        gp[0] += b[0]; gp[1] += b[1]; gp[2] += b[2];
+      }
+      qA = qB; tA = tB; xyA = xyB; xyB = xyC; camB = camC;
+    }
+#else
+#pragma unroll 2
+    for (int j = 0; j < nrow; ++j) {
       if (j >= mylen) continue;
+      const size_t idx = ((size_t)r0 + j) * 32 + lane;
+      const int cam = ld_stream(ell.cam + idx);
       const double2 xy = ld_stream(ell.xy + idx);
       const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
       const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
@@ -145,6 +183,7 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
         gp[0] += b[0]; gp[1] += b[1]; gp[2] += b[2];
       }
     }
+#endif
     if (points_var && pt >= 0) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) v.V[6 * (size_t)pt + k] = V[k];

@@ -33,6 +33,9 @@ namespace b200 {
 #ifndef B200_E1_MIN_CTAS   // ELL point-side linearisation (one thread per point): CTAs of 128 threads per SM
 #define B200_E1_MIN_CTAS 5   // 96 registers, no spills: 20 warps / SM (sweep r2: 3 -> 0.707, 4 -> 0.707, 5 -> 0.680, 6 -> 0.804 ms)
 #endif
+#ifndef B200_E1_PIPE       // ELL linearisation: 1 = register software pipeline (next camera record / index in flight), 0 = plain loop
+#define B200_E1_PIPE 0
+#endif
 #ifndef B200_EA_MIN_CTAS   // ELL pass A (mat-vec)
 #define B200_EA_MIN_CTAS 8
 #endif

@@ -192,6 +192,7 @@ struct b200sfm_gp_problem {
     B200_CUDA_OK(cudaFuncSetAttribute(gp_linearize_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g1));
     B200_CUDA_OK(cudaFuncSetAttribute(gp_linearize_points, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     B200_CUDA_OK(cudaFuncSetAttribute(gp_schur_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g3));
+    B200_CUDA_OK(cudaFuncSetAttribute((gp_schur_pass<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g3));
     B200_CUDA_OK(cudaFuncSetAttribute(gp_schur_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g3));
     B200_CUDA_OK(cudaFuncSetAttribute(gp_schur_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g3));
     B200_CUDA_OK(cudaStreamSynchronize(s));
@@ -312,8 +313,12 @@ struct b200sfm_gp_problem {
             m0 = timer_mv.next(); m1 = timer_mv.next();
             B200_CUDA_OK(cudaEventRecord(m0, s));
           }
-          B200_LAUNCH(ctx, gp_schur_pass<0>, n_tiles, kTile, smem_g3, v, pp.p, yw.p, nullptr, nullptr, nullptr, 0.0, radius,
-                      nullptr, nullptr, nullptr, ctl);
+          if (pcgh.depth > 1)   // iterations are queued ahead of the read-back: the pass tests the stopping flag
+            B200_LAUNCH(ctx, (gp_schur_pass<0, true>), n_tiles, kTile, smem_g3, v, pp.p, yw.p, nullptr, nullptr, nullptr, 0.0, radius,
+                        nullptr, nullptr, nullptr, ctl);
+          else
+            B200_LAUNCH(ctx, gp_schur_pass<0>, n_tiles, kTile, smem_g3, v, pp.p, yw.p, nullptr, nullptr, nullptr, 0.0, radius,
+                        nullptr, nullptr, nullptr, nullptr);
           if (profile) B200_CUDA_OK(cudaEventRecord(m1, s));
           ctx->allreduce_sum(yw.p, nC3);
           // unknown sensors: the pass already applied the direct term per observation (A = nullptr)
