@@ -31,10 +31,10 @@ namespace b200 {
 #define B200_PB_MIN_CTAS 7   // r2 sweep: 7 -> 0.575, 9 -> 0.583, 12 -> 0.693 ms per mat-vec
 #endif
 #ifndef B200_E1_MIN_CTAS   // ELL point-side linearisation (one thread per point): CTAs of 128 threads per SM
-#define B200_E1_MIN_CTAS 5   // 96 registers, no spills: 20 warps / SM (sweep r2: 3 -> 0.707, 4 -> 0.707, 5 -> 0.680, 6 -> 0.804 ms)
+#define B200_E1_MIN_CTAS 4   // with the register pipeline: 126 registers, no spills, 16 warps / SM (sweep r2, profiles/r2_sweeps.md)
 #endif
 #ifndef B200_E1_PIPE       // ELL linearisation: 1 = register software pipeline (next camera record / index in flight), 0 = plain loop
-#define B200_E1_PIPE 0
+#define B200_E1_PIPE 1
 #endif
 #ifndef B200_EA_MIN_CTAS   // ELL pass A (mat-vec)
 #define B200_EA_MIN_CTAS 8

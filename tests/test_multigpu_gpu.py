@@ -23,7 +23,13 @@ def _run(script, nproc, port):
            "--master-port", str(port), os.path.join(ROOT, "tests", script)]
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-4000:]
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):          # keep the full transcript of the ranks next to the other GPU-box artefacts
+        with open(os.path.join(out_dir, f"multigpu_{script}_{nproc}.log"), "w") as f:
+            f.write(r.stdout)
+    # the ranks' own lines first (the launcher's traceback at the end says nothing about the cause)
+    own = [ln for ln in r.stdout.splitlines() if not ln.startswith(("E  ", "  File", "    ")) and "torch/distributed" not in ln]
+    assert r.returncode == 0, "\n".join(own[-60:])
     return r.stdout
 
 
