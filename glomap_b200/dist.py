@@ -27,16 +27,18 @@ def shard_range(n_items: int, chunk: int, rank: int, world: int) -> tuple[int, i
 
 def shard_scene(scene, rank: int, world: int, chunk: int = 1):
     """Slice a full flat scene into the shard of ``rank`` (points
-    [a, b) and their observations); cameras/intrinsics are shared."""
+    [a, b) and their observations); cameras/intrinsics are replicated.  The shard owns COPIES of every array a
+    solver updates in place (poses, points, intrinsics): solving a shard never touches ``scene``."""
     from .synthetic import RigScene, Scene
     a, b = shard_range(scene.P, chunk, rank, world)
     o0, o1 = int(scene.pt_obs_begin[a]), int(scene.pt_obs_begin[b])
     if isinstance(scene, RigScene):   # known rigs: frames, sensors and intrinsics are replicated
-        return RigScene(scene.quat, scene.trans, scene.points[a:b], (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64),
-                        scene.obs_frame[o0:o1], scene.obs_sensor[o0:o1], scene.obs_xy[o0:o1], scene.sensor_quat,
-                        scene.sensor_trans, scene.sensor_intr, scene.intr_model, scene.intr_params), (a, b)
-    return Scene(scene.quat, scene.trans, scene.points[a:b], (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64),
-                 scene.obs_cam[o0:o1], scene.obs_xy[o0:o1], scene.cam_intr, scene.intr_model, scene.intr_params), (a, b)
+        return RigScene(scene.quat.copy(), scene.trans.copy(), scene.points[a:b].copy(),
+                        (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64), scene.obs_frame[o0:o1], scene.obs_sensor[o0:o1],
+                        scene.obs_xy[o0:o1], scene.sensor_quat.copy(), scene.sensor_trans.copy(), scene.sensor_intr,
+                        scene.intr_model, scene.intr_params.copy()), (a, b)
+    return Scene(scene.quat.copy(), scene.trans.copy(), scene.points[a:b].copy(), (scene.pt_obs_begin[a:b + 1] - o0).astype(np.int64),
+                 scene.obs_cam[o0:o1], scene.obs_xy[o0:o1], scene.cam_intr, scene.intr_model, scene.intr_params.copy()), (a, b)
 
 
 def broadcast_nccl_id(make_id, rank: int, world: int) -> bytes | None:

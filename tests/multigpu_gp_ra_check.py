@@ -24,7 +24,7 @@ def gp_solve(ctx, sc, t_obs, c0, X0, a, b, fixed_iters=0):
     ptb = np.ascontiguousarray(sc.pt_obs_begin[a:b + 1] - o0, np.int64)
     cam = np.ascontiguousarray(sc.obs_cam[o0:o1], np.int32)
     dirs = np.ascontiguousarray(t_obs[o0:o1], np.float64)
-    cen, pts, scl = c0.copy(), np.ascontiguousarray(X0[a:b]), np.ones(o1 - o0)
+    cen, pts, scl = c0.copy(), X0[a:b].copy(), np.ones(o1 - o0)   # copies: the solve writes its result in place
     opts = E.GlobalPositionerOptions()
     opts.solver_options.pcg_rel_tolerance = 1e-10
     opts.solver_options.pcg_max_iterations = 3000
