@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(128) bax_linearize_blocks(BAView v, ExtView ex
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4c = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4c = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const int blk = v.seg_intr[warp];
   const double* irc = intr_rec + (size_t)blk * kIntrRec;
   const double* src = sensor_of_seg(v, warp);
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(kEllThreads) bax_pass_a(BAView v, EllView ell,
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
       const int cam = ell.cam[idx];
       const double2 xy = ell.xy[idx];
-      const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-      const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+      const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+      const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
       const int sidx = ell.sensor ? (int)ell.sensor[idx] : 0;
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)sidx * kSensorRec : nullptr;
       const int blk = obs_intr_idx(t4, sr);
@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(128) bax_pass_b(BAView v, ExtView ex, BAViewV2
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4c = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4c = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const int blk = v.seg_intr[warp];
   const double* irc = intr_rec + (size_t)blk * kIntrRec;
   const double* src = sensor_of_seg(v, warp);

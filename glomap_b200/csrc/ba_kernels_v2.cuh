@@ -88,19 +88,27 @@ __global__ void __launch_bounds__(kPcgThreads) ba2_pcg_direction_pack(int nb, in
   }
 }
 
+// pts4[p] = {X_p, 0}: 32-B rows for the camera-order gathers (one LDG.E.256 per observation)
+__global__ void ba2_pad_points(int P, const double* __restrict__ points, double* __restrict__ pts4) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double x = points[3 * (size_t)p], y = points[3 * (size_t)p + 1], z = points[3 * (size_t)p + 2];
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(pts4 + 4 * (size_t)p), "d"(x), "d"(y), "d"(z), "d"(0.0) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // camera-order linearisation: U_c, g_c AND the camera-order rows Ac = {A_o, X_p}
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                          const double* __restrict__ intr_rec,
-                                                         const double* __restrict__ points, double huber_a) {
+                                                         const double* __restrict__ /*points: read through v2.z4 (padded copy)*/, double huber_a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4c = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4c = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const double* irc = intr_rec + (size_t)v.seg_intr[warp] * kIntrRec;
   const double* src = sensor_of_seg(v, warp);
   double U[21], g[6];
@@ -111,26 +119,32 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
   const int cmask = (int)(__double_as_longlong(t4c.w) & 0xff);
   const bool tvar = !(cmask & 2), rvar = !(cmask & 1);
   double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
-  // index -> point gather -> ~400 instructions is latency-bound (ncu r2: long-scoreboard 6.8 stalled warps per issue at 16
-  // resident warps): rows of iteration + 2 and the point of iteration + 1 are prefetched into L1 meanwhile
-  int pt_next = (b + lane < e) ? ld_stream(v.pt_c + b + lane) : 0;
-  if (b + lane + 32 < e) {
-    prefetch_l1(v.pt_c + b + lane + 32);
-    prefetch_l1(v.xy_c + b + lane + 32);
+  // index -> point gather -> ~400 instructions: ncu (r2b) shows 1/3 of all stall samples on the first use of the gathered
+  // point and on the address computed from the streamed index.  Register pipeline: the index of iteration + 2 and the
+  // point / pixel of iteration + 1 are in flight while iteration + 0 is computed.  The points come from the 32-B padded
+  // copy (pts4 = the z4 buffer, idle during linearisation): ONE 256-bit gather instead of three 64-bit ones
+  // (96 -> 32 L1 wavefronts per warp and observation).
+  const double* __restrict__ pts4 = v2.z4;
+  int i = b + lane;
+  int pt_nxt = 0;
+  double2 xy = make_double2(0, 0);
+  double4 Xc = make_double4(0, 0, 0, 0);
+  if (i < e) {
+    const int pt0 = ld_stream(v.pt_c + i);
+    if (i + 32 < e) pt_nxt = ld_stream(v.pt_c + i + 32);
+    xy = ld_stream(v.xy_c + i);
+    Xc = ld_rec32(pts4 + 4 * (size_t)pt0);
   }
-  for (int i = b + lane; i < e; i += 32, row += kJcDoubles * 32) {
-    const int pt = pt_next;
-    if (i + 64 < e) {
-      prefetch_l1(v.pt_c + i + 64);
-      prefetch_l1(v.xy_c + i + 64);
-    }
+  for (; i < e; i += 32, row += kJcDoubles * 32) {
+    double4 Xn = Xc;
+    double2 xyn = xy;
+    int pt_nn = 0;
     if (i + 32 < e) {
-      pt_next = ld_stream(v.pt_c + i + 32);
-      prefetch_l1(points + 3 * (size_t)pt_next);
-      prefetch_l1(points + 3 * (size_t)pt_next + 2);
+      Xn = ld_rec32(pts4 + 4 * (size_t)pt_nxt);
+      xyn = ld_stream(v.xy_c + i + 32);
     }
-    const double2 xy = ld_stream(v.xy_c + i);
-    const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
+    if (i + 64 < e) pt_nn = ld_stream(v.pt_c + i + 64);
+    const double X0 = Xc.x, X1 = Xc.y, X2 = Xc.z;
     ObsCore o;
     obs_core(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
     double Jp[6], A[6], bo[3];
@@ -162,6 +176,7 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
       for (int j = i2; j < 6; ++j) U[idx++] += s0 * Jc[0][j] + s1 * Jc[1][j];
       g[i2] += Jc[0][i2] * e0 + Jc[1][i2] * e1;
     }
+    Xc = Xn; xy = xyn; pt_nxt = pt_nn;
   }
 #pragma unroll
   for (int k = 0; k < 21; ++k) {
@@ -244,8 +259,8 @@ __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, con
 #pragma unroll
   for (int k = 0; k < 6; ++k) TT[k] = warp_sum(TT[k]);
   if (lane == 0) {
-    const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-    const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+    const double4 q4c = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+    const double4 t4c = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
     const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
     const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
     double R[9];
@@ -555,8 +570,8 @@ __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BA
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc[k] = warp_sum(acc[k]);
   if (lane < 6) {
-    const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-    const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+    const double4 q4c = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+    const double4 t4c = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
     const int mask = (int)(__double_as_longlong(t4c.w) & 0xff);
     const double q[4] = {q4c.x, q4c.y, q4c.z, q4c.w};
     double R[9];

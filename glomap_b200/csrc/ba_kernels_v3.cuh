@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
         camB = ld_stream(ell.cam + i0 + 32);
         xyB = ld_stream(ell.xy + i0 + 32);
       }
-      qA = *reinterpret_cast<const double4*>(cam_rec + (size_t)camA * kCamRec);
-      tA = *reinterpret_cast<const double4*>(cam_rec + (size_t)camA * kCamRec + 4);
+      qA = ld_rec32(cam_rec + (size_t)camA * kCamRec);
+      tA = ld_rec32(cam_rec + (size_t)camA * kCamRec + 4);
     }
     for (int j = 0; j < nrow; ++j) {
       if (j >= mylen) break;   // tracks are sorted by length inside a window: a lane is done when its own track is
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       int camC = 0;
       double2 xyC = xyB;
       if (j + 1 < mylen) {
-        qB = *reinterpret_cast<const double4*>(cam_rec + (size_t)camB * kCamRec);
-        tB = *reinterpret_cast<const double4*>(cam_rec + (size_t)camB * kCamRec + 4);
+        qB = ld_rec32(cam_rec + (size_t)camB * kCamRec);
+        tB = ld_rec32(cam_rec + (size_t)camB * kCamRec + 4);
       }
       if (j + 2 < mylen) {
         camC = ld_stream(ell.cam + idx + 64);
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
       const int cam = ld_stream(ell.cam + idx);
       const double2 xy = ld_stream(ell.xy + idx);
-      const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-      const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+      const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+      const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
       const double* ir = intr_rec + (size_t)obs_intr_idx(t4, sr) * kIntrRec;
       ObsCore o;
@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(kEllThreads) ba3_cost(BAView v, EllView ell, c
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
       const int cam = ld_stream(ell.cam + idx);
       const double2 xy = ld_stream(ell.xy + idx);
-      const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-      const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+      const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+      const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
       const double* ir = intr_rec + (size_t)obs_intr_idx(t4, sr) * kIntrRec;
       const double q[4] = {q4.x, q4.y, q4.z, q4.w};

@@ -180,7 +180,6 @@ struct b200sfm_ba_problem {
   DevBuf<double> W, V, Vinv, gp, lin /* U | gc | cost */, Sd, Minv, jscale_c, jscale_p, Dc;
   // pcg
   DevBuf<double> px, pr, pz, pp, pq, yw, bvec;
-  b200::PcgHost pcgh;
   DevBuf<double> scal;   // [0] cost [1] gmax | [2..5] bscal | [6] cand cost | [8..12] cscal
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_k1 = 0, smem_k3 = 0;
@@ -559,10 +558,12 @@ struct b200sfm_ba_problem {
         B200_LAUNCH(ctx, bax_linearize_blocks<0>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
         if (ext_k) B200_LAUNCH(ctx, bax_linearize_blocks<1>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
         if (ext_s) B200_LAUNCH(ctx, bax_linearize_blocks<2>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
-      } else if (use_v2)
+      } else if (use_v2) {
+        B200_LAUNCH(ctx, ba2_pad_points, cdiv(P, 256), 256, 0, P, points[cur].p, z4.p);   // z4 is idle until the mat-vec
         B200_LAUNCH(ctx, ba2_linearize_cams, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
-      else
+      } else {
         B200_LAUNCH(ctx, ba_linearize_cams, sgrid, 128, 0, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+      }
     }
     // cost and this rank's max|g_p| (own slot, zeros elsewhere) travel with U|gc through ONE sum all-reduce
     B200_CUDA_OK(cudaMemcpyAsync(cost_ptr(), scal.p, sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -698,21 +699,21 @@ struct b200sfm_ba_problem {
     // ---- PCG (loop control on the device, iterations queued ahead of the read-back: pcg.cuh) --------
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(nbk, kPcgThreads);
-    pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
-    double* part_pq = pcgh.d_part;
-    double* part_rz = pcgh.d_part + nblk;
-    double* part_rr = pcgh.d_part + 2 * (size_t)nblk;
-    PcgCtl* ctl = pcgh.d_ctl;
+    ctx->pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
+    double* part_pq = ctx->pcgh.d_part;
+    double* part_rz = ctx->pcgh.d_part + nblk;
+    double* part_rr = ctx->pcgh.d_part + 2 * (size_t)nblk;
+    PcgCtl* ctl = ctx->pcgh.d_ctl;
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
     const bool has_mv = points_var || ext;   // an observation pass per iteration (else S = U + D is block diagonal)
-    PcgResult pr_ = pcgh.run(
+    PcgResult pr_ = ctx->pcgh.run(
         s, max_it,
         [&]() { B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, nbk, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
         [&](int it) {
-          double* d_pp = pcgh.dots(it - 2);
-          double* d_pub = pcgh.dots(it - 1);
-          double* d_it = pcgh.dots(it);
+          double* d_pp = ctx->pcgh.dots(it - 2);
+          double* d_pub = ctx->pcgh.dots(it - 1);
+          double* d_it = ctx->pcgh.dots(it);
           if (points_var && use_v2 && !ext)
             B200_LAUNCH(ctx, ba2_pcg_direction_pack, nblk, kPcgThreads, 0, nbk, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance,
                         pz.p, pp.p, yw.p, d_pp, part_rz, part_rr, d_pub, ctl, cam_rec.p, xq.p);

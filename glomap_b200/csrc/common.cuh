@@ -129,6 +129,14 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void ld_nc_256(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+// One 32-B read-only gather as a value (LDG.E.256.CONSTANT).  `*reinterpret_cast<const double4*>` compiles to TWO
+// LDG.E.128 (double4 is 16-B aligned): with 32 lanes on 32 different records that is 64 L1 wavefronts instead of 32, and
+// the linearisation / cost kernels are bound by exactly that pipe (profiles/r2_ncu_summary.md).  p must be 32-B aligned.
+__device__ __forceinline__ double4 ld_rec32(const double* p) {
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
 // streaming (evict-first) scalar accesses
 template <class T>
 __device__ __forceinline__ T ld_stream(const T* p) {
@@ -158,19 +166,21 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 __device__ __forceinline__ double4 ld_keep4(const double* p, uint64_t pol) {
 #if B200_KEEP_HINTS
   double4 v;
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.z), "=d"(v.w) : "l"(p + 2), "l"(pol));
+  asm volatile("ld.global.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p), "l"(pol));
   return v;
 #else
-  return *reinterpret_cast<const double4*>(p);
+  return ld_rec32(p);   // one 256-bit gather (the array is written by the previous kernel, never by this one)
 #endif
 }
 __device__ __forceinline__ void st_keep4(double* p, double4 v, uint64_t pol) {
 #if B200_KEEP_HINTS
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p + 2), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w),
+               "l"(pol)
+               : "memory");
 #else
-  *reinterpret_cast<double4*>(p) = v;
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 #endif
 }
 // shared -> global (bulk async group)

@@ -11,6 +11,7 @@
 
 #include "../../include/b200sfm.h"
 #include "common.cuh"
+#include "pcg.cuh"
 
 struct NcclApi {
   void* lib = nullptr;
@@ -61,6 +62,9 @@ struct b200sfm_ctx {
   long long launches = 0;
   double* h_scal = nullptr;   // pinned readback area
   static constexpr int kHScal = 4096;
+  // PCG loop state (pinned control slots, events, device scratch): owned by the context, not by a problem, so that a
+  // one-shot solve does not pay cudaMallocHost / cudaMalloc / cudaFree (a device-wide synchronisation) on every call
+  b200::PcgHost pcgh;
 
   void allreduce_sum(double* buf, size_t n) {
     if (world == 1 || n == 0) return;

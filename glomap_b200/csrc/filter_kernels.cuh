@@ -23,8 +23,8 @@ __global__ void filter_reprojection(BAView v, const double* __restrict__ cam_rec
   if (o >= v.N) return;
   const int pt = v.obs_pt[o], cam = v.obs_cam[o];
   const double2 xy = v.obs_xy[o];
-  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const double q[4] = {q4.x, q4.y, q4.z, q4.w};
   double R[9];
   quat_to_R(q, R);
@@ -54,8 +54,8 @@ __global__ void filter_angle(BAView v, const double* __restrict__ cam_rec, const
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= v.N) return;
   const int pt = v.obs_pt[o], cam = v.obs_cam[o];
-  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const double q[4] = {q4.x, q4.y, q4.z, q4.w};
   double R[9];
   quat_to_R(q, R);
@@ -87,8 +87,8 @@ __global__ void filter_reprojection_normalized(BAView v, const double* __restric
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= v.N) return;
   const int pt = v.obs_pt[o], cam = v.obs_cam[o];
-  const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+  const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+  const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
   const double q[4] = {q4.x, q4.y, q4.z, q4.w};
   double R[9];
   quat_to_R(q, R);
@@ -133,8 +133,8 @@ __global__ void filter_triangulation_angle(BAView v, const double* __restrict__ 
     for (int s = 0; s < 2; ++s) {
       const unsigned oo = b + (s == 0 ? i : j);
       const int cam = v.obs_cam[oo];
-      const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-      const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
+      const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
+      const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
       const double q[4] = {q4.x, q4.y, q4.z, q4.w};
       double R[9];
       quat_to_R(q, R);

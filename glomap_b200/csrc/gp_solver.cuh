@@ -33,7 +33,6 @@ struct b200sfm_gp_problem {
   // linear system
   DevBuf<double> M, bw, jscale_s, Vinv, gX, Dp, jscale_p, out16, U, gc, Dc, Minv, jscale_c;
   DevBuf<double> px, pr, pz, pp, pq, yw, bvec, dX, ds, scal;
-  b200::PcgHost pcgh;
   b200::EventTimer timer_lin, timer_mv;
   size_t smem_g1 = 0, smem_g3 = 0;
 
@@ -296,24 +295,24 @@ struct b200sfm_gp_problem {
     // PCG (3x3 blocks; loop control on the device, pcg.cuh)
     const int max_it = std::max(1, o.pcg_max_iterations);
     const int nblk = cdiv(CB, kPcgThreads);
-    pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
-    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk, *part_rr = pcgh.d_part + 2 * (size_t)nblk;
-    PcgCtl* ctl = pcgh.d_ctl;
+    ctx->pcgh.ensure(max_it, (size_t)nblk * 3, ctx->world);
+    double *part_pq = ctx->pcgh.d_part, *part_rz = ctx->pcgh.d_part + nblk, *part_rr = ctx->pcgh.d_part + 2 * (size_t)nblk;
+    PcgCtl* ctl = ctx->pcgh.d_ctl;
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
-    PcgResult pr_ = pcgh.run(
+    PcgResult pr_ = ctx->pcgh.run(
         s, max_it,
         [&]() { B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, CB, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
         [&](int it) {
-          double* d_pub = pcgh.dots(it - 1);
+          double* d_pub = ctx->pcgh.dots(it - 1);
           B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, CB, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
-                      pp.p, yw.p, pcgh.dots(it - 2), part_rz, part_rr, nullptr, d_pub, ctl);
+                      pp.p, yw.p, ctx->pcgh.dots(it - 2), part_rz, part_rr, nullptr, d_pub, ctl);
           cudaEvent_t m0 = nullptr, m1 = nullptr;
           if (profile) {
             m0 = timer_mv.next(); m1 = timer_mv.next();
             B200_CUDA_OK(cudaEventRecord(m0, s));
           }
-          if (pcgh.depth > 1)   // iterations are queued ahead of the read-back: the pass tests the stopping flag
+          if (ctx->pcgh.depth > 1)   // iterations are queued ahead of the read-back: the pass tests the stopping flag
             B200_LAUNCH(ctx, (gp_schur_pass<0, true>), n_tiles, kTile, smem_g3, v, pp.p, yw.p, nullptr, nullptr, nullptr, 0.0, radius,
                         nullptr, nullptr, nullptr, ctl);
           else
@@ -324,7 +323,7 @@ struct b200sfm_gp_problem {
           // unknown sensors: the pass already applied the direct term per observation (A = nullptr)
           B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, CB, n_us > 0 ? nullptr : U.p, Dc.p, pp.p, yw.p, pq.p, part_pq, ctl);
           B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, CB, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq,
-                      part_rz, part_rr, pcgh.dots(it), ctl);
+                      part_rz, part_rr, ctx->pcgh.dots(it), ctl);
         },
         [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk, launched, part_rr, ctl); });
     if (profile) timer_mv.used = mv_ev0 + 2 * (size_t)std::min(pr_.iters, pr_.launched);

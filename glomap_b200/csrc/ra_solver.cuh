@@ -27,7 +27,6 @@ struct b200sfm_ra_problem {
   long long rows_total = 0;
   DevBuf<double> Rrel, w_edge, theta, res, w, b, z, u;
   DevBuf<double> deg, Minv, Azero, Dzero, rhs, svec, uvec, px, pr, pz, pp, pq, yw, part, scal;
-  b200::PcgHost pcgh;
   // CSR-by-node incidence lists (3-DoF frames without gravity): gather form of the Laplacian, see ra_kernels.cuh
   bool use_csr = false;
   int n_inc = 0;
@@ -269,14 +268,14 @@ struct b200sfm_ra_problem {
     // partial sums: nblk per-CTA Jacobi partials followed by nblk_c coarse partials (r.z only; zero for p.q and r.r)
     const int nblk_t = nblk + (use_2lvl ? nblk_c : 0);
     const int max_it = std::max(1, o.pcg_max_iterations);
-    pcgh.ensure(max_it, (size_t)nblk_t * 3, ctx->world);
+    ctx->pcgh.ensure(max_it, (size_t)nblk_t * 3, ctx->world);
     // a rotation-averaging PCG iteration is ~10 small kernels (~100 us at 100 k frames): the read-back round trip is a fifth
     // of it even on one GPU, so two iterations are always kept in flight here
-    if (!pcgh.depth_from_env) pcgh.depth = 2;
-    double *part_pq = pcgh.d_part, *part_rz = pcgh.d_part + nblk_t, *part_rr = pcgh.d_part + 2 * (size_t)nblk_t;
-    if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
-    PcgCtl* ctl = pcgh.d_ctl;
-    PcgResult r = pcgh.run(
+    if (!ctx->pcgh.depth_from_env) ctx->pcgh.depth = 2;
+    double *part_pq = ctx->pcgh.d_part, *part_rz = ctx->pcgh.d_part + nblk_t, *part_rr = ctx->pcgh.d_part + 2 * (size_t)nblk_t;
+    if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(ctx->pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
+    PcgCtl* ctl = ctx->pcgh.d_ctl;
+    PcgResult r = ctx->pcgh.run(
         s, max_it,
         [&]() {
           if (warm) {
@@ -291,14 +290,14 @@ struct b200sfm_ra_problem {
           if (use_2lvl) coarse_correct(pr.p, pz.p, part_rz + nblk, nullptr);
         },
         [&](int it) {
-          double* d_pub = pcgh.dots(it - 1);
+          double* d_pub = ctx->pcgh.dots(it - 1);
           B200_LAUNCH(ctx, pcg_direction<3>, nblk, kPcgThreads, 0, n, nblk_t, it, 0, o.pcg_rel_tolerance, pz.p, pp.p, yw.p,
-                      pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
+                      ctx->pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
           laplacian(v, square, pp.p, yw.p, ctl);
           ctx->allreduce_sum(yw.p, (size_t)n * 3);
           B200_LAUNCH(ctx, pcg_apply_diag<3>, nblk, kPcgThreads, 0, n, Azero.p, Dzero.p, pp.p, yw.p, pq.p, part_pq, ctl);
           B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk_t, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
-                      part_rr, pcgh.dots(it), ctl);
+                      part_rr, ctx->pcgh.dots(it), ctl);
           if (use_2lvl) coarse_correct(pr.p, pz.p, part_rz + nblk, ctl);
         },
         [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk_t, launched, part_rr, ctl); });
