@@ -246,7 +246,8 @@ def run_b200(args):
     n_global, p_global, nraw_global = (int(x) for x in tot.tolist())
     mask = E.first_frame_mask(C)
 
-    opts = E.BundleAdjusterOptions(optimize_intrinsics=False, profile_kernels=True, design=args.design)
+    opt_intr = bool(args.optimize_intrinsics)   # second bench line: the reference's default BA mode (bundle_adjustment.h:18)
+    opts = E.BundleAdjusterOptions(optimize_intrinsics=opt_intr, profile_kernels=True, design=args.design)
     opts.solver_options.max_num_iterations = args.lm_iters
     opts.solver_options.pcg_rel_tolerance = args.pcg_tol
     opts.solver_options.pcg_max_iterations = args.pcg_max
@@ -318,6 +319,14 @@ def run_b200(args):
         mv_name = "ba2_pcg_direction_pack + ba3_pass_a<0> + ba2_pass_b (implicit-Schur mat-vec, design v2, ELL-32 point side)"
         mv_model, li_model = "128*N + 144*P + 160*C per mat-vec", "68*N + 104*P + 64*C per launch"
         li_name = "ba3_linearize_points (Jacobian + point Schur blocks, one thread per point)"
+        if opt_intr:
+            # stored-row intrinsics path: B_o = rho' J_pt^T J_k (3 x nk doubles) streamed by both passes, written once by
+            # the point-order linearisation; SIMPLE_PINHOLE with the principal point fixed has nk = 1 (the focal length)
+            nk = 1
+            mv_bytes += 48 * nk * sc.N
+            li_bytes += 24 * nk * sc.N
+            mv_name = mv_name.replace("implicit-Schur mat-vec", "implicit-Schur mat-vec with stored intrinsics rows")
+            mv_model, li_model = f"(128 + 48*{nk})*N + 144*P + 160*C per mat-vec", f"(68 + 24*{nk})*N + 104*P + 64*C per launch"
     roof_mv = {"kernel": mv_name, "bound": "hbm",
                "achieved": mv_bytes / (ms_mv / max(n_mv, 1) * 1e-3) / 1e9 if n_mv else None, "peak": peak, "unit": "GB/s",
                "traffic": None, "peak_source": peak_src, "launches_timed": n_mv, "avg_ms": ms_mv / max(n_mv, 1),
@@ -357,7 +366,7 @@ def run_b200(args):
     for f in ("quat", "trans", "points", "intr_params"):
         arr, t = pinned(getattr(init, f)); keep.append(t); setattr(host, f, arr)
         state0[f] = np.array(arr, copy=True)
-    opts_e = E.BundleAdjusterOptions(optimize_intrinsics=False, design=args.design)
+    opts_e = E.BundleAdjusterOptions(optimize_intrinsics=opt_intr, design=args.design)
     opts_e.solver_options.max_num_iterations = args.lm_iters
     opts_e.solver_options.pcg_rel_tolerance = args.pcg_tol
     opts_e.solver_options.pcg_max_iterations = args.pcg_max
@@ -407,7 +416,8 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {C} cameras / {p_global} points / {nraw_global} observations "
-                                   f"({n_global} in tracks >= 3 views) global BA, SIMPLE_PINHOLE, intrinsics constant, "
+                                   f"({n_global} in tracks >= 3 views) global BA, SIMPLE_PINHOLE, "
+                                   + ("focal lengths refined (optimize_intrinsics, principal point fixed), " if opt_intr else "intrinsics constant, ") +
                                    f"0.5 px noise, start = GT perturbed 0.5 deg / 1% / 1%",
                        "parallelism": f"points sharded over {world} GPU(s), cameras replicated, NCCL all-reduce per PCG mat-vec",
                        "lm_iterations_per_step": lm_its / args.steps, "pcg_iterations_per_lm_iteration": pcg_its / max(lm_its, 1),
@@ -440,6 +450,8 @@ def main():
                     help="PCG forcing tolerance: 0.05 keeps the LM iteration count within +-1 of the exact-solve CPU arm "
                          "(profiles/r2_tolerance_sweep.md); looser values buy cheaper but MORE LM iterations and would inflate the metric")
     ap.add_argument("--pcg-max", type=int, default=200)
+    ap.add_argument("--optimize-intrinsics", type=int, default=0,
+                    help="1: refine the camera intrinsics too (the reference's default BA mode); the headline line keeps them constant")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-lm-iters", type=int, default=1, help="LM iterations of the CPU port per step / sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

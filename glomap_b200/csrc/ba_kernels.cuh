@@ -221,6 +221,7 @@ __device__ __forceinline__ void linearize_obs(const double4& q4, const double4& 
 // valid == false (point behind the camera): the observation contributes nothing (ObsLin convention).
 struct ObsCore {
   double J[6], e[2], rho0, rho1, RX[3], R[9];
+  double uv[2];   // normalised image coordinates (only read by the intrinsics rows: dead code elsewhere)
   bool valid;
 };
 __device__ __forceinline__ void obs_core(const double4& q4, const double4& t4, const double* __restrict__ ir,
@@ -240,10 +241,13 @@ __device__ __forceinline__ void obs_core(const double4& q4, const double4& t4, c
     o.e[0] = o.e[1] = 0.0;
     o.rho0 = 0.0;
     o.rho1 = 0.0;
+    o.uv[0] = o.uv[1] = 0.0;
     return;
   }
   double px, py;
   project_jac(ir, xc, yc, zc, px, py, o.J);
+  o.uv[0] = xc / zc;
+  o.uv[1] = yc / zc;
   if (sr) {   // chain through the constant cam_from_rig rotation: J <- J R_cr
 #pragma unroll
     for (int a = 0; a < 2; ++a) {

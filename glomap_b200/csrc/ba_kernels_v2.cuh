@@ -30,7 +30,41 @@ struct BAViewV2 {
   const double* Ap;   // [N][6]   (aliases BAView::W)
   double* Ac;         // camera-order rows, SoA-32 (see above)
   double* z4;         // [P][4]
+  // stored-row intrinsics path (NK > 0, see below): B_o = rho' J_pt^T J_k in camera order, the frame x intrinsics
+  // cross blocks of every image, the variable-parameter table and the number of frames (block C + k = intrinsics k)
+  double* Bc = nullptr;              // [rows32][3 * NK][32]
+  double* Ufk = nullptr;             // [C][6][NK]
+  const IntrVarRec* ivar = nullptr;  // [K]
+  int C = 0;
 };
+
+// ---------------------------------------------------------------------------
+// Variable intrinsics WITHOUT recomputing the projection chain in the mat-vec ("stored-row" path, NK <= 2 variable
+// parameters per camera: SIMPLE_PINHOLE f; SIMPLE_RADIAL f, k; PINHOLE fx, fy -- the reference default
+// optimize_intrinsics = true, optimize_principal_point = false, bundle_adjustment.cc:273-293).
+// Intrinsics block k is pseudo-camera block C + k of the reduced system (ba_kernels_ext.cuh).  With J_k = d e / d(params)
+// (2 x NK) and B_o = rho' J_pt^T J_k (3 x NK, stored next to A_o in BOTH orders, 24 NK bytes each):
+//     W^T x   per point:   s_p = sum_o ( A_o w_o + B_o x_k(o) )                    (pass A, x_k rides in the xq record)
+//     W z     per image:   y_f -= G^T sum_o A_o z_p,   y_k -= sum_o B_o^T z_p       (pass B)
+//     U x:    block diagonal U_ff, U_kk by pcg_apply_diag; the frame x intrinsics coupling is ONE 6 x NK block per image
+//             (an image has one camera):  y_f += U_fk x_k,  y_k += U_fk^T x_f       (ba2k_cross, C threads)
+// so the per-iteration cost over the constant-intrinsics path is 48 NK bytes per observation of streamed rows.
+// ---------------------------------------------------------------------------
+template <int NK>
+__device__ __forceinline__ void obs_intr_rows(const ObsCore& o, const double* __restrict__ ir, const IntrVarRec& iv,
+                                              const double Jp[6], double Jk[2][NK > 0 ? NK : 1],
+                                              double B[NK > 0 ? 3 * NK : 1]) {
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    double jx = 0.0, jy = 0.0;
+    if (j < iv.mb) intr_param_jac(ir, iv.pidx[j], o.uv[0], o.uv[1], 1.0, jx, jy);
+    if (!o.valid) jx = jy = 0.0;
+    Jk[0][j] = jx;
+    Jk[1][j] = jy;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) B[3 * j + c] = o.rho1 * (Jp[c] * jx + Jp[3 + c] * jy);
+  }
+}
 
 // xp[c] = { R^T x_r , R^T x_t, pad, pad }: 64-B rows, so pass A gathers a camera with one 256-bit and one
 // 128-bit load out of a single line  (masked dofs of x are zero already: PCG keeps them at 0)
@@ -62,7 +96,7 @@ __global__ void __launch_bounds__(kPcgThreads) ba2_pcg_direction_pack(int nb, in
                                                                       const double* __restrict__ part_rr,
                                                                       double* __restrict__ dots_pub, PcgCtl* __restrict__ ctl,
                                                                       const double* __restrict__ cam_rec,
-                                                                      double* __restrict__ xp) {
+                                                                      double* __restrict__ xp, int n_pack) {
   __shared__ double sh3[3];
   double beta;
   if (!pcg_direction_head(nblk, it, min_it, rel_tol, dots_pp, part_rz, part_rr, nullptr, dots_pub, ctl, sh3, beta)) return;
@@ -76,6 +110,7 @@ __global__ void __launch_bounds__(kPcgThreads) ba2_pcg_direction_pack(int nb, in
     p[i] = pv[k];
     yw[i] = 0.0;
   }
+  if (c >= n_pack) return;   // pseudo-camera blocks (intrinsics) have no record: their x rides in the frames' rows
   const double* r = cam_rec + (size_t)c * kCamRec;
   const double q[4] = {r[0], r[1], r[2], r[3]};
   double R[9];
@@ -99,7 +134,8 @@ __global__ void ba2_pad_points(int P, const double* __restrict__ points, double*
 // ---------------------------------------------------------------------------
 // camera-order linearisation: U_c, g_c AND the camera-order rows Ac = {A_o, X_p}
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
+template <int NK>
+__global__ void __launch_bounds__(128, NK > 0 ? 3 : B200_LC_MIN_CTAS) ba2_linearize_cams(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                          const double* __restrict__ intr_rec,
                                                          const double* __restrict__ /*points: read through v2.z4 (padded copy)*/, double huber_a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -119,6 +155,21 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
   const int cmask = (int)(__double_as_longlong(t4c.w) & 0xff);
   const bool tvar = !(cmask & 2), rvar = !(cmask & 1);
   double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
+  // stored-row intrinsics path: B_o rows, U_kk / g_k of the segment's intrinsics block and the image's 6 x NK cross block
+  constexpr int NKK = NK > 0 ? NK : 1;
+  const int blk = v.seg_intr[warp];
+  IntrVarRec iv{};
+  if (NK > 0) iv = v2.ivar[blk];
+  double* rowB = NK > 0 ? v2.Bc + (size_t)(v.seg_row0[warp] >> 5) * (3 * NK * 32) + lane : nullptr;
+  double Ukk[NKK * (NKK + 1) / 2], gk[NKK], Ufk[6][NKK];
+#pragma unroll
+  for (int k = 0; k < NKK * (NKK + 1) / 2; ++k) Ukk[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NKK; ++k) {
+    gk[k] = 0.0;
+#pragma unroll
+    for (int i2 = 0; i2 < 6; ++i2) Ufk[i2][k] = 0.0;
+  }
   // index -> point gather -> ~400 instructions: ncu (r2b) shows 1/3 of all stall samples on the first use of the gathered
   // point and on the address computed from the streamed index.  Register pipeline: the index of iteration + 2 and the
   // point / pixel of iteration + 1 are in flight while iteration + 0 is computed.  The points come from the 32-B padded
@@ -176,7 +227,43 @@ __global__ void __launch_bounds__(128, B200_LC_MIN_CTAS) ba2_linearize_cams(BAVi
       for (int j = i2; j < 6; ++j) U[idx++] += s0 * Jc[0][j] + s1 * Jc[1][j];
       g[i2] += Jc[0][i2] * e0 + Jc[1][i2] * e1;
     }
+    if (NK > 0) {
+      double Jk[2][NKK], Bo[3 * NKK];
+      obs_intr_rows<NK>(o, irc, iv, Jp, Jk, Bo);
+#pragma unroll
+      for (int k = 0; k < 3 * NK; ++k) st_stream(rowB + 32 * k, Bo[k]);
+      rowB += 3 * NK * 32;
+      int ik = 0;
+#pragma unroll
+      for (int a = 0; a < NK; ++a) {
+        const double s0 = o.rho1 * Jk[0][a], s1 = o.rho1 * Jk[1][a];
+#pragma unroll
+        for (int c = a; c < NK; ++c) Ukk[ik++] += s0 * Jk[0][c] + s1 * Jk[1][c];
+        gk[a] += Jk[0][a] * e0 + Jk[1][a] * e1;
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2) Ufk[i2][a] += Jc[0][i2] * s0 + Jc[1][i2] * s1;
+      }
+    }
     Xc = Xn; xy = xyn; pt_nxt = pt_nn;
+  }
+  if (NK > 0) {
+    const size_t kb = (size_t)(v2.C + blk);
+    int ik = 0;
+#pragma unroll
+    for (int a = 0; a < NK; ++a) {
+#pragma unroll
+      for (int c = a; c < NK; ++c) {
+        const double sacc = warp_sum(Ukk[ik++]);
+        if (lane == 0 && sacc != 0.0) atomicAdd(&v.U[kb * 21 + sym_idx(6, a, c)], sacc);
+      }
+      const double sg = warp_sum(gk[a]);
+      if (lane == 0 && sg != 0.0) atomicAdd(&v.gc[kb * 6 + a], sg);
+#pragma unroll
+      for (int i2 = 0; i2 < 6; ++i2) {
+        const double sf = warp_sum(Ufk[i2][a]);
+        if (lane == 0 && sf != 0.0) atomicAdd(&v2.Ufk[((size_t)cam * 6 + i2) * NK + a], sf);
+      }
+    }
   }
 #pragma unroll
   for (int k = 0; k < 21; ++k) {
@@ -496,6 +583,7 @@ __global__ void ba2_point_rhs_z(BAView v, BAViewV2 v2) {
 // ---------------------------------------------------------------------------
 // pass B (camera order): y_c -= [ 2 R sum (X x w) ; R sum w ],  w = A_o z_p
 // ---------------------------------------------------------------------------
+template <int NK>
 __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
                                                  double* __restrict__ y, const PcgCtl* __restrict__ ctl) {
   if (ctl && ctl->done) return;
@@ -505,6 +593,11 @@ __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BA
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   double acc[6] = {0, 0, 0, 0, 0, 0};
+  constexpr int NKK = NK > 0 ? NK : 1;
+  double accK[NKK];
+#pragma unroll
+  for (int k = 0; k < NKK; ++k) accK[k] = 0.0;
+  const double* rowB0 = NK > 0 ? v2.Bc + (size_t)(v.seg_row0[warp] >> 5) * (3 * NK * 32) + lane : nullptr;
   // two observations per lane and iteration: both index loads, then both gathers, are in flight together
   const double* row0 = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
   const uint64_t keep = l2_policy_evict_last();
@@ -541,6 +634,18 @@ __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BA
       for (int k = 0; k < kJcDoubles; ++k) c[k] = ld_stream(r1p + 32 * k);
       z0 = ld_keep4(v2.z4 + 4 * (size_t)pt0, keep);
       z1 = ld_keep4(v2.z4 + 4 * (size_t)(ok1 ? pt1 : pt0), keep);
+    }
+    if (NK > 0 && ok0) {   // y_k -= sum_o B_o^T z_p
+      const double* b0p = rowB0 + (size_t)j * (3 * NK * 32);
+      const double* b1p = ok1 ? b0p + 3 * NK * 32 : b0p;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        accK[k] += ld_stream(b0p + 32 * (3 * k)) * z0.x + ld_stream(b0p + 32 * (3 * k + 1)) * z0.y +
+                   ld_stream(b0p + 32 * (3 * k + 2)) * z0.z;
+        if (ok1)
+          accK[k] += ld_stream(b1p + 32 * (3 * k)) * z1.x + ld_stream(b1p + 32 * (3 * k + 1)) * z1.y +
+                     ld_stream(b1p + 32 * (3 * k + 2)) * z1.z;
+      }
     }
     if (ok0) {
       const double w0 = a[0] * z0.x + a[1] * z0.y + a[2] * z0.z;
@@ -580,6 +685,76 @@ __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BA
     const bool fixed = blk == 0 ? (mask & 1) : (mask & 2);
     const double s = R[3 * r] * acc[3 * blk] + R[3 * r + 1] * acc[3 * blk + 1] + R[3 * r + 2] * acc[3 * blk + 2];
     if (!fixed && s != 0.0) atomicAdd(&y[(size_t)cam * 6 + lane], -s);
+  }
+  if (NK > 0) {
+    const size_t kb = (size_t)(v2.C + v.seg_intr[warp]);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const double sk = warp_sum(accK[k]);
+      if (lane == 0 && sk != 0.0) atomicAdd(&y[kb * 6 + k], -sk);
+    }
+  }
+}
+
+// x_k of every image's intrinsics block into the two spare doubles of its xq row (pass A gathers ONE 64-B record)
+__global__ void ba2k_pack_xk(int C, const double* __restrict__ cam_rec, const double* __restrict__ x, double* __restrict__ xp,
+                             const PcgCtl* __restrict__ ctl) {
+  if (ctl && ctl->done) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int blk = (int)(__double_as_longlong(cam_rec[(size_t)c * kCamRec + 7]) >> 8);
+  xp[(size_t)c * kXqStride + 6] = x[(size_t)(C + blk) * 6];
+  xp[(size_t)c * kXqStride + 7] = x[(size_t)(C + blk) * 6 + 1];
+}
+
+// frame x intrinsics coupling of U x:  y_f += U_fk x_k,  y_k += U_fk^T x_f   (one thread per image; the y_k sums of a
+// CTA are combined in shared memory when the blocks fit, so a single shared camera costs one atomic per CTA and dof)
+template <int NK>
+__global__ void __launch_bounds__(256) ba2k_cross(int C, int K, const double* __restrict__ cam_rec, const double* __restrict__ Ufk,
+                                                  const double* __restrict__ x, double* __restrict__ y,
+                                                  const PcgCtl* __restrict__ ctl) {
+  constexpr int kBins = 256;
+  __shared__ double bins[kBins * NK];
+  if (ctl && ctl->done) return;
+  const bool use_bins = K <= kBins;
+  if (use_bins) {
+    for (int i = threadIdx.x; i < K * NK; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+  }
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const int blk = (int)(__double_as_longlong(cam_rec[(size_t)c * kCamRec + 7]) >> 8);
+    double xf[6], xk[NK], tk[NK];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xf[i] = x[(size_t)c * 6 + i];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      xk[k] = x[(size_t)(C + blk) * 6 + k];
+      tk[k] = 0.0;
+    }
+    const double* u = Ufk + (size_t)c * 6 * NK;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double yf = 0.0;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const double uik = u[i * NK + k];
+        yf += uik * xk[k];
+        tk[k] += uik * xf[i];
+      }
+      if (yf != 0.0) y[(size_t)c * 6 + i] += yf;   // this thread owns y_f of its image (pass B has finished: stream order)
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if (tk[k] == 0.0) continue;
+      if (use_bins) atomicAdd(&bins[blk * NK + k], tk[k]);
+      else atomicAdd(&y[(size_t)(C + blk) * 6 + k], tk[k]);
+    }
+  }
+  if (use_bins) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * NK; i += blockDim.x)
+      if (bins[i] != 0.0) atomicAdd(&y[(size_t)(C + i / NK) * 6 + (i % NK)], bins[i]);
   }
 }
 

@@ -33,6 +33,7 @@ struct EllView {
   const double2* xy;          // [rows * 32]
   const unsigned short* sensor;   // [rows * 32] (known rigs) or nullptr
   double* A;                  // [rows][6][32]
+  double* B = nullptr;        // [rows][3 * NK][32]  stored-row intrinsics path (ba_kernels_v2.cuh), else nullptr
 };
 
 // ---- structure build -------------------------------------------------------------------------------------------
@@ -87,13 +88,15 @@ __global__ void ell_scatter_obs(long long N, int min_views, const int* __restric
 // The per-observation chain  camera index -> camera record -> ~260 instructions  is latency-bound at 16-20 resident
 // warps (ncu r2: long-scoreboard 12.3 stalled warps per issue, 21 % issue-active); the index / pixel rows of iteration
 // j + 2 and the camera record of iteration j + 1 are therefore prefetched into L1 while observation j is computed.
-__global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_points(BAView v, EllView ell,
+template <int NK>
+__global__ void __launch_bounds__(kEllThreads, NK > 0 ? 3 : B200_E1_MIN_CTAS) ba3_linearize_points(BAView v, EllView ell,
                                                                                const double* __restrict__ cam_rec,
                                                                                const double* __restrict__ intr_rec,
                                                                                const double* __restrict__ points,
                                                                                double huber_a, int points_var,
                                                                                double* __restrict__ part_cost,
-                                                                               double* __restrict__ part_gmax) {
+                                                                               double* __restrict__ part_gmax,
+                                                                               const IntrVarRec* __restrict__ ivar) {
   const int slot = blockIdx.x * kEllThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int g = slot >> 5;
@@ -140,7 +143,8 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
         xyC = ld_stream(ell.xy + idx + 64);
       }
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
-      const double* ir = intr_rec + (size_t)obs_intr_idx(tA, sr) * kIntrRec;
+      const int blk = obs_intr_idx(tA, sr);
+      const double* ir = intr_rec + (size_t)blk * kIntrRec;
       ObsCore o;
       obs_core(qA, tA, ir, sr, X0, X1, X2, xyA, huber_a, o);
       cost += 0.5 * o.rho0;
@@ -154,6 +158,14 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
           V[k] += A[k];
         }
         gp[0] += b[0]; gp[1] += b[1]; gp[2] += b[2];
+        if (NK > 0) {   // B_o = rho' J_pt^T J_k next to A_o
+          constexpr int NKK = NK > 0 ? NK : 1;
+          double Jk[2][NKK], Bo[3 * NKK];
+          obs_intr_rows<NK>(o, ir, ivar[blk], Jp, Jk, Bo);
+          double* rowB = ell.B + ((size_t)r0 + j) * (3 * NK * 32) + lane;
+#pragma unroll
+          for (int k = 0; k < 3 * NK; ++k) st_stream(rowB + 32 * k, Bo[k]);
+        }
       }
       qA = qB; tA = tB; xyA = xyB; xyB = xyC; camB = camC;
     }
@@ -167,7 +179,8 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
       const double4 q4 = ld_rec32(cam_rec + (size_t)cam * kCamRec);
       const double4 t4 = ld_rec32(cam_rec + (size_t)cam * kCamRec + 4);
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
-      const double* ir = intr_rec + (size_t)obs_intr_idx(t4, sr) * kIntrRec;
+      const int blk = obs_intr_idx(t4, sr);
+      const double* ir = intr_rec + (size_t)blk * kIntrRec;
       ObsCore o;
       obs_core(q4, t4, ir, sr, X0, X1, X2, xy, huber_a, o);
       cost += 0.5 * o.rho0;
@@ -181,6 +194,14 @@ __global__ void __launch_bounds__(kEllThreads, B200_E1_MIN_CTAS) ba3_linearize_p
           V[k] += A[k];
         }
         gp[0] += b[0]; gp[1] += b[1]; gp[2] += b[2];
+        if (NK > 0) {
+          constexpr int NKK = NK > 0 ? NK : 1;
+          double Jk[2][NKK], Bo[3 * NKK];
+          obs_intr_rows<NK>(o, ir, ivar[blk], Jp, Jk, Bo);
+          double* rowB = ell.B + ((size_t)r0 + j) * (3 * NK * 32) + lane;
+#pragma unroll
+          for (int k = 0; k < 3 * NK; ++k) st_stream(rowB + 32 * k, Bo[k]);
+        }
       }
     }
 #endif
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(1024) ba3_reduce_partials(int n, const double*
 //   s_p = [g_p] + sum_o A_o v_o,  v_o = x'_t - 2 X_p x x'_r (xp = packed R^T x rows);  z_p = Vinv s_p
 //   MODE 0: z -> z4[P][4]                      (mat-vec)
 //   MODE 2: back-substitution epilogue (points_new, per-CTA partial step scalars bscal[cta][4])
-template <int MODE>
+template <int MODE, int NK>
 __global__ void __launch_bounds__(kEllThreads, MODE == 0 ? B200_EA_MIN_CTAS : B200_EA2_MIN_CTAS) ba3_pass_a(
     BAView v, EllView ell, BAViewV2 v2, const double* __restrict__ xp, const double* __restrict__ points,
     double* __restrict__ points_new, double radius, double* __restrict__ bscal, const PcgCtl* __restrict__ ctl) {
@@ -303,13 +324,29 @@ __global__ void __launch_bounds__(kEllThreads, MODE == 0 ? B200_EA_MIN_CTAS : B2
       const double a3 = ld_stream(row + 96), a4 = ld_stream(row + 128), a5 = ld_stream(row + 160);
       double xr0, xr1, xr2, xt0;
       ld_nc_256(xp + (size_t)cam * kXqStride, xr0, xr1, xr2, xt0);
-      const double2 xt12 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)cam * kXqStride + 4));
+      double4 xt;   // {x_t1, x_t2, x_k0, x_k1}: the intrinsics increments ride in the spare doubles of the row
+      if (NK > 0) {
+        xt = ld_rec32(xp + (size_t)cam * kXqStride + 4);
+      } else {
+        const double2 xt12 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)cam * kXqStride + 4));
+        xt = make_double4(xt12.x, xt12.y, 0.0, 0.0);
+      }
       const double w0 = xt0 - 2.0 * (X1 * xr2 - X2 * xr1);
-      const double w1 = xt12.x - 2.0 * (X2 * xr0 - X0 * xr2);
-      const double w2 = xt12.y - 2.0 * (X0 * xr1 - X1 * xr0);
+      const double w1 = xt.x - 2.0 * (X2 * xr0 - X0 * xr2);
+      const double w2 = xt.y - 2.0 * (X0 * xr1 - X1 * xr0);
       s0 += a0 * w0 + a1 * w1 + a2 * w2;
       s1 += a1 * w0 + a3 * w1 + a4 * w2;
       s2 += a2 * w0 + a4 * w1 + a5 * w2;
+      if (NK > 0) {   // + B_o x_k
+        const double* rowB = ell.B + ((size_t)r0 + j) * (3 * NK * 32) + lane;
+        const double xk[2] = {xt.z, xt.w};
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          s0 += ld_stream(rowB + 32 * (3 * k)) * xk[k];
+          s1 += ld_stream(rowB + 32 * (3 * k + 1)) * xk[k];
+          s2 += ld_stream(rowB + 32 * (3 * k + 2)) * xk[k];
+        }
+      }
     }
     if (pt >= 0) {
       const size_t p = (size_t)pt;

@@ -164,14 +164,19 @@ struct b200sfm_ba_problem {
   b200::EllView ell_view() {
     b200::EllView e;
     e.n_groups = ell_groups; e.row0 = ell_row0.p; e.pt = ell_pt.p; e.len = ell_len.p; e.cam = ell_cam.p; e.xy = ell_xy.p;
-    e.sensor = S > 0 ? ell_sensor.p : nullptr; e.A = ell_A.p;
+    e.sensor = S > 0 ? ell_sensor.p : nullptr; e.A = ell_A.p; e.B = kfast ? ell_B.p : nullptr;
     return e;
   }
   DevBuf<double> Jc, z4, xq, bpart, bpart2;
   size_t smem_k3v2 = 0;
+  // stored-row intrinsics path (ba_kernels_v2.cuh): <= 2 variable parameters per camera, no unknown cam_from_rig
+  bool kfast = false;
+  int nk = 0;
+  DevBuf<double> ell_B, Bc, Ufk;
   b200::BAViewV2 view2() {
     b200::BAViewV2 w;
     w.Ap = W.p; w.Ac = Jc.p; w.z4 = z4.p;
+    w.Bc = kfast ? Bc.p : nullptr; w.Ufk = kfast ? Ufk.p : nullptr; w.ivar = ivar.p; w.C = C;
     return w;
   }
   int cur = 0;
@@ -542,8 +547,13 @@ struct b200sfm_ba_problem {
     }
     if (use_ell) {
       const int nwp = ell_ctas * (kEllThreads / 32);   // one partial per warp
-      B200_LAUNCH(ctx, ba3_linearize_points, ell_ctas, kEllThreads, 0, v, ell_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a,
-                  points_var ? 1 : 0, ell_part.p, ell_part.p + nwp);
+#define B200_LIN_P(NKV)                                                                                                   \
+  B200_LAUNCH(ctx, ba3_linearize_points<NKV>, ell_ctas, kEllThreads, 0, v, ell_view(), cam_rec.p, intr_rec.p, points[cur].p, \
+              huber_a, points_var ? 1 : 0, ell_part.p, ell_part.p + nwp, ivar.p)
+      if (kfast && nk == 2) B200_LIN_P(2);
+      else if (kfast && nk == 1) B200_LIN_P(1);
+      else B200_LIN_P(0);
+#undef B200_LIN_P
       B200_LAUNCH(ctx, ba3_reduce_partials, 1, 1024, 0, nwp, ell_part.p, ell_part.p + nwp, scal.p, scal.p + 1);
     } else if (use_v2)
       B200_LAUNCH(ctx, ba_linearize_points<true>, n_tiles, kTile, smem_k1, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a,
@@ -554,13 +564,18 @@ struct b200sfm_ba_problem {
     if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
     if (n_segs > 0) {
       const int sgrid = cdiv((long long)n_segs * 32, 128);
-      if (ext) {
+      if (kfast) {
+        Ufk.zero(s);
+        B200_LAUNCH(ctx, ba2_pad_points, cdiv(P, 256), 256, 0, P, points[cur].p, z4.p);
+        if (nk == 2) B200_LAUNCH(ctx, ba2_linearize_cams<2>, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+        else B200_LAUNCH(ctx, ba2_linearize_cams<1>, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+      } else if (ext) {
         B200_LAUNCH(ctx, bax_linearize_blocks<0>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
         if (ext_k) B200_LAUNCH(ctx, bax_linearize_blocks<1>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
         if (ext_s) B200_LAUNCH(ctx, bax_linearize_blocks<2>, sgrid, 128, 0, v, ext_view(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
       } else if (use_v2) {
         B200_LAUNCH(ctx, ba2_pad_points, cdiv(P, 256), 256, 0, P, points[cur].p, z4.p);   // z4 is idle until the mat-vec
-        B200_LAUNCH(ctx, ba2_linearize_cams, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
+        B200_LAUNCH(ctx, ba2_linearize_cams<0>, sgrid, 128, 0, v, view2(), cam_rec.p, intr_rec.p, points[cur].p, huber_a);
       } else {
         B200_LAUNCH(ctx, ba_linearize_cams, sgrid, 128, 0, v, cam_rec.p, intr_rec.p, points[cur].p, huber_a);
       }
@@ -664,6 +679,28 @@ struct b200sfm_ba_problem {
     }
   }
 
+  void launch_pass_b(const b200::BAView& v, double* y, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    const int grid = cdiv((long long)n_segs * 32, 128);
+    if (kfast && nk == 2) B200_LAUNCH(ctx, ba2_pass_b<2>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
+    else if (kfast) B200_LAUNCH(ctx, ba2_pass_b<1>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
+    else B200_LAUNCH(ctx, ba2_pass_b<0>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
+  }
+  void launch_pass_a0(const b200::BAView& v, double radius, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    if (kfast && nk == 2)
+      B200_LAUNCH(ctx, (ba3_pass_a<0, 2>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
+    else if (kfast)
+      B200_LAUNCH(ctx, (ba3_pass_a<0, 1>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
+    else
+      B200_LAUNCH(ctx, (ba3_pass_a<0, 0>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
+  }
+  void launch_cross(const double* x, double* y, const b200::PcgCtl* ctl) {
+    using namespace b200;
+    if (nk == 2) B200_LAUNCH(ctx, ba2k_cross<2>, cdiv(C, 256), 256, 0, C, K, cam_rec.p, Ufk.p, x, y, ctl);
+    else B200_LAUNCH(ctx, ba2k_cross<1>, cdiv(C, 256), 256, 0, C, K, cam_rec.p, Ufk.p, x, y, ctl);
+  }
+
   // One trust-region step at the current linearisation: damping, preconditioner,
   // PCG on the reduced camera system, back-substitution, candidate + its cost.
   StepResult compute_step(const b200sfm_ba_opts& o, double radius, bool points_var, bool set_jscale_p, bool profile) {
@@ -674,7 +711,8 @@ struct b200sfm_ba_problem {
     if (points_var) B200_LAUNCH(ctx, ba_damp_points, cdiv(P, 256), 256, 0, P, V.p, jscale_p.p, set_jscale_p ? 1 : 0, radius, Vinv.p);
     B200_LAUNCH(ctx, ba_damp_cams, cdiv(nB6, 256), 256, 0, nbk, U(), jscale_c.p, radius, Dc.p);
     // Schur-Jacobi blocks need the stored A_o rows of the fast path; the extended path preconditions with block-Jacobi
-    const bool schur_jacobi = points_var && o.preconditioner == 1 && !ext;
+    const bool recomp = ext && !kfast;   // matrix-free extended mat-vec (ba_kernels_ext.cuh); kfast: stored rows
+    const bool schur_jacobi = points_var && o.preconditioner == 1 && !recomp;   // kfast: frames Schur-Jacobi, intrinsics block-Jacobi
     double* yrhs = Sd.p + (size_t)CB * 21;   // W Vinv g_p accumulates next to Sd so that both share one all-reduce
     Sd.zero(s);
     if (schur_jacobi && n_segs > 0) {
@@ -684,12 +722,12 @@ struct b200sfm_ba_problem {
     if (points_var) {
       if (use_v2) {
         B200_LAUNCH(ctx, ba2_point_rhs_z, cdiv(P, 256), 256, 0, v, view2());
-        if (ext) ext_matvec(nullptr, yrhs, o.thres_loss_function, radius, true, nullptr);
-        else if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yrhs, nullptr);
+        if (recomp) ext_matvec(nullptr, yrhs, o.thres_loss_function, radius, true, nullptr);
+        else if (n_segs > 0) launch_pass_b(v, yrhs, nullptr);
       } else {
         B200_LAUNCH(ctx, ba_schur_pass<1>, n_tiles, kTile, smem_k3, v, nullptr, yrhs, nullptr, nullptr, radius, nullptr);
       }
-    } else if (ext) {
+    } else if (recomp) {
       z4.zero(s);   // constant points: no Schur term, pass B still applies J^T J
     }
     if (schur_jacobi || points_var) ctx->allreduce_sum(Sd.p, (size_t)CB * 27);
@@ -707,6 +745,7 @@ struct b200sfm_ba_problem {
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
     const bool has_mv = points_var || ext;   // an observation pass per iteration (else S = U + D is block diagonal)
+    const bool pack_dir = points_var && use_v2 && !recomp;   // direction kernel also packs R^T p for pass A
     PcgResult pr_ = ctx->pcgh.run(
         s, max_it,
         [&]() { B200_LAUNCH(ctx, pcg_init<6>, nblk, kPcgThreads, 0, nbk, Minv.p, bvec.p, px.p, pr.p, pz.p, part_rz, part_rr); },
@@ -714,9 +753,11 @@ struct b200sfm_ba_problem {
           double* d_pp = ctx->pcgh.dots(it - 2);
           double* d_pub = ctx->pcgh.dots(it - 1);
           double* d_it = ctx->pcgh.dots(it);
-          if (points_var && use_v2 && !ext)
+          if (pack_dir) {
             B200_LAUNCH(ctx, ba2_pcg_direction_pack, nblk, kPcgThreads, 0, nbk, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance,
-                        pz.p, pp.p, yw.p, d_pp, part_rz, part_rr, d_pub, ctl, cam_rec.p, xq.p);
+                        pz.p, pp.p, yw.p, d_pp, part_rz, part_rr, d_pub, ctl, cam_rec.p, xq.p, C);
+            if (kfast) B200_LAUNCH(ctx, ba2k_pack_xk, cdiv(C, 256), 256, 0, C, cam_rec.p, pp.p, xq.p, ctl);
+          }
           else
             B200_LAUNCH(ctx, pcg_direction<6>, nblk, kPcgThreads, 0, nbk, nblk, it, o.pcg_min_iterations, o.pcg_rel_tolerance, pz.p,
                         pp.p, yw.p, d_pp, part_rz, part_rr, nullptr, d_pub, ctl);
@@ -727,15 +768,18 @@ struct b200sfm_ba_problem {
               e1 = timer_mv.next();
               B200_CUDA_OK(cudaEventRecord(e0, s));
             }
-            if (ext) {
+            if (recomp) {
               ext_matvec(pp.p, yw.p, o.thres_loss_function, radius, points_var, ctl);
+            } else if (kfast && !points_var) {
+              // constant points: no Schur term; U x = block diagonal (apply_diag) + the frame x intrinsics coupling
+              launch_cross(pp.p, yw.p, ctl);
             } else if (use_v2) {
               if (use_ell)
-                B200_LAUNCH(ctx, ba3_pass_a<0>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, nullptr, radius,
-                            nullptr, ctl);
+                launch_pass_a0(v, radius, ctl);
               else
                 B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
-              if (n_segs > 0) B200_LAUNCH(ctx, ba2_pass_b, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p, yw.p, ctl);
+              if (n_segs > 0) launch_pass_b(v, yw.p, ctl);
+              if (kfast) launch_cross(pp.p, yw.p, ctl);
             } else {
               B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr, nullptr,
                           nullptr, 0, ctl);
@@ -744,7 +788,7 @@ struct b200sfm_ba_problem {
             ctx->allreduce_sum(yw.p, nB6);
           }
           // extended path: J^T J is inside yw already, only the damping is added here
-          B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, nbk, ext ? nullptr : U(), Dc.p, pp.p, has_mv ? yw.p : nullptr, pq.p,
+          B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, nbk, recomp ? nullptr : U(), Dc.p, pp.p, has_mv ? yw.p : nullptr, pq.p,
                       part_pq, ctl);
           B200_LAUNCH(ctx, pcg_update<6>, nblk, kPcgThreads, 0, nbk, nblk, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
                       part_rr, d_it, ctl);
@@ -770,7 +814,7 @@ struct b200sfm_ba_problem {
     }
     if (points_var && use_v2) {
       const int nrow_part = use_ell ? ell_ctas : n_tiles;
-      if (ext) {
+      if (recomp) {
         ExtView ex = ext_view();
 #define B200_EXT_A2(WK, WS)                                                                                                  \
   B200_LAUNCH(ctx, (bax_pass_a<2, WK, WS>), ell_ctas, kEllThreads, 0, v, ell_view(), ex, view2(), cam_rec.p, intr_rec.p, px.p, \
@@ -782,8 +826,15 @@ struct b200sfm_ba_problem {
 #undef B200_EXT_A2
       } else {
         B200_LAUNCH(ctx, ba2_pack_x, cdiv(C, 256), 256, 0, C, px.p, cam_rec.p, xq.p);
-        if (use_ell)
-          B200_LAUNCH(ctx, ba3_pass_a<2>, ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
+        if (kfast) B200_LAUNCH(ctx, ba2k_pack_xk, cdiv(C, 256), 256, 0, C, cam_rec.p, px.p, xq.p, nullptr);
+        if (use_ell && kfast && nk == 2)
+          B200_LAUNCH(ctx, (ba3_pass_a<2, 2>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
+                      bpart.p, nullptr);
+        else if (use_ell && kfast)
+          B200_LAUNCH(ctx, (ba3_pass_a<2, 1>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
+                      bpart.p, nullptr);
+        else if (use_ell)
+          B200_LAUNCH(ctx, (ba3_pass_a<2, 0>), ell_ctas, kEllThreads, 0, v, ell_view(), view2(), xq.p, points[cur].p, points[nxt].p, radius,
                       bpart.p, nullptr);
         else
           B200_LAUNCH(ctx, ba2_pass_a<2>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, points[nxt].p, radius, bpart.p, nullptr);
@@ -856,6 +907,19 @@ struct b200sfm_ba_problem {
     B200_CUDA_OK(cudaStreamSynchronize(s));   // h_ivar upload
     use_v2 = ext || (o.design != 1);          // v1 (W blocks + atomics) only on request, constant intrinsics
     use_ell = use_v2 && (ext || !(getenv("B200SFM_ELL") && atoi(getenv("B200SFM_ELL")) == 0));   // point side: one thread per point
+    // intrinsics with <= 2 variable parameters per camera and no unknown cam_from_rig: stored B_o rows instead of the
+    // recomputed Jacobians of the extended path (B200SFM_KFAST=0 forces the matrix-free path, for comparison)
+    nk = 0;
+    if (ext_k)
+      for (int k = 0; k < K; ++k) nk = std::max(nk, h_ivar[k].mb);
+    kfast = ext_k && !ext_s && nk <= 2 && !(getenv("B200SFM_KFAST") && atoi(getenv("B200SFM_KFAST")) == 0);
+    if (kfast) {
+      const size_t cells = (size_t)std::max<long long>(ell_rows, 1) * 32;
+      if (ell_B.n < cells * 3 * nk) ell_B.alloc(cells * 3 * nk);
+      const size_t crow = (size_t)std::max<long long>(n_rows_padded, 32) * 3 * nk;
+      if (Bc.n < crow) Bc.alloc(crow);
+      if (Ufk.n < (size_t)C * 6 * nk) Ufk.alloc((size_t)C * 6 * nk);
+    }
     // v2: keep z4 (written by pass A, gathered by pass B) in the persisting part of L2
     const bool l2_persist = use_v2 && !(getenv("B200SFM_L2_PERSIST") && atoi(getenv("B200SFM_L2_PERSIST")) == 0);
     if (l2_persist) l2_persist_window(s, ctx->device, z4.p, z4.bytes());
@@ -879,6 +943,7 @@ struct b200sfm_ba_problem {
     double radius = 1e4, decrease = 2.0;
     int invalid = 0, it = 0, term = B200SFM_TERM_NONE;
     bool set_jscale_p = true;
+    double eta = o.pcg_rel_tolerance;
     const bool fixed = o.fixed_num_iterations > 0;
     const int max_it = fixed ? o.fixed_num_iterations : o.max_num_iterations;
     if (!fixed && gmax <= o.gradient_tolerance) term = B200SFM_TERM_GRADIENT_TOLERANCE;
@@ -886,7 +951,9 @@ struct b200sfm_ba_problem {
       if (it >= max_it) { term = B200SFM_TERM_MAX_ITERATIONS; break; }
       if (radius < 1e-32) { term = B200SFM_TERM_MIN_RADIUS; break; }
       ++it;
-      StepResult r = compute_step(o, radius, points_var, set_jscale_p, profile);
+      b200sfm_ba_opts oo = o;
+      oo.pcg_rel_tolerance = eta;   // forcing term: tightened after a rejected step (see gp_solver.cuh)
+      StepResult r = compute_step(oo, radius, points_var, set_jscale_p, profile);
       set_jscale_p = false;
       local.pcg_iterations += r.pcg_iters;
       if (!r.finite || !(r.model_cost_change > 0.0)) {
@@ -908,10 +975,12 @@ struct b200sfm_ba_problem {
         linearize(o.thres_loss_function, points_var, false, profile, cost, gmax);
         radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
         decrease = 2.0;
+        eta = o.pcg_rel_tolerance;
         if (!fixed && gmax <= o.gradient_tolerance) { term = B200SFM_TERM_GRADIENT_TOLERANCE; break; }
       } else {
         radius /= decrease;
         decrease *= 2;
+        eta = std::max(0.1 * eta, 1e-12);
       }
     }
     B200_CUDA_OK(cudaEventRecord(ev1, s));

@@ -288,6 +288,31 @@ def test_principal_point_flag_alone_frees_every_parameter():
     assert np.abs(dev.intr_params[:, 1] - init.intr_params[:, 1]).max() > 1e-3          # the principal point moved
 
 
+@pytest.mark.parametrize("model,K,points_var", [(S.SIMPLE_RADIAL, 3, True), (S.SIMPLE_PINHOLE, 40, True),
+                                                (S.SIMPLE_RADIAL, 1, False)])
+def test_stored_row_and_matrix_free_intrinsics_paths_agree(model, K, points_var, monkeypatch):
+    """<= 2 variable intrinsics per camera run on stored B_o rows (ba_kernels_v2.cuh, "kfast"); B200SFM_KFAST=0 forces
+    the matrix-free extended mat-vec (ba_kernels_ext.cuh) on the same problem.  Same reduced system, same
+    preconditioner for the intrinsics blocks is NOT required -- so the comparison is at a tight PCG tolerance, after a
+    fixed number of LM iterations (no termination test that could flip)."""
+    sc = S.make_scene(40, 3000, mean_track_len=8, seed=47, pixel_sigma=0.5, model=model, num_intrinsics=K)
+    init = S.perturb_scene(sc, rot_deg=0.2, center_frac=0.004, point_frac=0.004)
+    init.intr_params = sc.intr_params.copy()
+    init.intr_params[:, 0] *= 1.01
+    mask = E.first_frame_mask(sc.C)
+    for k in (1, 3, 5):
+        res = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("B200SFM_KFAST", flag)
+            ok, dev, st = _device_solve_intr(init, mask, tol=1e-13, fixed_num_iterations=k, optimize_points=points_var)
+            assert ok
+            res.append((st.final_cost, dev))
+        (c1, d1), (c0, d0) = res
+        assert abs(c1 - c0) <= 1e-9 * c0, (k, c1, c0)
+        assert np.abs(d1.intr_params - d0.intr_params).max() <= 1e-7 * np.abs(d0.intr_params).max()
+        assert np.abs(d1.trans - d0.trans).max() < 1e-7
+
+
 def test_many_per_image_cameras_at_bench_tolerance():
     """400 images, each with its own SIMPLE_RADIAL camera, PCG forcing tolerance 0.1: same minimum as the exact-solve
     oracle with the intrinsics held at the device's result (cost of the oracle's objective at the device solution)."""
