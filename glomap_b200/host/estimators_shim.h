@@ -8,8 +8,9 @@
 // (deterministic, unlike the reference's hash-map order), calls the GPU solver
 // and scatters the results back in place.  Known (constant) camera rigs are
 // supported in BundleAdjuster and GlobalPositioner (frames = pose blocks, every
-// image carries its sensor's cam_from_rig); unknown cam_from_rig / optimize_rig_poses
-// return false with a message on stderr.
+// image carries its sensor's cam_from_rig); optimize_rig_poses (BA) marks the non-reference sensors as unknowns
+// and writes the optimised cam_from_rig back.  Rigs with a not-yet-calibrated sensor (RA / GP: unknown cam_from_rig
+// blocks, available at the C ABI and in the Python host) return false with a message on stderr.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -157,13 +158,10 @@ class BundleAdjuster {
     // sensors = (rig, camera) pairs in sorted order; trivial frames use the identity cam_from_rig
     bool any_rig = false;
     for (auto& [id, im] : images) any_rig = any_rig || !im.HasTrivialFrame();
-    if (any_rig && options_.optimize_rig_poses) {
-      std::fprintf(stderr, "b200sfm: optimize_rig_poses (unknown cam_from_rig) is not supported\n");
-      return false;
-    }
     std::map<std::pair<rig_t, camera_t>, int> sidx;
     std::vector<double> sensor_q, sensor_t;
     std::vector<int32_t> sensor_intr;
+    std::vector<uint8_t> sensor_var;   // optimize_rig_poses: every non-reference sensor is an unknown (.cc:162-180,296-308)
     if (any_rig) {
       for (auto& [id, im] : images) sidx[{frames[im.frame_id].RigId(), im.camera_id}] = 0;
       int n = 0;
@@ -177,6 +175,8 @@ class BundleAdjuster {
         for (int k = 0; k < 4; ++k) sensor_q.push_back(cfr.rotation.coeffs().data()[k]);
         for (int k = 0; k < 3; ++k) sensor_t.push_back(cfr.translation[k]);
         sensor_intr.push_back(cidx[key.second]);
+        // NonRefSensors() of the rig (.cc:299); Image::HasTrivialFrame() is exactly IsRefSensor (scene/image.h:73-76)
+        sensor_var.push_back((options_.optimize_rig_poses && !b200host_adapt::IsRefSensor(rigs[key.first], key.second)) ? 1 : 0);
       }
       if (n > 65535) { std::fprintf(stderr, "b200sfm: too many rig sensors\n"); return false; }
     } else {
@@ -232,8 +232,20 @@ class BundleAdjuster {
                                          obs_cam.data(), obs_sensor.data(), obs_xy.data(), sensor_q.data(), sensor_t.data(),
                                          sensor_intr.data(), intr_model.data(), mask.data(), o.min_num_view_per_track, &prob);
       if (rc == B200SFM_OK) rc = b200sfm_ba_problem_set_state(prob, intr.data(), quat.data(), trans.data(), points.data());
+      if (rc == B200SFM_OK && options_.optimize_rig_poses) rc = b200sfm_ba_problem_set_sensor_variable(prob, sensor_var.data());
       if (rc == B200SFM_OK) rc = b200sfm_ba_problem_solve(prob, &o, &summary);
       if (rc == B200SFM_OK) rc = b200sfm_ba_problem_get_state(prob, intr.data(), quat.data(), trans.data(), points.data());
+      if (rc == B200SFM_OK && options_.optimize_rig_poses) {   // the optimised cam_from_rig back into the rigs, in place
+        rc = b200sfm_ba_problem_get_sensor_poses(prob, sensor_q.data(), sensor_t.data());
+        if (rc == B200SFM_OK)
+          for (auto& [key, idx] : sidx) {
+            if (!sensor_var[idx]) continue;
+            Rigid3d cfr;
+            for (int k = 0; k < 4; ++k) cfr.rotation.coeffs().data()[k] = sensor_q[4 * (size_t)idx + k];
+            for (int k = 0; k < 3; ++k) cfr.translation[k] = sensor_t[3 * (size_t)idx + k];
+            b200host_adapt::SetCamFromRig(rigs[key.first], key.second, cfr);
+          }
+      }
       b200sfm_ba_problem_free(prob);
     } else {
       rc = b200sfm_ba_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), K, ptb.data(), obs_cam.data(), obs_xy.data(),

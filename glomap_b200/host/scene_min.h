@@ -14,6 +14,10 @@ namespace b200host_adapt {
 inline glomap::Rigid3d CamFromRig(glomap::Rig& rig, glomap::camera_t camera_id) {
   return rig.SensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id));
 }
+// optimised cam_from_rig back into the rig (bundle_adjustment.cc:162-166 takes the same mutable reference)
+inline void SetCamFromRig(glomap::Rig& rig, glomap::camera_t camera_id, const glomap::Rigid3d& pose) {
+  rig.SensorFromRig(glomap::sensor_t(glomap::SensorType::CAMERA, camera_id)) = pose;
+}
 inline bool AllSensorsCalibrated(const glomap::Rig& rig) {
   for (const auto& [sensor_id, sensor] : rig.NonRefSensors())
     if (!sensor.has_value()) return false;
@@ -144,6 +148,9 @@ inline image_pair_t ImagePairToPairId(image_t a, image_t b) {   // colmap::Image
 }  // namespace b200host
 namespace b200host_adapt {
 inline b200host::Rigid3d CamFromRig(b200host::Rig& rig, b200host::camera_t camera_id) { return rig.SensorFromRig(camera_id); }
+inline void SetCamFromRig(b200host::Rig& rig, b200host::camera_t camera_id, const b200host::Rigid3d& pose) {
+  rig.cam_from_rig[camera_id] = pose;
+}
 // every non-reference sensor of the rig has a cam_from_rig (global_rotation_averaging.cc:47-59)
 inline bool AllSensorsCalibrated(const b200host::Rig& rig) { return rig.uncalibrated.empty(); }
 inline bool IsRefSensor(const b200host::Rig& rig, b200host::camera_t camera_id) { return camera_id == rig.ref_camera_id; }

@@ -40,6 +40,7 @@ static long long stub_filter(const char* name, double thr, uint8_t* keep) {
 struct b200sfm_gp_problem { b200sfm_ctx* ctx; };
 static struct b200sfm_ctx g_ctx;
 static long long g_gp_n = 0;
+static int g_ba_S = 0;   /* sensors of the last rig problem */
 
 static FILE* out(void) {
   const char* p = getenv("MOCK_DUMP");
@@ -102,6 +103,7 @@ int b200sfm_ba_problem_create_rig(b200sfm_ctx* ctx, int32_t F, int32_t P, int64_
   dump_d("obs_xy", obs_xy, 2 * N); dump_d("sensor_quat", sq, 4ll * S); dump_d("sensor_trans", stv, 3ll * S);
   DUMP_INT("sensor_intr", sintr, S); DUMP_INT("intr_model", intr_model, K); DUMP_INT("mask", mask, F);
   remember_ba(P, N, ptb);
+  g_ba_S = S;
   static struct b200sfm_ba_problem p; p.ctx = ctx; *o = &p;
   return B200SFM_OK;
 }
@@ -111,12 +113,18 @@ int b200sfm_ba_problem_set_state(b200sfm_ba_problem* p, const double* intr, cons
   return B200SFM_OK;
 }
 int b200sfm_ba_problem_set_sensor_variable(b200sfm_ba_problem* p, const uint8_t* v) {
-  (void)p; (void)v;
+  (void)p;
   dump_call("ba_problem_set_sensor_variable");
+  DUMP_INT("sensor_variable", v, g_ba_S);
   return B200SFM_OK;
 }
+/* a recognisable "optimised" cam_from_rig for every sensor: rotation 90 deg about z, translation (7 + s, 8, 9) */
 int b200sfm_ba_problem_get_sensor_poses(b200sfm_ba_problem* p, double* q, double* t) {
-  (void)p; (void)q; (void)t;
+  (void)p;
+  for (int s = 0; s < g_ba_S; ++s) {
+    if (q) { q[4 * s] = 0; q[4 * s + 1] = 0; q[4 * s + 2] = 0.70710678118654757; q[4 * s + 3] = 0.70710678118654757; }
+    if (t) { t[3 * s] = 7.0 + s; t[3 * s + 1] = 8; t[3 * s + 2] = 9; }
+  }
   return B200SFM_OK;
 }
 int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr, double* q, double* t, double* pts) {

@@ -106,6 +106,16 @@ int main() {
   rigs[1].uncalibrated.push_back(9);
   RotationEstimator rag2(rg);
   if (rag2.EstimateRotations(vg, rigs, frames, images)) return 7;
+  // optimize_rig_poses (bundle_adjustment.cc:162-180,296-308): the non-reference sensor (rig 1, camera 2) becomes an
+  // unknown and its optimised cam_from_rig is written back into the rig; the reference sensors stay untouched
+  BundleAdjusterOptions bor;
+  bor.optimize_rig_poses = true;
+  BundleAdjuster bar(bor);
+  if (!bar.Solve(rigs, cameras, frames, images, tracks)) return 8;
+  const Rigid3d& o2 = rigs[1].cam_from_rig[2];
+  std::printf("c2r %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", o2.rotation.c[0], o2.rotation.c[1], o2.rotation.c[2], o2.rotation.c[3],
+              o2.translation[0], o2.translation[1], o2.translation[2]);
+  std::printf("nrig1 %zu\n", rigs[1].cam_from_rig.size());
   std::printf("shim driver ok\n");
   return 0;
 }

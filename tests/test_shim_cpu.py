@@ -54,7 +54,9 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     calls = calls[1:]
     assert [c["_name"] for c in calls] == ["ba_problem_create_rig", "ba_problem_set_state", "ba_problem_solve",
                                            "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
-                                           "ra_solve_gravity", "ba_solve", "ra_solve"]
+                                           "ra_solve_gravity", "ba_solve", "ra_solve",
+                                           "ba_problem_create_rig", "ba_problem_set_state", "ba_problem_set_sensor_variable",
+                                           "ba_problem_solve"]
     # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
     img_ids = [101, 102, 201, 202, 301, 302, 401]
     kimg = {i: k for k, i in enumerate(img_ids)}
@@ -153,6 +155,13 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     want = [avg([R[101], Rs[1].T @ R[102]]), R[201], R[301], R[401]]       # frame 10 averages its two images (rotation_initializer.cc:95-117)
     got = G.so3_exp(mst["theta"].reshape(-1, 3))
     assert np.abs(got - np.array(want)).max() < 1e-12, np.abs(got - np.array(want)).max()
+    # ---- optimize_rig_poses: the non-reference sensor is marked as an unknown and its result lands in the rig ----------
+    rp = calls[10:14]
+    assert rp[0]["dims"].tolist() == [4, 3, 12, 3, 3, 1]
+    assert rp[2]["sensor_variable"].tolist() == [0, 1, 0]                    # sensors sorted: (1,1) ref, (1,2), (2,3) ref
+    c2r = np.array([float(x) for x in stdout_line(calls, "c2r")])
+    assert np.allclose(c2r, [0, 0, 0.70710678118654757, 0.70710678118654757, 8.0, 8.0, 9.0], atol=0)   # the mock's pose of sensor 1
+    assert stdout_line(calls, "nrig1") == ["1"]                              # no entry was created for the reference sensor
 
 
 def test_shim_typechecks_against_the_glomap_api():
