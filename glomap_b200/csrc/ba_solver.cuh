@@ -912,7 +912,8 @@ struct b200sfm_ba_problem {
     nk = 0;
     if (ext_k)
       for (int k = 0; k < K; ++k) nk = std::max(nk, h_ivar[k].mb);
-    kfast = ext_k && !ext_s && nk <= 2 && !(getenv("B200SFM_KFAST") && atoi(getenv("B200SFM_KFAST")) == 0);
+    // (S == 0: with rigs an image is a (frame, sensor) pair, and the cross block / x_k packing below are per frame)
+    kfast = ext_k && !ext_s && S == 0 && nk <= 2 && !(getenv("B200SFM_KFAST") && atoi(getenv("B200SFM_KFAST")) == 0);
     if (kfast) {
       const size_t cells = (size_t)std::max<long long>(ell_rows, 1) * 32;
       if (ell_B.n < cells * 3 * nk) ell_B.alloc(cells * 3 * nk);
@@ -943,7 +944,6 @@ struct b200sfm_ba_problem {
     double radius = 1e4, decrease = 2.0;
     int invalid = 0, it = 0, term = B200SFM_TERM_NONE;
     bool set_jscale_p = true;
-    double eta = o.pcg_rel_tolerance;
     const bool fixed = o.fixed_num_iterations > 0;
     const int max_it = fixed ? o.fixed_num_iterations : o.max_num_iterations;
     if (!fixed && gmax <= o.gradient_tolerance) term = B200SFM_TERM_GRADIENT_TOLERANCE;
@@ -951,9 +951,7 @@ struct b200sfm_ba_problem {
       if (it >= max_it) { term = B200SFM_TERM_MAX_ITERATIONS; break; }
       if (radius < 1e-32) { term = B200SFM_TERM_MIN_RADIUS; break; }
       ++it;
-      b200sfm_ba_opts oo = o;
-      oo.pcg_rel_tolerance = eta;   // forcing term: tightened after a rejected step (see gp_solver.cuh)
-      StepResult r = compute_step(oo, radius, points_var, set_jscale_p, profile);
+      StepResult r = compute_step(o, radius, points_var, set_jscale_p, profile);
       set_jscale_p = false;
       local.pcg_iterations += r.pcg_iters;
       if (!r.finite || !(r.model_cost_change > 0.0)) {
@@ -975,12 +973,10 @@ struct b200sfm_ba_problem {
         linearize(o.thres_loss_function, points_var, false, profile, cost, gmax);
         radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
         decrease = 2.0;
-        eta = o.pcg_rel_tolerance;
         if (!fixed && gmax <= o.gradient_tolerance) { term = B200SFM_TERM_GRADIENT_TOLERANCE; break; }
       } else {
         radius /= decrease;
         decrease *= 2;
-        eta = std::max(0.1 * eta, 1e-12);
       }
     }
     B200_CUDA_OK(cudaEventRecord(ev1, s));

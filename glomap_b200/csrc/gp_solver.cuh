@@ -391,12 +391,6 @@ struct b200sfm_gp_problem {
     local.usable = 1;
     local.num_observations = n_obs_used;
     double radius = 1e4, decrease = 2.0;
-    // Forcing term of the inexact Newton step.  A step computed to the caller's tolerance that the trust region then
-    // REJECTS may have been rejected for its inexactness, not for the model: measured at config 2 (profiles/r2_gp_diag.py),
-    // rel. tolerance 1e-3 ends after 57 iterations in a run of rejections -> collapsing radius -> "parameter tolerance"
-    // at cost 2.2, where the exact solve (the reference uses sparse Cholesky) keeps descending.  So every rejection
-    // tightens the tolerance tenfold for the retry and the next accepted step restores the caller's value.
-    double eta = o.pcg_rel_tolerance;
     int invalid = 0, it = 0, term = B200SFM_TERM_NONE;
     const bool fixed = o.fixed_num_iterations > 0;
     const int max_it = fixed ? o.fixed_num_iterations : o.max_num_iterations;
@@ -405,9 +399,7 @@ struct b200sfm_gp_problem {
     while (term == B200SFM_TERM_NONE) {
       if (it >= max_it) { term = B200SFM_TERM_MAX_ITERATIONS; break; }
       if (radius < 1e-32) { term = B200SFM_TERM_MIN_RADIUS; break; }
-      b200sfm_gp_opts oo = o;
-      oo.pcg_rel_tolerance = eta;
-      StepResult r = compute_step(oo, v, radius, first, points_var, profile);
+      StepResult r = compute_step(o, v, radius, first, points_var, profile);
       cost = r.cost;
       if (first) local.initial_cost = cost;
       first = false;
@@ -484,11 +476,9 @@ struct b200sfm_gp_problem {
         ++local.num_successful_steps;
         radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
         decrease = 2.0;
-        eta = o.pcg_rel_tolerance;
       } else {
         radius /= decrease;
         decrease *= 2;
-        eta = std::max(0.1 * eta, 1e-12);
       }
     }
     B200_CUDA_OK(cudaEventRecord(ev1, s));
