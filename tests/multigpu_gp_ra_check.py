@@ -63,13 +63,12 @@ def main():
     t_obs = E.world_bearings(sc.quat, S.bearings_from_scene(sc), sc.obs_cam)
     rng = np.random.default_rng(1)
     c0 = 100 * rng.uniform(-1, 1, size=(sc.C, 3)); X0 = 100 * rng.uniform(-1, 1, size=(sc.P, 3))
-    a, b = D.shard_range(sc.P, 500, rank, world)
+    a, b = D.shard_range(sc.P, 125, rank, world)   # 24 chunks: no empty shard up to 8 ranks
     cen, st = gp_solve(ctx, sc, t_obs, c0, X0, a, b)
-    # trajectory parity.  From the reference's random start (100 U(-1,1), global_positioning.cc:123-165) the first LM
-    # iterations are chaotic: the 1e-16 differences of a different summation order are amplified until line-search /
-    # accept decisions flip, so iteration COUNTS from a random start are not comparable (round 1 saw 39 vs 15 to the
-    # same cost).  The comparable quantity is the cost after a fixed number of iterations from a start inside the
-    # basin of attraction (ground truth perturbed by 1 %): it must agree to rounding.
+    # trajectory parity: the cost after a fixed number of iterations from a start inside the basin of attraction (ground
+    # truth perturbed by 1 %) must agree to rounding, and the natural run from the reference's random start
+    # (100 U(-1,1), global_positioning.cc:123-165) must take the same number of iterations (round 1's "39 vs 15" was this
+    # script handing the solver views of arrays an earlier solve had updated in place).
     cg = G.centers_from_pose(G.quat_xyzw_to_rotmat(sc.quat), sc.trans)
     c_near = cg + 0.1 * rng.normal(size=cg.shape); X_near = sc.points + 0.03 * rng.normal(size=sc.points.shape)
     gtraj = [gp_solve(ctx, sc, t_obs, c_near, X_near, a, b, fixed_iters=k)[1].final_cost for k in (1, 2, 3, 5)]
@@ -89,7 +88,7 @@ def main():
         rerr = np.abs(G.so3_exp(th) - G.so3_exp(th1)).max()
         print(f"GP multi({world})/single: its {st.iterations}/{st1.iterations} cost {st.final_cost:.10e}/{st1.final_cost:.10e} centre rel err {gerr:.2e}")
         print(f"RA multi({world})/single: L1 {rst.l1_iterations}/{rst1.l1_iterations} IRLS {rst.irls_iterations}/{rst1.irls_iterations} max |dR| {rerr:.2e}")
-        ok = (ok_traj and abs(st.final_cost - st1.final_cost) <= 1e-6 * max(st1.final_cost, 1e-12) + 1e-9 and gerr < 1e-5 and
+        ok = (ok_traj and st.iterations == st1.iterations and abs(st.final_cost - st1.final_cost) <= 1e-6 * max(st1.final_cost, 1e-12) + 1e-9 and gerr < 1e-5 and
               (rst.l1_iterations, rst.irls_iterations) == (rst1.l1_iterations, rst1.irls_iterations) and rerr < 1e-7)
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -22,7 +22,7 @@ def _run(script, nproc, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", script)]
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):          # keep the full transcript of the ranks next to the other GPU-box artefacts
         with open(os.path.join(out_dir, f"multigpu_{script}_{nproc}.log"), "w") as f:
