@@ -483,6 +483,133 @@ __global__ void ra_coarse_prolong(int n, RACoarse c, double* __restrict__ z, con
   z[3 * (size_t)i + 2] += c.zc[3 * a + 2];
 }
 
+// ---------------------------------------------------------------------------
+// Fused two-level PCG iteration (one GPU, CSR Laplacian): four kernels instead of seven
+//   ra2_direction      stopping rule + p = (z + P zc) + beta p   -- the prolongation is never materialised in z;
+//                      also writes the 32-B padded copy p4 the Laplacian gathers with one 256-bit load per incidence
+//   ra2_laplacian_dot  q = L p and the per-CTA partials of p.q    (replaces ra_laplacian_csr + pcg_apply_diag)
+//   pcg_update<3>      unchanged
+//   ra2_coarse         rc = P^T r, grid barrier, zc = Ac^-1 rc + coarse part of r.z   (replaces restrict + solve)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPcgThreads) ra2_direction(int n, int nblk, int it, double rel_tol,
+                                                             const double* __restrict__ z, double* __restrict__ p,
+                                                             double* __restrict__ p4, const double* __restrict__ zc,
+                                                             const int* __restrict__ agg_of,
+                                                             const double* __restrict__ dots_pp,
+                                                             const double* __restrict__ part_rz,
+                                                             const double* __restrict__ part_rr,
+                                                             const double* __restrict__ part_ref,
+                                                             double* __restrict__ dots_pub, PcgCtl* __restrict__ ctl) {
+  __shared__ double sh3[3];
+  double beta;
+  if (!pcg_direction_head(nblk, it, 0, rel_tol, dots_pp, part_rz, part_rr, part_ref, dots_pub, ctl, sh3, beta)) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int a = agg_of[c];
+  double pv[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const size_t i = 3 * (size_t)c + k;
+    const double zf = z[i] + zc[3 * a + k];
+    pv[k] = (it == 1) ? zf : zf + beta * p[i];
+    p[i] = pv[k];
+  }
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p4 + 4 * (size_t)c), "d"(pv[0]), "d"(pv[1]), "d"(pv[2]), "d"(0.0) : "memory");
+}
+
+// CTA b owns the nodes [128 b, 128 b + 128): each of its 4 warps walks 32 nodes, one after the other, lanes over incidences
+__global__ void __launch_bounds__(kPcgThreads) ra2_laplacian_dot(RACsr c, const double* __restrict__ p4, double* __restrict__ q,
+                                                                 double* __restrict__ part_pq, const PcgCtl* __restrict__ ctl) {
+  __shared__ double shw[kPcgThreads / 32];
+  if (ctl && ctl->done) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int node0 = blockIdx.x * kPcgThreads + wid * 32;
+  double dot = 0.0;
+  for (int j = 0; j < 32; ++j) {
+    const int node = node0 + j;
+    if (node >= c.n) break;
+    const int b = c.begin[node], e = c.begin[node + 1];
+    const double4 xs = ld_rec32(p4 + 4 * (size_t)node);
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+    for (int s = b + lane; s < e; s += 32) {
+      const double we = ld_stream(c.w_inc + s);
+      const int o = ld_stream(c.other + s);
+      double4 xo = make_double4(0, 0, 0, 0);
+      if (o >= 0) xo = ld_rec32(p4 + 4 * (size_t)o);
+      a0 += we * (xs.x - xo.x);
+      a1 += we * (xs.y - xo.y);
+      a2 += we * (xs.z - xo.z);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+      q[3 * (size_t)node] = a0; q[3 * (size_t)node + 1] = a1; q[3 * (size_t)node + 2] = a2;
+      dot += xs.x * a0 + xs.y * a1 + xs.z * a2;
+    }
+  }
+  if (lane == 0) shw[wid] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kPcgThreads / 32; ++w) s += shw[w];
+    part_pq[blockIdx.x] = s;
+  }
+}
+
+// restriction + coarse solve in one launch: every CTA restricts its 4 aggregates, all CTAs meet at a grid barrier (the
+// grid is <= 256 CTAs of 128 threads: co-resident on 148 SMs), then every warp applies one row of the coarse inverse.
+// bar[0] = arrival counter, bar[1] = generation (sense reversal: safe across launches, also across skipped ones)
+__global__ void __launch_bounds__(128) ra2_coarse(RACoarse c, const double* __restrict__ r, double* __restrict__ part_rz_extra,
+                                                  unsigned* __restrict__ bar, const PcgCtl* __restrict__ ctl) {
+  __shared__ double sh[4];
+  if (ctl && ctl->done) return;   // set by an earlier launch only: every CTA of this grid takes the same branch
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (a < c.nc) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int t = c.agg_begin[a] + lane; t < c.agg_begin[a + 1]; t += 32) {
+      const size_t node = (size_t)c.agg_nodes[t];
+      s0 += r[3 * node]; s1 += r[3 * node + 1]; s2 += r[3 * node + 2];
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { c.rc[3 * a] = s0; c.rc[3 * a + 1] = s1; c.rc[3 * a + 2] = s2; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* vb = bar;
+    const unsigned gen = vb[1];
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      vb[0] = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (vb[1] == gen) {}
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  double dot = 0.0;
+  if (a < c.nc) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    const double* row = c.Ac + (size_t)a * c.nc;
+    const volatile double* rc = c.rc;   // written by other CTAs of this launch
+    for (int b = lane; b < c.nc; b += 32) {
+      const double m = row[b];
+      s0 += m * rc[3 * b]; s1 += m * rc[3 * b + 1]; s2 += m * rc[3 * b + 2];
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+      c.zc[3 * a] = s0; c.zc[3 * a + 1] = s1; c.zc[3 * a + 2] = s2;
+      dot = s0 * rc[3 * a] + s1 * rc[3 * a + 1] + s2 * rc[3 * a + 2];
+    }
+  }
+  if (lane == 0) sh[wid] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) part_rz_extra[blockIdx.x] = sh[0] + sh[1] + sh[2] + sh[3];
+}
+
 // Minv (packed 3x3 diagonal) = 1/deg ; nodes without edges get identity
 __global__ void ra_build_precond(int n, const double* __restrict__ deg, double* __restrict__ Minv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

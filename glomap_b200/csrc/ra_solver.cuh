@@ -37,7 +37,8 @@ struct b200sfm_ra_problem {
   bool use_2lvl = false, coarse_l1_valid = false;
   int nc = 0, nblk_c = 0;
   DevBuf<int> agg_of, agg_begin, agg_nodes;
-  DevBuf<double> Ac, rc, zc;
+  DevBuf<double> Ac, rc, zc, p4;   // p4: 32-B padded copy of the PCG direction for the Laplacian gathers (fused iteration)
+  DevBuf<unsigned> gbar;           // grid barrier of ra2_coarse: {arrivals, generation}
   b200::RACoarse coarse() {
     b200::RACoarse c;
     c.nc = nc; c.agg_of = agg_of.p; c.agg_begin = agg_begin.p; c.agg_nodes = agg_nodes.p; c.Ac = Ac.p; c.rc = rc.p; c.zc = zc.p;
@@ -275,6 +276,36 @@ struct b200sfm_ra_problem {
     double *part_pq = ctx->pcgh.d_part, *part_rz = ctx->pcgh.d_part + nblk_t, *part_rr = ctx->pcgh.d_part + 2 * (size_t)nblk_t;
     if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(ctx->pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
     PcgCtl* ctl = ctx->pcgh.d_ctl;
+    // fused iteration (ra_kernels.cuh: ra2_*): four kernels, the prolongation folded into the direction update
+    const bool fused = use_2lvl && use_csr && ctx->world == 1 && !(getenv("B200SFM_RA_FUSED") && atoi(getenv("B200SFM_RA_FUSED")) == 0);
+    if (fused) {
+      if (p4.n < (size_t)n * 4) p4.alloc((size_t)n * 4);
+      if (gbar.n < 2) { gbar.alloc(2); gbar.zero(s); }
+      PcgResult rf = ctx->pcgh.run(
+          s, max_it,
+          [&]() {
+            if (warm) {
+              yw.zero(s);
+              laplacian(v, square, px.p, yw.p, nullptr);
+              B200_LAUNCH(ctx, ra_pcg_init_warm, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, yw.p, pr.p, pz.p, pp.p, part_pq, part_rz, part_rr);
+            } else {
+              B200_LAUNCH(ctx, pcg_init<3>, nblk, kPcgThreads, 0, n, Minv.p, rhs_vec, px.p, pr.p, pz.p, part_rz, part_rr);
+            }
+            B200_LAUNCH(ctx, ra2_coarse, nblk_c, 128, 0, coarse(), pr.p, part_rz + nblk, gbar.p, nullptr);
+          },
+          [&](int it) {
+            double* d_pub = ctx->pcgh.dots(it - 1);
+            B200_LAUNCH(ctx, ra2_direction, nblk, kPcgThreads, 0, n, nblk_t, it, o.pcg_rel_tolerance, pz.p, pp.p, p4.p, zc.p, agg_of.p,
+                        ctx->pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
+            B200_LAUNCH(ctx, ra2_laplacian_dot, nblk, kPcgThreads, 0, csr(), p4.p, pq.p, part_pq, ctl);
+            B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk_t, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
+                        part_rr, ctx->pcgh.dots(it), ctl);
+            B200_LAUNCH(ctx, ra2_coarse, nblk_c, 128, 0, coarse(), pr.p, part_rz + nblk, gbar.p, ctl);
+          },
+          [&](int launched) { B200_LAUNCH(ctx, pcg_finalize, 1, kPcgThreads, 0, nblk_t, launched, part_rr, ctl); });
+      finite = rf.finite;
+      return rf.iters;
+    }
     PcgResult r = ctx->pcgh.run(
         s, max_it,
         [&]() {

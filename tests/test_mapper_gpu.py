@@ -15,13 +15,15 @@ from glomap_b200 import geometry as G, mapper as M, synthetic as S
 pytestmark = pytest.mark.gpu
 
 
-def test_mapper_recovers_the_scene():
+@pytest.mark.parametrize("refine_intrinsics", [False, True])
+def test_mapper_recovers_the_scene(refine_intrinsics):
+    """refine_intrinsics = True is the reference's default BundleAdjusterOptions (bundle_adjustment.h:18)."""
     sc = S.make_scene(30, 2000, mean_track_len=6, seed=21, pixel_sigma=0.5)
     vg = S.view_graph_from_scene(sc, min_shared=15, noise_deg=0.5)
     start = sc.copy()
     start.quat[:] = [0, 0, 0, 1]; start.trans[:] = 0; start.points[:] = 0     # nothing but tracks and relative rotations
     opts = M.GlobalMapperOptions()
-    opts.opt_ba.optimize_intrinsics = False
+    opts.opt_ba.optimize_intrinsics = refine_intrinsics
     mapper = M.GlobalMapper(opts)
     ok, out = mapper.Solve(vg, start)
     assert ok, mapper.log
