@@ -282,22 +282,12 @@ __global__ void __launch_bounds__(128, NK > 0 ? 3 : B200_LC_MIN_CTAS) ba2_linear
 // frame:  Sd_c = Rb ( sum_o Gh^T N Gh ) Rb^T,  N = A_o Vinv_p A_o,
 //         Gh = [ -2 [X]x | I ],  Rb = blockdiag(R, R)
 // ---------------------------------------------------------------------------
-// NK > 0 (stored-row intrinsics path, more than one intrinsics block): also the Schur term of the segment's
-// intrinsics block, per observation:  Sd_kk += sum_o B_o^T Vinv B_o.  Exact when a point is seen once per block (one camera
-// per image); with cameras shared by several images it omits the cross terms between observations of one point -- still
-// SPD (B_o^T Vinv B_o <= rho' J_k^T J_k), just a weaker preconditioner; ONE shared camera is ba3k_schur_intr_shared.
-template <int NK>
 __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= v.n_segs) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  constexpr int NKK = NK > 0 ? NK : 1;
-  double SK[NKK * (NKK + 1) / 2];
-#pragma unroll
-  for (int k = 0; k < NKK * (NKK + 1) / 2; ++k) SK[k] = 0.0;
-  const double* rowB = NK > 0 ? v2.Bc + (size_t)(v.seg_row0[warp] >> 5) * (3 * NK * 32) + lane : nullptr;
   // world-frame accumulators: RR (sym 6), RT (full 9), TT (sym 6)
   double RR[6] = {0, 0, 0, 0, 0, 0}, RT[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, TT[6] = {0, 0, 0, 0, 0, 0};
   const double* row = v2.Ac + (size_t)(v.seg_row0[warp] >> 5) * (kJcDoubles * 32) + lane;
@@ -309,19 +299,6 @@ __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, con
     const double2* vp = reinterpret_cast<const double2*>(v.Vinv + (size_t)pt * 6);
     const double2 v0 = vp[0], v1 = vp[1], v2_ = vp[2];
     const double vi[6] = {v0.x, v0.y, v1.x, v1.y, v2_.x, v2_.y};
-    if (NK > 0) {
-      double Bo[3 * NKK], VB[3 * NKK];
-#pragma unroll
-      for (int k = 0; k < 3 * NK; ++k) Bo[k] = ld_stream(rowB + 32 * k);
-      rowB += 3 * NK * 32;
-#pragma unroll
-      for (int a = 0; a < NK; ++a) sym3_mul(vi, Bo + 3 * a, VB + 3 * a);
-      int ik = 0;
-#pragma unroll
-      for (int a = 0; a < NK; ++a)
-#pragma unroll
-        for (int c = a; c < NK; ++c) SK[ik++] += Bo[3 * c] * VB[3 * a] + Bo[3 * c + 1] * VB[3 * a + 1] + Bo[3 * c + 2] * VB[3 * a + 2];
-    }
     // T = Vinv A (columns), N = A T (symmetric 3x3)
     const double Ac0[3] = {A[0], A[1], A[2]}, Ac1[3] = {A[1], A[3], A[4]}, Ac2[3] = {A[2], A[4], A[5]};
     double T0[3], T1[3], T2[3];
@@ -361,17 +338,6 @@ __global__ void __launch_bounds__(128) ba2_schur_diag(BAView v, BAViewV2 v2, con
 #pragma unroll
       for (int c = 0; c < 3; ++c) RT[3 * r + c] += P[r][c];
     TT[0] += N[0][0]; TT[1] += N[0][1]; TT[2] += N[0][2]; TT[3] += N[1][1]; TT[4] += N[1][2]; TT[5] += N[2][2];
-  }
-  if (NK > 0) {
-    const size_t kb = (size_t)(v2.C + v.seg_intr[warp]);
-    int ik = 0;
-#pragma unroll
-    for (int a = 0; a < NK; ++a)
-#pragma unroll
-      for (int c = a; c < NK; ++c) {
-        const double sk = warp_sum(SK[ik++]);
-        if (lane == 0 && sk != 0.0) atomicAdd(&v.Sd[kb * 21 + sym_idx(6, a, c)], sk);
-      }
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) RR[k] = warp_sum(RR[k]);

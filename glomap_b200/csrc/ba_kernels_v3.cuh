@@ -398,64 +398,4 @@ __global__ void __launch_bounds__(kEllThreads, MODE == 0 ? B200_EA_MIN_CTAS : B2
   }
 }
 
-// ---- Schur term of ONE shared intrinsics block (stored-row path, K == 1), exact: every observation of a point belongs
-// to the block, so  Sd_kk = sum_p (sum_o B_o)^T Vinv_p (sum_o B_o).  One thread per point, per-CTA partials, then a
-// single-CTA sum in a fixed order (deterministic).
-template <int NK>
-__global__ void __launch_bounds__(kEllThreads) ba3k_schur_intr_shared(BAView v, EllView ell, double* __restrict__ part) {
-  __shared__ double scratch[32];
-  const int slot = blockIdx.x * kEllThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int g = slot >> 5;
-  double T[NK * (NK + 1) / 2];
-#pragma unroll
-  for (int k = 0; k < NK * (NK + 1) / 2; ++k) T[k] = 0.0;
-  if (g < ell.n_groups) {
-    const int pt = ell.pt[slot];
-    const int mylen = ell.len[slot];
-    const int r0 = ell.row0[g], nrow = ell.row0[g + 1] - r0;
-    double Bs[3 * NK];
-#pragma unroll
-    for (int k = 0; k < 3 * NK; ++k) Bs[k] = 0.0;
-#pragma unroll 4
-    for (int j = 0; j < nrow; ++j) {
-      if (j >= mylen) continue;
-      const double* rowB = ell.B + ((size_t)r0 + j) * (3 * NK * 32) + lane;
-#pragma unroll
-      for (int k = 0; k < 3 * NK; ++k) Bs[k] += ld_stream(rowB + 32 * k);
-    }
-    if (pt >= 0 && mylen > 0) {
-      const double2* vp = reinterpret_cast<const double2*>(v.Vinv + 6 * (size_t)pt);
-      const double2 va = vp[0], vb = vp[1], vc = vp[2];
-      const double vi[6] = {va.x, va.y, vb.x, vb.y, vc.x, vc.y};
-      double VB[3 * NK];
-#pragma unroll
-      for (int a = 0; a < NK; ++a) sym3_mul(vi, Bs + 3 * a, VB + 3 * a);
-      int ik = 0;
-#pragma unroll
-      for (int a = 0; a < NK; ++a)
-#pragma unroll
-        for (int c = a; c < NK; ++c) T[ik++] = Bs[3 * c] * VB[3 * a] + Bs[3 * c + 1] * VB[3 * a + 1] + Bs[3 * c + 2] * VB[3 * a + 2];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NK * (NK + 1) / 2; ++k) {
-    const double t = block_sum(T[k], scratch);
-    if (threadIdx.x == 0) part[(size_t)blockIdx.x * 3 + k] = t;
-  }
-}
-// Sd block of the shared camera (block index kb) += the per-CTA partials above
-__global__ void __launch_bounds__(256) ba3k_schur_intr_reduce(int n_part, int nk, const double* __restrict__ part, double* __restrict__ Sd_blk) {
-  __shared__ double scratch[32];
-  int ik = 0;
-  for (int a = 0; a < nk; ++a)
-    for (int c = a; c < nk; ++c, ++ik) {
-      double s = 0.0;
-      for (int i = threadIdx.x; i < n_part; i += blockDim.x) s += part[(size_t)i * 3 + ik];
-      s = block_sum(s, scratch);
-      if (threadIdx.x == 0) Sd_blk[sym_idx(6, a, c)] += s;
-      __syncthreads();
-    }
-}
-
 }  // namespace b200

@@ -716,17 +716,7 @@ struct b200sfm_ba_problem {
     double* yrhs = Sd.p + (size_t)CB * 21;   // W Vinv g_p accumulates next to Sd so that both share one all-reduce
     Sd.zero(s);
     if (schur_jacobi && n_segs > 0) {
-      if (use_v2) {
-        const int sg = cdiv((long long)n_segs * 32, 128);
-        if (kfast && K > 1 && nk == 2) B200_LAUNCH(ctx, ba2_schur_diag<2>, sg, 128, 0, v, view2(), cam_rec.p);
-        else if (kfast && K > 1) B200_LAUNCH(ctx, ba2_schur_diag<1>, sg, 128, 0, v, view2(), cam_rec.p);
-        else B200_LAUNCH(ctx, ba2_schur_diag<0>, sg, 128, 0, v, view2(), cam_rec.p);
-        if (kfast && K == 1) {   // one shared camera: its exact Schur term, in point order (ell_part is free here)
-          if (nk == 2) B200_LAUNCH(ctx, ba3k_schur_intr_shared<2>, ell_ctas, kEllThreads, 0, v, ell_view(), ell_part.p);
-          else B200_LAUNCH(ctx, ba3k_schur_intr_shared<1>, ell_ctas, kEllThreads, 0, v, ell_view(), ell_part.p);
-          B200_LAUNCH(ctx, ba3k_schur_intr_reduce, 1, 256, 0, ell_ctas, nk, ell_part.p, Sd.p + (size_t)C * 21);
-        }
-      }
+      if (use_v2) B200_LAUNCH(ctx, ba2_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v, view2(), cam_rec.p);
       else B200_LAUNCH(ctx, ba_schur_diag, cdiv((long long)n_segs * 32, 128), 128, 0, v);
     }
     if (points_var) {
