@@ -22,7 +22,7 @@ namespace b200 {
 #define B200_PA_MIN_CTAS 12
 #endif
 #ifndef B200_LC_MIN_CTAS   // v2 camera-order linearisation: 128 registers (a few spills) -> 4 CTAs of 4 warps; sweep: profiles/r1_v2_sweep.md
-#define B200_LC_MIN_CTAS 4
+#define B200_LC_MIN_CTAS 3   // r2: the register-pipelined kernel needs 166 registers without spills (3 CTAs): 54.7 vs 55.5 ms per solve at 4 CTAs / 128 registers + spills
 #endif
 #ifndef B200_PB_PREFETCH   // v2 pass B: load all point indices of a segment before the gathers (one latency per iteration)
 #define B200_PB_PREFETCH 1
