@@ -149,6 +149,12 @@ void b200sfm_destroy(b200sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+  if (ctx->comm_stream) {
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    cudaEventDestroy(ctx->ev_half);
+    cudaEventDestroy(ctx->ev_comm);
+  }
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);

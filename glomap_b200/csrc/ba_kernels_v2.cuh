@@ -585,11 +585,12 @@ __global__ void ba2_point_rhs_z(BAView v, BAViewV2 v2) {
 // ---------------------------------------------------------------------------
 template <int NK>
 __global__ void __launch_bounds__(128, B200_PB_MIN_CTAS) ba2_pass_b(BAView v, BAViewV2 v2, const double* __restrict__ cam_rec,
-                                                 double* __restrict__ y, const PcgCtl* __restrict__ ctl) {
+                                                 double* __restrict__ y, const PcgCtl* __restrict__ ctl, int seg_lo,
+                                                 int seg_hi) {
   if (ctl && ctl->done) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = seg_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);   // segments [seg_lo, seg_hi)
   const int lane = threadIdx.x & 31;
-  if (warp >= v.n_segs) return;
+  if (warp >= seg_hi) return;
   const int cam = v.seg_cam[warp];
   const int b = v.seg_begin[warp], e = v.seg_end[warp];
   double acc[6] = {0, 0, 0, 0, 0, 0};

@@ -120,6 +120,7 @@ struct b200sfm_ba_problem {
   int C = 0, P = 0, K = 0;
   long long N = 0;
   int Nv = 0, n_tiles = 0, n_segs = 0, min_views = 3;
+  int seg_mid = 0;   // first camera-order segment of a camera >= C / 2 (split all-reduce of the multi-GPU mat-vec)
   long long n_obs_used = 0;
 
   // structure
@@ -342,6 +343,13 @@ struct b200sfm_ba_problem {
                 S > 0 ? sensor_intr.p : nullptr, seg_cam.p, seg_sensor.p, seg_intr.p, seg_begin.p, seg_end.p);
     if (Nv > 0)
       B200_LAUNCH(ctx, k_gather_camorder, cdiv(Nv, 256), 256, 0, Nv, camord_obs.p, obs_pt.p, obs_xy.p, pt_c.p, xy_c.p);
+    seg_mid = n_segs;
+    if (ctx->world > 1 && n_segs > 0) {   // segments are sorted by camera (frame): split point of the overlapped all-reduce
+      std::vector<int> h_seg_cam(n_segs);
+      B200_CUDA_OK(cudaMemcpyAsync(h_seg_cam.data(), seg_cam.p, (size_t)n_segs * sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      seg_mid = (int)(std::lower_bound(h_seg_cam.begin(), h_seg_cam.end(), C / 2) - h_seg_cam.begin());
+    }
     // v2 camera-order rows: every segment starts on a 32-row group boundary
     {
       DevBuf<int> padded;
@@ -679,12 +687,14 @@ struct b200sfm_ba_problem {
     }
   }
 
-  void launch_pass_b(const b200::BAView& v, double* y, const b200::PcgCtl* ctl) {
+  void launch_pass_b(const b200::BAView& v, double* y, const b200::PcgCtl* ctl, int seg_lo = 0, int seg_hi = -1) {
     using namespace b200;
-    const int grid = cdiv((long long)n_segs * 32, 128);
-    if (kfast && nk == 2) B200_LAUNCH(ctx, ba2_pass_b<2>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
-    else if (kfast) B200_LAUNCH(ctx, ba2_pass_b<1>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
-    else B200_LAUNCH(ctx, ba2_pass_b<0>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl);
+    if (seg_hi < 0) seg_hi = n_segs;
+    if (seg_hi <= seg_lo) return;
+    const int grid = cdiv((long long)(seg_hi - seg_lo) * 32, 128);
+    if (kfast && nk == 2) B200_LAUNCH(ctx, ba2_pass_b<2>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl, seg_lo, seg_hi);
+    else if (kfast) B200_LAUNCH(ctx, ba2_pass_b<1>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl, seg_lo, seg_hi);
+    else B200_LAUNCH(ctx, ba2_pass_b<0>, grid, 128, 0, v, view2(), cam_rec.p, y, ctl, seg_lo, seg_hi);
   }
   void launch_pass_a0(const b200::BAView& v, double radius, const b200::PcgCtl* ctl) {
     using namespace b200;
@@ -745,6 +755,10 @@ struct b200sfm_ba_problem {
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
     const bool has_mv = points_var || ext;   // an observation pass per iteration (else S = U + D is block diagonal)
+    // several GPUs: split the per-iteration all-reduce at camera C/2 and overlap its first half with pass B (B200SFM_SPLIT_AR=0: off)
+    const bool split_ar = ctx->world > 1 && use_v2 && !recomp && points_var && C >= 64 &&
+                          !(getenv("B200SFM_SPLIT_AR") && atoi(getenv("B200SFM_SPLIT_AR")) == 0);
+    if (split_ar) ctx->ensure_comm_stream();
     const bool pack_dir = points_var && use_v2 && !recomp;   // direction kernel also packs R^T p for pass A
     PcgResult pr_ = ctx->pcgh.run(
         s, max_it,
@@ -778,14 +792,30 @@ struct b200sfm_ba_problem {
                 launch_pass_a0(v, radius, ctl);
               else
                 B200_LAUNCH(ctx, ba2_pass_a<0>, n_tiles, kTile, smem_k3v2, v, view2(), xq.p, points[cur].p, nullptr, radius, nullptr, ctl);
-              if (n_segs > 0) launch_pass_b(v, yw.p, ctl);
-              if (kfast) launch_cross(pp.p, yw.p, ctl);
+              if (kfast) launch_cross(pp.p, yw.p, ctl);   // before pass B: its y_f updates are plain stores of the owning thread
+              if (split_ar) {
+                // cameras below C/2 are complete after the first half of the (camera-sorted) segments: their all-reduce
+                // runs on the second stream while pass B works through the upper half
+                launch_pass_b(v, yw.p, ctl, 0, seg_mid);
+                B200_CUDA_OK(cudaEventRecord(ctx->ev_half, s));
+                B200_CUDA_OK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_half, 0));
+                ctx->allreduce_sum_on(ctx->comm_stream, yw.p, (size_t)(C / 2) * 6);
+                B200_CUDA_OK(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                launch_pass_b(v, yw.p, ctl, seg_mid, n_segs);
+              } else if (n_segs > 0) {
+                launch_pass_b(v, yw.p, ctl);
+              }
             } else {
               B200_LAUNCH(ctx, ba_schur_pass<0>, n_tiles, kTile, smem_k3, v, pp.p, yw.p, nullptr, nullptr, radius, nullptr, nullptr,
                           nullptr, 0, ctl);
             }
             if (profile) B200_CUDA_OK(cudaEventRecord(e1, s));
-            ctx->allreduce_sum(yw.p, nB6);
+            if (split_ar) {
+              ctx->allreduce_sum(yw.p + (size_t)(C / 2) * 6, nB6 - (size_t)(C / 2) * 6);   // upper half + pseudo-camera blocks
+              B200_CUDA_OK(cudaStreamWaitEvent(s, ctx->ev_comm, 0));
+            } else {
+              ctx->allreduce_sum(yw.p, nB6);
+            }
           }
           // extended path: J^T J is inside yw already, only the damping is added here
           B200_LAUNCH(ctx, pcg_apply_diag<6>, nblk, kPcgThreads, 0, nbk, recomp ? nullptr : U(), Dc.p, pp.p, has_mv ? yw.p : nullptr, pq.p,

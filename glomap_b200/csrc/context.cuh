@@ -66,11 +66,23 @@ struct b200sfm_ctx {
   // one-shot solve does not pay cudaMallocHost / cudaMalloc / cudaFree (a device-wide synchronisation) on every call
   b200::PcgHost pcgh;
 
-  void allreduce_sum(double* buf, size_t n) {
+  void allreduce_sum(double* buf, size_t n) { allreduce_sum_on(stream, buf, n); }
+  void allreduce_sum_on(cudaStream_t st, double* buf, size_t n) {
     if (world == 1 || n == 0) return;
     if (!comm) throw NcclError{"communicator was aborted after an earlier failure"};
-    ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclFloat64, ncclSum, comm, stream);
+    ncclResult_t r = nccl_api().AllReduce(buf, buf, n, ncclFloat64, ncclSum, comm, st);
     if (r != ncclSuccess) throw NcclError{std::string("ncclAllReduce(sum): ") + nccl_api().GetErrorString(r)};
+  }
+  // Second stream for the first half of a split all-reduce (the BA mat-vec reduces the cameras below C/2 while pass B
+  // still runs over the segments of the upper half): created on first use, destroyed with the context.  Every rank
+  // issues its collectives in the same order (comm stream first, then the main stream), as NCCL requires.
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_half = nullptr, ev_comm = nullptr;
+  void ensure_comm_stream() {
+    if (comm_stream) return;
+    B200_CUDA_OK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+    B200_CUDA_OK(cudaEventCreateWithFlags(&ev_half, cudaEventDisableTiming));
+    B200_CUDA_OK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
   }
   void allreduce_max(double* buf, size_t n) {
     if (world == 1 || n == 0) return;
