@@ -461,6 +461,8 @@ def main():
     if args.workload == "config5":
         # BASELINE.json config 5 (100 k-frame view graph): rotation averaging, the secondary metric of SURVEY.md 8(d)
         # (edges/s per L1 / IRLS iteration).  Single GPU; the line is printed by bench_secondary.py in the same JSON style.
+        if int(os.environ.get("RANK", "0")) != 0:
+            return   # one GPU: under torchrun only rank 0 measures
         import bench_secondary as B2
         B2.bench_ra(argparse.Namespace(frames=100_000, neighbours=100, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
                                        pcg_tol=1e-6))

@@ -517,15 +517,19 @@ __global__ void __launch_bounds__(kPcgThreads) ra2_direction(int n, int nblk, in
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p4 + 4 * (size_t)c), "d"(pv[0]), "d"(pv[1]), "d"(pv[2]), "d"(0.0) : "memory");
 }
 
-// CTA b owns the nodes [128 b, 128 b + 128): each of its 4 warps walks 32 nodes, one after the other, lanes over incidences
-__global__ void __launch_bounds__(kPcgThreads) ra2_laplacian_dot(RACsr c, const double* __restrict__ p4, double* __restrict__ q,
+// CTA b owns the nodes [128 b, 128 b + 128) -- the same split as the vector kernels, so part_pq has one entry per PCG block --
+// but runs kLapThreads = 512 threads: 16 warps of 8 nodes each, lanes over incidences (with 4 warps of 32 nodes the SM held
+// 21 warps and the fused solve was SLOWER than the unfused one: 630 vs 547 ms, gpurun_out/r2_ra5_fused.log)
+constexpr int kLapThreads = 512;
+constexpr int kLapNodesPerWarp = kPcgThreads / (kLapThreads / 32);
+__global__ void __launch_bounds__(kLapThreads) ra2_laplacian_dot(RACsr c, const double* __restrict__ p4, double* __restrict__ q,
                                                                  double* __restrict__ part_pq, const PcgCtl* __restrict__ ctl) {
-  __shared__ double shw[kPcgThreads / 32];
+  __shared__ double shw[kLapThreads / 32];
   if (ctl && ctl->done) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int node0 = blockIdx.x * kPcgThreads + wid * 32;
+  const int node0 = blockIdx.x * kPcgThreads + wid * kLapNodesPerWarp;
   double dot = 0.0;
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < kLapNodesPerWarp; ++j) {
     const int node = node0 + j;
     if (node >= c.n) break;
     const int b = c.begin[node], e = c.begin[node + 1];
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(kPcgThreads) ra2_laplacian_dot(RACsr c, const 
   if (threadIdx.x == 0) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kPcgThreads / 32; ++w) s += shw[w];
+    for (int w = 0; w < kLapThreads / 32; ++w) s += shw[w];
     part_pq[blockIdx.x] = s;
   }
 }

@@ -297,7 +297,7 @@ struct b200sfm_ra_problem {
             double* d_pub = ctx->pcgh.dots(it - 1);
             B200_LAUNCH(ctx, ra2_direction, nblk, kPcgThreads, 0, n, nblk_t, it, o.pcg_rel_tolerance, pz.p, pp.p, p4.p, zc.p, agg_of.p,
                         ctx->pcgh.dots(it - 2), part_rz, part_rr, (warm && it == 1) ? part_pq : nullptr, d_pub, ctl);
-            B200_LAUNCH(ctx, ra2_laplacian_dot, nblk, kPcgThreads, 0, csr(), p4.p, pq.p, part_pq, ctl);
+            B200_LAUNCH(ctx, ra2_laplacian_dot, nblk, kLapThreads, 0, csr(), p4.p, pq.p, part_pq, ctl);
             B200_LAUNCH(ctx, pcg_update<3>, nblk, kPcgThreads, 0, n, nblk_t, Minv.p, pp.p, pq.p, px.p, pr.p, pz.p, d_pub, part_pq, part_rz,
                         part_rr, ctx->pcgh.dots(it), ctl);
             B200_LAUNCH(ctx, ra2_coarse, nblk_c, 128, 0, coarse(), pr.p, part_rz + nblk, gbar.p, ctl);
