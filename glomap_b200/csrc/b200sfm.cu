@@ -360,6 +360,25 @@ int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, 
   });
 }
 
+int b200sfm_ba_problem_normalize(b200sfm_ba_problem* p, int32_t fixed_scale, double extent, double p0, double p1,
+                                 double* scale_out, double* translation_out) {
+  if (!p || !(extent > 0.0) || !(p0 >= 0.0) || !(p1 <= 1.0) || !(p0 <= p1)) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->normalize(fixed_scale != 0, extent, p0, p1, scale_out, translation_out);
+    return (int)B200SFM_OK;
+  });
+}
+
+int b200sfm_ba_problem_undistort(b200sfm_ba_problem* p, double* bearings_out) {
+  if (!p) return B200SFM_ERR_INVALID_ARG;
+  return guarded(p->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(p->ctx->device));
+    p->undistort(bearings_out);
+    return (int)B200SFM_OK;
+  });
+}
+
 int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_reprojection_error, uint8_t* keep,
                                            int64_t* num_tracks_changed) {
   if (!p || !keep) return B200SFM_ERR_INVALID_ARG;
@@ -373,7 +392,7 @@ int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_rep
 
 int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings, const uint8_t* cam_calibrated,
                                     double max_angle_error_deg, uint8_t* keep, int64_t* num_tracks_changed) {
-  if (!p || !keep || !bearings) return B200SFM_ERR_INVALID_ARG;
+  if (!p || !keep) return B200SFM_ERR_INVALID_ARG;   // bearings == NULL: the resident ones (b200sfm_ba_problem_undistort)
   return guarded(p->ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(p->ctx->device));
     const long long n = p->run_filter(1, max_angle_error_deg, bearings, cam_calibrated, keep);
@@ -385,7 +404,7 @@ int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearing
 int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* bearings,
                                                       double max_reprojection_error, uint8_t* keep,
                                                       int64_t* num_tracks_changed) {
-  if (!p || !keep || !bearings) return B200SFM_ERR_INVALID_ARG;
+  if (!p || !keep) return B200SFM_ERR_INVALID_ARG;   // bearings == NULL: the resident ones (b200sfm_ba_problem_undistort)
   return guarded(p->ctx, [&]() {
     B200_CUDA_OK(cudaSetDevice(p->ctx->device));
     const long long n = p->run_filter(3, max_reprojection_error, bearings, nullptr, keep);

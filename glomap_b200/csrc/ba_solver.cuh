@@ -16,6 +16,7 @@
 #include "ba_kernels_v3.cuh"
 #include "ba_kernels_ext.cuh"
 #include "filter_kernels.cuh"
+#include "processor_kernels.cuh"
 #include "context.cuh"
 #include "pcg.cuh"
 
@@ -602,6 +603,63 @@ struct b200sfm_ba_problem {
     gmax = ctx->h_scal[1];
   }
 
+  // ---- processors on the resident arrays (processor_kernels.cuh) ---------------------------------
+  DevBuf<double> bear_res;   // unit bearings of all observations [N][3], filled by undistort()
+  // UndistortImages (image_undistorter.cc:7-53) from the current intrinsics; h_out [N][3] may be null
+  void undistort(double* h_out) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    if (bear_res.n < (size_t)N * 3) bear_res.alloc((size_t)std::max<long long>(N, 1) * 3);
+    if (N > 0)
+      B200_LAUNCH(ctx, proc_undistort, cdiv(N, 256), 256, 0, N, S, obs_cam.p, S > 0 ? obs_sensor.p : nullptr, cam_intr.p,
+                  S > 0 ? sensor_intr.p : nullptr, intr_model.p, intr.p, obs_xy.p, bear_res.p);
+    if (h_out) bear_res.download(h_out, (size_t)N * 3, s);
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  // NormalizeReconstruction (reconstruction_normalizer.cc:5-104) on the current state; returns the similarity
+  // X' = scale X + t (identity rotation)
+  void normalize(bool fixed_scale, double extent, double p0, double p1, double* scale_out, double* t_out) {
+    using namespace b200;
+    cudaStream_t s = ctx->stream;
+    const int n_img = S > 0 ? C * S : C;
+    double scale = 1.0, t[3] = {0, 0, 0};
+    if (n_img > 0) {
+      DevBuf<float> c_in, c_out;
+      DevBuf<double> stats;
+      c_in.alloc((size_t)n_img * 3); c_out.alloc((size_t)n_img * 3); stats.alloc(9);
+      B200_LAUNCH(ctx, proc_image_centres, cdiv(n_img, 256), 256, 0, C, S, quat[cur].p, trans[cur].p, S > 0 ? sens_q[cur].p : nullptr,
+                  S > 0 ? sens_t[cur].p : nullptr, c_in.p, c_in.p + n_img, c_in.p + 2 * (size_t)n_img);
+      size_t need = 0;
+      cub::DeviceRadixSort::SortKeys(nullptr, need, c_in.p, c_out.p, n_img, 0, 32, s);
+      DevBuf<unsigned char> tmp;
+      tmp.alloc(need);
+      for (int a = 0; a < 3; ++a) {   // per-axis sort of the float coordinates (.cc:31-33)
+        size_t nb = need;
+        cub::DeviceRadixSort::SortKeys(tmp.p, nb, c_in.p + (size_t)a * n_img, c_out.p + (size_t)a * n_img, n_img, 0, 32, s);
+      }
+      const size_t P0 = (size_t)((n_img > 3) ? p0 * (n_img - 1) : 0);                     // .cc:35-38
+      const size_t P1 = (size_t)((n_img > 3) ? p1 * (n_img - 1) : n_img - 1);
+      B200_LAUNCH(ctx, proc_trimmed_stats, 1, 256, 0, (int)P0, (int)P1, c_out.p, c_out.p + n_img, c_out.p + 2 * (size_t)n_img, stats.p);
+      double h[9];
+      B200_CUDA_OK(cudaMemcpyAsync(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      double mean[3];
+      for (int a = 0; a < 3; ++a) mean[a] = h[6 + a] / (double)(P1 - P0 + 1);
+      if (!fixed_scale) {
+        const double d0 = h[3] - h[0], d1 = h[4] - h[1], d2 = h[5] - h[2];
+        const double old_extent = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        if (old_extent >= 2.220446049250313e-16) scale = extent / old_extent;             // .cc:54-60
+      }
+      for (int a = 0; a < 3; ++a) t[a] = -scale * mean[a];
+      B200_LAUNCH(ctx, proc_transform_frames, cdiv(C, 256), 256, 0, C, scale, t[0], t[1], t[2], quat[cur].p, trans[cur].p);
+      if (S > 0) B200_LAUNCH(ctx, proc_scale_shift3, cdiv(S, 256), 256, 0, (long long)S, scale, 0.0, 0.0, 0.0, sens_t[cur].p);   // .cc:70-79
+      if (P > 0) B200_LAUNCH(ctx, proc_scale_shift3, cdiv(P, 256), 256, 0, (long long)P, scale, t[0], t[1], t[2], points[cur].p);  // .cc:81-83
+      B200_CUDA_OK(cudaStreamSynchronize(s));   // the scratch buffers go out of scope
+    }
+    if (scale_out) *scale_out = scale;
+    if (t_out) { t_out[0] = t[0]; t_out[1] = t[1]; t_out[2] = t[2]; }
+  }
+
   // ---- track filters on the resident arrays (glomap/processors/track_filter.cc) -----------------
   // mode 0: reprojection (pixels), 1: angle (needs bearings), 2: triangulation angle (per track),
   // 3: reprojection in the normalised image plane (needs bearings)
@@ -629,19 +687,26 @@ struct b200sfm_ba_problem {
       if (mode == 0) {
         B200_LAUNCH(ctx, filter_reprojection, cdiv(N, 256), 256, 0, v, cam_rec.p, intr_rec.p, points[cur].p, thr, keep.p, changed.p);
       } else {
-        DevBuf<double> bear;
+        DevBuf<double> bear_up;
         DevBuf<unsigned char> cal;
-        bear.alloc((size_t)N * 3);
-        bear.upload(h_bearings, (size_t)N * 3, s);
+        const double* bear_p;
+        if (h_bearings) {
+          bear_up.alloc((size_t)N * 3);
+          bear_up.upload(h_bearings, (size_t)N * 3, s);
+          bear_p = bear_up.p;
+        } else {   // no host bearings: the resident ones of undistort() (computed now if they are not there yet)
+          if (bear_res.n < (size_t)N * 3) undistort(nullptr);
+          bear_p = bear_res.p;
+        }
         const int ncal = S > 0 ? S : C;
         if (h_calibrated) { cal.alloc(ncal); cal.upload(h_calibrated, ncal, s); }
         if (mode == 3)
-          B200_LAUNCH(ctx, filter_reprojection_normalized, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, thr,
+          B200_LAUNCH(ctx, filter_reprojection_normalized, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear_p, thr,
                       keep.p, changed.p);
         else
-          B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear.p, h_calibrated ? cal.p : nullptr,
+          B200_LAUNCH(ctx, filter_angle, cdiv(N, 256), 256, 0, v, cam_rec.p, points[cur].p, bear_p, h_calibrated ? cal.p : nullptr,
                       std::cos(thr * kPi / 180.0), std::cos(2.0 * thr * kPi / 180.0), keep.p, changed.p);
-        B200_CUDA_OK(cudaStreamSynchronize(s));   // bear / cal go out of scope
+        B200_CUDA_OK(cudaStreamSynchronize(s));   // bear_up / cal go out of scope
       }
       B200_LAUNCH(ctx, count_flags, cdiv(P, 256), 256, 0, P, changed.p, counter.p);
       keep.download(h_keep, N, s);

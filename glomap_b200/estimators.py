@@ -204,6 +204,22 @@ class BAProblem:
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_cost(self.handle, ct.byref(o), ct.byref(c)))
         return c.value
 
+    # -- processors on the resident state -------------------------------------------
+    def normalize(self, fixed_scale: bool = False, extent: float = 10.0, p0: float = 0.1, p1: float = 0.9):
+        """NormalizeReconstruction (glomap/processors/reconstruction_normalizer.cc:5-104) on the device state: returns
+        (scale, translation[3]) of the applied similarity X' = scale X + t."""
+        sc = ct.c_double()
+        t = np.zeros(3)
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_normalize(self.handle, int(fixed_scale), extent, p0, p1, ct.byref(sc), _ptr(t)))
+        return sc.value, t
+
+    def undistort(self, download: bool = True):
+        """UndistortImages (glomap/processors/image_undistorter.cc:7-53): unit bearings [N,3] of all observations from the
+        current intrinsics; they stay resident for the bearing-based filters (``bearings="resident"``)."""
+        out = np.empty((self.N, 3)) if download else None
+        _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_undistort(self.handle, _ptr(out)))
+        return out
+
     # -- track filters on the resident state (glomap/processors/track_filter.cc) --
     def filter_reprojection(self, max_reprojection_error: float, bearings=None):
         """TrackFilter::FilterTracksByReprojection: (keep [N] bool, #tracks changed).  Pixel space by default
@@ -212,7 +228,7 @@ class BAProblem:
         keep = np.empty(self.N, np.uint8)
         cnt = ct.c_int64()
         if bearings is not None:
-            b = _c(bearings, np.float64)
+            b = None if isinstance(bearings, str) else _c(bearings, np.float64)   # "resident": the device's own bearings
             _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_reprojection_normalized(
                 self.handle, _ptr(b), max_reprojection_error, _ptr(keep), ct.byref(cnt)))
             return keep.astype(bool), cnt.value
@@ -223,7 +239,7 @@ class BAProblem:
         """TrackFilter::FilterTracksByAngle."""
         keep = np.empty(self.N, np.uint8)
         cnt = ct.c_int64()
-        b = _c(bearings, np.float64)
+        b = None if isinstance(bearings, str) else _c(bearings, np.float64)       # "resident": the device's own bearings
         cal = None if cam_calibrated is None else _c(cam_calibrated, np.uint8)
         _lib.check(self.ctx.handle, self.lib.b200sfm_ba_problem_filter_angle(self.handle, _ptr(b), _ptr(cal), max_angle_error_deg, _ptr(keep), ct.byref(cnt)))
         return keep.astype(bool), cnt.value

@@ -92,10 +92,10 @@ class GlobalMapper:
             try:
                 prob.set_state(scene.intr_params, scene.quat, scene.trans, scene.points)
                 if kind == "angle":
-                    keep, n = prob.filter_angle(PR.undistort_images(scene), thr)
+                    keep, n = prob.filter_angle("resident", thr)                  # bearings: the device's own UndistortImages
                     scene = compact_observations(scene, keep)
                 elif kind == "reprojection":
-                    keep, n = prob.filter_reprojection(thr, PR.undistort_images(scene))
+                    keep, n = prob.filter_reprojection(thr, "resident")
                     scene = compact_observations(scene, keep)
                 else:
                     keep_t, n = prob.filter_triangulation_angle(thr)

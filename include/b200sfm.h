@@ -212,15 +212,27 @@ int b200sfm_ba_problem_cost(b200sfm_ba_problem* p, const b200sfm_ba_opts* opts, 
  * the caller compacts Track::observations. */
 int b200sfm_ba_problem_filter_reprojection(b200sfm_ba_problem* p, double max_reprojection_error, uint8_t* keep /*[N]*/,
                                            int64_t* num_tracks_changed);
-int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings /*[N][3] features_undist*/,
+int b200sfm_ba_problem_filter_angle(b200sfm_ba_problem* p, const double* bearings /*[N][3] features_undist, or NULL = resident*/,
                                     const uint8_t* cam_calibrated /*[C] or NULL*/, double max_angle_error_deg,
                                     uint8_t* keep /*[N]*/, int64_t* num_tracks_changed);
 /* FilterTracksByReprojection with in_normalized_image = true (track_filter.cc:24-31) -- the variant the mapper
  * calls (controllers/global_mapper.cc:176-181,254-259,289-294): error = |X_c.xy / X_c.z - b.xy / (b.z + EPS)|
  * against the undistorted feature b (Image::features_undist), threshold 1e-2 by default (types.h:21). */
-int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* bearings /*[N][3]*/,
+int b200sfm_ba_problem_filter_reprojection_normalized(b200sfm_ba_problem* p, const double* bearings /*[N][3] or NULL = resident*/,
                                                       double max_reprojection_error, uint8_t* keep /*[N]*/,
                                                       int64_t* num_tracks_changed);
+/* The two per-element processors the mapper runs between the solvers, on the resident problem.
+ * b200sfm_ba_problem_normalize -- glomap/processors/reconstruction_normalizer.cc:5-104 (NormalizeReconstruction): robust
+ * p0..p1 percentile box and trimmed mean of the image centres (float coordinates, sorted per axis), similarity with
+ * identity rotation X' = scale X + t applied to the frame poses, the cam_from_rig translations and the points of the
+ * CURRENT state; returns the similarity (either pointer may be NULL).
+ * b200sfm_ba_problem_undistort -- glomap/processors/image_undistorter.cc:7-53 (UndistortImages): unit bearing
+ * CamFromImg(xy).homogeneous().normalized() of every observation from the current intrinsics, kept on the device;
+ * bearings_out [N][3] may be NULL.  The two bearing-based filters below accept bearings == NULL and then use the resident
+ * bearings (computing them first if needed), which saves the 24 N-byte upload per call. */
+int b200sfm_ba_problem_normalize(b200sfm_ba_problem* p, int32_t fixed_scale, double extent, double p0, double p1,
+                                 double* scale_out, double* translation_out /*[3]*/);
+int b200sfm_ba_problem_undistort(b200sfm_ba_problem* p, double* bearings_out /*[N][3] or NULL*/);
 int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double min_angle_deg, uint8_t* keep_track /*[P]*/,
                                                   int64_t* num_tracks_removed);
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p);

@@ -127,6 +127,19 @@ int b200sfm_ba_problem_get_sensor_poses(b200sfm_ba_problem* p, double* q, double
   }
   return B200SFM_OK;
 }
+int b200sfm_ba_problem_normalize(b200sfm_ba_problem* p, int32_t fixed_scale, double extent, double p0, double p1, double* sc,
+                                 double* t) {
+  (void)p; (void)fixed_scale; (void)extent; (void)p0; (void)p1;
+  dump_call("ba_problem_normalize");
+  if (sc) *sc = 1.0;
+  if (t) t[0] = t[1] = t[2] = 0.0;
+  return B200SFM_OK;
+}
+int b200sfm_ba_problem_undistort(b200sfm_ba_problem* p, double* out) {
+  (void)p; (void)out;
+  dump_call("ba_problem_undistort");
+  return B200SFM_OK;
+}
 int b200sfm_ba_problem_get_state(b200sfm_ba_problem* p, double* intr, double* q, double* t, double* pts) {
   (void)p; (void)intr; (void)q; (void)t; (void)pts;
   return B200SFM_OK;

@@ -67,11 +67,16 @@ class FakeBAProblem:
     def set_state(self, intr, quat, trans, points):
         pass
 
+    @staticmethod
+    def _bearings(sc, bearings):   # "resident": the problem's own UndistortImages (device side: b200sfm_ba_problem_undistort)
+        from glomap_b200 import processors as PR
+        return PR.undistort_images(sc) if isinstance(bearings, str) else bearings
+
     def filter_angle(self, bearings, thr, cal=None):
-        return FO.filter_angle(self.sc, bearings, thr)
+        return FO.filter_angle(self.sc, self._bearings(self.sc, bearings), thr)
 
     def filter_reprojection(self, thr, bearings=None):
-        return FO.filter_reprojection_normalized(self.sc, bearings, thr)
+        return FO.filter_reprojection_normalized(self.sc, self._bearings(self.sc, bearings), thr)
 
     def filter_triangulation_angle(self, thr):
         return FO.filter_triangulation_angle(self.sc, thr)
