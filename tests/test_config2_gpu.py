@@ -168,3 +168,29 @@ def test_gp_config2_noisy_both_tolerances_recover_the_scene(gp_scene):
         err = np.linalg.norm((s * (R @ prob.centers.T)).T + t - cg, axis=1).max()
         assert err < 1e-1, (tol, err)
         assert gp.summary.final_cost < 1e-5 * gp.summary.initial_cost, (tol, gp.summary.final_cost)
+
+
+def test_composed_pipeline_at_config2():
+    """BASELINE.json config 2 end to end on one GPU (VERDICT r1 J1 / missing #3): rotation averaging (twice, with the relative
+    rotation filter in between) -> global positioning -> angle / reprojection filters -> staged bundle adjustment with the
+    reference's default options (intrinsics refined) -> normalisation, in the stage order of controllers/global_mapper.cc:
+    92-276, from NOTHING but the tracks and the noisy relative rotations.  Thresholds: the reference's noisy end-to-end
+    test (global_mapper_test.cc:213-215)."""
+    import time
+    from glomap_b200 import mapper as M
+    sc = S.make_scene(C2["C"], C2["P"], C2["L"], seed=1, pixel_sigma=0.5, chunk=C2["chunk"])
+    vg = S.view_graph_from_scene(sc, min_shared=20, noise_deg=0.5)
+    assert vg.E > 100_000
+    start = sc.copy()
+    start.quat[:] = [0, 0, 0, 1]; start.trans[:] = 0; start.points[:] = 0
+    mapper = M.GlobalMapper(M.GlobalMapperOptions())
+    t0 = time.perf_counter()
+    ok, out = mapper.Solve(vg, start)
+    dt = time.perf_counter() - t0
+    assert ok, mapper.log
+    rot, cen = G.compare_reconstructions(G.quat_xyzw_to_rotmat(out.quat), out.trans, G.quat_xyzw_to_rotmat(sc.quat), sc.trans)[:2]
+    print(f"config-2 pipeline: {vg.E} view-graph edges, {sc.N} observations -> rot {rot:.3e} deg, centre {cen:.3e}, "
+          f"{out.N} observations kept, {dt:.1f} s wall (host driver included)")
+    assert rot < 1e-1 and cen < 1e-1, (rot, cen, mapper.log)
+    assert out.N > 0.95 * sc.N, (out.N, sc.N)      # 0.5 px noise: the filters remove next to nothing
+    assert abs(out.intr_params[0, 0] / sc.intr_params[0, 0] - 1) < 1e-3
