@@ -820,9 +820,11 @@ struct b200sfm_ba_problem {
     StepResult res;
     const size_t mv_ev0 = timer_mv.used;
     const bool has_mv = points_var || ext;   // an observation pass per iteration (else S = U + D is block diagonal)
-    // several GPUs: split the per-iteration all-reduce at camera C/2 and overlap its first half with pass B (B200SFM_SPLIT_AR=0: off)
+    // several GPUs, opt-in (B200SFM_SPLIT_AR=1): split the per-iteration all-reduce at camera C/2 and overlap its first half
+    // with pass B over the upper half.  Measured on 2 GPUs it LOSES (28.97 vs 26.90 ms per step at config 4: two NCCL
+    // launches and two event hand-overs per iteration cost more than the 20 us they hide), so it is off by default.
     const bool split_ar = ctx->world > 1 && use_v2 && !recomp && points_var && C >= 64 &&
-                          !(getenv("B200SFM_SPLIT_AR") && atoi(getenv("B200SFM_SPLIT_AR")) == 0);
+                          (getenv("B200SFM_SPLIT_AR") && atoi(getenv("B200SFM_SPLIT_AR")) == 1);
     if (split_ar) ctx->ensure_comm_stream();
     const bool pack_dir = points_var && use_v2 && !recomp;   // direction kernel also packs R^T p for pass A
     PcgResult pr_ = ctx->pcgh.run(

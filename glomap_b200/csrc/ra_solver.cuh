@@ -276,8 +276,10 @@ struct b200sfm_ra_problem {
     double *part_pq = ctx->pcgh.d_part, *part_rz = ctx->pcgh.d_part + nblk_t, *part_rr = ctx->pcgh.d_part + 2 * (size_t)nblk_t;
     if (use_2lvl) B200_CUDA_OK(cudaMemsetAsync(ctx->pcgh.d_part, 0, (size_t)nblk_t * 3 * sizeof(double), s));
     PcgCtl* ctl = ctx->pcgh.d_ctl;
-    // fused iteration (ra_kernels.cuh: ra2_*): four kernels, the prolongation folded into the direction update
-    const bool fused = use_2lvl && use_csr && ctx->world == 1 && !(getenv("B200SFM_RA_FUSED") && atoi(getenv("B200SFM_RA_FUSED")) == 0);
+    // fused iteration (ra_kernels.cuh: ra2_*): four kernels, the prolongation folded into the direction update.  Opt-in
+    // (B200SFM_RA_FUSED=1): at config 5 it is SLOWER than the seven-kernel iteration (568 vs 547 ms per solve, 24 k vs 40 k
+    // launches; gpurun_out/r2_ra5_fused2.log) -- the launch count is not what bounds the iteration.
+    const bool fused = use_2lvl && use_csr && ctx->world == 1 && (getenv("B200SFM_RA_FUSED") && atoi(getenv("B200SFM_RA_FUSED")) == 1);
     if (fused) {
       if (p4.n < (size_t)n * 4) p4.alloc((size_t)n * 4);
       if (gbar.n < 2) { gbar.alloc(2); gbar.zero(s); }
