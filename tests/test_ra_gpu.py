@@ -123,14 +123,16 @@ def test_two_level_preconditioner_and_gather_laplacian_do_not_change_the_result(
     vg = S.make_lattice_view_graph(4096, 24, seed=3, noise_deg=1.0, outlier_ratio=0.05)
     R0 = E.initialize_from_maximum_spanning_tree(vg)
     out = {}
-    for name, csr, lvl in (("reference", "0", "0"), ("csr", "1", "0"), ("csr+2lvl", "1", "1")):
+    for name, csr, lvl, fused in (("reference", "0", "0", "0"), ("csr", "1", "0", "0"), ("csr+2lvl", "1", "1", "0"),
+                                  ("csr+2lvl fused", "1", "1", "1")):
         monkeypatch.setenv("B200SFM_RA_CSR", csr)
         monkeypatch.setenv("B200SFM_RA_2LVL", lvl)
+        monkeypatch.setenv("B200SFM_RA_FUSED", fused)   # the four-kernel iteration (opt-in: measured slower at config 5)
         est = E.RotationEstimator(E.RotationEstimatorOptions(skip_initialization=True, pcg_rel_tolerance=1e-11))
         ok, R = est.EstimateRotations(vg, R0)
         assert ok
         out[name] = (R, est.summary.l1_iterations, est.summary.irls_iterations, est.summary.pcg_iterations)
-    for name in ("csr", "csr+2lvl"):
+    for name in ("csr", "csr+2lvl", "csr+2lvl fused"):
         assert out[name][1:3] == out["reference"][1:3], (name, out[name][1:], out["reference"][1:])
         assert np.abs(out[name][0] - out["reference"][0]).max() < 1e-8, name
     assert out["csr+2lvl"][3] < 0.5 * out["csr"][3], (out["csr+2lvl"][3], out["csr"][3])     # and it pays: far fewer PCG iterations
