@@ -107,6 +107,10 @@ PROTOTYPES = {
     "b200sfm_ba_problem_filter_triangulation_angle": (c_int32, [c_void_p, c_double, c_void_p, P(c_int64)]),
     "b200sfm_ba_problem_normalize": (c_int32, [c_void_p, c_int32, c_double, c_double, c_double, P(c_double), c_void_p]),
     "b200sfm_ba_problem_undistort": (c_int32, [c_void_p, c_void_p]),
+    "b200sfm_tracks_establish": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, P(c_void_p),
+                                           P(c_int64), P(c_int64), P(c_int64)]),
+    "b200sfm_tracks_get": (c_int32, [c_void_p] * 5),
+    "b200sfm_tracks_free": (None, [c_void_p]),
     "b200sfm_gp_default_opts": (None, [P(GPOpts)]),
     "b200sfm_gp_solve": (c_int32, [c_void_p, P(GPOpts), c_int32, c_int32, c_int64] + [c_void_p] * 8 + [P(LMStats)]),
     "b200sfm_gp_problem_create": (c_int32, [c_void_p, c_int32, c_int32, c_int64] + [c_void_p] * 5 + [c_int32, P(c_void_p)]),

@@ -7,6 +7,7 @@
 #include "context.cuh"
 #include "gp_solver.cuh"
 #include "ra_solver.cuh"
+#include "track_kernels.cuh"
 
 namespace {
 
@@ -481,6 +482,64 @@ int b200sfm_ba_solve(b200sfm_ctx* ctx, const b200sfm_ba_opts* opts, int32_t C, i
     if (e) cudaEventDestroy(e);
   if (stats) *stats = st;
   return rc;
+}
+
+// ---- track establishment ----------------------------------------------------------
+int b200sfm_tracks_establish(b200sfm_ctx* ctx, int64_t num_matches, const uint64_t* gid1, const uint64_t* gid2, const double* xy1,
+                             const double* xy2, double thres_inconsistency, b200sfm_tracks** out, int64_t* num_tracks,
+                             int64_t* num_observations, int64_t* num_discarded) {
+  if (!ctx || !out || num_matches < 0 || (num_matches > 0 && (!gid1 || !gid2 || !xy1 || !xy2)) || !(thres_inconsistency >= 0.0))
+    return B200SFM_ERR_INVALID_ARG;
+  *out = nullptr;
+  b200sfm_tracks* t = nullptr;
+  int rc = guarded(ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(ctx->device));
+    t = new b200sfm_tracks();
+    t->ctx = ctx;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "global feature ids are 64-bit");
+    t->build(num_matches, reinterpret_cast<const unsigned long long*>(gid1), reinterpret_cast<const unsigned long long*>(gid2), xy1, xy2,
+             thres_inconsistency);
+    return (int)B200SFM_OK;
+  });
+  if (rc != B200SFM_OK) {
+    if (t) {
+      guarded(ctx, [&]() { delete t; return (int)B200SFM_OK; });
+    }
+    return rc;
+  }
+  *out = t;
+  if (num_tracks) *num_tracks = t->T;
+  if (num_observations) *num_observations = t->n_obs;
+  if (num_discarded) *num_discarded = t->discarded;
+  return B200SFM_OK;
+}
+
+int b200sfm_tracks_get(b200sfm_tracks* t, uint64_t* track_ids, int64_t* begin, uint32_t* obs_image, uint32_t* obs_feature) {
+  if (!t) return B200SFM_ERR_INVALID_ARG;
+  return guarded(t->ctx, [&]() {
+    B200_CUDA_OK(cudaSetDevice(t->ctx->device));
+    cudaStream_t s = t->ctx->stream;
+    if (t->T > 0) {
+      if (track_ids) B200_CUDA_OK(cudaMemcpyAsync(track_ids, t->track_id.p, (size_t)t->T * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      if (begin) B200_CUDA_OK(cudaMemcpyAsync(begin, t->begin.p, ((size_t)t->T + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      if (obs_image && t->n_obs > 0) B200_CUDA_OK(cudaMemcpyAsync(obs_image, t->obs_image.p, (size_t)t->n_obs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      if (obs_feature && t->n_obs > 0)
+        B200_CUDA_OK(cudaMemcpyAsync(obs_feature, t->obs_feature.p, (size_t)t->n_obs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    } else if (begin) {
+      begin[0] = 0;
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    return (int)B200SFM_OK;
+  });
+}
+
+void b200sfm_tracks_free(b200sfm_tracks* t) {
+  if (!t) return;
+  guarded(t->ctx, [&]() {
+    cudaSetDevice(t->ctx->device);
+    delete t;
+    return (int)B200SFM_OK;
+  });
 }
 
 // ---- GP ----------------------------------------------------------------------

@@ -118,6 +118,43 @@ def establish_full_tracks(pairs, features: dict, options: TrackEstablishmentOpti
     return Tracks(track_ids[perm], begin, img[pos], feat[pos]), discarded
 
 
+def establish_full_tracks_device(pairs, features: dict, options: TrackEstablishmentOptions | None = None, ctx=None):
+    """EstablishFullTracks on the GPU (b200sfm_tracks_establish: union-find, track collection, inconsistency rule); same
+    return value as ``establish_full_tracks``.  The host only concatenates the inlier matches of the valid pairs."""
+    import ctypes as ct
+
+    from . import _lib, estimators as E
+    o = options or TrackEstablishmentOptions()
+    ctx = ctx or E.default_context()
+    g1, g2 = _global_ids(pairs)
+    M = len(g1)
+    xy1, xy2 = np.empty((M, 2)), np.empty((M, 2))
+    pos = 0
+    for p in pairs:
+        if not p.is_valid or len(p.inliers) == 0:
+            continue
+        m = np.asarray(p.matches)[np.asarray(p.inliers, dtype=np.int64)]
+        k = len(m)
+        xy1[pos:pos + k] = np.asarray(features[int(p.image_id1)], dtype=np.float64)[m[:, 0]]
+        xy2[pos:pos + k] = np.asarray(features[int(p.image_id2)], dtype=np.float64)[m[:, 1]]
+        pos += k
+    g1, g2 = np.ascontiguousarray(g1, np.uint64), np.ascontiguousarray(g2, np.uint64)
+    h = ct.c_void_p()
+    nt, nobs, ndis = ct.c_int64(), ct.c_int64(), ct.c_int64()
+    ptr = lambda a: a.ctypes.data_as(ct.c_void_p) if len(a) else None   # noqa: E731
+    _lib.check(ctx.handle, ctx.lib.b200sfm_tracks_establish(ctx.handle, M, ptr(g1), ptr(g2), ptr(xy1), ptr(xy2),
+                                                            float(o.thres_inconsistency), ct.byref(h), ct.byref(nt), ct.byref(nobs),
+                                                            ct.byref(ndis)))
+    try:
+        T, n = nt.value, nobs.value
+        ids, begin = np.zeros(T, np.uint64), np.zeros(T + 1, np.int64)
+        img, feat = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        _lib.check(ctx.handle, ctx.lib.b200sfm_tracks_get(h, ptr(ids), begin.ctypes.data_as(ct.c_void_p), ptr(img), ptr(feat)))
+    finally:
+        ctx.lib.b200sfm_tracks_free(h)
+    return Tracks(ids, begin, img, feat), int(ndis.value)
+
+
 def find_tracks_for_problem(tracks: Tracks, registered_images, options: TrackEstablishmentOptions | None = None) -> Tracks:
     o = options or TrackEstablishmentOptions()
     reg = np.asarray(sorted(int(i) for i in registered_images), np.int64)

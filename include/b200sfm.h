@@ -237,6 +237,23 @@ int b200sfm_ba_problem_filter_triangulation_angle(b200sfm_ba_problem* p, double 
                                                   int64_t* num_tracks_removed);
 void b200sfm_ba_problem_free(b200sfm_ba_problem* p);
 
+/* ---- track establishment ---------------------------------------------------------------------
+ * TrackEngine::EstablishFullTracks (glomap/controllers/track_establishment.cc:5-17): the union-find over all inlier
+ * matches of the valid image pairs (BlindConcatenation, :19-63) and the collection of the components into tracks with the
+ * inconsistency rule (TrackCollection, :65-150) on the device.  Input: the M inlier matches as global feature ids
+ * gid = image_id << 32 | feature_id (:48-53) with the pixel of both features (Image::features).  Result: tracks in
+ * ascending track id (= smallest global id of the component, the reference's root rule :56-60), observations of a track
+ * in ascending global id; a track with two features of ONE image further apart than thres_inconsistency pixels keeps its
+ * id but loses its observations (:118-131) and is counted in num_discarded.  The order-dependent greedy selection
+ * FindTracksForProblem (:153-234) stays on the host. */
+typedef struct b200sfm_tracks b200sfm_tracks;
+int b200sfm_tracks_establish(b200sfm_ctx* ctx, int64_t num_matches, const uint64_t* gid1, const uint64_t* gid2,
+                             const double* xy1 /*[M][2]*/, const double* xy2 /*[M][2]*/, double thres_inconsistency,
+                             b200sfm_tracks** out, int64_t* num_tracks, int64_t* num_observations, int64_t* num_discarded);
+int b200sfm_tracks_get(b200sfm_tracks* t, uint64_t* track_ids /*[T]*/, int64_t* begin /*[T+1]*/, uint32_t* obs_image /*[n]*/,
+                       uint32_t* obs_feature /*[n]*/);
+void b200sfm_tracks_free(b200sfm_tracks* t);
+
 /* ---- (ii) global positioning (BATA) ----------------------------------------- */
 /* Mirror of GlobalPositionerOptions (global_positioning.h:9-54) + inherited
  * solver options (optimization_base.h:18-23) + PCG knobs.  Only the

@@ -257,3 +257,21 @@ int b200sfm_ra_solve_gravity(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t
   memset(st, 0, sizeof(*st)); st->usable = 1;
   return B200SFM_OK;
 }
+
+/* track establishment: not used by the host-logic tests; present so that the library exports the whole ABI */
+int b200sfm_tracks_establish(b200sfm_ctx* ctx, int64_t m, const uint64_t* g1, const uint64_t* g2, const double* xy1, const double* xy2,
+                             double thr, b200sfm_tracks** out, int64_t* nt, int64_t* no, int64_t* nd) {
+  (void)ctx; (void)m; (void)g1; (void)g2; (void)xy1; (void)xy2; (void)thr;
+  dump_call("tracks_establish");
+  if (out) *out = NULL;
+  if (nt) *nt = 0;
+  if (no) *no = 0;
+  if (nd) *nd = 0;
+  return B200SFM_OK;
+}
+int b200sfm_tracks_get(b200sfm_tracks* t, uint64_t* ids, int64_t* begin, uint32_t* im, uint32_t* ft) {
+  (void)t; (void)ids; (void)im; (void)ft;
+  if (begin) begin[0] = 0;
+  return B200SFM_OK;
+}
+void b200sfm_tracks_free(b200sfm_tracks* t) { (void)t; }
