@@ -91,3 +91,27 @@ def test_gp_cli_recovers_centres(tmp_path):
     c_est, c_gt = G.centers_from_pose(R, res.trans), G.centers_from_pose(R, sc.trans)
     s, Rr, t = G.umeyama_sim3(c_est, c_gt)
     assert np.linalg.norm((s * (Rr @ c_est.T)).T + t - c_gt, axis=1).max() < 1e-4
+
+
+def test_colmap_sparse_model_through_the_cli(tmp_path):
+    """SURVEY.md 8(f) item 3 end to end: a COLMAP sparse model (cameras.bin / images.bin / points3D.bin) -> flat binary
+    problem (`python -m glomap_b200.colmap_io to-flat`) -> `b200sfm_cli ba` on the GPU (intrinsics refined: the
+    reference default) -> COLMAP model again (`from-flat`), compared with the oracle's solve of the same problem."""
+    from glomap_b200 import colmap_io as CIO
+    sc = S.make_scene(18, 450, mean_track_len=6, seed=33, pixel_sigma=0.4, model=S.SIMPLE_RADIAL, num_intrinsics=2)
+    init = S.perturb_scene(sc, rot_deg=0.2, center_frac=0.004, point_frac=0.004)
+    model_in, model_out = tmp_path / "sparse_in", tmp_path / "sparse_out"
+    model_in.mkdir(); model_out.mkdir()
+    CIO.write_model(str(model_in), *CIO.model_from_scene(init))
+    flat, solved = str(tmp_path / "problem.bin"), str(tmp_path / "solved.bin")
+    CIO._main(["to-flat", str(model_in), flat])
+    _run("ba", "--problem", flat, "--output", solved, "--pcg_tol", "1e-12", "--optimize_intrinsics", "1")
+    CIO._main(["from-flat", str(model_in), solved, str(model_out)])
+    got, _ = CIO.scene_from_model(*CIO.read_model(str(model_out)))
+    start, _ = CIO.scene_from_model(*CIO.read_model(str(model_in)))     # what the solver saw (quaternions normalised by the format)
+    x, summ = B.solve_ba(start.quat, start.trans, start.points, start.pt_obs_begin, start.obs_cam, start.obs_xy, start.cam_intr,
+                         start.intr_model, start.intr_params, B.BAOptions(optimize_intrinsics=True), E.first_frame_mask(start.C))
+    assert np.abs(got.trans - x["trans"]).max() < 1e-5 and np.abs(got.points - x["points"]).max() < 1e-5
+    assert np.abs(got.intr_params[:, :4] - x["intr"][:, :4]).max() < 1e-4
+    Rg, Rx = G.quat_xyzw_to_rotmat(got.quat), G.quat_xyzw_to_rotmat(x["quat"])
+    assert np.abs(Rg - Rx).max() < 1e-6
