@@ -1017,18 +1017,14 @@ __global__ void ba_update_cams(int C, const double* __restrict__ quat, const dou
 
 
 // ===========================================================================
-// Intrinsics (optimize_intrinsics, bundle_adjustment.cc:273-286): the variable
-// parameters of the K shared intrinsics blocks (m = sum m_b <= kMaxIntrDof) form
-// a dense BORDER of the reduced camera system:
-//      [ S_cc  B  ] [dc]   [b_c]        B  = S_ck = U_ck - W_c V^-1 W_k^T   (6C x m)
-//      [ B^T   Ck ] [dk] = [b_k]        Ck = U_kk + D_k - W_k V^-1 W_k^T    (m x m)
-// PCG runs on  S_cc - B Ck^-1 B^T ; dk = Ck^-1 (b_k - B^T dc).
+// Intrinsics (optimize_intrinsics, bundle_adjustment.cc:273-293): the variable-parameter table of an intrinsics block and
+// the Jacobian of the projection with respect to one parameter.  The blocks themselves are pseudo-camera blocks of the
+// reduced system (ba_kernels_ext.cuh; stored-row fast path in ba_kernels_v2.cuh) -- round 1's dense border is gone.
 // ===========================================================================
-constexpr int kMaxIntrDof = 12;
 constexpr int kMaxBlockDof = 5;
 
 struct IntrVarRec {   // per intrinsics block
-  int col0;           // first column of this block in the border
+  int col0;           // reserved (0)
   int mb;             // number of variable parameters
   int pidx[kMaxBlockDof];
   int pad;
@@ -1058,100 +1054,6 @@ __device__ __forceinline__ void intr_param_jac(const double* __restrict__ ir, in
   jy *= w;
 }
 
-// Camera-order pass: U_ck (6 x m_b) of every camera into B, and per-segment
-// partials of U_kk (packed 15) and g_k (5) -> part[seg][20]
-__global__ void __launch_bounds__(128) ba_intr_cams(BAView v, const double* __restrict__ cam_rec,
-                                                   const double* __restrict__ intr_rec,
-                                                   const IntrVarRec* __restrict__ ivar,
-                                                   const double* __restrict__ points, double huber_a, int m,
-                                                   double* __restrict__ B, double* __restrict__ part) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= v.n_segs) return;
-  const int cam = v.seg_cam[warp];
-  const int b = v.seg_begin[warp], e = v.seg_end[warp];
-  const double4 q4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-  const double4 t4c = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-  const int blk = v.seg_intr[warp];
-  const double* irc = intr_rec + (size_t)blk * kIntrRec;
-  const double* src = sensor_of_seg(v, warp);
-  const IntrVarRec iv = ivar[blk];
-  double Uck[6][kMaxBlockDof], Ukk[15], gk[kMaxBlockDof];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < kMaxBlockDof; ++j) Uck[i][j] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 15; ++k) Ukk[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < kMaxBlockDof; ++k) gk[k] = 0.0;
-  if (iv.mb > 0) {
-    for (int i = b + lane; i < e; i += 32) {
-      const int pt = v.pt_c[i];
-      const double2 xy = v.xy_c[i];
-      const double X0 = points[3 * (size_t)pt], X1 = points[3 * (size_t)pt + 1], X2 = points[3 * (size_t)pt + 2];
-      ObsLin o;
-      linearize_obs(q4c, t4c, irc, src, X0, X1, X2, xy, huber_a, o);
-      if (!o.valid) continue;
-      double Jk[2][kMaxBlockDof];
-#pragma unroll
-      for (int j = 0; j < kMaxBlockDof; ++j) {
-        Jk[0][j] = Jk[1][j] = 0.0;
-        if (j < iv.mb) intr_param_jac(irc, iv.pidx[j], o.u, o.v, o.w, Jk[0][j], Jk[1][j]);
-      }
-      int idx = 0;
-#pragma unroll
-      for (int a = 0; a < kMaxBlockDof; ++a) {
-#pragma unroll
-        for (int c = a; c < kMaxBlockDof; ++c) Ukk[idx++] += Jk[0][a] * Jk[0][c] + Jk[1][a] * Jk[1][c];
-        gk[a] += Jk[0][a] * o.r[0] + Jk[1][a] * o.r[1];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          Uck[r][a] += o.Jr[r] * Jk[0][a] + o.Jr[3 + r] * Jk[1][a];
-          Uck[3 + r][a] += o.Jt[r] * Jk[0][a] + o.Jt[3 + r] * Jk[1][a];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < kMaxBlockDof; ++j) {
-      const double sacc = warp_sum(Uck[i][j]);
-      if (lane == 0 && j < iv.mb && sacc != 0.0) atomicAdd(&B[((size_t)cam * 6 + i) * m + iv.col0 + j], sacc);
-    }
-#pragma unroll
-  for (int k = 0; k < 15; ++k) {
-    const double sacc = warp_sum(Ukk[k]);
-    if (lane == 0) part[(size_t)warp * 20 + k] = sacc;
-  }
-#pragma unroll
-  for (int k = 0; k < kMaxBlockDof; ++k) {
-    const double sacc = warp_sum(gk[k]);
-    if (lane == 0) part[(size_t)warp * 20 + 15 + k] = sacc;
-  }
-}
-
-// out[blk][20] = sum over the segments whose image uses block blk (one CTA per block, deterministic)
-__global__ void __launch_bounds__(256) ba_intr_reduce_segs(int n_segs, const int* __restrict__ seg_intr,
-                                                          const double* __restrict__ part, double* __restrict__ out) {
-  __shared__ double scratch[32];
-  const int blk = blockIdx.x;
-  double acc[20];
-#pragma unroll
-  for (int k = 0; k < 20; ++k) acc[k] = 0.0;
-  for (int sgm = threadIdx.x; sgm < n_segs; sgm += blockDim.x) {
-    if (seg_intr[sgm] != blk) continue;
-#pragma unroll
-    for (int k = 0; k < 20; ++k) acc[k] += part[(size_t)sgm * 20 + k];
-  }
-#pragma unroll
-  for (int k = 0; k < 20; ++k) {
-    const double t = block_sum(acc[k], scratch);
-    if (threadIdx.x == 0) out[(size_t)blk * 20 + k] = t;
-  }
-}
-
 // column sums of a [rows][ncol] partial buffer (one CTA per column, deterministic)
 __global__ void __launch_bounds__(256) ba_colsum(int rows, int ncol, const double* __restrict__ part,
                                                  double* __restrict__ out) {
@@ -1161,233 +1063,6 @@ __global__ void __launch_bounds__(256) ba_colsum(int rows, int ncol, const doubl
   for (int r = threadIdx.x; r < rows; r += blockDim.x) a += part[(size_t)r * ncol + c];
   a = block_sum(a, scratch);
   if (threadIdx.x == 0) out[c] = a;
-}
-
-// Point-order pass: s_p^(j) = sum_o W_k,o[j,:]^T, z^(j) = Vinv s^(j);
-//   spk[P][3m] = s;  B[cam][:, j] -= W_c,o z^(j);
-//   part[tile][0 .. m(m+1)/2) += s^(a).z^(b)  (a <= b),  part[tile][npair + a] += s^(a).Vinv g_p
-struct KISmem {
-  alignas(128) double Wt[kTile * kWDoubles];
-  double red[3 * kMaxIntrDof][kTile + 1];
-  double sk[3 * kMaxIntrDof][kTilePts + 1];   // s then z
-  double acc[kMaxIntrDof * (kMaxIntrDof + 1) / 2 + kMaxIntrDof];
-  unsigned pb[kTilePts + 1];
-  double X[3][kTilePts + 1];
-  alignas(8) uint64_t mbar;
-};
-
-__global__ void __launch_bounds__(kTile) ba_intr_points(BAView v, const double* __restrict__ cam_rec,
-                                                        const double* __restrict__ intr_rec,
-                                                        const IntrVarRec* __restrict__ ivar,
-                                                        const double* __restrict__ points, double huber_a, int m,
-                                                        double* __restrict__ spk, double* __restrict__ B,
-                                                        double* __restrict__ part) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];   // dynamic shared memory starts 128-B aligned (no static __shared__ in these kernels)
-  KISmem& sm = *reinterpret_cast<KISmem*>(smem_raw);
-  const int tile = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int4 td = v.tile_desc[tile];
-  const int p0 = td.x, npts = td.y, n = td.w;
-  const unsigned o0 = (unsigned)td.z, o1 = o0 + (unsigned)n;
-  const int npair = m * (m + 1) / 2;
-  const int nacc = npair + m;
-  if (tid == 0) {
-    mbar_init(&sm.mbar, 1);
-    fence_mbar_init();
-  }
-  if (tid < npts) {
-    sm.pb[tid] = v.pt_begin[p0 + tid];
-    if (tid == npts - 1) sm.pb[npts] = o1;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sm.X[k][tid] = points[3 * (size_t)(p0 + tid) + k];
-  }
-  for (int i = tid; i < nacc; i += kTile) sm.acc[i] = 0.0;
-  for (int r = 0; r < 3 * m; ++r)
-    if (tid < npts) sm.sk[r][tid] = 0.0;
-  __syncthreads();
-  uint32_t phase = 0;
-  const int nchunks = (n + kTile - 1) / kTile;
-  // ---- s_p ---------------------------------------------------------------------------
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int c0 = ch * kTile;
-    const int nc = min(kTile, n - c0);
-    for (int r = 0; r < 3 * m; ++r) sm.red[r][tid] = 0.0;
-    if (tid < nc) {
-      const unsigned oi = o0 + c0 + tid;
-      const int pl = v.obs_pt[oi] - p0;
-      if ((int)(sm.pb[pl + 1] - sm.pb[pl]) >= v.min_views) {
-        const int cam = v.obs_cam[oi];
-        const double4 q4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec);
-        const double4 t4 = *reinterpret_cast<const double4*>(cam_rec + (size_t)cam * kCamRec + 4);
-        const double* sr = sensor_of_obs(v, oi);
-        const int blk = obs_intr_idx(t4, sr);
-        const double* ir = intr_rec + (size_t)blk * kIntrRec;
-        const IntrVarRec iv = ivar[blk];
-        if (iv.mb > 0) {
-          ObsLin o;
-          linearize_obs(q4, t4, ir, sr, sm.X[0][pl], sm.X[1][pl], sm.X[2][pl], v.obs_xy[oi], huber_a, o);
-          if (o.valid) {
-            for (int j = 0; j < iv.mb; ++j) {
-              double jx, jy;
-              intr_param_jac(ir, iv.pidx[j], o.u, o.v, o.w, jx, jy);
-#pragma unroll
-              for (int k = 0; k < 3; ++k) sm.red[3 * (iv.col0 + j) + k][tid] = jx * o.Jp[k] + jy * o.Jp[3 + k];   // W_k[j,k]
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    for (int item = tid; item < npts * 3 * m; item += kTile) {
-      const int j = item / (3 * m), r = item - 3 * m * j;
-      const int lo = max((int)sm.pb[j] - (int)(o0 + c0), 0), hi = min((int)sm.pb[j + 1] - (int)(o0 + c0), nc);
-      double a = 0.0;
-      for (int i = lo; i < hi; ++i) a += sm.red[r][i];
-      sm.sk[r][j] += a;
-    }
-    __syncthreads();
-  }
-  // ---- per point: store s, z = Vinv s, border partials ------------------------------------
-  if (tid < 64) {   // two warps cover kTilePts points
-    const bool has = tid < npts && (int)(sm.pb[tid + 1] - sm.pb[tid]) >= v.min_views;
-    double vi[6] = {0, 0, 0, 0, 0, 0}, vg[3] = {0, 0, 0};
-    const size_t p = (size_t)(p0 + min(tid, max(npts - 1, 0)));
-    if (has) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vi[k] = v.Vinv[6 * p + k];
-      const double g[3] = {v.gp[3 * p], v.gp[3 * p + 1], v.gp[3 * p + 2]};
-      sym3_mul(vi, g, vg);
-    }
-    // b_k partial and s.z pairs need s (before it is overwritten by z): first pass computes z into registers per column
-    for (int a = 0; a < m; ++a) {
-      double sa[3] = {0, 0, 0}, za[3] = {0, 0, 0};
-      if (has) {
-        sa[0] = sm.sk[3 * a][tid]; sa[1] = sm.sk[3 * a + 1][tid]; sa[2] = sm.sk[3 * a + 2][tid];
-        sym3_mul(vi, sa, za);
-        spk[p * 3 * m + 3 * a] = sa[0];
-        spk[p * 3 * m + 3 * a + 1] = sa[1];
-        spk[p * 3 * m + 3 * a + 2] = sa[2];
-      }
-      double bk = warp_sum(sa[0] * vg[0] + sa[1] * vg[1] + sa[2] * vg[2]);
-      if ((tid & 31) == 0 && bk != 0.0) atomicAdd(&sm.acc[npair + a], bk);
-      // pairs (c <= a): s^(c) . z^(a)   (symmetric)
-      for (int c = 0; c <= a; ++c) {
-        // rows of columns c < a already hold z^(c): s^(c).z^(a) == z^(c).s^(a) (Vinv symmetric)
-        double val = 0.0;
-        if (has) {
-          if (c < a) val = sm.sk[3 * c][tid] * sa[0] + sm.sk[3 * c + 1][tid] * sa[1] + sm.sk[3 * c + 2][tid] * sa[2];
-          else val = sa[0] * za[0] + sa[1] * za[1] + sa[2] * za[2];
-        }
-        val = warp_sum(val);
-        if ((tid & 31) == 0 && val != 0.0) atomicAdd(&sm.acc[a * (a + 1) / 2 + c], val);
-      }
-      if (has) { sm.sk[3 * a][tid] = za[0]; sm.sk[3 * a + 1][tid] = za[1]; sm.sk[3 * a + 2][tid] = za[2]; }
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < nacc; i += kTile) part[(size_t)tile * nacc + i] = sm.acc[i];
-  // ---- B[cam][:, j] -= W_c,o z_p^(j) -------------------------------------------------------------
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int c0 = ch * kTile;
-    const int nc = min(kTile, n - c0);
-    __syncthreads();
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&sm.mbar, (uint32_t)nc * kWBytes);
-      tma_load_1d(sm.Wt, v.W + (size_t)(o0 + c0) * kWDoubles, (uint32_t)nc * kWBytes, &sm.mbar);
-    }
-    mbar_wait(&sm.mbar, phase);
-    phase ^= 1;
-    if (tid < nc) {
-      const unsigned oi = o0 + c0 + tid;
-      const int cam = v.obs_cam[oi];
-      const int pl = v.obs_pt[oi] - p0;
-      const double* wr = sm.Wt + tid * kWDoubles;
-      for (int j = 0; j < m; ++j) {
-        const double z0 = sm.sk[3 * j][pl], z1 = sm.sk[3 * j + 1][pl], z2 = sm.sk[3 * j + 2][pl];
-        if (z0 == 0.0 && z1 == 0.0 && z2 == 0.0) continue;
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-          atomicAdd(&B[((size_t)cam * 6 + r) * m + j], -(wr[3 * r] * z0 + wr[3 * r + 1] * z1 + wr[3 * r + 2] * z2));
-      }
-    }
-  }
-}
-
-// ---- border inside PCG -----------------------------------------------------------------------------
-// part_bt[blk][m] = sum_{c in blk} B_c^T p_c
-__global__ void __launch_bounds__(128) pcg_border_dots(int C, int m, const double* __restrict__ B,
-                                                      const double* __restrict__ p, double* __restrict__ part_bt) {
-  __shared__ double scratch[32];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  double pc[6] = {0, 0, 0, 0, 0, 0};
-  if (c < C) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) pc[k] = p[(size_t)c * 6 + k];
-  }
-  for (int j = 0; j < m; ++j) {
-    double a = 0.0;
-    if (c < C) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) a += B[((size_t)c * 6 + k) * m + j] * pc[k];
-    }
-    a = block_sum(a, scratch);
-    if (threadIdx.x == 0) part_bt[(size_t)blockIdx.x * m + j] = a;
-  }
-}
-// t = sum part_bt; w = CkInv t; q_c -= B_c w; part_pq[blk] = sum p.q   (also usable with q == nullptr to only get t)
-__global__ void __launch_bounds__(128) pcg_border_apply(int C, int m, int nblk, const double* __restrict__ B,
-                                                       const double* __restrict__ CkInv,
-                                                       const double* __restrict__ part_bt, const double* __restrict__ p,
-                                                       double* __restrict__ q, double* __restrict__ part_pq,
-                                                       double* __restrict__ t_out) {
-  __shared__ double scratch[32];
-  __shared__ double t[kMaxIntrDof], w[kMaxIntrDof];
-  if (threadIdx.x < 32) {
-    for (int j = 0; j < m; ++j) {
-      double a = 0.0;
-      for (int i = threadIdx.x; i < nblk; i += 32) a += part_bt[(size_t)i * m + j];
-      a = warp_sum(a);
-      if (threadIdx.x == 0) t[j] = a;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < m) {
-    double a = 0.0;
-    for (int j = 0; j < m; ++j) a += CkInv[threadIdx.x * m + j] * t[j];
-    w[threadIdx.x] = a;
-    if (blockIdx.x == 0 && t_out) t_out[threadIdx.x] = t[threadIdx.x];
-  }
-  __syncthreads();
-  if (q == nullptr) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  double pq = 0.0;
-  if (c < C) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double corr = 0.0;
-      for (int j = 0; j < m; ++j) corr += B[((size_t)c * 6 + k) * m + j] * w[j];
-      const double qv = q[(size_t)c * 6 + k] - corr;
-      q[(size_t)c * 6 + k] = qv;
-      pq += qv * p[(size_t)c * 6 + k];
-    }
-  }
-  pq = block_sum(pq, scratch);
-  if (threadIdx.x == 0) part_pq[blockIdx.x] = pq;
-}
-// b_c -= B v   (v = Ck^-1 b_k, m values in global memory); masked dofs keep b = 0
-__global__ void ba_border_rhs(int C, int m, const double* __restrict__ B, const double* __restrict__ vvec,
-                              const double* __restrict__ jscale_c, double* __restrict__ b) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * 6 || jscale_c[i] < 0.0) return;
-  double a = 0.0;
-  for (int j = 0; j < m; ++j) a += B[(size_t)i * m + j] * vvec[j];
-  b[i] -= a;
-}
-// zero the border rows of constant / unobserved camera dofs
-__global__ void ba_border_mask(int C, int m, const double* __restrict__ jscale_c, double* __restrict__ B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * 6 || jscale_c[i] >= 0.0) return;
-  for (int j = 0; j < m; ++j) B[(size_t)i * m + j] = 0.0;
 }
 
 }  // namespace b200
