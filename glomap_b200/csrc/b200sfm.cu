@@ -49,6 +49,11 @@ int guarded(b200sfm_ctx* ctx, F&& f) {
 // A rank that fails while its peers are inside a collective must not leave them blocked for ever: abort the
 // communicator (the peers' pending collectives then fail instead of waiting) before the status is returned.
 int finish(b200sfm_ctx* ctx, int rc) {
+  // a peer-memory all-reduce that gave up waiting for a rank (p2p_allreduce.cuh) leaves an error word behind
+  if (ctx && ctx->world > 1 && ctx->p2p.ready && rc == B200SFM_OK && ctx->p2p.timed_out(ctx->stream)) {
+    ctx->err = "peer-memory all-reduce timed out waiting for a rank";
+    rc = B200SFM_ERR_NCCL;
+  }
   if (ctx && ctx->world > 1 && ctx->comm && (rc == B200SFM_ERR_CUDA || rc == B200SFM_ERR_NCCL)) {
     if (nccl_api().CommAbort) nccl_api().CommAbort(ctx->comm);
     ctx->comm = nullptr;
@@ -109,6 +114,22 @@ int create_common(int device, b200sfm_ctx** out) {
 
 }  // namespace
 
+namespace {
+struct DevBufRaw {
+  void* p = nullptr;
+  size_t n = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= n) return true;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return false;
+    n = bytes;
+    return true;
+  }
+  ~DevBufRaw() { if (p) cudaFree(p); }
+};
+}  // namespace
+
 extern "C" {
 
 int b200sfm_version(void) { return B200SFM_VERSION; }
@@ -142,6 +163,27 @@ int b200sfm_create_dist(int device, int rank, int world_size, const void* nccl_i
       *out = nullptr;
       return B200SFM_ERR_NCCL;
     }
+    // Peer-memory all-reduce for the per-iteration vectors (p2p_allreduce.cuh).  B200SFM_P2P_AR=0 keeps NCCL; a rank
+    // without peer access to the others makes every rank fall back (the verdict is exchanged inside setup()).
+    const char* pe = getenv("B200SFM_P2P_AR");
+    if (!(pe && atoi(pe) == 0)) {
+      DevBufRaw stage;   // gather over NCCL: every rank fills its slot of a zeroed buffer, the sum is the concatenation
+      auto gather = [&](void* host, size_t bytes_per_rank) -> bool {
+        const size_t words = (bytes_per_rank + 7) / 8, total = words * (size_t)world_size;
+        if (!stage.ensure(total * 8)) return false;
+        std::vector<unsigned long long> h(total, 0ull);
+        std::memcpy(h.data() + words * rank, reinterpret_cast<char*>(host) + bytes_per_rank * rank, bytes_per_rank);
+        if (cudaMemcpyAsync(stage.p, h.data(), total * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return false;
+        if (nccl_api().AllReduce(stage.p, stage.p, total, ncclUint64, ncclSum, c->comm, c->stream) != ncclSuccess) return false;
+        if (cudaMemcpyAsync(h.data(), stage.p, total * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+        for (int r = 0; r < world_size; ++r)
+          std::memcpy(reinterpret_cast<char*>(host) + bytes_per_rank * r, h.data() + words * r, bytes_per_rank);
+        return true;
+      };
+      c->p2p.setup(device, rank, world_size, /*cap doubles*/ (size_t)1 << 19, gather);
+      cudaGetLastError();
+    }
   }
   return B200SFM_OK;
 }
@@ -150,6 +192,19 @@ void b200sfm_destroy(b200sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+  if (ctx->p2p.ready) {   // the peers have this rank's buffer mapped: everybody stops using it before anybody frees
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) {
+      double* d = nullptr;
+      if (cudaMalloc(&d, sizeof(double)) == cudaSuccess) {
+        cudaMemsetAsync(d, 0, sizeof(double), ctx->stream);
+        nccl_api().AllReduce(d, d, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d);
+      }
+    }
+    ctx->p2p.release();
+  }
   if (ctx->comm_stream) {
     cudaStreamSynchronize(ctx->comm_stream);
     cudaStreamDestroy(ctx->comm_stream);

@@ -128,9 +128,31 @@ __global__ void __launch_bounds__(kEllThreads, NK > 0 ? 3 : B200_E1_MIN_CTAS) ba
       qA = ld_rec32(cam_rec + (size_t)camA * kCamRec);
       tA = ld_rec32(cam_rec + (size_t)camA * kCamRec + 4);
     }
+#if B200_E1_PIPE >= 2   // experiment: records two observations ahead (index three ahead)
+    double4 qB2 = qA, tB2 = tA;
+    int camC2 = 0;
+    if (mylen > 1) {
+      qB2 = ld_rec32(cam_rec + (size_t)camB * kCamRec);
+      tB2 = ld_rec32(cam_rec + (size_t)camB * kCamRec + 4);
+    }
+    if (mylen > 2) camC2 = ld_stream(ell.cam + (size_t)r0 * 32 + lane + 64);
+#endif
     for (int j = 0; j < nrow; ++j) {
       if (j >= mylen) break;   // tracks are sorted by length inside a window: a lane is done when its own track is
       const size_t idx = ((size_t)r0 + j) * 32 + lane;
+#if B200_E1_PIPE >= 2
+      double4 qB = qB2, tB = tB2;          // record of j + 1 (gathered during j - 1)
+      double4 qC = qB2, tC = tB2;
+      int camC = 0, camD = 0;
+      double2 xyC = xyB;
+      if (j + 2 < mylen) {
+        qC = ld_rec32(cam_rec + (size_t)camC2 * kCamRec);
+        tC = ld_rec32(cam_rec + (size_t)camC2 * kCamRec + 4);
+        xyC = ld_stream(ell.xy + idx + 64);
+      }
+      if (j + 3 < mylen) camD = ld_stream(ell.cam + idx + 96);
+      (void)camC;
+#else
       double4 qB = qA, tB = tA;
       int camC = 0;
       double2 xyC = xyB;
@@ -142,6 +164,7 @@ __global__ void __launch_bounds__(kEllThreads, NK > 0 ? 3 : B200_E1_MIN_CTAS) ba
         camC = ld_stream(ell.cam + idx + 64);
         xyC = ld_stream(ell.xy + idx + 64);
       }
+#endif
       const double* sr = ell.sensor ? v.sensor_rec + (size_t)ell.sensor[idx] * kSensorRec : nullptr;
       const int blk = obs_intr_idx(tA, sr);
       const double* ir = intr_rec + (size_t)blk * kIntrRec;
@@ -167,7 +190,11 @@ __global__ void __launch_bounds__(kEllThreads, NK > 0 ? 3 : B200_E1_MIN_CTAS) ba
           for (int k = 0; k < 3 * NK; ++k) st_stream(rowB + 32 * k, Bo[k]);
         }
       }
+#if B200_E1_PIPE >= 2
+      qA = qB; tA = tB; qB2 = qC; tB2 = tC; xyA = xyB; xyB = xyC; camC2 = camD;
+#else
       qA = qB; tA = tB; xyA = xyB; xyB = xyC; camB = camC;
+#endif
     }
 #else
 #pragma unroll 2

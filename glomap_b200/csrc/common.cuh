@@ -132,9 +132,16 @@ __device__ __forceinline__ void ld_nc_256(const double* p, double& a, double& b,
 // One 32-B read-only gather as a value (LDG.E.256.CONSTANT).  `*reinterpret_cast<const double4*>` compiles to TWO
 // LDG.E.128 (double4 is 16-B aligned): with 32 lanes on 32 different records that is 64 L1 wavefronts instead of 32, and
 // the linearisation / cost kernels are bound by exactly that pipe (profiles/r2_ncu_summary.md).  p must be 32-B aligned.
+#ifndef B200_REC_CG
+#define B200_REC_CG 0
+#endif
 __device__ __forceinline__ double4 ld_rec32(const double* p) {
   double4 r;
+#if B200_REC_CG   // experiment: cache the gathered records in L2 only
+  asm("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#else
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#endif
   return r;
 }
 // streaming (evict-first) scalar accesses

@@ -11,6 +11,7 @@
 
 #include "../../include/b200sfm.h"
 #include "common.cuh"
+#include "p2p_allreduce.cuh"
 #include "pcg.cuh"
 
 struct NcclApi {
@@ -66,7 +67,18 @@ struct b200sfm_ctx {
   // one-shot solve does not pay cudaMallocHost / cudaMalloc / cudaFree (a device-wide synchronisation) on every call
   b200::PcgHost pcgh;
 
-  void allreduce_sum(double* buf, size_t n) { allreduce_sum_on(stream, buf, n); }
+  // small sums go over peer memory when it is set up (p2p_allreduce.cuh), everything else through NCCL
+  b200::P2PAllReduce p2p;
+  long long p2p_calls = 0;
+  void allreduce_sum(double* buf, size_t n) {
+    if (world > 1 && p2p.ready && n > 0 && n <= p2p.cap) {
+      p2p.launch(stream, buf, n);
+      ++p2p_calls;
+      ++launches;
+      return;
+    }
+    allreduce_sum_on(stream, buf, n);
+  }
   void allreduce_sum_on(cudaStream_t st, double* buf, size_t n) {
     if (world == 1 || n == 0) return;
     if (!comm) throw NcclError{"communicator was aborted after an earlier failure"};
