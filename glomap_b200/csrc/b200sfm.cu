@@ -165,8 +165,11 @@ int b200sfm_create_dist(int device, int rank, int world_size, const void* nccl_i
     }
     // Peer-memory all-reduce for the per-iteration vectors (p2p_allreduce.cuh).  B200SFM_P2P_AR=0 keeps NCCL; a rank
     // without peer access to the others makes every rank fall back (the verdict is exchanged inside setup()).
+    // Default: from 4 ranks up.  On 2 GPUs NCCL's 2-hop exchange is already as fast (measured 26.9 ms per step with NCCL,
+    // 28.2 ms with the first version of this kernel); on 8 its ring costs ~85 us per call.  B200SFM_P2P_AR=1 forces it on.
     const char* pe = getenv("B200SFM_P2P_AR");
-    if (!(pe && atoi(pe) == 0)) {
+    const bool want_p2p = pe ? atoi(pe) != 0 : world_size >= 4;
+    if (want_p2p) {
       DevBufRaw stage;   // gather over NCCL: every rank fills its slot of a zeroed buffer, the sum is the concatenation
       auto gather = [&](void* host, size_t bytes_per_rank) -> bool {
         const size_t words = (bytes_per_rank + 7) / 8, total = words * (size_t)world_size;

@@ -55,7 +55,11 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_sum(double* __restr
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double* mine = peers.buf[rank] + slot_off;
-  for (size_t i = t0; i < n; i += stride) mine[i] = data[i];
+  {
+    const size_t n2p = n / 2;
+    for (size_t i = t0; i < n2p; i += stride) reinterpret_cast<double2*>(mine)[i] = reinterpret_cast<const double2*>(data)[i];
+    if ((n & 1) && t0 == 0) mine[n - 1] = data[n - 1];
+  }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -75,10 +79,23 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_sum(double* __restr
     }
   }
   __syncthreads();
-  for (size_t i = t0; i < n; i += stride) {
+  // (the acquire above orders these reads after the peers' publication; peer memory is not cached in this GPU's L2 and
+  //  L1 is bypassed with .cv, so plain vector loads are enough -- every load of a thread is in flight at once)
+  const size_t n2 = n / 2;
+  for (size_t i = t0; i < n2; i += stride) {
+    double2 s = make_double2(0.0, 0.0);
+#pragma unroll 8
+    for (int r = 0; r < world; ++r) {   // fixed order: bitwise identical on all ranks
+      const double2 v = __ldcv(reinterpret_cast<const double2*>(peers.buf[r] + slot_off) + i);
+      s.x += v.x;
+      s.y += v.y;
+    }
+    reinterpret_cast<double2*>(data)[i] = s;
+  }
+  if ((n & 1) && t0 == 0) {
     double s = 0.0;
-    for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(peers.buf[r] + slot_off + i);   // fixed order: identical on all ranks
-    data[i] = s;
+    for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(peers.buf[r] + slot_off + n - 1);
+    data[n - 1] = s;
   }
 }
 
@@ -146,7 +163,8 @@ struct P2PAllReduce {
   }
   void launch(cudaStream_t s, double* data, size_t n) {
     ++epoch;
-    const int grid = (int)std::min<size_t>(std::max<size_t>((n + kP2PThreads * 4 - 1) / (kP2PThreads * 4), 1), 120);
+    // one double2 per thread when the vector fits (a single round of NVLink latency), at most 120 co-resident CTAs
+    const int grid = (int)std::min<size_t>(std::max<size_t>((n / 2 + kP2PThreads - 1) / kP2PThreads, 1), 120);
     p2p_allreduce_sum<<<grid, kP2PThreads, 0, s>>>(data, n, world, rank, peers, (epoch & 1) * cap, epoch, counter,
                                                     reinterpret_cast<int*>(counter + 1));
     B200_CUDA_OK(cudaGetLastError());
