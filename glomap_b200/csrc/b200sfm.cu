@@ -165,10 +165,10 @@ int b200sfm_create_dist(int device, int rank, int world_size, const void* nccl_i
     }
     // Peer-memory all-reduce for the per-iteration vectors (p2p_allreduce.cuh).  B200SFM_P2P_AR=0 keeps NCCL; a rank
     // without peer access to the others makes every rank fall back (the verdict is exchanged inside setup()).
-    // Default: from 4 ranks up.  On 2 GPUs NCCL's 2-hop exchange is already as fast (measured 26.9 ms per step with NCCL,
-    // 28.2 ms with the first version of this kernel); on 8 its ring costs ~85 us per call.  B200SFM_P2P_AR=1 forces it on.
+    // OPT-IN (B200SFM_P2P_AR=1).  Measured at config 4 (profiles/r2_scaling.md): 28.2 vs 26.9 ms per step on 2 GPUs and
+    // 15.1 vs 13.75 ms on 8 -- NCCL's all-reduce of this size is faster than this kernel on both, so NCCL stays the default.
     const char* pe = getenv("B200SFM_P2P_AR");
-    const bool want_p2p = pe ? atoi(pe) != 0 : world_size >= 4;
+    const bool want_p2p = pe && atoi(pe) == 1;
     if (want_p2p) {
       DevBufRaw stage;   // gather over NCCL: every rank fills its slot of a zeroed buffer, the sum is the concatenation
       auto gather = [&](void* host, size_t bytes_per_rank) -> bool {

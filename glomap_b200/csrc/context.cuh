@@ -71,7 +71,7 @@ struct b200sfm_ctx {
   b200::P2PAllReduce p2p;
   long long p2p_calls = 0;
   void allreduce_sum(double* buf, size_t n) {
-    if (world > 1 && p2p.ready && n > 0 && n <= p2p.cap) {
+    if (world > 1 && p2p.ready && n > 0 && n <= p2p.cap && (reinterpret_cast<uintptr_t>(buf) & 15) == 0) {   // double2 accesses
       p2p.launch(stream, buf, n);
       ++p2p_calls;
       ++launches;

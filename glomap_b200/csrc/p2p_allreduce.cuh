@@ -1,11 +1,13 @@
 // p2p_allreduce.cuh -- one-shot sum all-reduce over NVLink peer memory for the small, latency-bound vectors of the
 // multi-GPU solvers (the 6 C doubles of every PCG mat-vec: 480 KB at config 4).
 //
-// NCCL serves that size with its ring: 2 (N - 1) dependent hops, ~85 us on 8 GPUs (measured through bench.py: 13.75 ms
-// per step where the kernels account for 6.5 ms; profiles/r2_scaling.md) -- per PCG iteration, 53 times per solve.  Here
-// every rank publishes its vector in a buffer the peers have mapped (CUDA IPC), raises one flag per peer, and then reads
-// all N published vectors straight over NVLink / NVSwitch and adds them IN RANK ORDER: one hop instead of 14, and the
-// result is bitwise identical on every rank (the replicated PCG control flow relies on that).
+// EXPERIMENT, opt-in (B200SFM_P2P_AR=1): it is correct (2- and 8-rank parity of the BA solve) but SLOWER than NCCL's
+// all-reduce of this size on both 2 GPUs (28.2 vs 26.9 ms per step) and 8 GPUs (15.1 vs 13.75 ms), profiles/r2_scaling.md.
+// Every rank publishes its vector in a buffer the peers have mapped (CUDA IPC), raises one flag per peer, and then reads
+// all N published vectors straight over NVLink / NVSwitch and adds them IN RANK ORDER: one hop, and the result is
+// bitwise identical on every rank (the replicated PCG control flow relies on that).  What it pays for that hop -- a
+// system-scope fence after the publication, N release stores and an acquire spin per call -- costs more than NCCL's
+// protocol does; the next thing to try is publishing straight from the producing kernel (pass B) instead of a copy.
 //
 //   kernel, per rank:   publish my vector  ->  last CTA: release-store epoch into flag[me] of every peer
 //                       every CTA: acquire-spin until my flag[r] >= epoch for all r  ->  sum_r buf_r[i] (r = 0 .. N-1)
