@@ -6,8 +6,8 @@
 // Every rank publishes its vector in a buffer the peers have mapped (CUDA IPC), raises one flag per peer, and then reads
 // all N published vectors straight over NVLink / NVSwitch and adds them IN RANK ORDER: one hop, and the result is
 // bitwise identical on every rank (the replicated PCG control flow relies on that).  What it pays for that hop -- a
-// system-scope fence after the publication, N release stores and an acquire spin per call -- costs more than NCCL's
-// protocol does; the next thing to try is publishing straight from the producing kernel (pass B) instead of a copy.
+// system-scope fence after the publication, N flag stores and an acquire spin per call -- costs more than NCCL's
+// protocol does (the measured build still issued one release store, i.e. one system fence, PER PEER); the next thing to try is publishing straight from the producing kernel (pass B) instead of a copy.
 //
 //   kernel, per rank:   publish my vector  ->  last CTA: release-store epoch into flag[me] of every peer
 //                       every CTA: acquire-spin until my flag[r] >= epoch for all r  ->  sum_r buf_r[i] (r = 0 .. N-1)
@@ -27,6 +27,9 @@ namespace b200 {
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -67,8 +70,9 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_sum(double* __restr
   if (threadIdx.x == 0) {
     if (atomicAdd(counter, 1u) == gridDim.x - 1) {   // the last CTA of this rank: the whole vector is published
       *counter = 0;                                  // (every CTA has arrived; the next launch starts from 0)
-      __threadfence_system();
-      for (int r = 0; r < world; ++r) st_release_sys_u64(peers.flags[r] + rank, epoch);
+      __threadfence_system();                        // ONE system fence, then plain (relaxed) flag stores: a release store
+      for (int r = 0; r < world; ++r)                // per peer compiles to a MEMBAR.ALL.SYS each (profiles/r2_sass_excerpt.txt)
+        st_relaxed_sys_u64(peers.flags[r] + rank, epoch);
     }
   }
   if (threadIdx.x < world) {
