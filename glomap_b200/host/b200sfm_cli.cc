@@ -270,6 +270,10 @@ static int RunFlat(int argc, char** argv, bool is_ba) {
   }
   for (int64_t t = 0; t < p.P; ++t)
     for (int k = 0; k < 3; ++k) p.points[3 * t + k] = tracks[(track_t)(t + 1)].xyz[k];
+  for (int64_t k = 0; k < p.K; ++k) {   // refined intrinsics (optimize_intrinsics): BundleAdjuster writes camera.params in place
+    const Camera& c = cameras[(camera_t)(k + 1)];
+    for (size_t j = 0; j < c.params.size() && j < 12; ++j) p.intr[k * 12 + j] = c.params[j];
+  }
   return FlatIO(args["output"], p, true) ? 0 : 1;
 }
 
