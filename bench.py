@@ -63,49 +63,110 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """SM clock and throttle reasons DURING the timed region.  Two sources, because the timed region of the default run
+    is only ~150 ms: (1) NVML in-process (pynvml), polled every 5 ms by a thread between mark_begin() and stop();
+    (2) `nvidia-smi -lms 50` with timestamps, launched with start() BEFORE the warm-up (the tool needs a few hundred ms
+    to come up) and filtered to the same window.  The NVML samples are used when there are any, else nvidia-smi's."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml_rows, self.nvml_on, self.nvml_th = [], False, None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+    def _poll_nvml(self):
+        nv = self._nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while self.nvml_on:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                self.nvml_rows.append((sm, [n for n, bit in names if mask & bit]))
+            except Exception:
+                break
+            time.sleep(0.005)
+
+    def mark_begin(self):
+        """Start of the timed region."""
+        import datetime
+        self.t_begin = datetime.datetime.now()
+        if getattr(self, "_nv", None) is not None:
+            self.nvml_on = True
+            self.nvml_th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.nvml_th.start()
+
+    @staticmethod
+    def parse_smi(rows, t_begin, t_end):
+        """(sm clocks, max clocks, reasons) of the nvidia-smi rows whose timestamp lies in [t_begin, t_end] (no window: all)."""
+        import datetime
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                a, b = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            if t_begin is not None and t_end is not None and not (t_begin <= ts <= t_end):
+                continue
+            sm.append(a); mx.append(b)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        return sm, mx, reasons
+
+    def stop(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+        self.nvml_on = False
+        if self.nvml_th is not None:
+            self.nvml_th.join(timeout=1)
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.nvml_rows:
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted({n for r in self.nvml_rows for n in r[1]})
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self._mx, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML, 5 ms polling inside the timed region"}
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
+        sm, mx, reasons = self.parse_smi(self.rows, self.t_begin, self.t_end)
+        src = "nvidia-smi -lms 50, rows inside the timed region"
+        if not sm:   # a region shorter than one sampling period: the rows since the warm-up (same clocks, same load pattern)
+            sm, mx, reasons = self.parse_smi(self.rows, None, None)
+            src = "nvidia-smi -lms 50, rows since the warm-up (none fell inside the timed region)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": src}
 
 
 def shard_range(P, chunk, rank, world):
@@ -268,13 +329,15 @@ def run_b200(args):
     prob.set_state(init.intr_params, init.quat, init.trans, init.points)
     prob.save_state()
     stats = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()            # nvidia-smi needs a few hundred ms to come up: launched before the warm-up
     for _ in range(args.warmup):
         prob.restore_state()
         prob.solve(opts)
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()       # the samples reported are those between here and stop()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     e0.record(stream)
