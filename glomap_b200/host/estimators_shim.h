@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <array>
 #include <map>
+#include <limits>
 #include <queue>
+#include <set>
 #include <random>
 #include <string>
 #include <vector>
@@ -537,7 +539,7 @@ class RotationEstimator {
   }
 
   // global_rotation_averaging.cc:40-85 (3-DoF frames and, with use_gravity, 1-DoF frames that carry a gravity
-  // prior; trivial frames and known rigs -- unknown cam_from_rig rotations are not estimated).
+  // prior; trivial frames, known rigs and rigs with sensors whose cam_from_rig rotation is estimated alongside).
   bool EstimateRotations(const ViewGraph& view_graph, std::unordered_map<rig_t, Rig>& rigs,
                          std::unordered_map<frame_t, Frame>& frames, std::unordered_map<image_t, Image>& images) {
     if (options_.use_gravity) {   // .cc:47-59: gravity-aligned averaging needs every rig calibrated
@@ -561,6 +563,37 @@ class RotationEstimator {
     if (n == 0) return false;
     std::vector<double> theta(3 * (size_t)n);
     for (auto& [id, f] : fsorted) QuatToAngleAxis(f->RigFromWorld().rotation.coeffs().data(), &theta[3 * (size_t)fidx[id]]);   // .cc:223-224
+    // Cameras whose cam_from_rig rotation has to be estimated (.cc:162-194): non-reference sensors of the rigs of the
+    // registered images without a cam_from_rig, or with one whose translation is still NaN (its rotation is then the
+    // initial value, .cc:186-190; else zero, .cc:239-241).  They become nodes n, n + 1, ... in ascending camera id.
+    std::map<camera_t, rig_t> cam_rig;
+    for (auto& [id, im] : images) {
+      const auto fit = frames.find(im.frame_id);
+      if (fit == frames.end() || !fit->second.is_registered) continue;
+      cam_rig[im.camera_id] = fit->second.RigId();
+    }
+    std::map<camera_t, int> ucam;
+    for (auto& [cam, rig_id] : cam_rig) {
+      Rig& rig = rigs[rig_id];
+      if (b200host_adapt::IsRefSensor(rig, cam)) continue;
+      const bool has = b200host_adapt::HasCamFromRig(rig, cam);
+      bool nan_t = false;
+      if (has) {
+        const Rigid3d c = b200host_adapt::CamFromRig(rig, cam);
+        for (int k = 0; k < 3; ++k) nan_t = nan_t || std::isnan(c.translation[k]);
+      }
+      if (!has || nan_t) {
+        const int node = n + (int)ucam.size();
+        ucam[cam] = node;
+        double aa[3] = {0, 0, 0};
+        if (has) {
+          const Rigid3d c = b200host_adapt::CamFromRig(rig, cam);
+          QuatToAngleAxis(c.rotation.coeffs().data(), aa);
+        }
+        theta.insert(theta.end(), aa, aa + 3);
+      }
+    }
+    const int n_cams = (int)ucam.size();
     // use_gravity (.cc:207-217): a frame with a gravity prior keeps theta = (0, phi, 0), phi = RotUpToAngle(R_align^T R);
     // the first such frame (sorted-id order) is the fixed one
     std::vector<uint8_t> has_gravity(n, 0);
@@ -588,7 +621,7 @@ class RotationEstimator {
     std::map<image_pair_t, const ImagePair*> psorted;
     for (const auto& [id, pr] : view_graph.image_pairs)
       if (pr.is_valid) psorted[id] = &pr;
-    std::vector<int32_t> ei, ej;
+    std::vector<int32_t> ei, ej, eci, ecj;
     std::vector<double> Rrel, w;
     for (const auto& [id, pr] : psorted) {
       const auto i1 = images.find(pr->image_id1), i2 = images.find(pr->image_id2);
@@ -599,7 +632,11 @@ class RotationEstimator {
       QuatToR(pr->cam2_from_cam1.rotation.coeffs().data(), R);
       // known rigs: the unknowns are the frame rotations, R_rel = R_c2r2^T R_21 R_c1r1 (.cc:274-309); an image
       // pair inside one frame is a self loop and is skipped (.cc:300-303)
-      const bool rig1 = !i1->second.HasTrivialFrame(), rig2 = !i2->second.HasTrivialFrame();
+      // (has_sensor_from_rig of the reference: a non-reference sensor with a KNOWN cam_from_rig; an unknown one
+      //  contributes the identity here and its own -I / +I block, .cc:281-296,425-440)
+      const auto u1 = ucam.find(i1->second.camera_id), u2 = ucam.find(i2->second.camera_id);
+      const bool rig1 = !i1->second.HasTrivialFrame() && u1 == ucam.end();
+      const bool rig2 = !i2->second.HasTrivialFrame() && u2 == ucam.end();
       if (rig1 && rig2 && f1->second == f2->second) continue;
       if (rig1) {
         const Rigid3d c = b200host_adapt::CamFromRig(rigs[frames[i1->second.frame_id].RigId()], i1->second.camera_id);
@@ -634,6 +671,8 @@ class RotationEstimator {
       }
       ei.push_back(f1->second);
       ej.push_back(f2->second);
+      eci.push_back(u1 == ucam.end() || i1->second.HasTrivialFrame() ? -1 : u1->second);
+      ecj.push_back(u2 == ucam.end() || i2->second.HasTrivialFrame() ? -1 : u2->second);
       Rrel.insert(Rrel.end(), R, R + 9);
       w.push_back(pr->weight);
     }
@@ -645,11 +684,27 @@ class RotationEstimator {
     o.irls_loss_parameter_sigma = options_.irls_loss_parameter_sigma;
     o.weight_type = options_.weight_type == RotationEstimatorOptions::HALF_NORM ? 1 : 0;
     o.use_weight = options_.use_weight; o.pcg_rel_tolerance = options_.pcg_rel_tolerance;
-    const int rc = any_gravity
-                       ? b200sfm_ra_solve_gravity(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(),
-                                                  has_gravity.data(), fixed_frame, theta.data(), &summary)
-                       : b200sfm_ra_solve(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), 0,
-                                          theta.data(), &summary);
+    int rc;
+    if (n_cams > 0) {   // frames that hold an image of each unknown camera (the quaternion average of .cc:675-693 runs over them)
+      std::map<camera_t, std::set<int>> cam_frames_of;
+      for (auto& [id, im] : images) {
+        const auto u = ucam.find(im.camera_id);
+        const auto f = fidx.find(im.frame_id);
+        if (u != ucam.end() && f != fidx.end() && !im.HasTrivialFrame()) cam_frames_of[im.camera_id].insert(f->second);
+      }
+      std::vector<int32_t> cfb(1, 0), cf;
+      for (auto& [cam, node] : ucam) {
+        for (int f : cam_frames_of[cam]) cf.push_back(f);
+        cfb.push_back((int32_t)cf.size());
+      }
+      rc = b200sfm_ra_solve_rig(ctx, &o, n, n_cams, (int64_t)ei.size(), ei.data(), ej.data(), eci.data(), ecj.data(), Rrel.data(),
+                                w.data(), cfb.data(), cf.data(), 0, theta.data(), &summary);
+    } else if (any_gravity) {
+      rc = b200sfm_ra_solve_gravity(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), has_gravity.data(),
+                                    fixed_frame, theta.data(), &summary);
+    } else {
+      rc = b200sfm_ra_solve(ctx, &o, n, (int64_t)ei.size(), ei.data(), ej.data(), Rrel.data(), w.data(), 0, theta.data(), &summary);
+    }
     if (rc != B200SFM_OK) { std::fprintf(stderr, "b200sfm_ra_solve: %s\n", b200sfm_last_error(ctx)); return false; }
     if (!summary.usable) return false;                                                        // NaN (.cc:508-512,590-593)
     for (auto& [id, f] : fsorted) {                                                           // ConvertResults (.cc:787-798)
@@ -667,6 +722,12 @@ class RotationEstimator {
         AngleAxisToQuat(&theta[3 * (size_t)i], qout);
       }
       for (int k = 0; k < 3; ++k) f->RigFromWorld().translation[k] = 0.0;                     // Vector3d::Zero() (.cc:795)
+    }
+    for (auto& [cam, node] : ucam) {   // the estimated cam_from_rig rotations, translation not known yet (.cc:800-813)
+      Rigid3d c;
+      AngleAxisToQuat(&theta[3 * (size_t)node], c.rotation.coeffs().data());
+      for (int k = 0; k < 3; ++k) c.translation[k] = std::numeric_limits<double>::quiet_NaN();
+      b200host_adapt::SetCamFromRig(rigs[cam_rig[cam]], cam, c);
     }
     return true;
   }

@@ -241,9 +241,16 @@ int b200sfm_gp_problem_restore_state(b200sfm_gp_problem* p) { (void)p; return B2
 int b200sfm_ra_solve_rig(b200sfm_ctx* ctx, const b200sfm_ra_opts* o, int32_t nf, int32_t nc, int64_t ne, const int32_t* ei,
                          const int32_t* ej, const int32_t* eci, const int32_t* ecj, const double* R, const double* w,
                          const int32_t* cfb, const int32_t* cf, int32_t fixed, double* theta, b200sfm_ra_stats* st) {
-  (void)ctx; (void)o; (void)nf; (void)nc; (void)ne; (void)ei; (void)ej; (void)eci; (void)ecj; (void)R; (void)w; (void)cfb; (void)cf;
-  (void)fixed; (void)theta;
+  (void)ctx; (void)o;
   dump_call("ra_solve_rig");
+  int32_t dims[4] = {nf, nc, (int32_t)ne, fixed};
+  DUMP_INT("dims", dims, 4);
+  DUMP_INT("ei", ei, ne); DUMP_INT("ej", ej, ne); DUMP_INT("eci", eci, ne); DUMP_INT("ecj", ecj, ne);
+  dump_d("R_rel", R, 9 * ne); dump_d("w", w, ne);
+  DUMP_INT("cam_frames_begin", cfb, nc + 1); DUMP_INT("cam_frames", cf, cfb ? cfb[nc] : 0);
+  dump_d("theta", theta, 3ll * (nf + nc));
+  /* a recognisable result for the camera nodes: rotation 0.3 rad about z */
+  for (int c = 0; c < nc; ++c) { theta[3 * (nf + c)] = 0; theta[3 * (nf + c) + 1] = 0; theta[3 * (nf + c) + 2] = 0.3; }
   if (st) { memset(st, 0, sizeof(*st)); st->usable = 1; }
   return B200SFM_OK;
 }

@@ -116,6 +116,16 @@ int main() {
   std::printf("c2r %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", o2.rotation.c[0], o2.rotation.c[1], o2.rotation.c[2], o2.rotation.c[3],
               o2.translation[0], o2.translation[1], o2.translation[2]);
   std::printf("nrig1 %zu\n", rigs[1].cam_from_rig.size());
+  // rotation averaging with a sensor whose cam_from_rig is not known yet (global_rotation_averaging.cc:162-245,800-813):
+  // camera 2 of rig 1 loses its calibration -> one extra rotation node, its estimate lands in the rig with a NaN translation
+  rigs[1].uncalibrated.clear();
+  rigs[1].cam_from_rig.erase(2);
+  rigs[1].uncalibrated.push_back(2);
+  RotationEstimator rau(ro);   // skip_initialization = true
+  if (!rau.EstimateRotations(vg, rigs, frames, images)) return 9;
+  const Rigid3d& e2 = rigs[1].cam_from_rig[2];
+  std::printf("est2 %.17g %.17g %.17g %.17g %d\n", e2.rotation.c[0], e2.rotation.c[1], e2.rotation.c[2], e2.rotation.c[3],
+              (int)std::isnan(e2.translation[0]));
   std::printf("shim driver ok\n");
   return 0;
 }

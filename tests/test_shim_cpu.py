@@ -56,7 +56,7 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
                                            "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
                                            "ra_solve_gravity", "ba_solve", "ra_solve",
                                            "ba_problem_create_rig", "ba_problem_set_state", "ba_problem_set_sensor_variable",
-                                           "ba_problem_solve"]
+                                           "ba_problem_solve", "ra_solve_rig"]
     # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
     img_ids = [101, 102, 201, 202, 301, 302, 401]
     kimg = {i: k for k, i in enumerate(img_ids)}
@@ -162,6 +162,17 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     c2r = np.array([float(x) for x in stdout_line(calls, "c2r")])
     assert np.allclose(c2r, [0, 0, 0.70710678118654757, 0.70710678118654757, 8.0, 8.0, 9.0], atol=0)   # the mock's pose of sensor 1
     assert stdout_line(calls, "nrig1") == ["1"]                              # no entry was created for the reference sensor
+    # ---- rotation averaging with an uncalibrated sensor (camera 2 of rig 1): one extra rotation node -----------------
+    ru = calls[14]
+    assert ru["dims"].tolist() == [4, 1, 5, 0]                              # frames, unknown cameras, edges, fixed frame
+    # pairs in ascending pair id: (101,102) (101,201) (102,301) (202,302) (301,401); the pair inside frame 10 is KEPT
+    assert ru["ei"].tolist() == [0, 0, 0, 1, 2] and ru["ej"].tolist() == [0, 1, 2, 2, 3]
+    assert ru["eci"].tolist() == [-1, -1, 4, 4, -1] and ru["ecj"].tolist() == [4, -1, -1, 4, -1]
+    assert np.abs(ru["R_rel"].reshape(-1, 3, 3) - Rrel).max() < 1e-15       # no known cam_from_rig factor is left in any pair
+    assert ru["cam_frames_begin"].tolist() == [0, 3] and ru["cam_frames"].tolist() == [0, 1, 2]
+    assert np.abs(ru["theta"].reshape(-1, 3)[4]).max() == 0                 # no prior value: zero (.cc:239-241)
+    est2 = stdout_line(calls, "est2")
+    assert np.allclose([float(x) for x in est2[:4]], [0, 0, np.sin(0.15), np.cos(0.15)], atol=1e-15) and est2[4] == "1"
 
 
 def test_shim_typechecks_against_the_glomap_api():
