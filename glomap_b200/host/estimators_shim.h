@@ -335,6 +335,10 @@ class GlobalPositioner {
     }
     std::vector<double> obs_off;      // known rigs: R_cw^T t_cam_from_rig per observation (.cc:339-345)
     std::vector<uint8_t> obs_cal;     // the loss is chosen per CAMERA (.cc:313-316)
+    // sensors whose cam_from_rig translation is still NaN (rotation averaging estimated their rotation only): their
+    // centre in the rig frame is an unknown of this solve, RigUnknownBATAPairwiseDirectionError (.cc:355-372)
+    std::map<std::pair<rig_t, camera_t>, int> usens;
+    std::vector<int32_t> obs_usens;
     std::map<track_t, Track*> tsorted;
     for (auto& [id, t] : tracks) tsorted[id] = &t;
     const int P = (int)tsorted.size();
@@ -357,10 +361,15 @@ class GlobalPositioner {
           Rigid3d cfr;
           if (!it->second.HasTrivialFrame())
             cfr = b200host_adapt::CamFromRig(rigs[frames[it->second.frame_id].RigId()], it->second.camera_id);
+          int us = -1;
           if (std::isnan(cfr.translation[0]) || std::isnan(cfr.translation[1]) || std::isnan(cfr.translation[2])) {
-            std::fprintf(stderr, "b200sfm: unknown cam_from_rig (RigUnknownBATA) is not supported\n");
-            return false;
+            const auto key = std::make_pair(frames[it->second.frame_id].RigId(), it->second.camera_id);
+            auto u = usens.find(key);
+            if (u == usens.end()) u = usens.emplace(key, (int)usens.size()).first;
+            us = u->second;
+            cfr.translation[0] = cfr.translation[1] = cfr.translation[2] = 0.0;   // no known offset: the centre is the unknown
           }
+          obs_usens.push_back(us);
           double Rs[9], bb[3], tt[3];
           QuatToR(cfr.rotation.coeffs().data(), Rs);
           for (int k = 0; k < 3; ++k) {   // R_cr^T b, R_cr^T t_cr
@@ -400,9 +409,29 @@ class GlobalPositioner {
       rc = b200sfm_gp_problem_create(ctx, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),
                                      calibrated.data(), nullptr, o.min_num_view_per_track, &prob);
       if (rc == B200SFM_OK) rc = b200sfm_gp_problem_set_rig_terms(prob, obs_off.data(), obs_cal.data());
+      // unknown sensor centres: U(-1, 1)^3 when the positions are optimised (.cc:440-453), in order of first appearance
+      std::vector<double> ucen(3 * usens.size(), 0.0);
+      if (!usens.empty()) {
+        if (options_.optimize_positions)
+          for (double& v : ucen) v = U(random_generator_);
+        if (rc == B200SFM_OK)
+          rc = b200sfm_gp_problem_set_rig_unknown(prob, (int32_t)usens.size(), obs_usens.data(), Rm.data(), ucen.data());
+      }
       if (rc == B200SFM_OK) rc = b200sfm_gp_problem_set_state(prob, centers.data(), points.data(), scales.data());
       if (rc == B200SFM_OK) rc = b200sfm_gp_problem_solve(prob, &o, &summary);
       if (rc == B200SFM_OK) rc = b200sfm_gp_problem_get_state(prob, centers.data(), points.data(), scales.data());
+      if (rc == B200SFM_OK && !usens.empty()) {
+        rc = b200sfm_gp_problem_get_rig_unknown(prob, ucen.data());
+        if (rc == B200SFM_OK)
+          for (auto& [key, idx] : usens) {   // ConvertResults: centre -> translation = -(R_cr u)  (.cc:578-582)
+            Rigid3d cfr = b200host_adapt::CamFromRig(rigs[key.first], key.second);
+            double Rs[9];
+            QuatToR(cfr.rotation.coeffs().data(), Rs);
+            for (int k = 0; k < 3; ++k)
+              cfr.translation[k] = -(Rs[3 * k] * ucen[3 * idx] + Rs[3 * k + 1] * ucen[3 * idx + 1] + Rs[3 * k + 2] * ucen[3 * idx + 2]);
+            b200host_adapt::SetCamFromRig(rigs[key.first], key.second, cfr);
+          }
+      }
       b200sfm_gp_problem_free(prob);
     } else {
       rc = b200sfm_gp_solve(ctx, &o, C, P, (int64_t)obs_cam.size(), ptb.data(), obs_cam.data(), obs_dir.data(),

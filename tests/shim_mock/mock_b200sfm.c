@@ -175,12 +175,23 @@ int b200sfm_gp_problem_set_rig_terms(b200sfm_gp_problem* p, const double* off, c
   dump_d("obs_offset", off, 3 * g_gp_n); DUMP_INT("obs_calibrated", cal, g_gp_n);
   return B200SFM_OK;
 }
+static int g_gp_su = 0;
 int b200sfm_gp_problem_set_rig_unknown(b200sfm_gp_problem* p, int32_t su, const int32_t* os, const double* fr, const double* c) {
-  (void)p; (void)su; (void)os; (void)fr; (void)c;
+  (void)p; (void)fr;
   dump_call("gp_problem_set_rig_unknown");
+  int32_t dims[1] = {su};
+  DUMP_INT("dims", dims, 1);
+  DUMP_INT("obs_unknown_sensor", os, g_gp_n);
+  dump_d("centers", c, 3ll * su);
+  g_gp_su = su;
   return B200SFM_OK;
 }
-int b200sfm_gp_problem_get_rig_unknown(b200sfm_gp_problem* p, double* c) { (void)p; (void)c; return B200SFM_OK; }
+/* a recognisable "estimated" centre for every unknown sensor: (1 + s, 2, 3) */
+int b200sfm_gp_problem_get_rig_unknown(b200sfm_gp_problem* p, double* c) {
+  (void)p;
+  for (int s = 0; s < g_gp_su; ++s) { c[3 * s] = 1.0 + s; c[3 * s + 1] = 2; c[3 * s + 2] = 3; }
+  return B200SFM_OK;
+}
 int b200sfm_gp_problem_set_state(b200sfm_gp_problem* p, const double* c, const double* x, const double* s) { (void)p; (void)c; (void)x; (void)s; return B200SFM_OK; }
 int b200sfm_gp_problem_get_state(b200sfm_gp_problem* p, double* c, double* x, double* s) { (void)p; (void)c; (void)x; (void)s; return B200SFM_OK; }
 int b200sfm_gp_problem_solve(b200sfm_gp_problem* p, const b200sfm_gp_opts* o, b200sfm_lm_stats* st) {

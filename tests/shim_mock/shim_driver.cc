@@ -126,6 +126,14 @@ int main() {
   const Rigid3d& e2 = rigs[1].cam_from_rig[2];
   std::printf("est2 %.17g %.17g %.17g %.17g %d\n", e2.rotation.c[0], e2.rotation.c[1], e2.rotation.c[2], e2.rotation.c[3],
               (int)std::isnan(e2.translation[0]));
+  // global positioning with that sensor: its cam_from_rig translation is NaN -> RigUnknownBATA (global_positioning.cc:355-372):
+  // the sensor centre is an unknown, and ConvertResults turns the estimate into a translation (.cc:578-582)
+  GlobalPositionerOptions gu;
+  gu.generate_random_positions = false; gu.generate_random_points = false; gu.optimize_positions = false;
+  GlobalPositioner gpu(gu);
+  if (!gpu.Solve(vg, rigs, cameras, frames, images, tracks)) return 10;
+  const Rigid3d& g2 = rigs[1].cam_from_rig[2];
+  std::printf("gpt2 %.17g %.17g %.17g\n", g2.translation[0], g2.translation[1], g2.translation[2]);
   std::printf("shim driver ok\n");
   return 0;
 }

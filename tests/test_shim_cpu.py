@@ -56,7 +56,9 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
                                            "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_solve", "ra_solve",
                                            "ra_solve_gravity", "ba_solve", "ra_solve",
                                            "ba_problem_create_rig", "ba_problem_set_state", "ba_problem_set_sensor_variable",
-                                           "ba_problem_solve", "ra_solve_rig"]
+                                           "ba_problem_solve", "ra_solve_rig",
+                                           "gp_problem_create", "gp_problem_set_rig_terms", "gp_problem_set_rig_unknown",
+                                           "gp_problem_solve"]
     # ---- the world of shim_driver.cc ---------------------------------------------------------------------------
     img_ids = [101, 102, 201, 202, 301, 302, 401]
     kimg = {i: k for k, i in enumerate(img_ids)}
@@ -171,6 +173,17 @@ def test_shim_flattening_of_a_rig_world(tmp_path):
     assert np.abs(ru["R_rel"].reshape(-1, 3, 3) - Rrel).max() < 1e-15       # no known cam_from_rig factor is left in any pair
     assert ru["cam_frames_begin"].tolist() == [0, 3] and ru["cam_frames"].tolist() == [0, 1, 2]
     assert np.abs(ru["theta"].reshape(-1, 3)[4]).max() == 0                 # no prior value: zero (.cc:239-241)
+    # ---- global positioning with that sensor (translation NaN): RigUnknownBATA -------------------------------------------
+    gu = calls[17]
+    assert gu["dims"].tolist() == [1]
+    assert gu["obs_unknown_sensor"].tolist() == [0 if sensor_of[i] == 1 else -1 for i, _ in obs]   # the images of (rig 1, camera 2)
+    assert np.array_equal(gu["centers"], np.zeros(3))                      # optimize_positions = false: no random draw
+    off = calls[16]["obs_offset"].reshape(-1, 3)
+    assert np.abs(off[[sensor_of[i] == 1 for i, _ in obs]]).max() == 0      # no known offset is left for those observations
+    # ConvertResults: translation = -(R_cr u) with the mock's centre u = (1, 2, 3) and R_cr = the 0.3 rad z-rotation RA estimated
+    c3, s3 = np.cos(0.3), np.sin(0.3)
+    want_t = -(np.array([[c3, -s3, 0], [s3, c3, 0], [0, 0, 1]]) @ np.array([1.0, 2.0, 3.0]))
+    assert np.allclose([float(x) for x in stdout_line(calls, "gpt2")], want_t, atol=1e-15)
     est2 = stdout_line(calls, "est2")
     assert np.allclose([float(x) for x in est2[:4]], [0, 0, np.sin(0.15), np.cos(0.15)], atol=1e-15) and est2[4] == "1"
 
