@@ -599,6 +599,7 @@ class RotationEstimator {
     for (auto& [id, im] : images) {
       const auto fit = frames.find(im.frame_id);
       if (fit == frames.end() || !fit->second.is_registered) continue;
+      if (im.HasTrivialFrame()) continue;   // == IsRefSensor of its rig (scene/image.h:73-76): never estimated
       cam_rig[im.camera_id] = fit->second.RigId();
     }
     std::map<camera_t, int> ucam;
